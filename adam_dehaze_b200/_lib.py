@@ -1,0 +1,127 @@
+"""ctypes binding of libadb200.so — the C-ABI declared in include/adb200.h.
+
+There is no CPU fallback: if the library is missing it is built (nvcc) and if that fails, or a call returns a
+non-zero status, an exception is raised.  Nothing here imports the oracle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libadb200.so")
+
+# --- enums (mirror include/adb200.h)
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+CONV_S1, CONV_S2, CONVT_4X4S2 = 0, 1, 2
+EPI_FEATURE, EPI_DOT, EPI_IMAGE = 0, 1, 2
+IMG_BLEND, IMG_RESIDUAL, IMG_GUIDED = 0, 1, 2
+
+
+class AdbError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("src0", C.c_void_p), ("c0", C.c_int32), ("c0_pitch", C.c_int32),
+        ("src1", C.c_void_p), ("c1", C.c_int32), ("c1_pitch", C.c_int32),
+        ("n", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
+        ("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
+        ("w_packed", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("cout", C.c_int32), ("cout_pad", C.c_int32),
+        ("act", C.c_int32),
+        ("epi", C.c_int32),
+        ("residual", C.c_void_p), ("res_pitch", C.c_int32),
+        ("dst", C.c_void_p), ("dst_pitch", C.c_int32), ("dst_c_off", C.c_int32),
+        ("dot_w", C.c_void_p), ("dot_b", C.c_float), ("dot_out", C.c_void_p),
+        ("img_mode", C.c_int32),
+        ("img_x", C.c_void_p), ("img_out", C.c_void_p), ("img_index", C.c_void_p),
+        ("img_guidance", C.c_void_p), ("img_alpha", C.c_void_p),
+        ("n_dev", C.c_void_p), ("n_start", C.c_int32),
+        ("tune_mt", C.c_int32), ("tune_stages", C.c_int32), ("tune_acc_stages", C.c_int32),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> argtypes (all return int status unless listed in _SPECIAL)
+SIGNATURES = {
+    "adb_version": [],
+    "adb_device_check": [],
+    "adb_kernel_error_flag": [],
+    "adb_conv2d": [C.POINTER(ConvDesc), _P],
+    "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "adb_attn_pool": [_P, _I, _I, _I, _I, _P, _I, _P, _P],
+    "adb_attn_gate_stats": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P],
+    "adb_attn_apply": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "adb_maxpool3x3s2": [_P, _I, _I, _I, _I, _P, _P],
+    "adb_global_avgpool": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "adb_head_mlp": [_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
+    "adb_route": [_P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "adb_blend3": [_P, _P, _P, _P, _F, _I, _L, _P, _P, _P],
+    "adb_l1_mse_fwd": [_P, _P, _L, _P, _P],
+    "adb_l1_bwd": [_P, _P, _L, _F, _P, _P],
+    "adb_mse_bwd": [_P, _P, _L, _F, _P, _P],
+    "adb_ce_fwd_bwd": [_P, _P, _I, _I, _F, _P, _P, _P],
+}
+_SPECIAL = {
+    "adb_last_error": ([], C.c_char_p),
+    "adb_conv2d_flops": ([C.POINTER(ConvDesc)], C.c_double),
+}
+EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
+
+_lib = None
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) and return the ctypes library object."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        if not build_if_missing:
+            raise AdbError(f"{_LIB_PATH} is missing; run `python -m adam_dehaze_b200.build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(_LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name, (argtypes, restype) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().adb_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status, what=""):
+    if status != 0:
+        raise AdbError(f"{what or 'libadb200'} failed with status {status}: {last_error()}")
+
+
+def call(name, *args):
+    """Call an int-status entry point and raise AdbError on failure."""
+    fn = getattr(load(), name)
+    check(fn(*args), name)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,576 @@
+// conv_igemm.cu — implicit-GEMM convolution for sm_100a: TMA-fed, tcgen05.mma into TMEM, fused epilogues.
+//
+// GEMM view:  D[pixel, cout] = sum_k A[pixel, k] * B[cout, k],  k = (tap, input channel).
+//   A: NHWC bf16 feature map(s).  One K step = one filter tap x one chunk of Ck channels; the producer fetches it as a
+//      5-D TMA box {Ck, TW, 1, TH*MT, 1} at the tap-shifted coordinate — out-of-image pixels are zero-filled by the
+//      TMA unit, which is the convolution's zero padding.  Stride-2 convs read the same buffer through a
+//      space-to-depth view {2C, W/2, 2, H/2, N}; ConvTranspose2d(4,2,1) runs as four 2x2 sub-pixel phases whose outputs
+//      are stored through the same view of the destination.  A channel concat is two tensor maps walked back to back.
+//   B: packed weights [cout][k] bf16, K-major, one 2-D TMA box {Ck, BN} per K step.
+//   D: fp32 accumulators in TMEM, 128 pixels (lanes) x BN columns; MT sub-tiles share each B box.
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> affine/residual/activation -> swizzled smem -> TMA store, or the fused
+// image/dot epilogues).  The grid is persistent: one CTA per SM walking tiles round-robin; TMEM accumulators are
+// double buffered when they fit so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Reference arithmetic replaced: nn.Conv2d/ConvTranspose2d + BatchNorm2d(eval) + ReLU/Tanh/Sigmoid (+ residual add),
+// /root/reference/models/dehazing/base_model.py:4-41 and the branch forwards low_intensity.py:33-45,
+// medium_intensity.py:78-117, high_intensity.py:92-138.
+#include "adb_ptx.cuh"
+#include "adb_host.h"
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+using namespace adb;
+
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;          // first epilogue warp
+constexpr int kMaxTaps = 16;
+constexpr int kMaxGroups = 4;
+constexpr int kMaxStages = 12;
+
+struct Tap {
+  int16_t c_mul;  // A channel coordinate = c_mul * channel_pitch(src) + chunk*Ck   (space-to-depth column phase)
+  int8_t dw;      // A column coordinate = tile w0 + dw
+  int8_t p;       // A row-phase coordinate
+  int8_t dh;      // A row coordinate = tile h0 + dh
+};
+
+struct ConvK {
+  // batch
+  int n, n_start;
+  const int* n_dev;
+  // tile grid (per group)
+  int grid_h, grid_w;      // extent of the pixel grid tiles cover (output H/W; input H/W for ConvTranspose phases)
+  int TW, TH, MT;
+  int tiles_w, tiles_h;
+  // K walk
+  int Ck, row_bytes;
+  int chunks0, chunks1, pitch0, pitch1;
+  int ntaps, ngroups;
+  Tap taps[kMaxGroups][kMaxTaps];
+  // N
+  int BN, n_tiles_n, bn_cols, cout_pad;
+  // pipeline
+  int stages, acc_stages, tmem_cols;
+  int a_stage_bytes, b_stage_bytes;   // smem slot sizes (1024-aligned)
+  int stage_tx_bytes;                 // bytes the two TMA boxes of one K step deliver
+  uint32_t idesc;
+  // epilogue
+  int epi, act;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  int res_pitch;
+  int Cs, n_slabs, slab_bytes;           // FEATURE: output slab channels (TMA store box inner dim)
+  int out_c_off[kMaxGroups];             // 5-D store coordinate 0 base per group
+  int out_p[kMaxGroups];                 // 5-D store coordinate 2 per group
+  const float* dot_w; float dot_b; float* dot_out;
+  int img_mode;
+  const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
+  int* err_flag;
+};
+
+struct SmemLayout {
+  // byte offsets from the 1024-aligned base
+  uint32_t a_off, b_off, slab_off, scale_off, bar_off, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int stages, int a_stage_bytes, int b_stage_bytes, int slab_bytes,
+                                                  int n_slab_bufs, int cout_pad) {
+  SmemLayout L;
+  uint32_t off = 0;
+  L.a_off = off; off += (uint32_t)stages * a_stage_bytes;
+  L.b_off = off; off += (uint32_t)stages * b_stage_bytes;
+  L.slab_off = off; off += (uint32_t)n_slab_bufs * slab_bytes;
+  L.scale_off = off; off += (uint32_t)cout_pad * 8;      // scale then shift, fp32
+  off = (off + 15u) & ~15u;
+  L.bar_off = off; off += 8u * (2 * kMaxStages + 4) + 16;  // full[], empty[], tmem_full[2], tmem_empty[2], tmem ptr
+  L.total = off;
+  return L;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ADB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ADB_ACT_TANH) return tanhf(v);
+  if (act == ADB_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+struct TileCoord { int nt, g, w0, h0, img; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t) {
+  TileCoord c;
+  c.nt = t % P.n_tiles_n; t /= P.n_tiles_n;
+  c.g = t % P.ngroups;    t /= P.ngroups;
+  c.w0 = (t % P.tiles_w) * P.TW; t /= P.tiles_w;
+  c.h0 = (t % P.tiles_h) * (P.TH * P.MT);
+  c.img = t / P.tiles_h;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ ConvK P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+
+  const SmemLayout L = smem_layout(P.stages, P.a_stage_bytes, P.b_stage_bytes, P.slab_bytes, 2, P.cout_pad);
+  const uint32_t a_base = base + L.a_off;
+  const uint32_t b_base = base + L.b_off;
+  const uint32_t slab_base = base + L.slab_off;
+  float* s_scale = reinterpret_cast<float*>(base_ptr + L.scale_off);
+  float* s_shift = s_scale + P.cout_pad;
+  const uint32_t bar_base = base + L.bar_off;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 8u * (2 * kMaxStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // live image count of this launch (routed buckets carry it on the device)
+  int n_eff = P.n;
+  if (P.n_dev) n_eff = max(0, min(P.n, *P.n_dev - P.n_start));
+  const int tiles_per_img = P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
+  const int total_tiles = n_eff * tiles_per_img;
+  const int kiters = P.ntaps * (P.chunks0 + P.chunks1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= kEpiWarp0) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.cout_pad; i += 128) {
+      s_scale[i] = P.scale[i];
+      s_shift[i] = P.shift[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ======================================================= TMA producer
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t stage_bytes = (uint32_t)P.stage_tx_bytes;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(P, t);
+      int kcoord = 0;
+      const int brow = tc.g * P.cout_pad + tc.nt * P.BN;
+      for (int tap = 0; tap < P.ntaps; ++tap) {
+        const Tap e = P.taps[tc.g][tap];
+        for (int src = 0; src < 2; ++src) {
+          const int chunks = src ? P.chunks1 : P.chunks0;
+          const int cbase = e.c_mul * (src ? P.pitch1 : P.pitch0);
+          const CUtensorMap* tm = src ? &tmA1 : &tmA0;
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(empty_bar(stage), phase ^ 1u, P.err_flag, 1);
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, tm, full_bar(stage),
+                        cbase + ch * P.Ck, tc.w0 + e.dw, e.p, tc.h0 + e.dh, tc.img);
+            tma_load_2d(b_base + (uint32_t)stage * P.b_stage_bytes, &tmB, full_bar(stage), kcoord, brow);
+            kcoord += P.Ck;
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ======================================================= MMA issuer
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int ksteps = P.Ck / 16;
+    const uint32_t sub_bytes = 128u * P.row_bytes;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u, P.err_flag, 2);
+      tc_fence_after();
+      for (int k = 0; k < kiters; ++k) {
+        mbar_wait(full_bar(stage), phase, P.err_flag, 3);
+        tc_fence_after();
+        const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
+        const uint32_t b_s = b_base + (uint32_t)stage * P.b_stage_bytes;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t bdesc = make_kmajor_desc(b_s + kk * 32u, P.row_bytes);
+          for (int mt = 0; mt < P.MT; ++mt) {
+            const uint64_t adesc = make_kmajor_desc(a_s + mt * sub_bytes + kk * 32u, P.row_bytes);
+            umma_bf16(tmem_base + (uint32_t)((acc * P.MT + mt) * P.bn_cols), adesc, bdesc, P.idesc,
+                      (k | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+      if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ======================================================= epilogue (128 threads, thread = pixel row)
+    const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..127 == TMEM lane == tile row
+    const int ew = warp - kEpiWarp0;                    // TMEM sub-partition of this warp
+    const int th_l = et / P.TW, tw_l = et % P.TW;
+    int acc = 0; uint32_t acc_phase = 0;
+    int slab_buf = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(P, t);
+      mbar_wait(tfull_bar(acc), acc_phase, P.err_flag, 4);
+      tc_fence_after();
+      const int ch0 = tc.nt * P.BN;   // first output channel of this N tile
+      for (int mt = 0; mt < P.MT; ++mt) {
+        const int h = tc.h0 + mt * P.TH + th_l;
+        const int w = tc.w0 + tw_l;
+        const bool inb = (h < P.grid_h) && (w < P.grid_w);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * P.MT + mt) * P.bn_cols);
+        if (P.epi == ADB_EPI_FEATURE) {
+          const size_t pix = ((size_t)tc.img * P.grid_h + h) * P.grid_w + w;
+          const __nv_bfloat16* res_row = (P.residual && inb) ? P.residual + pix * P.res_pitch + ch0 : nullptr;
+          const int c16_per_slab = P.Cs / 16;
+          for (int sl = 0; sl < P.n_slabs; ++sl) {
+            const uint32_t sbuf = slab_base + (uint32_t)slab_buf * P.slab_bytes;
+            // the TMA store that last read this buffer must have drained
+            if (et == 0) tma_store_wait_read<1>();
+            named_bar_sync(1, 128);
+            for (int c16 = 0; c16 < c16_per_slab; ++c16) {
+              const int cl = sl * P.Cs + c16 * 16;   // channel offset inside the N tile
+              float v[16];
+              tmem_ld16(taddr + (uint32_t)cl, v);
+              tmem_ld_wait();
+              float r[16];
+              if (res_row) {
+                const uint4* rp = reinterpret_cast<const uint4*>(res_row + cl);
+                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+                const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
+                  r[2 * i] = __low2float(b2);
+                  r[2 * i + 1] = __high2float(b2);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = 0.f;
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int c = ch0 + cl + 2 * i;
+                float y0 = apply_act(fmaf(v[2 * i], s_scale[c], s_shift[c]) + r[2 * i], P.act);
+                float y1 = apply_act(fmaf(v[2 * i + 1], s_scale[c + 1], s_shift[c + 1]) + r[2 * i + 1], P.act);
+                pk[i] = pack_bf16x2(y0, y1);
+              }
+              const uint32_t row_off = (uint32_t)et * (uint32_t)(P.Cs * 2) + (uint32_t)c16 * 32u;
+              const uint32_t a0 = sbuf + swizzle_addr(row_off, (uint32_t)(P.Cs * 2));
+              const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, (uint32_t)(P.Cs * 2));
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (et == 0) {
+              tma_store_5d(&tmOut, sbuf, P.out_c_off[tc.g] + ch0 + sl * P.Cs, tc.w0, P.out_p[tc.g],
+                           tc.h0 + mt * P.TH, tc.img);
+              tma_store_commit();
+            }
+            slab_buf ^= 1;
+          }
+        } else if (P.epi == ADB_EPI_DOT) {
+          float v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          float g = P.dot_b;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float y = apply_act(fmaf(v[i], s_scale[i], s_shift[i]), P.act);
+            g = fmaf(y, __ldg(P.dot_w + i), g);
+          }
+          g = 1.f / (1.f + __expf(-g));
+          if (inb) P.dot_out[((size_t)tc.img * P.grid_h + h) * P.grid_w + w] = g;
+        } else {  // ADB_EPI_IMAGE
+          float v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          if (inb) {
+            const int pos = P.n_start + tc.img;
+            const size_t row = P.img_index ? (size_t)P.img_index[pos] : (size_t)pos;
+            const size_t plane = (size_t)P.grid_h * P.grid_w;
+            const size_t o = row * 3 * plane + (size_t)h * P.grid_w + w;
+            float gd = 1.f, alpha = 0.f;
+            if (P.img_mode == ADB_IMG_GUIDED) gd = P.img_guidance[((size_t)tc.img * P.grid_h + h) * P.grid_w + w];
+            if (P.img_mode == ADB_IMG_BLEND) alpha = __ldg(P.img_alpha);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float y = apply_act(fmaf(v[c], s_scale[c], s_shift[c]), P.act);
+              const float x = __ldg(P.img_x + o + c * plane);
+              float out;
+              if (P.img_mode == ADB_IMG_BLEND) out = (1.f - alpha) * x + alpha * y;
+              else out = fminf(fmaxf(x + y * gd, 0.f), 1.f);
+              P.img_out[o + c * plane] = out;
+            }
+          }
+        }
+      }
+      // accumulator stage fully read -> hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  // ---------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+inline int pick_chunk(int c) { return (c % 64 == 0) ? 64 : (c % 32 == 0) ? 32 : (c % 16 == 0) ? 16 : 0; }
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
+  memset(&P, 0, sizeof(P));
+  ADB_REQUIRE(d != nullptr, "adb_conv2d: null descriptor");
+  ADB_REQUIRE(d->src0 && d->c0 > 0 && d->c0_pitch >= d->c0 && d->c0_pitch % 8 == 0, "adb_conv2d: bad src0 (c0=%d pitch=%d)", d->c0, d->c0_pitch);
+  ADB_REQUIRE((d->src1 == nullptr) == (d->c1 == 0), "adb_conv2d: src1/c1 mismatch");
+  if (d->src1) ADB_REQUIRE(d->c1 > 0 && d->c1_pitch >= d->c1 && d->c1_pitch % 8 == 0, "adb_conv2d: bad src1 (c1=%d pitch=%d)", d->c1, d->c1_pitch);
+  ADB_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in > 0, "adb_conv2d: bad n/h/w %d/%d/%d", d->n, d->h_in, d->w_in);
+  ADB_REQUIRE(d->w_packed && d->scale && d->shift, "adb_conv2d: null weights/scale/shift");
+  ADB_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 16 == 0 && d->cout_pad <= 512, "adb_conv2d: bad cout %d / cout_pad %d", d->cout, d->cout_pad);
+
+  int Ck = pick_chunk(d->c0);
+  if (d->src1) Ck = std::min(Ck, pick_chunk(d->c1));
+  ADB_REQUIRE(Ck > 0 && d->c0 % Ck == 0 && (d->c1 % Ck) == 0, "adb_conv2d: channel counts %d/%d must be multiples of 16", d->c0, d->c1);
+  P.Ck = Ck; P.row_bytes = Ck * 2;
+  P.chunks0 = d->c0 / Ck; P.chunks1 = d->c1 / Ck;
+  P.pitch0 = d->c0_pitch; P.pitch1 = d->src1 ? d->c1_pitch : d->c0_pitch;
+
+  // ---- taps
+  if (d->kind == ADB_CONV_S1) {
+    ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "adb_conv2d: %dx%d taps unsupported (max %d)", d->kh, d->kw, kMaxTaps);
+    out_h = d->h_in + 2 * d->pad - d->kh + 1;
+    out_w = d->w_in + 2 * d->pad - d->kw + 1;
+    ADB_REQUIRE(out_h == d->h_in && out_w == d->w_in, "adb_conv2d: stride-1 convs must be 'same' (pad=(k-1)/2)");
+    P.ngroups = 1; P.ntaps = d->kh * d->kw;
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        Tap& t = P.taps[0][r * d->kw + s];
+        t.c_mul = 0; t.dw = (int8_t)(s - d->pad); t.p = 0; t.dh = (int8_t)(r - d->pad);
+      }
+    P.grid_h = out_h; P.grid_w = out_w;
+  } else if (d->kind == ADB_CONV_S2) {
+    ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "adb_conv2d: %dx%d taps unsupported", d->kh, d->kw);
+    ADB_REQUIRE(d->h_in % 2 == 0 && d->w_in % 2 == 0, "adb_conv2d: stride-2 convs need even H/W (got %dx%d)", d->h_in, d->w_in);
+    out_h = (d->h_in + 2 * d->pad - d->kh) / 2 + 1;
+    out_w = (d->w_in + 2 * d->pad - d->kw) / 2 + 1;
+    ADB_REQUIRE(out_h == d->h_in / 2 && out_w == d->w_in / 2, "adb_conv2d: stride-2 conv must halve H/W");
+    P.ngroups = 1; P.ntaps = d->kh * d->kw;
+    auto fl2 = [](int u) { return (u >= 0) ? u / 2 : -((-u + 1) / 2); };
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        Tap& t = P.taps[0][r * d->kw + s];
+        int u = r - d->pad, v = s - d->pad;
+        t.dh = (int8_t)fl2(u); t.p = (int8_t)(u - 2 * fl2(u));
+        t.dw = (int8_t)fl2(v); t.c_mul = (int16_t)(v - 2 * fl2(v));
+      }
+    P.grid_h = out_h; P.grid_w = out_w;
+  } else if (d->kind == ADB_CONVT_4X4S2) {
+    ADB_REQUIRE(d->src1 == nullptr || true, "");
+    out_h = d->h_in * 2; out_w = d->w_in * 2;
+    P.ngroups = 4; P.ntaps = 4;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 2; ++j) {
+            Tap& t = P.taps[a * 2 + b][i * 2 + j];
+            t.c_mul = 0; t.p = 0;
+            t.dh = (int8_t)(a ? 1 - i : -i);
+            t.dw = (int8_t)(b ? 1 - j : -j);
+          }
+    P.grid_h = d->h_in; P.grid_w = d->w_in;
+  } else {
+    return adbh::fail(ADB_ERR_INVALID, "adb_conv2d: unknown kind %d", d->kind);
+  }
+  ktot = P.ntaps * (d->c0 + d->c1);
+
+  // ---- tiles
+  int TW = 128;
+  while (TW > P.grid_w && TW > 8) TW >>= 1;
+  P.TW = TW; P.TH = 128 / TW;
+  P.BN = d->cout_pad;
+  P.n_tiles_n = 1;
+  if (d->cout_pad > 256) {
+    ADB_REQUIRE(d->cout_pad % 32 == 0, "adb_conv2d: cout_pad %d > 256 must split evenly", d->cout_pad);
+    P.n_tiles_n = 2; P.BN = d->cout_pad / 2;
+  }
+  ADB_REQUIRE(P.BN % 16 == 0 && P.BN >= 16 && P.BN <= 256, "adb_conv2d: N tile %d invalid", P.BN);
+  P.cout_pad = d->cout_pad;
+  P.bn_cols = (2 * round_up(P.BN, 32) <= 512) ? round_up(P.BN, 32) : P.BN;
+  int mt = d->tune_mt > 0 ? d->tune_mt : 1;
+  ADB_REQUIRE(mt == 1 || mt == 2, "adb_conv2d: tune_mt must be 1 or 2");
+  if (mt * P.bn_cols > 512) mt = 1;
+  if (d->epi != ADB_EPI_FEATURE) mt = std::min(mt, 2);
+  P.MT = mt;
+  P.tiles_w = (P.grid_w + TW - 1) / TW;
+  P.tiles_h = (P.grid_h + P.TH * mt - 1) / (P.TH * mt);
+  int acc = 512 / (mt * P.bn_cols);
+  acc = std::min(acc, 2);
+  if (d->tune_acc_stages > 0) acc = std::min(acc, d->tune_acc_stages);
+  ADB_REQUIRE(acc >= 1, "adb_conv2d: accumulators do not fit TMEM");
+  P.acc_stages = acc;
+  P.tmem_cols = pow2_at_least(acc * mt * P.bn_cols);
+  P.idesc = make_idesc_bf16(128, (uint32_t)P.BN);
+
+  // ---- smem
+  P.a_stage_bytes = round_up(mt * 128 * P.row_bytes, 1024);
+  P.b_stage_bytes = round_up(P.BN * P.row_bytes, 1024);
+  P.stage_tx_bytes = mt * 128 * P.row_bytes + P.BN * P.row_bytes;
+  if (d->epi == ADB_EPI_FEATURE) {
+    P.Cs = pick_chunk(P.BN);
+    P.n_slabs = P.BN / P.Cs;
+    P.slab_bytes = 128 * P.Cs * 2;
+  } else {
+    ADB_REQUIRE(P.BN == 16 && P.n_tiles_n == 1, "adb_conv2d: DOT/IMAGE epilogues need cout_pad == 16");
+    P.Cs = 16; P.n_slabs = 0; P.slab_bytes = 1024;
+  }
+  adbh::DeviceInfo di;
+  int st = adbh::device_info(&di);
+  if (st != ADB_OK) return st;
+  const int budget = di.max_smem_optin - 1024;  // alignment slack
+  const int stage_bytes = P.a_stage_bytes + P.b_stage_bytes;
+  const SmemLayout fixed = smem_layout(0, 0, 0, P.slab_bytes, 2, P.cout_pad);
+  int stages = (budget - (int)fixed.total) / stage_bytes;
+  stages = std::min(stages, kMaxStages);
+  if (d->tune_stages > 0) stages = std::min(stages, d->tune_stages);
+  ADB_REQUIRE(stages >= 2, "adb_conv2d: pipeline does not fit shared memory (stage %d B)", stage_bytes);
+  P.stages = stages;
+
+  // ---- batch / epilogue
+  P.n = d->n; P.n_start = d->n_start; P.n_dev = d->n_dev;
+  P.epi = d->epi; P.act = d->act;
+  P.scale = d->scale; P.shift = d->shift;
+  if (d->epi == ADB_EPI_FEATURE) {
+    ADB_REQUIRE(d->dst && d->dst_pitch % 8 == 0 && d->dst_c_off >= 0 && d->dst_c_off + d->cout_pad <= d->dst_pitch,
+                "adb_conv2d: dst pitch %d cannot hold channels [%d, %d)", d->dst_pitch, d->dst_c_off, d->dst_c_off + d->cout_pad);
+    ADB_REQUIRE(d->dst_c_off % 8 == 0, "adb_conv2d: dst_c_off must be a multiple of 8");
+    if (d->residual) {
+      ADB_REQUIRE(d->kind != ADB_CONVT_4X4S2, "adb_conv2d: residual unsupported for ConvTranspose");
+      ADB_REQUIRE(d->res_pitch >= d->cout_pad && d->res_pitch % 8 == 0, "adb_conv2d: residual pitch %d too small", d->res_pitch);
+    }
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+    P.res_pitch = d->res_pitch;
+    for (int g = 0; g < P.ngroups; ++g) {
+      if (d->kind == ADB_CONVT_4X4S2) { P.out_c_off[g] = (g & 1) * d->dst_pitch + d->dst_c_off; P.out_p[g] = g >> 1; }
+      else { P.out_c_off[g] = d->dst_c_off; P.out_p[g] = 0; }
+    }
+  } else if (d->epi == ADB_EPI_DOT) {
+    ADB_REQUIRE(d->dot_w && d->dot_out && d->kind != ADB_CONVT_4X4S2, "adb_conv2d: DOT epilogue needs dot_w/dot_out");
+    P.dot_w = d->dot_w; P.dot_b = d->dot_b; P.dot_out = d->dot_out;
+  } else if (d->epi == ADB_EPI_IMAGE) {
+    ADB_REQUIRE(d->img_x && d->img_out && d->cout == 3 && d->kind == ADB_CONV_S1, "adb_conv2d: IMAGE epilogue needs img_x/img_out, cout == 3");
+    ADB_REQUIRE(d->img_mode != ADB_IMG_GUIDED || d->img_guidance, "adb_conv2d: GUIDED needs img_guidance");
+    ADB_REQUIRE(d->img_mode != ADB_IMG_BLEND || d->img_alpha, "adb_conv2d: BLEND needs img_alpha");
+    P.img_mode = d->img_mode; P.img_x = d->img_x; P.img_out = d->img_out; P.img_index = d->img_index;
+    P.img_guidance = d->img_guidance; P.img_alpha = d->img_alpha;
+  } else {
+    return adbh::fail(ADB_ERR_INVALID, "adb_conv2d: unknown epilogue %d", d->epi);
+  }
+  return ADB_OK;
+}
+
+// 5-D view {C, W, P, H, N} of an NHWC bf16 buffer; s2d = space-to-depth (stride-2 read / sub-pixel write) view.
+int make_act_tmap(CUtensorMap* m, const void* base, int pitch, int n, int h, int w, bool s2d, int box_c, int box_w,
+                  int box_h, int span) {
+  uint64_t dims[5], strides[4];
+  uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
+  const uint64_t px = (uint64_t)pitch * 2;
+  if (!s2d) {
+    dims[0] = pitch; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
+    strides[0] = px; strides[1] = px * w; strides[2] = px * w; strides[3] = px * w * h;
+  } else {
+    dims[0] = 2 * (uint64_t)pitch; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n;
+    strides[0] = 2 * px; strides[1] = px * w; strides[2] = 2 * px * w; strides[3] = px * w * h;
+  }
+  return adbh::make_tmap_bf16(m, base, 5, dims, strides, box, span);
+}
+
+}  // namespace
+
+extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
+  ConvK P;
+  int out_h = 0, out_w = 0, ktot = 0;
+  int st = build(d, P, out_h, out_w, ktot);
+  if (st != ADB_OK) return st;
+  adbh::DeviceInfo di;
+  st = adbh::device_info(&di);
+  if (st != ADB_OK) return st;
+  if (di.cc_major != 10) return adbh::fail(ADB_ERR_NO_DEVICE, "adb_conv2d: device sm_%d%d is not sm_100", di.cc_major, di.cc_minor);
+  P.err_flag = adbh::kernel_err_flag();
+
+  alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
+  const bool s2d_in = d->kind == ADB_CONV_S2;
+  st = make_act_tmap(&tmA0, d->src0, d->c0_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, P.TW, P.TH * P.MT, P.row_bytes);
+  if (st != ADB_OK) return st;
+  if (d->src1) {
+    st = make_act_tmap(&tmA1, d->src1, d->c1_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, P.TW, P.TH * P.MT, P.row_bytes);
+    if (st != ADB_OK) return st;
+  } else {
+    tmA1 = tmA0;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)P.ngroups * d->cout_pad};
+    uint64_t strides[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {(uint32_t)P.Ck, (uint32_t)P.BN};
+    st = adbh::make_tmap_bf16(&tmB, d->w_packed, 2, dims, strides, box, P.row_bytes);
+    if (st != ADB_OK) return st;
+  }
+  if (d->epi == ADB_EPI_FEATURE) {
+    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->n, out_h, out_w, d->kind == ADB_CONVT_4X4S2, P.Cs, P.TW, P.TH, P.Cs * 2);
+    if (st != ADB_OK) return st;
+  } else {
+    tmOut = tmA0;
+  }
+
+  const SmemLayout L = smem_layout(P.stages, P.a_stage_bytes, P.b_stage_bytes, P.slab_bytes, 2, P.cout_pad);
+  int smem = (int)L.total + 1024;
+  smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
+  static int configured_for = 0;
+  if (configured_for < smem) {
+    ADB_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+    configured_for = di.max_smem_optin;
+  }
+  const long long max_tiles = (long long)d->n * P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
+  const int grid = (int)std::min<long long>(max_tiles, di.sm_count);
+  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmOut, P);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+extern "C" double adb_conv2d_flops(const adb_conv_desc* d) {
+  if (!d) return 0.0;
+  // true (unpadded) work: 2 * output pixels * kh*kw*cin * cout
+  double cin = (double)d->c0 + d->c1;
+  if (d->kind == ADB_CONVT_4X4S2) return 2.0 * d->n * (double)d->h_in * d->w_in * 4.0 * 4.0 * cin * d->cout;
+  double oh = d->kind == ADB_CONV_S2 ? d->h_in / 2 : d->h_in;
+  double ow = d->kind == ADB_CONV_S2 ? d->w_in / 2 : d->w_in;
+  return 2.0 * d->n * oh * ow * d->kh * d->kw * cin * d->cout;
+}

@@ -1,0 +1,633 @@
+// pointwise.cu — the HBM-bound kernels of the hot path: stem packing, layout conversion, the AttentionBlock passes,
+// pooling, the classifier head, the soft blend and the loss reductions.  All are vectorised (16-byte accesses),
+// coalesced, and reduce with warp shuffles; grids are sized in multiples of the SM count.
+#include "adb_ptx.cuh"
+#include "adb_host.h"
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ int live_images(int n, const int* n_dev, int n_start) {
+  return n_dev ? max(0, min(n, *n_dev - n_start)) : n;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    f[2 * i] = __low2float(b);
+    f[2 * i + 1] = __high2float(b);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  q.x = adb::pack_bf16x2(f[0], f[1]); q.y = adb::pack_bf16x2(f[2], f[3]);
+  q.z = adb::pack_bf16x2(f[4], f[5]); q.w = adb::pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+inline int grid_for(long long work_items, int threads, int sm_count, int waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)sm_count * waves;
+  return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+
+// ------------------------------------------------------------------ stem pack
+// out[i,h,wo,j] (bf16, kp channels), j = s*3 + c  <-  x[row(i), c, h, wo*stride + s - pad]
+__global__ void stem_pack_kernel(const float* __restrict__ x, const int* __restrict__ index, const int* n_dev, int n_start,
+                                 int n, int h, int w, int wo, int kw, int pad, int stride, int kp,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int groups = kp / 8;
+  const long long total = (long long)n_eff * h * wo * groups;
+  const size_t plane = (size_t)h * w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % groups);
+    long long p = t / groups;
+    const int xo = (int)(p % wo); p /= wo;
+    const int y = (int)(p % h);
+    const int i = (int)(p / h);
+    const int pos = n_start + i;
+    const size_t row = index ? (size_t)index[pos] : (size_t)pos;
+    const float* xi = x + row * 3 * plane + (size_t)y * w;
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = g * 8 + q;
+      const int s = j / 3, c = j - 3 * s;
+      const int xx = xo * stride + s - pad;
+      f[q] = (s < kw && xx >= 0 && xx < w) ? __ldg(xi + c * plane + xx) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + (((size_t)i * h + y) * wo + xo) * kp + g * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------ layout converters
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int h, int w, int pitch,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int groups = pitch / 8;
+  const size_t plane = (size_t)h * w;
+  const long long total = (long long)n * plane * groups;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const size_t pix = t % plane;
+    long long r = t / plane;
+    const int g = (int)(r % groups);
+    const int i = (int)(r / groups);
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = g * 8 + q;
+      f[q] = ch < c ? __ldg(x + ((size_t)i * c + ch) * plane + pix) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)i * plane + pix) * pitch + g * 8) = pack8(f);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int n, int c, int h, int w, int pitch,
+                                    float* __restrict__ out) {
+  const int groups = (c + 7) / 8;
+  const size_t plane = (size_t)h * w;
+  const long long total = (long long)n * plane * groups;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const size_t pix = t % plane;
+    long long r = t / plane;
+    const int g = (int)(r % groups);
+    const int i = (int)(r / groups);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((size_t)i * plane + pix) * pitch + g * 8)), f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = g * 8 + q;
+      if (ch < c) out[((size_t)i * c + ch) * plane + pix] = f[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ AttentionBlock pass 1: per-(image, channel) sum and max
+__global__ void pool_init_kernel(float* buf, int n, int c) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * 2 * c) buf[t] = ((t / c) & 1) ? -INFINITY : 0.f;
+}
+
+// block = G x PY threads (G = c/8 channel groups); grid = (chunks, n).  Each thread streams its 8 channels down a pixel
+// chunk with 16-byte loads (a warp reads whole pixel rows: coalesced), then the PY partials meet in shared memory.
+__global__ void attn_pool_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
+                                 int n_start, int pix_per_block, float* __restrict__ pool) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int img = blockIdx.y;
+  if (img >= n_eff) return;
+  const int G = c / 8;
+  const int PY = blockDim.x / G;
+  const int g = threadIdx.x % G, py = threadIdx.x / G;
+  extern __shared__ float sm[];  // [PY][c] sums then [PY][c] maxes
+  float s[8], m[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { s[q] = 0.f; m[q] = -INFINITY; }
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  const long long p1 = min(hw, p0 + pix_per_block);
+  if (py < PY) {
+    const __nv_bfloat16* base = x + (size_t)img * hw * c + g * 8;
+    for (long long p = p0 + py; p < p1; p += PY) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * c)), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { s[q] += f[q]; m[q] = fmaxf(m[q], f[q]); }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sm[py * c + g * 8 + q] = s[q];
+      sm[(PY + py) * c + g * 8 + q] = m[q];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int r = 0; r < PY; ++r) { ss += sm[r * c + ch]; mm = fmaxf(mm, sm[(PY + r) * c + ch]); }
+    atomicAdd(pool + ((size_t)img * 2 + 0) * c + ch, ss);
+    atomic_max_float(pool + ((size_t)img * 2 + 1) * c + ch, mm);
+  }
+}
+
+// gate[n][c] = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max));  one block per image
+__global__ void attn_gate_kernel(const float* __restrict__ pool, int n, float inv_hw, int c, int cr, const int* n_dev,
+                                 int n_start, const float* __restrict__ w1, const float* __restrict__ w2,
+                                 float* __restrict__ gate) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int img = blockIdx.x;
+  if (img >= n_eff) return;
+  extern __shared__ float sm[];  // avg[c], mx[c], hid[cr]
+  float* avg = sm; float* mx = sm + c; float* hid = sm + 2 * c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    avg[ch] = pool[((size_t)img * 2 + 0) * c + ch] * inv_hw;
+    mx[ch] = pool[((size_t)img * 2 + 1) * c + ch];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < cr; j += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int ch = lane; ch < c; ch += 32) { const float wv = w1[(size_t)j * c + ch]; a = fmaf(wv, avg[ch], a); b = fmaf(wv, mx[ch], b); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) hid[j] = fmaxf(a, 0.f) + fmaxf(b, 0.f);   // W2 is linear: W2 relu(a) + W2 relu(b) = W2 (relu(a)+relu(b))
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float v = 0.f;
+    for (int j = 0; j < cr; ++j) v = fmaf(w2[(size_t)ch * cr + j], hid[j], v);
+    gate[(size_t)img * c + ch] = 1.f / (1.f + __expf(-v));
+  }
+}
+
+// pass 2: per pixel, mean and max over channels of x*gate.  LP lanes share a pixel (LP = 16 or 32), each lane owns
+// 16-byte channel groups l, l+LP, ...; a segmented shuffle tree finishes the reduction.
+template <int LP>
+__global__ void attn_stats_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
+                                  int n_start, const float* __restrict__ gate, float* __restrict__ stats) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int G = c / 8;
+  const int sub = threadIdx.x % LP;
+  constexpr int PPW = 32 / LP;   // pixels per warp iteration
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long stride = ((long long)gridDim.x * blockDim.x >> 5) * PPW;
+  const long long total = (long long)n_eff * hw;
+  const float inv_c = 1.f / (float)c;
+  for (long long pw = warp_id * PPW; pw < total; pw += stride) {   // warp-uniform trip count (shuffles below)
+    const long long p = pw + (threadIdx.x & 31) / LP;
+    const bool live = p < total;
+    float s = 0.f, m = -INFINITY;
+    if (live) {
+      const int img = (int)(p / hw);
+      const __nv_bfloat16* px = x + (size_t)p * c;
+      const float* gt = gate + (size_t)img * c;
+      for (int g = sub; g < G; g += LP) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(px + g * 8)), f);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + g * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + g * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const float v = f[q] * gg[q]; s += v; m = fmaxf(m, v); }
+      }
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (live && sub == 0) *reinterpret_cast<float2*>(stats + (size_t)p * 2) = make_float2(s * inv_c, m);
+  }
+}
+
+// pass 3: y = x * gate * sigmoid(conv7x7(stats)); the LP lanes of a pixel split the 98 stencil taps.
+template <int LP>
+__global__ void attn_apply_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, const int* n_dev,
+                                  int n_start, const float* __restrict__ gate, const float* __restrict__ stats,
+                                  const float* __restrict__ wsp, __nv_bfloat16* __restrict__ y) {
+  __shared__ float s_w[98];
+  for (int i = threadIdx.x; i < 98; i += blockDim.x) s_w[i] = wsp[i];
+  __syncthreads();
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int G = c / 8;
+  const int sub = threadIdx.x % LP;
+  const long long hw = (long long)h * w;
+  constexpr int PPW = 32 / LP;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long stride = ((long long)gridDim.x * blockDim.x >> 5) * PPW;
+  const long long total = (long long)n_eff * hw;
+  for (long long pw = warp_id * PPW; pw < total; pw += stride) {
+    const long long p = pw + (threadIdx.x & 31) / LP;
+    const bool live = p < total;
+    float acc = 0.f;
+    int img = 0;
+    if (live) {
+      img = (int)(p / hw);
+      const int rem = (int)(p - (long long)img * hw);
+      const int py = rem / w, px = rem - py * w;
+      const float* st = stats + (size_t)img * hw * 2;
+      for (int t = sub; t < 98; t += LP) {
+        const int ch = t / 49, k = t - ch * 49;
+        const int dy = k / 7 - 3, dx = k - (k / 7) * 7 - 3;
+        const int yy = py + dy, xx = px + dx;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc = fmaf(s_w[t], __ldg(st + ((size_t)yy * w + xx) * 2 + ch), acc);
+      }
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live) {
+      const float sp = 1.f / (1.f + __expf(-acc));
+      const __nv_bfloat16* pxp = x + (size_t)p * c;
+      __nv_bfloat16* pyp = y + (size_t)p * c;
+      const float* gt = gate + (size_t)img * c;
+      for (int g = sub; g < G; g += LP) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pxp + g * 8)), f);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + g * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + g * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = f[q] * gg[q] * sp;
+        *reinterpret_cast<uint4*>(pyp + g * 8) = pack8(f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pooling for the HDEN backbone
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int ho, int wo,
+                                    __nv_bfloat16* __restrict__ y) {
+  const int G = c / 8;
+  const long long total = (long long)n * ho * wo * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int i = (int)(p / ho);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = yo * 2 - 1 + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = xo * 2 - 1 + dx;
+        if (xx < 0 || xx >= w) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)i * h + yy) * w + xx) * c + g * 8)), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * c + g * 8) = pack8(m);
+  }
+}
+
+__global__ void avgpool_finish_kernel(const float* __restrict__ pool, int n, int c, float inv_hw, float* __restrict__ y) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * c) y[t] = pool[((size_t)(t / c) * 2) * c + (t % c)] * inv_hw;
+}
+
+// logits = W2 relu(W1 f + b1) + b2, fp32, one block per image
+__global__ void head_mlp_kernel(const float* __restrict__ feat, int f, const float* __restrict__ w1,
+                                const float* __restrict__ b1, int hidden, const float* __restrict__ w2,
+                                const float* __restrict__ b2, int classes, float* __restrict__ logits) {
+  extern __shared__ float sm[];  // feat[f], hid[hidden]
+  float* sf = sm; float* hid = sm + f;
+  const int img = blockIdx.x;
+  for (int i = threadIdx.x; i < f; i += blockDim.x) sf[i] = feat[(size_t)img * f + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < hidden; j += nwarps) {
+    float a = 0.f;
+    for (int i = lane; i < f; i += 32) a = fmaf(w1[(size_t)j * f + i], sf[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) hid[j] = fmaxf(a + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int k = warp; k < classes; k += nwarps) {
+    float a = 0.f;
+    for (int j = lane; j < hidden; j += 32) a = fmaf(w2[(size_t)k * hidden + j], hid[j], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) logits[(size_t)img * classes + k] = a + b2[k];
+  }
+}
+
+// ------------------------------------------------------------------ soft blend
+__global__ void blend_weights_kernel(const float* __restrict__ lw, float temperature, int b, float* __restrict__ wout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  float a = lw[i * 3 + 0], c = lw[i * 3 + 1], d = lw[i * 3 + 2];
+  if (temperature > 0.f) {
+    a /= temperature; c /= temperature; d /= temperature;
+    const float m = fmaxf(a, fmaxf(c, d));
+    a = expf(a - m); c = expf(c - m); d = expf(d - m);
+    const float s = a + c + d;
+    a /= s; c /= s; d /= s;
+  }
+  wout[i * 3 + 0] = a; wout[i * 3 + 1] = c; wout[i * 3 + 2] = d;
+}
+
+__global__ void blend3_kernel(const float4* __restrict__ y0, const float4* __restrict__ y1, const float4* __restrict__ y2,
+                              const float* __restrict__ wts, int b, long long chw4, float4* __restrict__ out) {
+  const long long total = (long long)b * chw4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / chw4);
+    const float w0 = __ldg(wts + i * 3), w1 = __ldg(wts + i * 3 + 1), w2 = __ldg(wts + i * 3 + 2);
+    const float4 a = __ldg(y0 + t), c = __ldg(y1 + t), d = __ldg(y2 + t);
+    float4 o;
+    // same association order as the reference's three in-place adds into zeros (routing.py:121-127)
+    o.x = ((0.f + w0 * a.x) + w1 * c.x) + w2 * d.x;
+    o.y = ((0.f + w0 * a.y) + w1 * c.y) + w2 * d.y;
+    o.z = ((0.f + w0 * a.z) + w1 * c.z) + w2 * d.z;
+    o.w = ((0.f + w0 * a.w) + w1 * c.w) + w2 * d.w;
+    out[t] = o;
+  }
+}
+
+// ------------------------------------------------------------------ losses
+__global__ void l1_mse_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, long long numel, float inv,
+                                  float* __restrict__ out2) {
+  float a = 0.f, s = 0.f;
+  const long long n4 = numel / 4;
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 u = __ldg(p4 + i), v = __ldg(t4 + i);
+    const float d0 = u.x - v.x, d1 = u.y - v.y, d2 = u.z - v.z, d3 = u.w - v.w;
+    a += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+    s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = n4 * 4 + threadIdx.x; i < numel; i += blockDim.x) { const float d = p[i] - t[i]; a += fabsf(d); s += d * d; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
+  __shared__ float sa[32], ss[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sa[warp] = a; ss[warp] = s; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    a = lane < nw ? sa[lane] : 0.f; s = lane < nw ? ss[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
+    if (lane == 0) { atomicAdd(out2, a * inv); atomicAdd(out2 + 1, s * inv); }
+  }
+}
+
+template <int MODE>  // 0: L1, 1: MSE
+__global__ void pix_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, long long numel, float k,
+                               float* __restrict__ g) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    const float d = p[i] - t[i];
+    g[i] = MODE == 0 ? (d > 0.f ? k : (d < 0.f ? -k : 0.f)) : 2.f * d * k;
+  }
+}
+
+__global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int b, int classes,
+                          float grad_scale, float* __restrict__ loss, float* __restrict__ grad) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    const float* l = logits + (size_t)i * classes;
+    float m = -INFINITY;
+    for (int k = 0; k < classes; ++k) m = fmaxf(m, l[k]);
+    float s = 0.f;
+    for (int k = 0; k < classes; ++k) s += expf(l[k] - m);
+    const float lse = m + logf(s);
+    const int y = (int)labels[i];
+    acc += lse - l[y];
+    if (grad)
+      for (int k = 0; k < classes; ++k)
+        grad[(size_t)i * classes + k] = (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) * grad_scale / (float)b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float sa[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sa[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += sa[i];
+    *loss = tot / (float)b;
+  }
+}
+
+int sm_count() {
+  adbh::DeviceInfo di;
+  if (adbh::device_info(&di) != ADB_OK) return 0;
+  return di.sm_count;
+}
+
+}  // namespace
+
+#define ADB_LAUNCH_OK() ADB_CUDA_OK(cudaGetLastError())
+
+extern "C" {
+
+int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n, int32_t h,
+                  int32_t w, int32_t kw, int32_t pad, int32_t stride, int32_t kp, void* out, void* stream) {
+  ADB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "adb_stem_pack: bad arguments");
+  ADB_REQUIRE(kp % 8 == 0 && kp >= kw * 3 && (stride == 1 || stride == 2), "adb_stem_pack: kp %d must be a multiple of 8 >= 3*kw", kp);
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const int wo = (w + 2 * pad - kw) / stride + 1;
+  const long long total = (long long)n * h * wo * (kp / 8);
+  stem_pack_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
+      x, index, n_dev, n_start, n, h, w, wo, kw, pad, stride, kp, reinterpret_cast<__nv_bfloat16*>(out));
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_nchw_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, void* out, void* stream) {
+  ADB_REQUIRE(x && out && n > 0 && c > 0 && c_pitch >= c && c_pitch % 8 == 0, "adb_nchw_to_nhwc_bf16: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const long long total = (long long)n * h * w * (c_pitch / 8);
+  nchw_to_nhwc_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(x, n, c, h, w, c_pitch, reinterpret_cast<__nv_bfloat16*>(out));
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, float* out, void* stream) {
+  ADB_REQUIRE(x && out && n > 0 && c > 0 && c_pitch >= c && c_pitch % 8 == 0, "adb_nhwc_bf16_to_nchw: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const long long total = (long long)n * h * w * ((c + 7) / 8);
+  nhwc_to_nchw_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, c, h, w, c_pitch, out);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+static int launch_pool(const void* x, int n, int h, int w, int c, const int* n_dev, int n_start, float* pool_buf, cudaStream_t st) {
+  ADB_REQUIRE(x && pool_buf && n > 0 && c % 8 == 0 && c / 8 <= 256, "attention/avg pool: channels %d must be a multiple of 8 (<= 2048)", c);
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  pool_init_kernel<<<(n * 2 * c + 255) / 256, 256, 0, st>>>(pool_buf, n, c);
+  const int G = c / 8;
+  const int PY = std::max(1, 256 / G);
+  const int threads = G * PY;
+  const long long hw = (long long)h * w;
+  // enough blocks for ~4 waves over the SMs, at least 256 pixels each
+  long long chunks = std::max<long long>(1, std::min<long long>((hw + 255) / 256, (4LL * sms + n - 1) / n));
+  const int ppb = (int)((hw + chunks - 1) / chunks);
+  chunks = (hw + ppb - 1) / ppb;
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  attn_pool_kernel<<<grid, threads, 2 * PY * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, ppb, pool_buf);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                  float* pool_buf, void* stream) {
+  return launch_pool(x, n, h, w, c, n_dev, n_start, pool_buf, (cudaStream_t)stream);
+}
+
+int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                        const float* pool_buf, const float* w1, const float* w2, int32_t c_red, float* gate, float* stats,
+                        void* stream) {
+  ADB_REQUIRE(x && pool_buf && w1 && w2 && gate && stats && n > 0 && c % 8 == 0 && c_red > 0, "adb_attn_gate_stats: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hw = (long long)h * w;
+  attn_gate_kernel<<<n, 256, (2 * c + c_red) * sizeof(float), st>>>(pool_buf, n, 1.f / (float)hw, c, c_red, n_dev, n_start, w1, w2, gate);
+  ADB_LAUNCH_OK();
+  const int G = c / 8;
+  const long long total = (long long)n * hw;
+  if (G <= 16) {
+    attn_stats_kernel<16><<<grid_for(total * 16, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, gate, stats);
+  } else {
+    attn_stats_kernel<32><<<grid_for(total * 32, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, gate, stats);
+  }
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                   const float* gate, const float* stats, const float* w_spatial, void* y, void* stream) {
+  ADB_REQUIRE(x && gate && stats && w_spatial && y && n > 0 && c % 8 == 0, "adb_attn_apply: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * h * w;
+  if (c / 8 <= 16) {
+    attn_apply_kernel<16><<<grid_for(total * 16, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, n_dev, n_start, gate, stats, w_spatial, reinterpret_cast<__nv_bfloat16*>(y));
+  } else {
+    attn_apply_kernel<32><<<grid_for(total * 32, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, n_dev, n_start, gate, stats, w_spatial, reinterpret_cast<__nv_bfloat16*>(y));
+  }
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0, "adb_maxpool3x3s2: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, ho, wo, reinterpret_cast<__nv_bfloat16*>(y));
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+// y[n][c] = mean over h*w; scratch is fp32 [n][2][c].
+int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch, float* y, void* stream) {
+  ADB_REQUIRE(x && y && scratch && n > 0, "adb_global_avgpool: bad arguments");
+  int st = launch_pool(x, n, h, w, c, nullptr, 0, scratch, (cudaStream_t)stream);
+  if (st != ADB_OK) return st;
+  avgpool_finish_kernel<<<(n * c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, n, c, 1.f / ((float)h * (float)w), y);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
+                 const float* w2, const float* b2, int32_t classes, float* logits, void* stream) {
+  ADB_REQUIRE(feat && w1 && b1 && w2 && b2 && logits && n > 0 && f > 0 && hidden > 0 && classes > 0, "adb_head_mlp: bad arguments");
+  ADB_REQUIRE((size_t)(f + hidden) * sizeof(float) <= 48 * 1024, "adb_head_mlp: feature dim too large");
+  head_mlp_kernel<<<n, 256, (f + hidden) * sizeof(float), (cudaStream_t)stream>>>(feat, f, w1, b1, hidden, w2, b2, classes, logits);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_blend3(const float* y0, const float* y1, const float* y2, const float* logits_or_weights, float temperature,
+               int32_t b, int64_t chw, float* weights_out, float* out, void* stream) {
+  ADB_REQUIRE(y0 && y1 && y2 && logits_or_weights && weights_out && out && b > 0 && chw > 0 && chw % 4 == 0, "adb_blend3: bad arguments (chw must be a multiple of 4)");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  blend_weights_kernel<<<(b + 127) / 128, 128, 0, st>>>(logits_or_weights, temperature, b, weights_out);
+  const long long total = (long long)b * (chw / 4);
+  blend3_kernel<<<grid_for(total, 256, sms, 16), 256, 0, st>>>(reinterpret_cast<const float4*>(y0), reinterpret_cast<const float4*>(y1),
+                                                             reinterpret_cast<const float4*>(y2), weights_out, b, chw / 4, reinterpret_cast<float4*>(out));
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_l1_mse_fwd(const float* pred, const float* target, int64_t numel, float* out2, void* stream) {
+  ADB_REQUIRE(pred && target && out2 && numel > 0, "adb_l1_mse_fwd: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  ADB_CUDA_OK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
+  l1_mse_fwd_kernel<<<grid_for(numel / 4 + 1, 256, sms, 4), 256, 0, st>>>(pred, target, numel, 1.f / (float)numel, out2);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_l1_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream) {
+  ADB_REQUIRE(pred && target && grad && numel > 0, "adb_l1_bwd: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  pix_bwd_kernel<0><<<grid_for(numel, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(pred, target, numel, grad_scale / (float)numel, grad);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_mse_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream) {
+  ADB_REQUIRE(pred && target && grad && numel > 0, "adb_mse_bwd: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  pix_bwd_kernel<1><<<grid_for(numel, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(pred, target, numel, grad_scale / (float)numel, grad);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale, float* loss,
+                   float* grad_logits, void* stream) {
+  ADB_REQUIRE(logits && labels && loss && b > 0 && classes > 0, "adb_ce_fwd_bwd: bad arguments");
+  ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(labels), b, classes, grad_scale, loss, grad_logits);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+/* adb200.h — C ABI of libadb200.so: the B200 (sm_100a) kernels under the ADAM-Dehaze hot path.
+ *
+ * The reference (talha-alam/ADAM-Dehaze) has no FFI layer: its hot path is a set of torch.nn.Module.forward
+ * bodies.  Each entry point below replaces the library calls one of those bodies makes; the
+ * reference file:line it stands in for is cited at each declaration.  The Python modules in
+ * adam_dehaze_b200/models/ (same names/signatures as the reference modules) bind these with ctypes — see
+ * INTEGRATION.md for the stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: raw DEVICE pointers, ints, an explicit cudaStream_t passed as void*;
+ *   - return 0 on success, a negative adb_status otherwise; adb_last_error() gives the thread-local message;
+ *   - never allocate device memory, never synchronise the stream, never take ownership of a buffer;
+ *   - activations are NHWC bf16 ("feature maps"), images are NCHW fp32 in [0,1] (the reference's tensor contract,
+ *     data/dataset.py:97-99);
+ *   - `n_dev` (nullable) is a device int holding the live image count of a routed bucket; when non-NULL a launch
+ *     processes images [n_start, min(n_start + n, *n_dev)) and is a no-op beyond it, so routing needs no host
+ *     round-trip (replaces the torch.any()/nonzero() syncs of models/routing.py:55-61).
+ */
+#ifndef ADB200_H
+#define ADB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ADB_OK = 0,
+  ADB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  ADB_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  ADB_ERR_NO_DEVICE = -3, /* no sm_100 device or driver entry point missing */
+  ADB_ERR_KERNEL = -4     /* in-kernel protocol time-out flag was raised */
+} adb_status;
+
+/* activation applied by the conv epilogue */
+enum { ADB_ACT_NONE = 0, ADB_ACT_RELU = 1, ADB_ACT_TANH = 2, ADB_ACT_SIGMOID = 3 };
+
+/* convolution kinds (the geometry the implicit-GEMM producer walks) */
+enum {
+  ADB_CONV_S1 = 0,     /* kh x kw, stride 1, zero padding `pad` (nn.Conv2d in ConvBlock, base_model.py:11-13) */
+  ADB_CONV_S2 = 1,     /* kh x kw, stride 2, zero padding `pad`; H and W even (encoder downsamples, medium:25,35; high:26,36) */
+  ADB_CONVT_4X4S2 = 2  /* nn.ConvTranspose2d(k=4, s=2, p=1) as four 2x2 sub-pixel phases (medium:53,63; high:57,68) */
+};
+
+/* epilogue kinds */
+enum {
+  ADB_EPI_FEATURE = 0, /* y = act(acc*scale + shift (+ residual)) -> NHWC bf16 feature map (ConvBlock/ResidualBlock, base_model.py:23,36-41) */
+  ADB_EPI_DOT = 1,     /* g = sigmoid(dot(act(acc*scale+shift), dot_w) + dot_b) -> fp32 [n,h,w] (detail_branch tail, high:84-89) */
+  ADB_EPI_IMAGE = 2    /* final 3-channel head fused with the output arithmetic, NCHW fp32 out (low:45; medium:117; high:135-138) */
+};
+
+/* image-epilogue arithmetic (ADB_EPI_IMAGE); v = act(acc*scale+shift) per colour channel */
+enum {
+  ADB_IMG_BLEND = 0,      /* out = (1-alpha)*x + alpha*v          (LightweightDehazeModel, low_intensity.py:45) */
+  ADB_IMG_RESIDUAL = 1,   /* out = clamp(x + v, 0, 1)             (MediumIntensityDehazeModel, medium_intensity.py:117) */
+  ADB_IMG_GUIDED = 2      /* out = clamp(x + v*guidance, 0, 1)    (HighIntensityDehazeModel, high_intensity.py:135-138) */
+};
+
+typedef struct adb_conv_desc {
+  /* --- inputs: one or two NHWC bf16 feature maps read as a channel concatenation [src0 | src1]
+         (torch.cat([up, skip], 1) never materialised: medium:100,111; high:117,129) */
+  const void* src0; int32_t c0; int32_t c0_pitch;  /* channels used / channel pitch of the buffer */
+  const void* src1; int32_t c1; int32_t c1_pitch;  /* src1 == NULL, c1 == 0 for a single source */
+  int32_t n, h_in, w_in;                            /* images in this launch, input height/width */
+  /* --- geometry */
+  int32_t kind, kh, kw, pad;
+  /* --- weights, packed by adb_pack order (see below), bf16 [groups][cout_pad][ktot]; epilogue affine fp32 [cout_pad] */
+  const void* w_packed; const float* scale; const float* shift;
+  int32_t cout, cout_pad;                           /* cout_pad: multiple of 16, >= 16, <= 512 */
+  int32_t act;
+  /* --- epilogue */
+  int32_t epi;
+  const void* residual; int32_t res_pitch;          /* FEATURE: optional NHWC bf16 residual, same n/h/w as dst */
+  void* dst; int32_t dst_pitch; int32_t dst_c_off;  /* FEATURE: NHWC bf16 dst buffer, channel pitch, first channel written */
+  const float* dot_w; float dot_b; float* dot_out;  /* DOT */
+  int32_t img_mode;                                 /* IMAGE */
+  const float* img_x;       /* NCHW fp32 hazy input batch the bucket was gathered from */
+  float* img_out;           /* NCHW fp32 output batch (scatter target) */
+  const int32_t* img_index; /* nullable: image i of this launch is batch row img_index[n_start+i] of img_x/img_out */
+  const float* img_guidance;/* GUIDED: fp32 [n,h,w] of this launch's images */
+  const float* img_alpha;   /* BLEND: device scalar (skip_alpha parameter, low_intensity.py:31) */
+  /* --- routed-bucket dynamic batch */
+  const int32_t* n_dev; int32_t n_start;
+  /* --- tuning (0 = choose automatically) */
+  int32_t tune_mt, tune_stages, tune_acc_stages;
+} adb_conv_desc;
+
+/* Weight packing order expected in w_packed (done on the host side by adam_dehaze_b200/engine.py):
+ *   ADB_CONV_S1 / ADB_CONV_S2:  w_packed[co][(r*kw + s)*(c0+c1) + c] = W[co][c][r][s]
+ *   ADB_CONVT_4X4S2:            phase g = a*2 + b (a = oh&1, b = ow&1); tap (i,j), i,j in {0,1};
+ *                               r = a ? 2*i : 1 + 2*i   (input row  q + (a ? 1-i : -i));  s likewise from b, j
+ *                               w_packed[g][co][(i*2 + j)*cin + ci] = Wt[ci][co][r][s]
+ *   ktot must be a multiple of the K chunk (the largest of 64/32/16 dividing c0 and c1).
+ */
+
+/* Library / device */
+const char* adb_last_error(void);
+int adb_version(void);
+int adb_device_check(void);                 /* 0 when the current device is sm_100 and the TMA encoder resolved */
+
+/* Implicit-GEMM convolution on tcgen05/TMEM tiles fed by TMA (bf16 x bf16 -> fp32).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d(eval) + activation (+ residual add) of
+ * models/dehazing/base_model.py:4-41 and the encoder/decoder/head convs of medium_intensity.py:16-76,
+ * high_intensity.py:17-90, low_intensity.py:16-28. */
+int adb_conv2d(const adb_conv_desc* desc, void* stream);
+/* FLOPs (2*MAC) the descriptor's launch performs for n images — the figure bench.py's roofline uses. */
+double adb_conv2d_flops(const adb_conv_desc* desc);
+
+/* Image -> stem operand.  out[i,h,w, s*3+c] = x[idx(i), c, h, w*stride + s - pad] (0 outside), zero-padded to kp
+ * channels, bf16.  Makes a kh x kw x 3 stem a kh x 1 conv with kp channels (stem convs low:16, medium:16, high:17,85). */
+int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n,
+                  int32_t h, int32_t w, int32_t kw, int32_t pad, int32_t stride, int32_t kp,
+                  void* out, void* stream);
+
+/* Layout converters (tests, classifier features): NCHW fp32 <-> NHWC bf16 */
+int adb_nchw_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, void* out, void* stream);
+int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, float* out, void* stream);
+
+/* AttentionBlock (base_model.py:43-78) as three HBM-bound passes over an NHWC bf16 map x[n,h,w,c]:
+ *  1) pool:   sum_c, max_c over h*w per (image, channel)                        (avg_pool/max_pool, :64-66)
+ *  2) gate:   gate = sigmoid(fc(avg)+fc(max)) (fc = w2*relu(w1*.)), then per pixel the channel mean and max of
+ *             x*gate -> stats[n,h,w,2] fp32                                      (:66-73)
+ *  3) apply:  y = x*gate*sigmoid(conv7x7(stats))                                 (:74-78)
+ * pool_buf: fp32 [n][2][c] (sum, max) zero/-inf initialised by the call itself. */
+int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                  float* pool_buf, void* stream);
+int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                        const float* pool_buf, const float* w1 /*[c/r][c]*/, const float* w2 /*[c][c/r]*/, int32_t c_red,
+                        float* gate /*[n][c]*/, float* stats /*[n,h,w,2]*/, void* stream);
+int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+                   const float* gate, const float* stats, const float* w_spatial /*[2][7][7]*/, void* y, void* stream);
+
+/* Pooling for the HDEN backbones (torchvision resnet/densenet called from models/classifier.py:24-36,91). */
+int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
+int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*[n][2][c]*/,
+                       float* y /*[n][c] fp32*/, void* stream);
+/* Classifier head, fp32: logits = W2*relu(W1*f + b1) + b2 (models/classifier.py:72-78, eval mode: dropout = identity). */
+int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
+                 const float* w2, const float* b2, int32_t classes, float* logits, void* stream);
+
+/* Routing (models/routing.py:40-61): intensity = argmax(logits,1) (first max wins, NaN counts as max, like
+ * torch.argmax), masks, and a stable 3-way compaction: bucket k lists the ascending batch rows with intensity == k.
+ * intensity_in (nullable) overrides the argmax (HardRouter.forward(x, intensity=...), routing.py:23,40).
+ * Outputs: intensity int64[b]; masks uint8[3][b]; bucket_index int32[3][b]; bucket_count int32[3]. */
+int adb_route(const float* logits, const int64_t* intensity_in, int32_t b, int32_t classes,
+              int64_t* intensity, uint8_t* masks, int32_t* bucket_index, int32_t* bucket_count, void* stream);
+
+/* Soft/gated blend (routing.py:111-127, 215-221): w = softmax(logits/T) (or given weights when temperature <= 0),
+ * out = sum_k w[:,k] * y_k, NCHW fp32. */
+int adb_blend3(const float* y0, const float* y1, const float* y2, const float* logits_or_weights, float temperature,
+               int32_t b, int64_t chw, float* weights_out /*[b][3]*/, float* out, void* stream);
+
+/* Loss reductions (training/loss.py:121,81,177) forward + backward w.r.t. pred/logits.
+ * l1: mean|p-t|, mse: mean (p-t)^2 — one pass, warp-shuffle + one atomic per block; grad_scale multiplies dL/dp. */
+int adb_l1_mse_fwd(const float* pred, const float* target, int64_t numel, float* out2 /*[l1, mse]*/, void* stream);
+int adb_l1_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
+int adb_mse_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
+int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale,
+                   float* loss /*[1]*/, float* grad_logits /*nullable [b][classes]*/, void* stream);
+
+/* Read and clear the device-side kernel error flag (non-zero => a bounded mbarrier wait expired). Synchronises. */
+int adb_kernel_error_flag(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADB200_H */

@@ -1,0 +1,248 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv (adb_conv2d) against torch fp32 convolutions on the same bf16-rounded
+operands.  Tolerance: inputs/weights are exactly representable, so the only differences are fp32 accumulation order
+and the final bf16 rounding of the output: |err| <= 1e-2 * max|ref| + 1e-3 (stated per test)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from adam_dehaze_b200 import ops
+    return ops
+
+
+def _rand_fm(n, c, h, w, seed, relu=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, c, h, w, generator=g)
+    if relu:
+        x = x.relu()
+    return x.to(torch.bfloat16).float().cuda()
+
+
+def _rand_w(shape, seed, fan_in):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) / fan_in ** 0.5).to(torch.bfloat16).float().cuda()
+
+
+def _bn(c, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.rand(c, generator=g).cuda() + 0.5, torch.randn(c, generator=g).cuda() * 0.1,
+            torch.randn(c, generator=g).cuda() * 0.1, torch.rand(c, generator=g).cuda() + 0.5, 1e-5)
+
+
+def _bn_ref(y, bn):
+    g, b, m, v, eps = bn
+    return (y - m.view(1, -1, 1, 1)) / torch.sqrt(v.view(1, -1, 1, 1) + eps) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+
+
+def _close(out, ref, rel=1e-2, abs_=1e-3):
+    err = (out - ref).abs().max().item()
+    bound = rel * ref.abs().max().item() + abs_
+    assert err <= bound, f"max err {err:.4g} > {bound:.4g} (ref max {ref.abs().max().item():.4g})"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    from adam_dehaze_b200 import _lib
+    torch.cuda.synchronize()
+    _lib.call("adb_kernel_error_flag")
+
+
+def test_layout_roundtrip():
+    ops = _ops()
+    x = _rand_fm(2, 20, 9, 13, 0)
+    y = ops.nchw_to_nhwc(x, 24)
+    assert y.shape == (2, 9, 13, 24)
+    assert torch.equal(y[..., :20].permute(0, 3, 1, 2).float(), x)
+    assert torch.equal(y[..., 20:].float(), torch.zeros_like(y[..., 20:].float()))
+    z = ops.nhwc_to_nchw(y, 20)
+    assert torch.equal(z, x)
+
+
+CONV_CASES = [
+    # (cin, cout, k, n, h, w, tune)
+    (64, 64, 3, 1, 32, 32, None),
+    (64, 64, 1, 1, 16, 16, None),
+    (32, 32, 3, 2, 32, 64, None),
+    (16, 16, 3, 1, 32, 32, None),
+    (96, 96, 3, 1, 64, 64, None),
+    (192, 192, 3, 1, 32, 32, None),
+    (384, 384, 3, 1, 16, 32, None),
+    (256, 256, 3, 1, 16, 16, None),
+    (128, 128, 3, 1, 24, 40, None),          # ragged tiles (w not a power of two)
+    (64, 48, 3, 1, 32, 32, None),
+    (64, 64, 3, 4, 128, 256, None),          # many tiles per CTA: pipeline/accumulator phase wrap
+    (64, 64, 3, 2, 64, 128, {"mt": 2}),
+    (96, 96, 3, 2, 64, 128, {"mt": 2}),
+    (64, 64, 3, 2, 64, 128, {"stages": 2, "acc": 1}),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,n,h,w,tune", CONV_CASES)
+def test_conv_s1(cin, cout, k, n, h, w, tune):
+    ops = _ops()
+    x = _rand_fm(n, cin, h, w, 1)
+    wt = _rand_w((cout, cin, k, k), 2, cin * k * k)
+    bn = _bn(cout, 3)
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), tune=tune)
+    out = ops.nhwc_to_nchw(y, cout)
+    ref = F.relu(_bn_ref(F.conv2d(x, wt, padding=k // 2), bn))
+    _close(out, ref)
+    if spec.cout_pad > cout:
+        assert y[..., cout:].float().abs().max().item() == 0.0
+
+
+def test_conv_bias_residual():
+    ops = _ops()
+    x = _rand_fm(2, 64, 32, 48, 4)
+    res = _rand_fm(2, 64, 32, 48, 5)
+    wt = _rand_w((64, 64, 3, 3), 6, 576)
+    bias = torch.randn(64, device="cuda") * 0.1
+    spec = ops.ConvSpec.from_conv(wt, bias=bias, act=ops.ACT_RELU)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), residual=ops.nchw_to_nhwc(res))
+    ref = F.relu(F.conv2d(x, wt, bias, padding=1) + res)
+    _close(ops.nhwc_to_nchw(y), ref)
+
+
+@pytest.mark.parametrize("act", ["tanh", "sigmoid", "none"])
+def test_conv_activations(act):
+    ops = _ops()
+    x = _rand_fm(1, 32, 16, 32, 7)
+    wt = _rand_w((32, 32, 3, 3), 8, 288)
+    code = {"tanh": ops.ACT_TANH, "sigmoid": ops.ACT_SIGMOID, "none": ops.ACT_NONE}[act]
+    fn = {"tanh": torch.tanh, "sigmoid": torch.sigmoid, "none": lambda t: t}[act]
+    y = ops.conv2d(ops.ConvSpec.from_conv(wt, act=code), ops.nchw_to_nhwc(x))
+    _close(ops.nhwc_to_nchw(y), fn(F.conv2d(x, wt, padding=1)))
+
+
+@pytest.mark.parametrize("cin,cout,k,pad,n,h,w", [(64, 128, 4, 1, 1, 32, 32), (96, 192, 4, 1, 2, 64, 64),
+                                                  (64, 128, 3, 1, 1, 32, 64), (64, 128, 1, 0, 1, 32, 32)])
+def test_conv_s2(cin, cout, k, pad, n, h, w):
+    ops = _ops()
+    x = _rand_fm(n, cin, h, w, 9)
+    wt = _rand_w((cout, cin, k, k), 10, cin * k * k)
+    bn = _bn(cout, 11)
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU, stride=2, pad=pad)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x))
+    ref = F.relu(_bn_ref(F.conv2d(x, wt, stride=2, padding=pad), bn))
+    assert y.shape[1:3] == ref.shape[2:]
+    _close(ops.nhwc_to_nchw(y, cout), ref)
+
+
+@pytest.mark.parametrize("cin,cout,n,h,w", [(128, 64, 1, 16, 16), (384, 192, 1, 16, 32), (256, 64, 2, 32, 32)])
+def test_conv_transpose(cin, cout, n, h, w):
+    ops = _ops()
+    x = _rand_fm(n, cin, h, w, 12)
+    wt = _rand_w((cin, cout, 4, 4), 13, cin * 4)
+    bias = torch.randn(cout, device="cuda") * 0.1
+    bn = _bn(cout, 14)
+    spec = ops.ConvSpec.from_convT(wt, bias=bias, bn=bn, act=ops.ACT_RELU)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x))
+    ref = F.relu(_bn_ref(F.conv_transpose2d(x, wt, bias, stride=2, padding=1), bn))
+    assert tuple(y.shape[1:3]) == (2 * h, 2 * w)
+    _close(ops.nhwc_to_nchw(y, cout), ref)
+
+
+@pytest.mark.parametrize("c0,c1,cout", [(64, 64, 64), (96, 96, 96), (192, 192, 96)])
+def test_conv_concat_sources(c0, c1, cout):
+    ops = _ops()
+    a = _rand_fm(1, c0, 32, 32, 15)
+    b = _rand_fm(1, c1, 32, 32, 16)
+    wt = _rand_w((cout, c0 + c1, 3, 3), 17, (c0 + c1) * 9)
+    spec = ops.ConvSpec.from_conv(wt, act=ops.ACT_RELU)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(a), ops.nchw_to_nhwc(b))
+    ref = F.relu(F.conv2d(torch.cat([a, b], 1), wt, padding=1))
+    _close(ops.nhwc_to_nchw(y, cout), ref)
+
+
+def test_conv_into_channel_slice():
+    ops = _ops()
+    x = _rand_fm(1, 64, 16, 16, 18)
+    wt = _rand_w((32, 64, 3, 3), 19, 576)
+    dst = torch.zeros((1, 16, 16, 96), dtype=torch.bfloat16, device="cuda")
+    ops.conv2d(ops.ConvSpec.from_conv(wt), ops.nchw_to_nhwc(x), dst=dst, dst_c_off=64)
+    ref = F.conv2d(x, wt, padding=1)
+    _close(ops.nhwc_to_nchw(dst)[:, 64:], ref)
+    assert dst[..., :64].float().abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("k,cout,kp", [(7, 64, 32), (3, 32, 16), (7, 96, 32), (3, 16, 16)])
+def test_stem(k, cout, kp):
+    ops = _ops()
+    g = torch.Generator().manual_seed(20)
+    x = torch.rand(2, 3, 32, 64, generator=g).cuda()
+    wt = _rand_w((cout, 3, k, k), 21, 3 * k * k)
+    bn = _bn(cout, 22)
+    spec = ops.ConvSpec.from_stem(wt, kp, bn=bn, act=ops.ACT_RELU)
+    packed = ops.stem_pack(x, k, k // 2, kp)
+    y = ops.conv2d(spec, packed)
+    xr = x.to(torch.bfloat16).float()
+    ref = F.relu(_bn_ref(F.conv2d(xr, wt, padding=k // 2), bn))
+    _close(ops.nhwc_to_nchw(y, cout), ref)
+
+
+def test_dot_epilogue():
+    ops = _ops()
+    x = _rand_fm(2, 16, 32, 64, 23)
+    wt = _rand_w((16, 16, 3, 3), 24, 144)
+    bn = _bn(16, 25)
+    dw = torch.randn(16, device="cuda")
+    out = torch.empty((2, 32, 64), dtype=torch.float32, device="cuda")
+    ops.conv2d(ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU), ops.nchw_to_nhwc(x), epi=ops.EPI_DOT, dot=(dw, 0.25, out))
+    feat = F.relu(_bn_ref(F.conv2d(x, wt, padding=1), bn))
+    ref = torch.sigmoid((feat * dw.view(1, -1, 1, 1)).sum(1) + 0.25)
+    _close(out, ref, rel=2e-3, abs_=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["blend", "residual", "guided"])
+def test_image_epilogue(mode):
+    ops = _ops()
+    g = torch.Generator().manual_seed(26)
+    xb = torch.rand(5, 3, 32, 64, generator=g).cuda()
+    index = torch.tensor([4, 1, 3], dtype=torch.int32, device="cuda")
+    feat = _rand_fm(3, 32, 32, 64, 27)
+    wt = _rand_w((3, 32, 3, 3), 28, 288)
+    bias = torch.randn(3, device="cuda") * 0.1
+    out = torch.zeros_like(xb)
+    guid = torch.rand(3, 32, 64, device="cuda")
+    alpha = torch.tensor(0.1, device="cuda")
+    if mode == "blend":
+        spec = ops.ConvSpec.from_conv(wt, bias=bias, act=ops.ACT_SIGMOID)
+        img = dict(mode=ops.IMG_BLEND, x=xb, out=out, index=index, alpha=alpha)
+    elif mode == "residual":
+        spec = ops.ConvSpec.from_conv(wt, bias=bias, act=ops.ACT_TANH)
+        img = dict(mode=ops.IMG_RESIDUAL, x=xb, out=out, index=index)
+    else:
+        spec = ops.ConvSpec.from_conv(wt, bias=bias, act=ops.ACT_TANH)
+        img = dict(mode=ops.IMG_GUIDED, x=xb, out=out, index=index, guidance=guid)
+    ops.conv2d(spec, ops.nchw_to_nhwc(feat), epi=ops.EPI_IMAGE, image=img)
+    v = F.conv2d(feat, wt, bias, padding=1)
+    xs = xb[index.long()]
+    if mode == "blend":
+        ref = 0.9 * xs + 0.1 * torch.sigmoid(v)
+    elif mode == "residual":
+        ref = torch.clamp(xs + torch.tanh(v), 0, 1)
+    else:
+        ref = torch.clamp(xs + torch.tanh(v) * guid.unsqueeze(1), 0, 1)
+    _close(out[index.long()], ref, rel=2e-3, abs_=2e-4)
+    untouched = [i for i in range(5) if i not in (4, 1, 3)]
+    assert out[untouched].abs().max().item() == 0.0
+
+
+def test_dynamic_bucket_count():
+    """n_dev < n: images beyond the live count are not touched (routed bucket without a host round-trip)."""
+    ops = _ops()
+    x = _rand_fm(4, 64, 16, 32, 29)
+    wt = _rand_w((64, 64, 3, 3), 30, 576)
+    n_dev = torch.tensor([5], dtype=torch.int32, device="cuda")   # bucket holds 5 images, this launch covers [3, 7)
+    dst = torch.full((4, 16, 32, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.conv2d(ops.ConvSpec.from_conv(wt), ops.nchw_to_nhwc(x), dst=dst, n_dev=n_dev, n_start=3)
+    ref = F.conv2d(x, wt, padding=1)
+    _close(ops.nhwc_to_nchw(dst)[:2], ref[:2])
+    assert (dst[2:].float() == 7.0).all()

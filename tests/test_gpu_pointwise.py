@@ -1,0 +1,129 @@
+"""GPU parity of the HBM-bound kernels (attention passes, pooling, head, routing, blend, losses) against torch fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from adam_dehaze_b200 import ops
+    return ops
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("c,h,w,n", [(96, 32, 64, 2), (192, 16, 32, 2), (384, 8, 16, 1), (96, 37, 21, 1)])
+def test_attention_block(c, h, w, n):
+    """AttentionBlock (base_model.py:64-78) on a bf16 map; tolerance 1e-2 relative (bf16 output rounding)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, c, h, w, generator=g).relu().to(torch.bfloat16).float().cuda()
+    fc0 = (torch.randn(c // 16, c, 1, 1, generator=g) / c ** 0.5).cuda()
+    fc2 = (torch.randn(c, c // 16, 1, 1, generator=g) / (c // 16) ** 0.5).cuda()
+    wsp = (torch.randn(1, 2, 7, 7, generator=g) / 98 ** 0.5).cuda()
+    y = ops.attention(ops.nchw_to_nhwc(x), ops.AttnParams(fc0, fc2, wsp))
+    fc = lambda t: F.conv2d(F.relu(F.conv2d(t, fc0)), fc2)
+    ch = torch.sigmoid(fc(F.adaptive_avg_pool2d(x, 1)) + fc(F.adaptive_max_pool2d(x, 1)))
+    xr = x * ch
+    sp = torch.sigmoid(F.conv2d(torch.cat([xr.mean(1, keepdim=True), xr.max(1, keepdim=True)[0]], 1), wsp, padding=3))
+    ref = xr * sp
+    out = ops.nhwc_to_nchw(y)
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_maxpool_avgpool_head():
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 64, 33, 48, generator=g).to(torch.bfloat16).float().cuda()
+    xh = ops.nchw_to_nhwc(x)
+    mp = ops.nhwc_to_nchw(ops.maxpool3x3s2(xh))
+    assert torch.equal(mp, F.max_pool2d(x, 3, 2, 1))
+    ap = ops.global_avgpool(xh)
+    assert torch.allclose(ap, x.mean((2, 3)), rtol=1e-4, atol=1e-5)
+    feat = torch.randn(4, 512, generator=g).cuda()
+    w1 = torch.randn(256, 512, generator=g).cuda() / 22
+    b1 = torch.randn(256, generator=g).cuda()
+    w2 = torch.randn(3, 256, generator=g).cuda() / 16
+    b2 = torch.randn(3, generator=g).cuda()
+    logits = ops.head_mlp(feat, w1, b1, w2, b2)
+    ref = F.linear(F.relu(F.linear(feat, w1, b1)), w2, b2)
+    assert torch.allclose(logits, ref, rtol=1e-4, atol=1e-4)
+
+
+def _route_ref(logits):
+    inten = torch.argmax(logits, dim=1)
+    return inten, [torch.nonzero(inten == k).flatten() for k in range(3)]
+
+
+@pytest.mark.parametrize("b", [1, 7, 32, 256, 1500, 4097])
+def test_route_bit_exact(b):
+    """argmax + bucket lists must equal torch.argmax / nonzero exactly, incl. exact ties, 1-ulp gaps and NaNs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(b)
+    logits = torch.randn(b, 3, generator=g)
+    if b >= 7:
+        logits[1] = torch.tensor([0.5, 0.5, 0.5])                       # 3-way tie -> class 0
+        logits[2] = torch.tensor([0.1, 0.7, 0.7])                       # tie -> first max (1)
+        v = torch.tensor(0.3)
+        logits[3] = torch.stack([v, torch.nextafter(v, torch.tensor(1.0)), v])  # 1-ulp gap -> 1
+        logits[4] = torch.tensor([0.2, float("nan"), 5.0])              # NaN counts as max
+        logits[5] = torch.tensor([float("-inf"), float("-inf"), float("-inf")])
+        logits[6] = torch.tensor([-0.0, 0.0, -0.0])                     # signed zeros tie -> 0
+    logits = logits.cuda()
+    inten, masks, bidx, bcnt = ops.route(logits)
+    ref_int, ref_lists = _route_ref(logits)
+    assert torch.equal(inten, ref_int)
+    cnt = bcnt.cpu().tolist()
+    for k in range(3):
+        assert torch.equal(masks[k], ref_int == k)
+        assert cnt[k] == ref_lists[k].numel()
+        assert torch.equal(bidx[k, :cnt[k]].long(), ref_lists[k])
+    assert sum(cnt) == b
+
+
+def test_route_given_intensity():
+    ops = _ops()
+    inten_in = torch.tensor([2, 0, 1, 1, 0, 2, 2, 5], device="cuda")
+    inten, masks, bidx, bcnt = ops.route(intensity=inten_in)
+    assert torch.equal(inten, inten_in)
+    assert bcnt.cpu().tolist() == [2, 2, 3]     # class 5 is routed nowhere, as in routing.py:46-50
+    assert bidx[0, :2].tolist() == [1, 4] and bidx[1, :2].tolist() == [2, 3] and bidx[2, :3].tolist() == [0, 5, 6]
+
+
+def test_blend3():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    ys = [torch.rand(4, 3, 16, 32, generator=g).cuda() for _ in range(3)]
+    logits = torch.randn(4, 3, generator=g).cuda()
+    out, wts = ops.blend3(*ys, logits, 0.5)
+    w = F.softmax(logits / 0.5, dim=1)
+    ref = torch.zeros_like(ys[0])
+    for i in range(3):
+        ref += w[:, i].view(4, 1, 1, 1) * ys[i]
+    assert torch.allclose(wts, w, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_losses():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    p = torch.rand(3, 3, 33, 47, generator=g).cuda()
+    t = torch.rand(3, 3, 33, 47, generator=g).cuda()
+    out = ops.l1_mse(p, t)
+    assert torch.allclose(out[0], F.l1_loss(p, t), rtol=1e-4)
+    assert torch.allclose(out[1], F.mse_loss(p, t), rtol=1e-4)
+    logits = torch.randn(16, 3, generator=g).cuda().requires_grad_(True)
+    labels = torch.randint(0, 3, (16,), generator=g).cuda()
+    loss, grad = ops.cross_entropy(logits.detach(), labels, grad_scale=0.2)
+    ref = F.cross_entropy(logits, labels)
+    (0.2 * ref).backward()
+    assert torch.allclose(loss[0], ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(grad, logits.grad, rtol=1e-4, atol=1e-6)
