@@ -21,6 +21,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define ADB_API __attribute__((visibility("default")))
+#else
+#define ADB_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -95,27 +101,27 @@ typedef struct adb_conv_desc {
  */
 
 /* Library / device */
-const char* adb_last_error(void);
-int adb_version(void);
-int adb_device_check(void);                 /* 0 when the current device is sm_100 and the TMA encoder resolved */
+ADB_API const char* adb_last_error(void);
+ADB_API int adb_version(void);
+ADB_API int adb_device_check(void);                 /* 0 when the current device is sm_100 and the TMA encoder resolved */
 
 /* Implicit-GEMM convolution on tcgen05/TMEM tiles fed by TMA (bf16 x bf16 -> fp32).
  * Replaces nn.Conv2d / nn.ConvTranspose2d + BatchNorm2d(eval) + activation (+ residual add) of
  * models/dehazing/base_model.py:4-41 and the encoder/decoder/head convs of medium_intensity.py:16-76,
  * high_intensity.py:17-90, low_intensity.py:16-28. */
-int adb_conv2d(const adb_conv_desc* desc, void* stream);
+ADB_API int adb_conv2d(const adb_conv_desc* desc, void* stream);
 /* FLOPs (2*MAC) the descriptor's launch performs for n images — the figure bench.py's roofline uses. */
-double adb_conv2d_flops(const adb_conv_desc* desc);
+ADB_API double adb_conv2d_flops(const adb_conv_desc* desc);
 
 /* Image -> stem operand.  out[i,h,w, s*3+c] = x[idx(i), c, h, w*stride + s - pad] (0 outside), zero-padded to kp
  * channels, bf16.  Makes a kh x kw x 3 stem a kh x 1 conv with kp channels (stem convs low:16, medium:16, high:17,85). */
-int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n,
+ADB_API int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n,
                   int32_t h, int32_t w, int32_t kw, int32_t pad, int32_t stride, int32_t kp,
                   void* out, void* stream);
 
 /* Layout converters (tests, classifier features): NCHW fp32 <-> NHWC bf16 */
-int adb_nchw_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, void* out, void* stream);
-int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, float* out, void* stream);
+ADB_API int adb_nchw_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, void* out, void* stream);
+ADB_API int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t c_pitch, float* out, void* stream);
 
 /* AttentionBlock (base_model.py:43-78) as three HBM-bound passes over an NHWC bf16 map x[n,h,w,c]:
  *  1) pool:   sum_c, max_c over h*w per (image, channel)                        (avg_pool/max_pool, :64-66)
@@ -123,44 +129,44 @@ int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_
  *             x*gate -> stats[n,h,w,2] fp32                                      (:66-73)
  *  3) apply:  y = x*gate*sigmoid(conv7x7(stats))                                 (:74-78)
  * pool_buf: fp32 [n][2][c] (sum, max) zero/-inf initialised by the call itself. */
-int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+ADB_API int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                   float* pool_buf, void* stream);
-int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+ADB_API int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                         const float* pool_buf, const float* w1 /*[c/r][c]*/, const float* w2 /*[c][c/r]*/, int32_t c_red,
                         float* gate /*[n][c]*/, float* stats /*[n,h,w,2]*/, void* stream);
-int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
+ADB_API int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                    const float* gate, const float* stats, const float* w_spatial /*[2][7][7]*/, void* y, void* stream);
 
 /* Pooling for the HDEN backbones (torchvision resnet/densenet called from models/classifier.py:24-36,91). */
-int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
-int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*[n][2][c]*/,
+ADB_API int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
+ADB_API int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*[n][2][c]*/,
                        float* y /*[n][c] fp32*/, void* stream);
 /* Classifier head, fp32: logits = W2*relu(W1*f + b1) + b2 (models/classifier.py:72-78, eval mode: dropout = identity). */
-int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
+ADB_API int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
                  const float* w2, const float* b2, int32_t classes, float* logits, void* stream);
 
 /* Routing (models/routing.py:40-61): intensity = argmax(logits,1) (first max wins, NaN counts as max, like
  * torch.argmax), masks, and a stable 3-way compaction: bucket k lists the ascending batch rows with intensity == k.
  * intensity_in (nullable) overrides the argmax (HardRouter.forward(x, intensity=...), routing.py:23,40).
  * Outputs: intensity int64[b]; masks uint8[3][b]; bucket_index int32[3][b]; bucket_count int32[3]. */
-int adb_route(const float* logits, const int64_t* intensity_in, int32_t b, int32_t classes,
+ADB_API int adb_route(const float* logits, const int64_t* intensity_in, int32_t b, int32_t classes,
               int64_t* intensity, uint8_t* masks, int32_t* bucket_index, int32_t* bucket_count, void* stream);
 
 /* Soft/gated blend (routing.py:111-127, 215-221): w = softmax(logits/T) (or given weights when temperature <= 0),
  * out = sum_k w[:,k] * y_k, NCHW fp32. */
-int adb_blend3(const float* y0, const float* y1, const float* y2, const float* logits_or_weights, float temperature,
+ADB_API int adb_blend3(const float* y0, const float* y1, const float* y2, const float* logits_or_weights, float temperature,
                int32_t b, int64_t chw, float* weights_out /*[b][3]*/, float* out, void* stream);
 
 /* Loss reductions (training/loss.py:121,81,177) forward + backward w.r.t. pred/logits.
  * l1: mean|p-t|, mse: mean (p-t)^2 — one pass, warp-shuffle + one atomic per block; grad_scale multiplies dL/dp. */
-int adb_l1_mse_fwd(const float* pred, const float* target, int64_t numel, float* out2 /*[l1, mse]*/, void* stream);
-int adb_l1_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
-int adb_mse_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
-int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale,
+ADB_API int adb_l1_mse_fwd(const float* pred, const float* target, int64_t numel, float* out2 /*[l1, mse]*/, void* stream);
+ADB_API int adb_l1_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
+ADB_API int adb_mse_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* grad, void* stream);
+ADB_API int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale,
                    float* loss /*[1]*/, float* grad_logits /*nullable [b][classes]*/, void* stream);
 
 /* Read and clear the device-side kernel error flag (non-zero => a bounded mbarrier wait expired). Synchronises. */
-int adb_kernel_error_flag(void);
+ADB_API int adb_kernel_error_flag(void);
 
 #ifdef __cplusplus
 }
