@@ -24,14 +24,15 @@ def pad16(c):
 
 
 # --------------------------------------------------------------------------- packing (host logic, CPU-testable)
-def fold_bn(cout, bias=None, bn=None, cout_pad=None):
+def fold_bn(cout, bias=None, bn=None, cout_pad=None, device=None):
     """Epilogue affine of Conv(+bias) -> BatchNorm(eval): y = acc*scale + shift  (base_model.py:11-16).
 
     bn = (weight, bias, running_mean, running_var, eps) or None.  Returns fp32 (scale, shift) of length cout_pad
     (zero in the padding so padded channels come out as act(0)).
     """
     cout_pad = cout_pad or pad16(cout)
-    dev = (bias if bias is not None else bn[0]).device if (bias is not None or bn is not None) else "cpu"
+    dev = device if device is not None else ((bias if bias is not None else bn[0]).device
+                                             if (bias is not None or bn is not None) else "cpu")
     scale = torch.ones(cout, dtype=torch.float32, device=dev)
     shift = torch.zeros(cout, dtype=torch.float32, device=dev)
     if bias is not None:
@@ -99,19 +100,19 @@ class ConvSpec:
     def from_conv(weight, bias=None, bn=None, act=ACT_NONE, stride=1, pad=None):
         co, ci, kh, kw = weight.shape
         pad = kh // 2 if pad is None else pad
-        scale, shift = fold_bn(co, bias, bn)
+        scale, shift = fold_bn(co, bias, bn, device=weight.device)
         return ConvSpec(CONV_S1 if stride == 1 else CONV_S2, kh, kw, pad, co, pack_conv_weight(weight), scale, shift, act)
 
     @staticmethod
     def from_convT(weight, bias=None, bn=None, act=ACT_NONE):
         ci, co, kh, kw = weight.shape
-        scale, shift = fold_bn(co, bias, bn)
+        scale, shift = fold_bn(co, bias, bn, device=weight.device)
         return ConvSpec(CONVT_4X4S2, 4, 4, 1, co, pack_convT_weight(weight), scale, shift, act)
 
     @staticmethod
     def from_stem(weight, kp, bias=None, bn=None, act=ACT_NONE):
         co, ci, kh, kw = weight.shape
-        scale, shift = fold_bn(co, bias, bn)
+        scale, shift = fold_bn(co, bias, bn, device=weight.device)
         return ConvSpec(CONV_S1, kh, 1, kh // 2, co, pack_stem_weight(weight, kp), scale, shift, act)
 
 
