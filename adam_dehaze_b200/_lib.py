@@ -49,15 +49,18 @@ SIGNATURES = {
     "adb_device_check": [],
     "adb_kernel_error_flag": [],
     "adb_conv2d": [C.POINTER(ConvDesc), _P],
-    "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_attn_pool": [_P, _I, _I, _I, _I, _P, _I, _P, _P],
     "adb_attn_gate_stats": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P],
     "adb_attn_apply": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
-    "adb_maxpool3x3s2": [_P, _I, _I, _I, _I, _P, _P],
+    "adb_maxpool3x3s2": [_P, _I, _I, _I, _I, _P, _I, _P],
     "adb_global_avgpool": [_P, _I, _I, _I, _I, _P, _P, _P],
+    "adb_affine_relu": [_P, _L, _I, _I, _P, _P, _P, _I, _P],
+    "adb_avgpool2x2": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "adb_head_mlp": [_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
+    "adb_linear": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "adb_route": [_P, _P, _I, _I, _P, _P, _P, _P, _P],
     "adb_blend3": [_P, _P, _P, _P, _F, _I, _L, _P, _P, _P],
     "adb_l1_mse_fwd": [_P, _P, _L, _P, _P],

@@ -367,14 +367,16 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
   // ---- taps
   if (d->kind == ADB_CONV_S1) {
     ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "adb_conv2d: %dx%d taps unsupported (max %d)", d->kh, d->kw, kMaxTaps);
-    out_h = d->h_in + 2 * d->pad - d->kh + 1;
-    out_w = d->w_in + 2 * d->pad - d->kw + 1;
-    ADB_REQUIRE(out_h == d->h_in && out_w == d->w_in, "adb_conv2d: stride-1 convs must be 'same' (pad=(k-1)/2)");
+    // 'same' convolution: the padding is implied by the (odd) kernel extents, so a kh x 1 stem conv pads rows only
+    ADB_REQUIRE(d->kh % 2 == 1 && d->kw % 2 == 1, "adb_conv2d: stride-1 convs need odd kernel extents (got %dx%d)", d->kh, d->kw);
+    const int pad_h = (d->kh - 1) / 2, pad_w = (d->kw - 1) / 2;
+    ADB_REQUIRE(d->pad == std::max(pad_h, pad_w), "adb_conv2d: stride-1 convs must be 'same' (pad=(k-1)/2, got %d)", d->pad);
+    out_h = d->h_in; out_w = d->w_in;
     P.ngroups = 1; P.ntaps = d->kh * d->kw;
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) {
         Tap& t = P.taps[0][r * d->kw + s];
-        t.c_mul = 0; t.dw = (int8_t)(s - d->pad); t.p = 0; t.dh = (int8_t)(r - d->pad);
+        t.c_mul = 0; t.dw = (int8_t)(s - pad_w); t.p = 0; t.dh = (int8_t)(r - pad_h);
       }
     P.grid_h = out_h; P.grid_w = out_w;
   } else if (d->kind == ADB_CONV_S2) {

@@ -40,32 +40,38 @@ inline int grid_for(long long work_items, int threads, int sm_count, int waves =
 }
 
 // ------------------------------------------------------------------ stem pack
-// out[i,h,wo,j] (bf16, kp channels), j = s*3 + c  <-  x[row(i), c, h, wo*stride + s - pad]
+// out[i,ho,wo,j] (bf16, kp channels), j = (r*kw + s)*3 + c  <-  x[row(i), c, ho*sh + r - ph, wo*stride + s - pad]
+// kh == 1: rows are not unrolled (ho = h, ph = 0, sh = 1) — the consumer conv walks the kh row taps itself.
+// kh  > 1: full im2col (sh = stride, ph = pad) — the consumer is a 1x1 conv (stride-2 HDEN stems).
 __global__ void stem_pack_kernel(const float* __restrict__ x, const int* __restrict__ index, const int* n_dev, int n_start,
-                                 int n, int h, int w, int wo, int kw, int pad, int stride, int kp,
+                                 int n, int h, int w, int ho, int wo, int kh, int kw, int pad, int stride, int kp,
                                  __nv_bfloat16* __restrict__ out) {
   const int n_eff = live_images(n, n_dev, n_start);
   const int groups = kp / 8;
-  const long long total = (long long)n_eff * h * wo * groups;
+  const long long total = (long long)n_eff * ho * wo * groups;
   const size_t plane = (size_t)h * w;
+  const int sh = kh > 1 ? stride : 1, ph = kh > 1 ? pad : 0;
+  const int taps = kh * kw;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(t % groups);
     long long p = t / groups;
     const int xo = (int)(p % wo); p /= wo;
-    const int y = (int)(p % h);
-    const int i = (int)(p / h);
+    const int yo = (int)(p % ho);
+    const int i = (int)(p / ho);
     const int pos = n_start + i;
     const size_t row = index ? (size_t)index[pos] : (size_t)pos;
-    const float* xi = x + row * 3 * plane + (size_t)y * w;
+    const float* xi = x + row * 3 * plane;
     float f[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int j = g * 8 + q;
-      const int s = j / 3, c = j - 3 * s;
+      const int tap = j / 3, c = j - 3 * tap;
+      const int r = tap / kw, s = tap - r * kw;
+      const int yy = yo * sh + r - ph;
       const int xx = xo * stride + s - pad;
-      f[q] = (s < kw && xx >= 0 && xx < w) ? __ldg(xi + c * plane + xx) : 0.f;
+      f[q] = (tap < taps && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + c * plane + (size_t)yy * w + xx) : 0.f;
     }
-    *reinterpret_cast<uint4*>(out + (((size_t)i * h + y) * wo + xo) * kp + g * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(out + (((size_t)i * ho + yo) * wo + xo) * kp + g * 8) = pack8(f);
   }
 }
 
@@ -281,7 +287,7 @@ __global__ void attn_apply_kernel(const __nv_bfloat16* __restrict__ x, int n, in
 
 // ------------------------------------------------------------------ pooling for the HDEN backbone
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int ho, int wo,
-                                    __nv_bfloat16* __restrict__ y) {
+                                    __nv_bfloat16* __restrict__ y, int pitch_out) {
   const int G = c / 8;
   const long long total = (long long)n * ho * wo * G;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -305,7 +311,57 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int n, 
         for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
       }
     }
-    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * c + g * 8) = pack8(m);
+    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * pitch_out + g * 8) = pack8(m);
+  }
+}
+
+// y[p, 0:c] = relu(x[p, 0:c] * scale + shift) — DenseNet pre-activation (norm -> relu ahead of a conv), NHWC bf16
+__global__ void affine_relu_kernel(const __nv_bfloat16* __restrict__ x, long long pixels, int c, int pitch_in,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   __nv_bfloat16* __restrict__ y, int pitch_out) {
+  const int G = c / 8;
+  const long long total = pixels * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long p = t / G;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)p * pitch_in + g * 8)), f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + g * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + g * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = fmaxf(fmaf(f[q], sc[q], sh[q]), 0.f);
+    *reinterpret_cast<uint4*>(y + (size_t)p * pitch_out + g * 8) = pack8(f);
+  }
+}
+
+// 2x2 average pool, stride 2 (DenseNet transition), NHWC bf16
+__global__ void avgpool2x2_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int pitch_in,
+                                  __nv_bfloat16* __restrict__ y, int pitch_out) {
+  const int G = c / 8, ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int i = (int)(p / ho);
+    float a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)i * h + 2 * yo + dy) * w + 2 * xo + dx) * pitch_in + g * 8)), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] += f[q];
+      }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] *= 0.25f;
+    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * pitch_out + g * 8) = pack8(a);
   }
 }
 
@@ -338,6 +394,23 @@ __global__ void head_mlp_kernel(const float* __restrict__ feat, int f, const flo
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) logits[(size_t)img * classes + k] = a + b2[k];
+  }
+}
+
+// y = act(W x + b), fp32, one block per row (gate MLP of GatedRouter, routing.py:155-163)
+__global__ void linear_kernel(const float* __restrict__ x, int fin, const float* __restrict__ w, const float* __restrict__ b,
+                              int fout, int relu, float* __restrict__ y) {
+  extern __shared__ float sm[];
+  const int row = blockIdx.x;
+  for (int i = threadIdx.x; i < fin; i += blockDim.x) sm[i] = x[(size_t)row * fin + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < fout; j += nwarps) {
+    float a = 0.f;
+    for (int i = lane; i < fin; i += 32) a = fmaf(w[(size_t)j * fin + i], sm[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) { a += b ? b[j] : 0.f; y[(size_t)row * fout + j] = relu ? fmaxf(a, 0.f) : a; }
   }
 }
 
@@ -455,15 +528,16 @@ int sm_count() {
 extern "C" {
 
 int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n, int32_t h,
-                  int32_t w, int32_t kw, int32_t pad, int32_t stride, int32_t kp, void* out, void* stream) {
-  ADB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "adb_stem_pack: bad arguments");
-  ADB_REQUIRE(kp % 8 == 0 && kp >= kw * 3 && (stride == 1 || stride == 2), "adb_stem_pack: kp %d must be a multiple of 8 >= 3*kw", kp);
+                  int32_t w, int32_t kh, int32_t kw, int32_t pad, int32_t stride, int32_t kp, void* out, void* stream) {
+  ADB_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && kh >= 1 && kw >= 1, "adb_stem_pack: bad arguments");
+  ADB_REQUIRE(kp % 8 == 0 && kp >= kh * kw * 3 && (stride == 1 || stride == 2), "adb_stem_pack: kp %d must be a multiple of 8 >= 3*kh*kw", kp);
   const int sms = sm_count();
   if (!sms) return ADB_ERR_NO_DEVICE;
   const int wo = (w + 2 * pad - kw) / stride + 1;
-  const long long total = (long long)n * h * wo * (kp / 8);
+  const int ho = kh > 1 ? (h + 2 * pad - kh) / stride + 1 : h;
+  const long long total = (long long)n * ho * wo * (kp / 8);
   stem_pack_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
-      x, index, n_dev, n_start, n, h, w, wo, kw, pad, stride, kp, reinterpret_cast<__nv_bfloat16*>(out));
+      x, index, n_dev, n_start, n, h, w, ho, wo, kh, kw, pad, stride, kp, reinterpret_cast<__nv_bfloat16*>(out));
   ADB_LAUNCH_OK();
   return ADB_OK;
 }
@@ -549,13 +623,37 @@ int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, co
   return ADB_OK;
 }
 
-int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream) {
-  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0, "adb_maxpool3x3s2: bad arguments");
+int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, int32_t pitch_out, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && pitch_out >= c && pitch_out % 8 == 0, "adb_maxpool3x3s2: bad arguments");
   const int sms = sm_count();
   if (!sms) return ADB_ERR_NO_DEVICE;
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, ho, wo, reinterpret_cast<__nv_bfloat16*>(y));
+  maxpool3x3s2_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, ho, wo, reinterpret_cast<__nv_bfloat16*>(y), pitch_out);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_affine_relu(const void* x, int64_t pixels, int32_t c, int32_t pitch_in, const float* scale, const float* shift,
+                    void* y, int32_t pitch_out, void* stream) {
+  ADB_REQUIRE(x && y && scale && shift && pixels > 0 && c % 8 == 0 && pitch_in % 8 == 0 && pitch_out % 8 == 0 && pitch_in >= c && pitch_out >= c,
+              "adb_affine_relu: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  affine_relu_kernel<<<grid_for(pixels * (c / 8), 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), pixels, c, pitch_in, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), pitch_out);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_avgpool2x2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pitch_in, void* y, int32_t pitch_out, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0 && pitch_in >= c && pitch_out >= c && pitch_in % 8 == 0 && pitch_out % 8 == 0,
+              "adb_avgpool2x2: bad arguments");
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  avgpool2x2_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, pitch_in, reinterpret_cast<__nv_bfloat16*>(y), pitch_out);
   ADB_LAUNCH_OK();
   return ADB_OK;
 }
@@ -575,6 +673,14 @@ int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const
   ADB_REQUIRE(feat && w1 && b1 && w2 && b2 && logits && n > 0 && f > 0 && hidden > 0 && classes > 0, "adb_head_mlp: bad arguments");
   ADB_REQUIRE((size_t)(f + hidden) * sizeof(float) <= 48 * 1024, "adb_head_mlp: feature dim too large");
   head_mlp_kernel<<<n, 256, (f + hidden) * sizeof(float), (cudaStream_t)stream>>>(feat, f, w1, b1, hidden, w2, b2, classes, logits);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_linear(const float* x, int32_t n, int32_t fin, const float* w, const float* b, int32_t fout, int32_t relu,
+               float* y, void* stream) {
+  ADB_REQUIRE(x && w && y && n > 0 && fin > 0 && fout > 0 && (size_t)fin * sizeof(float) <= 48 * 1024, "adb_linear: bad arguments");
+  linear_kernel<<<n, 256, fin * sizeof(float), (cudaStream_t)stream>>>(x, fin, w, b, fout, relu, y);
   ADB_LAUNCH_OK();
   return ADB_OK;
 }

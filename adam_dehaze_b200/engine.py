@@ -1,0 +1,490 @@
+"""Execution engine: turns the drop-in nn.Modules (parameter containers with the reference's state_dict layout) into
+sequences of fused libadb200 launches on NHWC bf16 feature maps.
+
+One engine per module instance.  It (re)packs weights whenever a parameter or BN buffer changes (torch `_version`
+counters), owns the activation buffers of a micro-batch, and walks a routed bucket micro-batch by micro-batch with the
+bucket's live count kept on the device (`n_dev`) — no host synchronisation anywhere on the path.
+
+Inference only for now: BatchNorm uses running statistics (module.eval()).  Calling a module in train() mode raises —
+there is no silent fallback to torch ops.
+"""
+import torch
+
+from . import ops
+from .ops import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_DOT, EPI_IMAGE, IMG_BLEND, IMG_GUIDED, IMG_RESIDUAL,
+                  AttnParams, ConvSpec)
+
+# activation bytes one image may take before the micro-batch is cut (per branch pass)
+_MICRO_BATCH_BYTES = 24 << 30
+_MAX_MICRO_BATCH = 16
+
+
+def bn_args(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+
+
+def require_inference(module, what):
+    if module.training:
+        raise NotImplementedError(
+            f"{what}: the B200 path implements inference (BatchNorm with running statistics); call .eval() first. "
+            "Training kernels (dgrad/wgrad, batch-statistics BN) are not part of this build and there is no torch fallback.")
+
+
+def require_cuda(x, what):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError(f"{what}: expected a CUDA tensor — this package runs on B200 (sm_100a) only and has no CPU path")
+    if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"{what}: expected an NCHW float32 image batch with 3 channels, got {tuple(x.shape)} {x.dtype}")
+
+
+def require_cuda_any(x, what):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4):
+        raise RuntimeError(f"{what}: expected a 4-D CUDA tensor — this package runs on B200 (sm_100a) only and has no CPU path")
+
+
+def block_engine(module):
+    eng = module.__dict__.get("_adb_engine")
+    if eng is None:
+        eng = BlockEngine(module)
+        module.__dict__["_adb_engine"] = eng
+    return eng
+
+
+class _Versioned:
+    """Re-pack when any tensor of the module changed in place (optimizer step, load_state_dict, .to())."""
+
+    def __init__(self, module):
+        self.module = module
+        self._sig = None
+
+    def signature(self):
+        items = list(self.module.named_parameters()) + list(self.module.named_buffers())
+        return tuple((k, t.data_ptr(), t._version, str(t.device)) for k, t in items)
+
+    def stale(self):
+        sig = self.signature()
+        if sig != self._sig:
+            self._sig = sig
+            return True
+        return False
+
+
+def _conv_block_spec(cb, act_override=None, stem_kp=None, stride=1, pad=None):
+    """ConvBlock (Conv2d [+BN] [+ReLU]) -> one fused launch spec."""
+    conv = cb.block[0]
+    bn = None
+    act = ACT_NONE
+    for m in list(cb.block)[1:]:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            bn = bn_args(m)
+        elif isinstance(m, torch.nn.ReLU):
+            act = ACT_RELU
+    if act_override is not None:
+        act = act_override
+    if stem_kp:
+        return ConvSpec.from_stem(conv.weight, stem_kp, bias=conv.bias, bn=bn, act=act)
+    return ConvSpec.from_conv(conv.weight, bias=conv.bias, bn=bn, act=act, stride=conv.stride[0], pad=conv.padding[0])
+
+
+def _res_specs(rb):
+    return (_conv_block_spec(rb.conv1), _conv_block_spec(rb.conv2, act_override=ACT_RELU))  # ReLU after the residual add
+
+
+def _attn_params(ab):
+    return AttnParams(ab.fc[0].weight, ab.fc[2].weight, ab.conv_spatial.weight)
+
+
+class BranchEngine:
+    """Runs LightweightDehazeModel / MediumIntensityDehazeModel / HighIntensityDehazeModel forwards."""
+
+    def __init__(self, model, kind):
+        assert kind in ("light", "unet", "unet_attn")
+        self.model, self.kind = model, kind
+        self._ver = _Versioned(model)
+        self.S = None
+        self._bufs = {}
+        self.tune = None
+
+    # ------------------------------------------------------------------ packing
+    def specs(self):
+        if self.S is not None and not self._ver.stale():
+            return self.S
+        m = self.model
+        S = {}
+        if self.kind == "light":
+            S["init"] = _conv_block_spec(m.init_conv, stem_kp=16)
+            S["res"] = [_res_specs(rb) for rb in m.residual_blocks]
+            S["out0"] = _conv_block_spec(m.output_conv[0])
+            S["out1"] = ConvSpec.from_conv(m.output_conv[1].weight, bias=m.output_conv[1].bias, act=ACT_SIGMOID)
+        else:
+            attn = self.kind == "unet_attn"
+            S["init"] = _conv_block_spec(m.init_conv, stem_kp=32)
+            S["enc"] = []
+            for e in m.encoder:
+                d = {"down": _conv_block_spec(e[0]), "res": [_res_specs(e[1]), _res_specs(e[2])]}
+                if attn:
+                    d["attn"] = _attn_params(e[3])
+                S["enc"].append(d)
+            if attn:
+                S["bott"] = [(_res_specs(m.bottleneck[0]), _attn_params(m.bottleneck[1])),
+                             (_res_specs(m.bottleneck[2]), _attn_params(m.bottleneck[3]))]
+            else:
+                S["bott"] = [(_res_specs(m.bottleneck[0]), None), (_res_specs(m.bottleneck[1]), None)]
+            S["dec"] = []
+            for dmod in m.decoder:
+                d = {"up": ConvSpec.from_convT(dmod[0].weight, bias=dmod[0].bias, bn=bn_args(dmod[1]), act=ACT_RELU),
+                     "res": _res_specs(dmod[3])}
+                if attn:
+                    d["attn"] = _attn_params(dmod[4])
+                S["dec"].append(d)
+            S["out0"] = _conv_block_spec(m.output_conv[0])
+            S["out1"] = _conv_block_spec(m.output_conv[1])
+            S["out2"] = ConvSpec.from_conv(m.output_conv[2].weight, bias=m.output_conv[2].bias, act=ACT_TANH)
+            if attn:
+                S["det0"] = _conv_block_spec(m.detail_branch[0], stem_kp=16)
+                S["det1"] = _conv_block_spec(m.detail_branch[1])
+                w = m.detail_branch[2].weight.detach().float().reshape(-1)
+                dot_w = torch.zeros(16, dtype=torch.float32, device=w.device)
+                dot_w[:w.numel()] = w
+                # the 1x1 bias rides in the launch descriptor: one host read per re-pack, none per forward
+                S["det_dot"] = (dot_w.contiguous(), float(m.detail_branch[2].bias.detach().float().item()))
+        self.S = S
+        return S
+
+    # ------------------------------------------------------------------ buffers
+    def bytes_per_image(self, h, w):
+        c = self.model.base_channels
+        px = h * w
+        if self.kind == "light":
+            return px * (16 + 3 * c) * 2
+        # stem operand + full-res maps (f0, x2, tmp, head) + half/quarter-res pyramids + guidance path
+        full = px * (32 + 4 * c + 16 + 2 * 16) * 2 + px * 4
+        return full + (px // 4) * 3 * 2 * c * 2 + (px // 16) * 2 * 4 * c * 2
+
+    def micro_batch(self, h, w, limit):
+        mb = max(1, min(_MAX_MICRO_BATCH, _MICRO_BATCH_BYTES // max(1, self.bytes_per_image(h, w))))
+        return int(min(mb, limit))
+
+    def _buf(self, name, shape, device, dtype=torch.bfloat16):
+        key = (name, tuple(shape), str(device), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._bufs[key] = t
+        return t
+
+    def release_buffers(self):
+        self._bufs.clear()
+
+    # ------------------------------------------------------------------ execution
+    def forward(self, x, out=None, index=None, n_dev=None, count=None):
+        """x: NCHW fp32 CUDA batch.  Without routing arguments the whole batch is processed in order.  With
+        (index int32[>=count], n_dev device int) only bucket rows index[0:*n_dev] are read and their outputs scattered
+        to the same rows of `out`; `count` is the host-side upper bound of the bucket size (default: batch size)."""
+        require_cuda(x, type(self.model).__name__)
+        require_inference(self.model, type(self.model).__name__)
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if self.kind != "light" and (h % 4 or w % 4):
+            raise ValueError(f"{type(self.model).__name__}: H and W must be multiples of 4 on the B200 path (got {h}x{w})")
+        if out is None:
+            out = torch.empty_like(x)
+        upper = b if count is None else int(count)
+        S = self.specs()
+        mb = self.micro_batch(h, w, upper)
+        run = self._run_light if self.kind == "light" else self._run_unet
+        for start in range(0, upper, mb):
+            run(S, x, out, index, n_dev, start, min(mb, upper - start), mb)
+        return out
+
+    def _kw(self, n_dev, n_start, n):
+        kw = {"n": n, "n_dev": n_dev, "n_start": n_start}
+        if self.tune:
+            kw["tune"] = self.tune
+        return kw
+
+    def _res(self, specs, f, tmp, kw):
+        """ResidualBlock (base_model.py:36-41): conv-bn-relu -> conv-bn -> += f -> relu, in place on f."""
+        ops.conv2d(specs[0], f, dst=tmp, **kw)
+        ops.conv2d(specs[1], tmp, dst=f, residual=f, **kw)
+        return f
+
+    def _run_light(self, S, x, out, index, n_dev, n_start, n, cap):
+        dev = x.device
+        _, _, h, w = x.shape
+        c = S["init"].cout_pad
+        kw = self._kw(n_dev, n_start, n)
+        x3 = self._buf("x3", (cap, h, w, 16), dev)
+        f = self._buf("f", (cap, h, w, c), dev)
+        t = self._buf("t", (cap, h, w, c), dev)
+        ops.stem_pack(x, 3, 1, 16, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x3)
+        ops.conv2d(S["init"], x3, dst=f, **kw)
+        for specs in S["res"]:
+            self._res(specs, f, t, kw)
+        ops.conv2d(S["out0"], f, dst=t, **kw)
+        ops.conv2d(S["out1"], t, epi=EPI_IMAGE,
+                   image=dict(mode=IMG_BLEND, x=x, out=out, index=index, alpha=self.model.skip_alpha), **kw)
+
+    def _run_unet(self, S, x, out, index, n_dev, n_start, n, cap):
+        dev = x.device
+        _, _, h, w = x.shape
+        attn = self.kind == "unet_attn"
+        c = S["init"].cout_pad
+        kw = self._kw(n_dev, n_start, n)
+        scratch = self._bufs.setdefault(("attn_scratch", cap, str(dev)), {})
+
+        def attend(ap, f):
+            return ops.attention(f, ap, n=n, n_dev=n_dev, n_start=n_start, out=f, scratch=scratch)
+
+        guidance = None
+        if attn:
+            x3 = self._buf("x3", (cap, h, w, 16), dev)
+            g0 = self._buf("g0", (cap, h, w, 16), dev)
+            guidance = self._buf("guidance", (cap, h, w), dev, torch.float32)
+            ops.stem_pack(x, 3, 1, 16, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x3)
+            ops.conv2d(S["det0"], x3, dst=g0, **kw)
+            dot_w, dot_b = S["det_dot"]
+            ops.conv2d(S["det1"], g0, epi=EPI_DOT, dot=(dot_w, dot_b, guidance), **kw)
+
+        x7 = self._buf("x7", (cap, h, w, 32), dev)
+        f0 = self._buf("f0", (cap, h, w, c), dev)
+        ops.stem_pack(x, 7, 3, 32, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x7)
+        ops.conv2d(S["init"], x7, dst=f0, **kw)
+
+        feats = [f0]
+        hh, ww, cc = h, w, c
+        for li, e in enumerate(S["enc"]):
+            hh, ww, cc = hh // 2, ww // 2, e["down"].cout_pad
+            f = self._buf(f"f{li + 1}", (cap, hh, ww, cc), dev)
+            t = self._buf(f"t{li + 1}", (cap, hh, ww, cc), dev)
+            ops.conv2d(e["down"], feats[-1], dst=f, **kw)
+            for specs in e["res"]:
+                self._res(specs, f, t, kw)
+            if attn:
+                attend(e["attn"], f)
+            feats.append(f)
+
+        # bottleneck works on a copy-free alias: feats[-1] is only needed as the bottleneck input
+        bt = feats[-1]
+        t2 = self._buf("t2", tuple(bt.shape), dev)
+        for specs, ap in S["bott"]:
+            self._res(specs, bt, t2, kw)
+            if ap is not None:
+                attend(ap, bt)
+
+        # decoder 0: up(bottleneck) -> res (-> attn); then cat with feats[1]
+        d0 = S["dec"][0]
+        x1 = self._buf("x1", tuple(feats[1].shape), dev)
+        t1 = self._buf("t1", tuple(feats[1].shape), dev)
+        ops.conv2d(d0["up"], bt, dst=x1, **kw)
+        self._res(d0["res"], x1, t1, kw)
+        if attn:
+            attend(d0["attn"], x1)
+        # decoder 1 reads cat([x1, feats[1]]) without materialising it
+        d1 = S["dec"][1]
+        x2 = self._buf("x2", tuple(f0.shape), dev)
+        tf = self._buf("tf", tuple(f0.shape), dev)
+        ops.conv2d(d1["up"], x1, feats[1], dst=x2, **kw)
+        self._res(d1["res"], x2, tf, kw)
+        if attn:
+            attend(d1["attn"], x2)
+        # head reads cat([x2, f0])
+        ops.conv2d(S["out0"], x2, f0, dst=tf, **kw)
+        r1 = self._buf("r1", (cap, h, w, S["out1"].cout_pad), dev)
+        ops.conv2d(S["out1"], tf, dst=r1, **kw)
+        img = dict(mode=IMG_GUIDED if attn else IMG_RESIDUAL, x=x, out=out, index=index, guidance=guidance)
+        ops.conv2d(S["out2"], r1, epi=EPI_IMAGE, image=img, **kw)
+
+
+class BlockEngine:
+    """Stand-alone forwards of the building blocks (ConvBlock / ResidualBlock / AttentionBlock) on NCHW fp32 CUDA
+    tensors — layout conversion on both sides, used for unit-level parity tests and ad-hoc composition."""
+
+    def __init__(self, module):
+        self.module = module
+        self._ver = _Versioned(module)
+        self._spec = None
+
+    def _get(self, build):
+        if self._spec is None or self._ver.stale():
+            self._spec = build()
+        return self._spec
+
+    def conv_block(self, x):
+        require_inference(self.module, "ConvBlock")
+        spec = self._get(lambda: _conv_block_spec(self.module))
+        cin = x.shape[1]
+        if cin % 16:
+            raise ValueError("ConvBlock on the B200 path needs in_channels to be a multiple of 16 (3-channel stems run "
+                             "inside the branch models through adb_stem_pack)")
+        y = ops.conv2d(spec, ops.nchw_to_nhwc(x, cin))
+        return ops.nhwc_to_nchw(y, spec.cout)
+
+    def residual_block(self, x):
+        require_inference(self.module, "ResidualBlock")
+        specs = self._get(lambda: _res_specs(self.module))
+        f = ops.nchw_to_nhwc(x, x.shape[1])
+        t = ops.conv2d(specs[0], f)
+        y = ops.conv2d(specs[1], t, residual=f)
+        return ops.nhwc_to_nchw(y, specs[1].cout)
+
+    def attention_block(self, x):
+        ap = self._get(lambda: _attn_params(self.module))
+        y = ops.attention(ops.nchw_to_nhwc(x, x.shape[1]), ap)
+        return ops.nhwc_to_nchw(y, x.shape[1])
+
+
+class ResNetEngine:
+    """torchvision resnet18/34 trunk (BasicBlock) + the reference head, models/classifier.py:24-36,72-97."""
+
+    def __init__(self, classifier):
+        self.clf = classifier
+        self._ver = _Versioned(classifier)
+        self.S = None
+
+    def specs(self):
+        if self.S is not None and not self._ver.stale():
+            return self.S
+        bb = self.clf.backbone
+        S = {"stem": None, "layers": []}
+        S["stem"] = _stem7x7s2_spec(bb.conv1, bb.bn1)
+        for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
+            blocks = []
+            for blk in layer:
+                stride = blk.conv1.stride[0]
+                c1 = ConvSpec.from_conv(blk.conv1.weight, bn=bn_args(blk.bn1), act=ACT_RELU, stride=stride, pad=1)
+                c2 = ConvSpec.from_conv(blk.conv2.weight, bn=bn_args(blk.bn2), act=ACT_RELU, pad=1)
+                ds = None
+                if blk.downsample is not None:
+                    ds = ConvSpec.from_conv(blk.downsample[0].weight, bn=bn_args(blk.downsample[1]), act=ACT_NONE,
+                                            stride=blk.downsample[0].stride[0], pad=0)
+                blocks.append((c1, c2, ds))
+            S["layers"].append(blocks)
+        head = self.clf.classifier
+        S["head"] = tuple(t.detach().float().contiguous() for t in (head[1].weight, head[1].bias, head[4].weight, head[4].bias))
+        self.S = S
+        return S
+
+    def forward(self, x, chunk=None):
+        require_cuda(x, "FogIntensityClassifier")
+        require_inference(self.clf, "FogIntensityClassifier")
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
+        S = self.specs()
+        # bound the activation footprint: the stem operand is 320 B per stem-output pixel
+        per_img = (h // 2) * (w // 2) * (320 + 2 * 128) + (h // 4) * (w // 4) * 3 * 128
+        chunk = chunk or max(1, min(b, (8 << 30) // max(1, per_img)))
+        feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
+        for s in range(0, b, chunk):
+            n = min(chunk, b - s)
+            xs = x[s:s + n]
+            cols = ops.stem_pack(xs, 7, 3, 160, stride=2, kh=7)
+            f = ops.conv2d(S["stem"], cols)
+            del cols
+            f = ops.maxpool3x3s2(f)
+            for blocks in S["layers"]:
+                for (c1, c2, ds) in blocks:
+                    t = ops.conv2d(c1, f)
+                    idn = ops.conv2d(ds, f) if ds is not None else f
+                    f = ops.conv2d(c2, t, residual=idn)
+            feats[s:s + n] = ops.global_avgpool(f)
+        w1, b1, w2, b2 = S["head"]
+        return ops.head_mlp(feats, w1, b1, w2, b2), feats
+
+
+def _stem7x7s2_spec(conv, bn):
+    """7x7 stride-2 3->C stem as a 1x1 conv over the adb_stem_pack full-im2col operand (K = 147 -> 160)."""
+    w = conv.weight
+    co = w.shape[0]
+    wp = torch.zeros(ops.pad16(co), 160, dtype=torch.bfloat16, device=w.device)
+    wp[:co, :147] = w.detach().float().permute(0, 2, 3, 1).reshape(co, 147).to(torch.bfloat16)
+    scale, shift = ops.fold_bn(co, None, bn_args(bn), device=w.device)
+    return ConvSpec(ops.CONV_S1, 1, 1, 0, co, wp.contiguous(), scale, shift, ACT_RELU)
+
+
+class DenseNetEngine:
+    """torchvision densenet121 trunk + the reference head (north_star HDEN; the reference itself ships no DenseNet arm).
+
+    Dense blocks are concat-free: every layer's 3x3 conv stores its 32 new channels straight into the block's
+    [n,h,w,C_total] buffer at its channel offset.  norm2/relu2 ride in conv1's epilogue; norm1/relu1 (a different affine
+    of the same concat per layer) is one adb_affine_relu pass ahead of conv1."""
+
+    def __init__(self, classifier):
+        self.clf = classifier
+        self._ver = _Versioned(classifier)
+        self.S = None
+
+    @staticmethod
+    def _affine(bn):
+        s, b = ops.fold_bn(bn.num_features, None, bn_args(bn), cout_pad=bn.num_features, device=bn.weight.device)
+        return s, b
+
+    def specs(self):
+        if self.S is not None and not self._ver.stale():
+            return self.S
+        ft = self.clf.backbone.features
+        S = {"stem": _stem7x7s2_spec(ft.conv0, ft.norm0), "blocks": [], "trans": []}
+        for bi in range(4):
+            layers = []
+            for layer in getattr(ft, f"denseblock{bi + 1}").children():
+                pre = self._affine(layer.norm1)
+                c1 = ConvSpec.from_conv(layer.conv1.weight, bn=bn_args(layer.norm2), act=ACT_RELU, pad=0)
+                c2 = ConvSpec.from_conv(layer.conv2.weight, act=ACT_NONE, pad=1)
+                layers.append((pre, c1, c2))
+            S["blocks"].append(layers)
+            if bi < 3:
+                tr = getattr(ft, f"transition{bi + 1}")
+                S["trans"].append((self._affine(tr.norm), ConvSpec.from_conv(tr.conv.weight, act=ACT_NONE, pad=0)))
+        S["final"] = self._affine(ft.norm5)
+        head = self.clf.classifier
+        S["head"] = tuple(t.detach().float().contiguous() for t in (head[1].weight, head[1].bias, head[4].weight, head[4].bias))
+        self.S = S
+        return S
+
+    def forward(self, x, chunk=None):
+        require_cuda(x, "FogIntensityClassifier")
+        require_inference(self.clf, "FogIntensityClassifier")
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
+        S = self.specs()
+        per_img = (h // 2) * (w // 2) * (320 + 128) + (h // 4) * (w // 4) * 2 * (256 + 256 + 128)
+        chunk = chunk or max(1, min(b, (8 << 30) // max(1, per_img)))
+        feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
+        dev = x.device
+        for s in range(0, b, chunk):
+            n = min(chunk, b - s)
+            cols = ops.stem_pack(x[s:s + n], 7, 3, 160, stride=2, kh=7)
+            f = ops.conv2d(S["stem"], cols)
+            del cols
+            c_in = f.shape[3]
+            hh, ww = (f.shape[1] - 1) // 2 + 1, (f.shape[2] - 1) // 2 + 1
+            pending = ("max", f)   # the op that produces the next block's input writes straight into its buffer
+            for bi, layers in enumerate(S["blocks"]):
+                c_total = c_in + 32 * len(layers)
+                buf = torch.empty((n, hh, ww, c_total), dtype=torch.bfloat16, device=dev)
+                if pending[0] == "max":
+                    ops.maxpool3x3s2(pending[1], out=buf)
+                else:
+                    ops.avgpool2x2(pending[1], c=c_in, out=buf)
+                pending = None
+                c = c_in
+                for (pre, c1, c2) in layers:
+                    a = ops.affine_relu(buf, c, pre[0], pre[1])
+                    t = ops.conv2d(c1, a)
+                    ops.conv2d(c2, t, dst=buf, dst_c_off=c)
+                    c += 32
+                if bi < 3:
+                    pre, conv = S["trans"][bi]
+                    a = ops.affine_relu(buf, c, pre[0], pre[1])
+                    pending = ("avg", ops.conv2d(conv, a))
+                    c_in = conv.cout
+                    hh, ww = hh // 2, ww // 2
+                else:
+                    a = ops.affine_relu(buf, c, S["final"][0], S["final"][1])
+                    feats[s:s + n] = ops.global_avgpool(a)
+        w1, b1, w2, b2 = S["head"]
+        return ops.head_mlp(feats, w1, b1, w2, b2), feats

@@ -1,0 +1,115 @@
+"""Drop-in for models/routing.py — Hard / Soft / Gated routers (reference routing.py:5-252).
+
+HardRouter: one libadb200 launch turns the HDEN logits into `intensity` + three ascending bucket index lists + their
+counts, all on the device; each branch then walks its bucket with the count read on the device, so the batch is never
+synchronised with the host (the reference pays >= 9 syncs per batch, routing.py:55-61) and the gathered sub-batches /
+scattered outputs are never materialised (the stem reads through the index list, the last conv writes through it).
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .. import engine as _engine
+
+_NAMES = ("low", "medium", "high")
+
+
+class HardRouter(nn.Module):
+    def __init__(self, models, classifier=None, device="cuda"):
+        super().__init__()
+        self.models = nn.ModuleDict(models)
+        self.classifier = classifier
+        self.device = device
+
+    def forward(self, x, intensity=None):
+        """Returns (outputs, {'intensity', 'low_mask', 'medium_mask', 'high_mask'}) like routing.py:23-68.
+
+        NB: the reference's drivers call router(x, logits) positionally, which binds logits to
+        `intensity`; like the reference we take `intensity` literally (int64 class ids)."""
+        _engine.require_cuda(x, "HardRouter")
+        x = x.contiguous()
+        outputs = torch.zeros_like(x)
+        if intensity is None and self.classifier is not None:
+            with torch.no_grad():
+                logits, _ = self.classifier(x)
+            inten, masks, bidx, bcnt = ops.route(logits=logits)
+        elif intensity is not None:
+            if intensity.dim() != 1 or intensity.shape[0] != x.shape[0] or intensity.is_floating_point():
+                # the reference compares `intensity == k` elementwise; a [B,3] float logits tensor yields masks that
+                # select nothing consistently — we refuse instead of returning zeros silently
+                raise ValueError("HardRouter.forward(x, intensity): intensity must be an integer tensor of shape [B]")
+            inten, masks, bidx, bcnt = ops.route(intensity=intensity.to(x.device))
+        else:
+            raise ValueError("HardRouter needs a classifier or an explicit intensity tensor")
+        for name, model in self.models.items():
+            k = _NAMES.index(name)
+            model.forward_bucket(x, outputs, bidx[k], bcnt[k:k + 1], count=x.shape[0])
+        return outputs, {"intensity": inten, "low_mask": masks[0], "medium_mask": masks[1], "high_mask": masks[2]}
+
+
+class SoftRouter(nn.Module):
+    def __init__(self, models, classifier=None, temperature=1.0, device="cuda"):
+        super().__init__()
+        self.models = nn.ModuleDict(models)
+        self.classifier = classifier
+        self.temperature = temperature
+        self.device = device
+
+    def forward(self, x, classifier_logits=None):
+        """Returns (blend, {'weights', 'individual_outputs'}) like routing.py:90-132."""
+        _engine.require_cuda(x, "SoftRouter")
+        if classifier_logits is None and self.classifier is not None:
+            logits, _ = self.classifier(x)
+        else:
+            logits = classifier_logits
+        if logits is None:
+            raise ValueError("SoftRouter needs a classifier or precomputed logits")
+        outs = {name: self.models[name](x) for name in _NAMES if name in self.models}
+        if len(outs) != 3:
+            raise NotImplementedError("SoftRouter on the B200 path blends exactly the three branches low/medium/high")
+        blend, weights = ops.blend3(outs["low"], outs["medium"], outs["high"], logits, self.temperature)
+        return blend, {"weights": weights, "individual_outputs": outs}
+
+
+class GatedRouter(nn.Module):
+    def __init__(self, models, classifier=None, feature_dim=512, device="cuda"):
+        super().__init__()
+        self.models = nn.ModuleDict(models)
+        self.classifier = classifier
+        self.device = device
+        self.gate_network = nn.Sequential(
+            nn.Linear(feature_dim, 256), nn.ReLU(inplace=True), nn.Dropout(0.3),
+            nn.Linear(256, 128), nn.ReLU(inplace=True),
+            nn.Linear(128, len(models)), nn.Softmax(dim=1),
+        )
+        self.use_feature_fusion = False
+
+    def forward(self, x):
+        """Returns (blend, {'gate_weights', 'individual_outputs'}) like routing.py:173-226 (eval mode)."""
+        _engine.require_cuda(x, "GatedRouter")
+        _engine.require_inference(self, "GatedRouter")
+        if self.classifier is None:
+            raise NotImplementedError("GatedRouter without a classifier (uniform weights) is not built on the B200 path")
+        _, feats = self.classifier(x)
+        g = self.gate_network
+        hid = ops.linear(feats, g[0].weight, g[0].bias, relu=True)
+        gate_logits = ops.head_mlp(hid, g[3].weight.detach(), g[3].bias.detach(), g[5].weight.detach(), g[5].bias.detach())
+        outs = {name: self.models[name](x) for name in _NAMES if name in self.models}
+        if len(outs) != 3:
+            raise NotImplementedError("GatedRouter on the B200 path blends exactly the three branches low/medium/high")
+        blend, weights = ops.blend3(outs["low"], outs["medium"], outs["high"], gate_logits, 1.0)
+        return blend, {"gate_weights": weights, "individual_outputs": outs}
+
+
+def create_router(models, classifier, config):
+    """Factory with the reference's config keys (routing.py:228-252)."""
+    kind = config["routing"]["type"]
+    if kind == "hard":
+        return HardRouter(models=models, classifier=classifier, device=config["device"])
+    if kind == "soft":
+        return SoftRouter(models=models, classifier=classifier, temperature=config["routing"]["temperature"],
+                          device=config["device"])
+    if kind == "gated":
+        feature_dim = getattr(classifier, "feature_dim", 512)
+        return GatedRouter(models=models, classifier=classifier, feature_dim=feature_dim, device=config["device"])
+    raise ValueError(f"Unsupported routing type: {kind}")

@@ -14,8 +14,8 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, 
 
 __all__ = [
     "pad16", "fold_bn", "pack_conv_weight", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
-    "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "head_mlp",
-    "route", "blend3", "l1_mse", "cross_entropy",
+    "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "head_mlp",
+    "linear", "route", "blend3", "l1_mse", "cross_entropy",
 ]
 
 
@@ -177,15 +177,16 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     return ret
 
 
-def stem_pack(x, kw, pad, kp, *, stride=1, index=None, n_dev=None, n_start=0, n=None, out=None):
-    """NCHW fp32 image batch -> [n, h, wo, kp] bf16 stem operand (horizontal taps unrolled into channels)."""
+def stem_pack(x, kw, pad, kp, *, stride=1, kh=1, index=None, n_dev=None, n_start=0, n=None, out=None):
+    """NCHW fp32 image batch -> [n, ho, wo, kp] bf16 stem operand (taps unrolled into channels, see adb200.h)."""
     assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.shape[1] == 3
     b, _, h, w = x.shape
     n = b if n is None else n
     wo = (w + 2 * pad - kw) // stride + 1
+    ho = (h + 2 * pad - kh) // stride + 1 if kh > 1 else h
     if out is None:
-        out = torch.empty((n, h, wo, kp), dtype=torch.bfloat16, device=x.device)
-    _lib.call("adb_stem_pack", _lib.ptr(x), _lib.ptr(index), _lib.ptr(n_dev), n_start, n, h, w, kw, pad, stride, kp,
+        out = torch.empty((n, ho, wo, kp), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_stem_pack", _lib.ptr(x), _lib.ptr(index), _lib.ptr(n_dev), n_start, n, h, w, kh, kw, pad, stride, kp,
               _lib.ptr(out), _lib.current_stream())
     return out
 
@@ -239,10 +240,12 @@ def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
     return out
 
 
-def maxpool3x3s2(x):
+def maxpool3x3s2(x, out=None):
+    """3x3/2 max pool (pad 1); `out` may be a wider buffer (channel pitch >= c) whose first c channels are written."""
     n, h, w, c = x.shape
-    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
-    _lib.call("adb_maxpool3x3s2", _lib.ptr(x), n, h, w, c, _lib.ptr(out), _lib.current_stream())
+    if out is None:
+        out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_maxpool3x3s2", _lib.ptr(x), n, h, w, c, _lib.ptr(out), out.shape[3], _lib.current_stream())
     return out
 
 
@@ -254,12 +257,42 @@ def global_avgpool(x):
     return out
 
 
+def affine_relu(x, c, scale, shift, out=None):
+    """relu(x[..., :c]*scale + shift) -> NHWC bf16 with pitch c (DenseNet pre-activation)."""
+    n, h, w, p = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_affine_relu", _lib.ptr(x), n * h * w, c, p, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(out),
+              out.shape[3], _lib.current_stream())
+    return out
+
+
+def avgpool2x2(x, c=None, out=None):
+    n, h, w, p = x.shape
+    c = c or p
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_avgpool2x2", _lib.ptr(x), n, h, w, c, p, _lib.ptr(out), out.shape[3], _lib.current_stream())
+    return out
+
+
 def head_mlp(feat, w1, b1, w2, b2):
     n, f = feat.shape
+    w1, b1, w2, b2 = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
     logits = torch.empty((n, w2.shape[0]), dtype=torch.float32, device=feat.device)
     _lib.call("adb_head_mlp", _lib.ptr(feat), n, f, _lib.ptr(w1), _lib.ptr(b1), w1.shape[0], _lib.ptr(w2), _lib.ptr(b2),
               w2.shape[0], _lib.ptr(logits), _lib.current_stream())
     return logits
+
+
+def linear(x, w, b=None, relu=False):
+    n, fin = x.shape
+    w = w.detach().float().contiguous()
+    b = None if b is None else b.detach().float().contiguous()
+    y = torch.empty((n, w.shape[0]), dtype=torch.float32, device=x.device)
+    _lib.call("adb_linear", _lib.ptr(x.contiguous()), n, fin, _lib.ptr(w), _lib.ptr(b), w.shape[0], int(relu), _lib.ptr(y),
+              _lib.current_stream())
+    return y
 
 
 def route(logits=None, intensity=None, batch=None):

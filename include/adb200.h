@@ -113,10 +113,13 @@ ADB_API int adb_conv2d(const adb_conv_desc* desc, void* stream);
 /* FLOPs (2*MAC) the descriptor's launch performs for n images — the figure bench.py's roofline uses. */
 ADB_API double adb_conv2d_flops(const adb_conv_desc* desc);
 
-/* Image -> stem operand.  out[i,h,w, s*3+c] = x[idx(i), c, h, w*stride + s - pad] (0 outside), zero-padded to kp
- * channels, bf16.  Makes a kh x kw x 3 stem a kh x 1 conv with kp channels (stem convs low:16, medium:16, high:17,85). */
+/* Image -> stem operand (bf16, kp channels, zero padded):
+ *   out[i,ho,wo,(r*kw+s)*3+c] = x[idx(i), c, ho*sh + r - ph, wo*stride + s - pad]   (0 outside the image)
+ * kh == 1: only the horizontal taps are unrolled (sh = 1, ph = 0, ho = h), which turns a kh x kw x 3 stem into a
+ *          kh x 1 conv over kp channels (dehazing stems: low:16, medium:16, high:17,85);
+ * kh  > 1: full im2col with the stride on both axes; the stem becomes a 1x1 conv (stride-2 HDEN stem, classifier.py:24). */
 ADB_API int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n,
-                  int32_t h, int32_t w, int32_t kw, int32_t pad, int32_t stride, int32_t kp,
+                  int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t pad, int32_t stride, int32_t kp,
                   void* out, void* stream);
 
 /* Layout converters (tests, classifier features): NCHW fp32 <-> NHWC bf16 */
@@ -138,12 +141,23 @@ ADB_API int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32
                    const float* gate, const float* stats, const float* w_spatial /*[2][7][7]*/, void* y, void* stream);
 
 /* Pooling for the HDEN backbones (torchvision resnet/densenet called from models/classifier.py:24-36,91). */
-ADB_API int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
+ADB_API int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, int32_t pitch_out, void* stream);
 ADB_API int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*[n][2][c]*/,
                        float* y /*[n][c] fp32*/, void* stream);
+/* DenseNet121 HDEN arm (north_star; torchvision densenet121 — the reference has no DenseNet):
+ * pre-activation y = relu(x*scale + shift) on the first c channels of an NHWC bf16 map (norm1/relu1 ahead of conv1),
+ * and the 2x2/2 average pool of the transitions. */
+ADB_API int adb_affine_relu(const void* x, int64_t pixels, int32_t c, int32_t pitch_in, const float* scale, const float* shift,
+                    void* y, int32_t pitch_out, void* stream);
+ADB_API int adb_avgpool2x2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pitch_in, void* y,
+                   int32_t pitch_out, void* stream);
 /* Classifier head, fp32: logits = W2*relu(W1*f + b1) + b2 (models/classifier.py:72-78, eval mode: dropout = identity). */
 ADB_API int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
                  const float* w2, const float* b2, int32_t classes, float* logits, void* stream);
+
+/* y[n][fout] = act(W x + b), fp32 (first layer of the GatedRouter gate MLP, routing.py:155-163). */
+ADB_API int adb_linear(const float* x, int32_t n, int32_t fin, const float* w, const float* b /*nullable*/, int32_t fout,
+               int32_t relu, float* y, void* stream);
 
 /* Routing (models/routing.py:40-61): intensity = argmax(logits,1) (first max wins, NaN counts as max, like
  * torch.argmax), masks, and a stable 3-way compaction: bucket k lists the ascending batch rows with intensity == k.

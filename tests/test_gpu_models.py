@@ -1,0 +1,190 @@
+"""GPU parity of the drop-in modules against the oracle (pinned on the reference, tests/test_oracle_golden.py) on the
+same seeded random-init weights and inputs.  Tolerances are the north_star's: dehazed outputs max-abs <= 2e-2 on [0,1]
+images and PSNR >= 45 dB against the fp32 reference; route decisions and bucket indices bit-exact."""
+import pytest
+import torch
+
+from helpers import CONFIG, golden, make_branch, make_classifier, psnr, rand_image, randomize_bn
+
+import adam_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 2e-2
+MIN_PSNR = 45.0
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+    torch.cuda.synchronize()
+    torch.set_grad_enabled(True)
+
+
+def _check_image(out, ref):
+    err = (out - ref).abs().max().item()
+    p = psnr(out, ref)
+    assert err <= MAX_ABS, f"max-abs {err:.4g} > {MAX_ABS}"
+    assert p >= MIN_PSNR, f"PSNR {p:.2f} dB < {MIN_PSNR}"
+    return err, p
+
+
+@pytest.mark.parametrize("name", ["low", "medium", "high"])
+def test_branch_vs_golden_fixture(name):
+    """The committed reference outputs (tests/golden) at the fixture sizes, incl. config 1 (Light, 1x3x256x256)."""
+    g = golden(f"branch_{name}.pt")
+    m = make_branch(name).cuda()
+    for case in g["cases"]:
+        n, h, w = case["shape"]
+        out = m(rand_image(n, h, w, case["seed"]).cuda())
+        _check_image(out.cpu(), case["out"])
+
+
+@pytest.mark.parametrize("name,n,h,w", [("low", 3, 128, 256), ("medium", 2, 128, 192), ("high", 2, 128, 192),
+                                        ("high", 1, 256, 512)])
+def test_branch_vs_oracle_trained_like_stats(name, n, h, w):
+    """Non-trivial BN statistics (folding exercised) and synthetic hazy inputs; oracle runs in fp32 on the same GPU."""
+    m = randomize_bn(make_branch(name)).cuda()
+    hazy, _, _ = oracle.synth_hazy(n, h, w, seed=11, device="cuda")
+    ref = oracle.BRANCH_FORWARD[name](m.state_dict(), hazy)
+    out = m(hazy)
+    _check_image(out, ref)
+    assert out.dtype == torch.float32 and out.shape == hazy.shape
+    out2 = m(hazy)
+    assert torch.equal(out, out2)                      # eval forward is deterministic run to run
+
+
+def test_batch_composition_independence():
+    """Bucketing by branch is legal only if a sample's output does not depend on its batch mates."""
+    m = make_branch("medium").cuda()
+    x = rand_image(3, 64, 64, 5).cuda()
+    full = m(x)
+    for i in range(3):
+        assert torch.equal(full[i:i + 1], m(x[i:i + 1].contiguous()))
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "densenet121"])
+def test_classifier_logits(arch):
+    """HDEN in bf16 vs the fp32 oracle: logits within 2e-2 abs (stated), argmax identical whenever the fp32 top-2
+    margin exceeds twice that."""
+    clf = randomize_bn(make_classifier(arch)).cuda()
+    x, _, _ = oracle.synth_hazy(4, 128, 160 if arch == "resnet18" else 128, seed=3, device="cuda")
+    ref_logits, ref_feats = oracle.classifier_forward(clf.state_dict(), x, arch)
+    logits, feats = clf(x)
+    assert logits.shape == (4, 3) and feats.shape == (4, clf.feature_dim) and logits.dtype == torch.float32
+    assert (logits - ref_logits).abs().max().item() <= 2e-2, (logits - ref_logits).abs().max().item()
+    rel = (feats - ref_feats).abs().max().item() / ref_feats.abs().max().item()
+    assert rel <= 3e-2, rel
+    top2 = ref_logits.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 4e-2
+    assert torch.equal(logits.argmax(1)[safe], ref_logits.argmax(1)[safe])
+
+
+def test_classifier_golden_fixture():
+    g = golden("classifier_resnet18.pt")
+    clf = make_classifier("resnet18").cuda()
+    n, h, w = g["shape"]
+    logits, feats = clf(rand_image(n, h, w, g["seed"]).cuda())
+    assert (logits.cpu() - g["logits"]).abs().max().item() <= 2e-2
+    assert torch.equal(logits.argmax(1).cpu(), g["logits"].argmax(1))
+
+
+def _router(kind, branches, clf):
+    from adam_dehaze_b200.models.routing import create_router
+    cfg = dict(CONFIG, routing={"type": kind, "temperature": 0.5})
+    return create_router(branches, clf, cfg).eval()
+
+
+def test_hard_router_given_intensity_bit_exact_routes():
+    branches = {n: make_branch(n).cuda() for n in ("low", "medium", "high")}
+    clf = make_classifier().cuda()
+    router = _router("hard", branches, clf)
+    x, _, labels = oracle.synth_hazy(7, 64, 96, seed=2, device="cuda")
+    labels = torch.tensor([2, 0, 1, 1, 0, 2, 2], device="cuda")
+    out, info = router(x, intensity=labels)
+    sds = {n: m.state_dict() for n, m in branches.items()}
+    ref, ref_int, buckets = oracle.hard_route(sds, x, intensity=labels)
+    assert torch.equal(info["intensity"], ref_int)
+    for k, key in enumerate(("low_mask", "medium_mask", "high_mask")):
+        assert info[key].dtype == torch.bool and torch.equal(info[key], ref_int == k)
+    _check_image(out, ref)
+    # an image routed to branch k equals that branch run alone on it (gather/scatter through index lists)
+    for k, name in enumerate(("low", "medium", "high")):
+        idx = buckets[k]
+        assert torch.equal(out[idx], branches[name](x[idx].contiguous()))
+
+
+def test_hard_router_natural_and_crafted_logits():
+    g = golden("routing.pt")
+    branches = {n: make_branch(n).cuda() for n in ("low", "medium", "high")}
+    clf = make_classifier().cuda()
+    router = _router("hard", branches, clf)
+    n, h, w = g["shape"]
+    x = rand_image(n, h, w, g["seed"]).cuda()
+    out, info = router(x)                                # natural: random-init HDEN collapses to one class
+    assert torch.equal(info["intensity"].cpu(), g["natural_intensity"])
+    _check_image(out.cpu(), g["natural_out"])
+    out_c, info_c = router(x, intensity=g["crafted_intensity"].cuda())
+    assert torch.equal(torch.stack([info_c["low_mask"], info_c["medium_mask"], info_c["high_mask"]]).cpu(), g["crafted_masks"])
+    _check_image(out_c.cpu(), g["crafted_out"])
+    with pytest.raises(ValueError):
+        router(x, g["crafted_logits"].cuda())            # the positional-logits trap is refused loudly
+
+
+def test_soft_and_gated_router():
+    g = golden("routing.pt")
+    branches = {n: make_branch(n).cuda() for n in ("low", "medium", "high")}
+    clf = make_classifier().cuda()
+    n, h, w = g["shape"]
+    x = rand_image(n, h, w, g["seed"]).cuda()
+    soft = _router("soft", branches, clf)
+    out, info = soft(x, g["crafted_logits"].cuda())
+    assert torch.allclose(info["weights"].cpu(), g["soft_weights"], atol=1e-6)
+    _check_image(out.cpu(), g["soft_out"])
+    assert set(info["individual_outputs"]) == {"low", "medium", "high"}
+    torch.manual_seed(1)
+    gated = _router("gated", branches, clf).cuda()
+    out_g, info_g = gated(x)
+    _, feats = clf(x)
+    ref_w = oracle.gate_weights({k: v for k, v in gated.state_dict().items()}, feats)
+    assert torch.allclose(info_g["gate_weights"], ref_w, atol=1e-5)
+    outs = info_g["individual_outputs"]
+    ref = sum(ref_w[:, i].view(-1, 1, 1, 1) * outs[k] for i, k in enumerate(("low", "medium", "high")))
+    assert torch.allclose(out_g, ref, atol=1e-5)
+
+
+def test_losses_forward_backward():
+    from adam_dehaze_b200.training.loss import DehazingLoss, JointLoss, get_dehazing_loss
+    torch.set_grad_enabled(True)
+    pred = rand_image(2, 32, 48, 1).cuda().requires_grad_(True)
+    tgt = rand_image(2, 32, 48, 2).cuda()
+    logits = torch.randn(2, 3, device="cuda", requires_grad=True)
+    labels = torch.tensor([2, 0], device="cuda")
+    jl = JointLoss(1.0, 0.2, 0.5, dehazing_loss=DehazingLoss(1.0, 0.0, 0.0))
+    total, parts = jl(pred, tgt, logits, labels)
+    total.backward()
+    p2 = pred.detach().clone().requires_grad_(True)
+    l2 = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.l1_loss(p2, tgt) + 0.2 * torch.nn.functional.cross_entropy(l2, labels)
+    ref.backward()
+    assert abs(total.item() - ref.item()) <= 1e-2 * abs(ref.item())          # north_star: 1e-2 relative
+    assert torch.allclose(pred.grad, p2.grad, rtol=1e-2, atol=1e-9)
+    assert torch.allclose(logits.grad, l2.grad, rtol=1e-2, atol=1e-7)
+    assert set(parts) == {"dehazing", "classification", "detection", "total", "dehazing_components"}
+    with pytest.raises(NotImplementedError):
+        get_dehazing_loss(CONFIG)(pred, tgt)             # content / LPIPS terms are refused, never silently dropped
+
+
+def test_blocks_standalone():
+    from adam_dehaze_b200.models.dehazing.base_model import AttentionBlock, ResidualBlock
+    g = golden("blocks.pt")
+    torch.manual_seed(42)
+    rb, ab = ResidualBlock(32).eval().cuda(), AttentionBlock(96).eval().cuda()
+    xr = torch.randn(1, 32, 16, 24, generator=torch.Generator().manual_seed(5)).cuda()
+    xa = torch.randn(1, 96, 16, 24, generator=torch.Generator().manual_seed(6)).relu().cuda()
+    out_r, out_a = rb(xr).cpu(), ab(xa).cpu()
+    assert (out_r - g["res_out"]).abs().max().item() <= 2e-2 * g["res_out"].abs().max().item()
+    assert (out_a - g["attn_out"]).abs().max().item() <= 2e-2 * g["attn_out"].abs().max().item()
