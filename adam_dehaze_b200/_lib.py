@@ -71,6 +71,7 @@ SIGNATURES = {
 _SPECIAL = {
     "adb_last_error": ([], C.c_char_p),
     "adb_conv2d_flops": ([C.POINTER(ConvDesc)], C.c_double),
+    "adb_pool_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
 }
 EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

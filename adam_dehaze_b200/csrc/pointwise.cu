@@ -117,22 +117,27 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int n, 
 }
 
 // ------------------------------------------------------------------ AttentionBlock pass 1: per-(image, channel) sum and max
-__global__ void pool_init_kernel(float* buf, int n, int c) {
+// Scratch layout (floats): [n][2][c] result | [n] block tickets (int) | [n][chunks][2][c] per-block partials.
+// Deterministic: blocks publish partials, the last block of an image (ticket) folds them in chunk order.
+__global__ void pool_init_kernel(int* tickets, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n * 2 * c) buf[t] = ((t / c) & 1) ? -INFINITY : 0.f;
+  if (t < n) tickets[t] = 0;
 }
 
 // block = G x PY threads (G = c/8 channel groups); grid = (chunks, n).  Each thread streams its 8 channels down a pixel
 // chunk with 16-byte loads (a warp reads whole pixel rows: coalesced), then the PY partials meet in shared memory.
 __global__ void attn_pool_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
-                                 int n_start, int pix_per_block, float* __restrict__ pool) {
+                                 int n_start, int pix_per_block, float* __restrict__ pool, int* __restrict__ tickets,
+                                 float* __restrict__ partials) {
   const int n_eff = live_images(n, n_dev, n_start);
   const int img = blockIdx.y;
   if (img >= n_eff) return;
+  const int chunks = gridDim.x;
   const int G = c / 8;
   const int PY = blockDim.x / G;
   const int g = threadIdx.x % G, py = threadIdx.x / G;
   extern __shared__ float sm[];  // [PY][c] sums then [PY][c] maxes
+  __shared__ int s_last;
   float s[8], m[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) { s[q] = 0.f; m[q] = -INFINITY; }
@@ -153,11 +158,25 @@ __global__ void attn_pool_kernel(const __nv_bfloat16* __restrict__ x, int n, lon
     }
   }
   __syncthreads();
+  float* mine = partials + ((size_t)img * chunks + blockIdx.x) * 2 * c;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float ss = 0.f, mm = -INFINITY;
     for (int r = 0; r < PY; ++r) { ss += sm[r * c + ch]; mm = fmaxf(mm, sm[(PY + r) * c + ch]); }
-    atomicAdd(pool + ((size_t)img * 2 + 0) * c + ch, ss);
-    atomic_max_float(pool + ((size_t)img * 2 + 1) * c + ch, mm);
+    mine[ch] = ss;
+    mine[c + ch] = mm;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tickets + img, 1) == chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* all = partials + (size_t)img * chunks * 2 * c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float ss = 0.f, mm = -INFINITY;
+    for (int k = 0; k < chunks; ++k) { ss += all[(size_t)k * 2 * c + ch]; mm = fmaxf(mm, all[(size_t)k * 2 * c + c + ch]); }
+    pool[((size_t)img * 2 + 0) * c + ch] = ss;
+    pool[((size_t)img * 2 + 1) * c + ch] = mm;
   }
 }
 
@@ -562,23 +581,38 @@ int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_
   return ADB_OK;
 }
 
+static void pool_geometry(int n, int h, int w, int sms, long long* chunks, int* ppb) {
+  const long long hw = (long long)h * w;
+  // enough blocks for ~4 waves over the SMs, at least 256 pixels each
+  long long ch = std::max<long long>(1, std::min<long long>((hw + 255) / 256, (4LL * sms + n - 1) / n));
+  *ppb = (int)((hw + ch - 1) / ch);
+  *chunks = (hw + *ppb - 1) / *ppb;
+}
+
 static int launch_pool(const void* x, int n, int h, int w, int c, const int* n_dev, int n_start, float* pool_buf, cudaStream_t st) {
   ADB_REQUIRE(x && pool_buf && n > 0 && c % 8 == 0 && c / 8 <= 256, "attention/avg pool: channels %d must be a multiple of 8 (<= 2048)", c);
   const int sms = sm_count();
   if (!sms) return ADB_ERR_NO_DEVICE;
-  pool_init_kernel<<<(n * 2 * c + 255) / 256, 256, 0, st>>>(pool_buf, n, c);
+  long long chunks; int ppb;
+  pool_geometry(n, h, w, sms, &chunks, &ppb);
+  int* tickets = reinterpret_cast<int*>(pool_buf + (size_t)n * 2 * c);
+  float* partials = pool_buf + (size_t)n * 2 * c + ((n + 3) / 4) * 4;
+  pool_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(tickets, n);
   const int G = c / 8;
   const int PY = std::max(1, 256 / G);
   const int threads = G * PY;
-  const long long hw = (long long)h * w;
-  // enough blocks for ~4 waves over the SMs, at least 256 pixels each
-  long long chunks = std::max<long long>(1, std::min<long long>((hw + 255) / 256, (4LL * sms + n - 1) / n));
-  const int ppb = (int)((hw + chunks - 1) / chunks);
-  chunks = (hw + ppb - 1) / ppb;
   dim3 grid((unsigned)chunks, (unsigned)n);
-  attn_pool_kernel<<<grid, threads, 2 * PY * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, ppb, pool_buf);
+  attn_pool_kernel<<<grid, threads, 2 * PY * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, (long long)h * w, c,
+                                                                       n_dev, n_start, ppb, pool_buf, tickets, partials);
   ADB_LAUNCH_OK();
   return ADB_OK;
+}
+
+int64_t adb_pool_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c) {
+  const int sms = sm_count();
+  long long chunks; int ppb;
+  pool_geometry(n, h, w, sms > 0 ? sms : 148, &chunks, &ppb);
+  return (int64_t)n * 2 * c + ((n + 3) / 4) * 4 + (int64_t)n * chunks * 2 * c;
 }
 
 int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,

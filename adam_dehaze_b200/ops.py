@@ -217,6 +217,10 @@ class AttnParams:
         self.wsp = conv_spatial.detach().float().reshape(98).contiguous()
 
 
+def pool_scratch_floats(n, h, w, c):
+    return int(_lib.load().adb_pool_scratch_floats(n, h, w, c))
+
+
 def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
     """AttentionBlock forward on an NHWC bf16 map: pool -> gate + channel stats -> spatial gate apply."""
     nb, h, w, c = x.shape
@@ -225,7 +229,9 @@ def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
     dev = x.device
     if scratch is None:
         scratch = {}
-    pool = scratch.setdefault(("pool", nb, c), torch.empty((nb, 2, c), dtype=torch.float32, device=dev))
+    pool = scratch.get(("pool", nb, h, w, c))
+    if pool is None:
+        pool = scratch[("pool", nb, h, w, c)] = torch.empty(pool_scratch_floats(nb, h, w, c), dtype=torch.float32, device=dev)
     gate = scratch.setdefault(("gate", nb, c), torch.empty((nb, c), dtype=torch.float32, device=dev))
     stats = scratch.setdefault(("stats", nb, h, w), torch.empty((nb, h, w, 2), dtype=torch.float32, device=dev))
     if out is None:
@@ -251,7 +257,7 @@ def maxpool3x3s2(x, out=None):
 
 def global_avgpool(x):
     n, h, w, c = x.shape
-    scratch = torch.empty((n, 2, c), dtype=torch.float32, device=x.device)
+    scratch = torch.empty(pool_scratch_floats(n, h, w, c), dtype=torch.float32, device=x.device)
     out = torch.empty((n, c), dtype=torch.float32, device=x.device)
     _lib.call("adb_global_avgpool", _lib.ptr(x), n, h, w, c, _lib.ptr(scratch), _lib.ptr(out), _lib.current_stream())
     return out

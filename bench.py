@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark: dehazed images/s at 1024x2048 for the adaptive HDEN -> Light/Medium/Complex mix.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--hden densenet121|resnet18]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch of B synthetic hazy images per GPU (BASELINE.json configs[3]: batch 256,
+beta in {0.03,0.06,0.09} round-robin, 1024x2048): HDEN classifies the full-resolution batch, the device-side router
+buckets it, each branch dehazes its bucket.  A random-init HDEN sends every image to one class, so the mix is injected
+through the reference's own `HardRouter.forward(x, intensity=labels)` parameter while HDEN still runs inside the timed
+region.  Work is sharded by image: every rank owns B images, no data-path collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step through the public module API from
+pinned HOST buffers, H2D of the batch and D2H of the dehazed batch inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 1024, 2048
+METRIC = "dehazed images/sec @1024x2048 adaptive mix (HDEN -> Light/Medium/Complex)"
+UNIT = "images/s"
+
+CFG = {
+    "classifier": {"model": "densenet121", "num_classes": 3, "pretrained": False},
+    "dehazing": {"low": {"model_type": "lightweight", "channels": 32, "blocks": 3},
+                 "medium": {"model_type": "standard", "channels": 64, "blocks": 6},
+                 "high": {"model_type": "complex", "channels": 96, "blocks": 9}},
+    "routing": {"type": "hard", "temperature": 0.5},
+    "device": "cuda",
+}
+
+# algorithmic conv/linear FLOPs (2*MAC) per image at 1024x2048 from the reference graph
+TFLOP_PER_IMAGE = {"low": 0.278, "medium": 3.591, "high": 8.059, "densenet121": 0.237, "resnet18": 0.152}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--hden", default="densenet121", choices=["densenet121", "resnet18"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--width", type=int, default=W)
+    return ap.parse_args()
+
+
+def build_models(cfg, device):
+    """Random-init (seed 42) branches + HDEN through the drop-in factories, eval mode."""
+    import torch
+    from adam_dehaze_b200.models.classifier import create_classifier
+    from adam_dehaze_b200.models.dehazing.high_intensity import create_high_intensity_model
+    from adam_dehaze_b200.models.dehazing.low_intensity import create_low_intensity_model
+    from adam_dehaze_b200.models.dehazing.medium_intensity import create_medium_intensity_model
+    torch.manual_seed(42)
+    branches = {"low": create_low_intensity_model(cfg), "medium": create_medium_intensity_model(cfg),
+                "high": create_high_intensity_model(cfg)}
+    clf = create_classifier(cfg)
+    for m in list(branches.values()) + [clf]:
+        m.eval().to(device)
+    return branches, clf
+
+
+def synth_batch_on_device(n, h, w, dev, seed):
+    """The synthetic hazy recipe of SURVEY.md §8d / utils/helpers.py:241-258, generated on the device:
+    I = clip(J*t + 0.8(1-t)), t = exp(-beta*d), beta = {0.03,0.06,0.09}[i % 3].  Returns (hazy fp32 NCHW, labels int64)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, h, device=dev), torch.linspace(0, 1, w, device=dev), indexing="ij")
+    d = (0.3 + 0.7 * torch.sqrt((xx - 0.5) ** 2 + (yy - 0.2) ** 2)) * 100.0
+    labels = torch.arange(n, device=dev) % 3
+    betas = torch.tensor([0.03, 0.06, 0.09], device=dev)
+    hazy = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+    for i in range(n):   # image by image: keeps the generator's scratch small
+        t = torch.exp(-betas[labels[i]] * d)
+        hazy[i] = torch.clamp(torch.rand((3, h, w), generator=g, device=dev) * t + 0.8 * (1 - t), 0, 1)
+    return hazy, labels
+
+
+# --------------------------------------------------------------------------- CPU leg (oracle port of the reference path)
+def cpu_sample(hden, h=256, w=512, threads=None, repeats=1, warm=0):
+    """One image per branch + HDEN on the three, fp32 on the host cores, through the oracle (a port of the reference
+    arithmetic).  Returns (images/s scaled to 1024x2048, seconds per sample, description).  FLOPs are linear in pixels
+    (SURVEY.md §8), so the rate at h x w is scaled by (h*w)/(1024*2048)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import adam_oracle as oracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    branches, clf = build_models(dict(CFG, classifier=dict(CFG["classifier"], model=hden)), device="cpu")
+    sds = {k: m.state_dict() for k, m in branches.items()}
+    csd = clf.state_dict()
+    hazy, _, labels = oracle.synth_hazy(3, h, w, device="cpu")
+    times = []
+    with torch.no_grad():
+        for it in range(warm + repeats):
+            t0 = time.perf_counter()
+            oracle.classifier_forward(csd, hazy, hden)
+            oracle.hard_route(sds, hazy, intensity=labels)
+            if it >= warm:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    scale = (h * w) / float(H * W)
+    return 3.0 * scale / sec, sec, f"1 image per branch + HDEN({hden}) on the 3, {h}x{w} fp32 (rate scaled by pixel ratio {scale:.4f}), {threads} threads, oracle port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    vals = []
+    desc = ""
+    # warm-up + timed steps, each step one bounded sample
+    total = args.warmup + args.steps
+    for it in range(total):
+        v, sec, desc = cpu_sample(args.hden, threads=threads)
+        if it >= args.warmup:
+            vals.append((v, sec))
+    value = sum(v for v, _ in vals) / len(vals)
+    ms = 1000.0 * sum(s for _, s in vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"adaptive mix 1/3 Light, 1/3 Medium, 1/3 Complex + HDEN {args.hden}, 1024x2048 equivalent", "hden": args.hden},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1]); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))   # synthetic-input recipe only (never the measured path)
+    from adam_dehaze_b200 import _lib, ops
+    from adam_dehaze_b200.models.routing import create_router
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.load().adb_device_check(), "adb_device_check")
+    torch.set_grad_enabled(False)
+
+    cfg = dict(CFG, classifier=dict(CFG["classifier"], model=args.hden))
+    branches, clf = build_models(cfg, device=dev)
+    router = create_router(branches, clf, cfg).eval()
+    B, Hh, Ww = args.batch, args.height, args.width
+    hazy, labels = synth_batch_on_device(B, Hh, Ww, dev, seed=42 + rank)
+
+    launches = {"n": 0}
+    kernels_per_call = {"adb_conv2d": 1, "adb_stem_pack": 1, "adb_attn_pool": 2, "adb_attn_gate_stats": 2, "adb_attn_apply": 1,
+                        "adb_maxpool3x3s2": 1, "adb_global_avgpool": 3, "adb_head_mlp": 1, "adb_route": 1, "adb_blend3": 2,
+                        "adb_affine_relu": 1, "adb_avgpool2x2": 1, "adb_linear": 1, "adb_nchw_to_nhwc_bf16": 1, "adb_nhwc_bf16_to_nchw": 1}
+    _orig_call = _lib.call
+
+    def counting_call(name, *a):
+        launches["n"] += kernels_per_call.get(name, 1)
+        return _orig_call(name, *a)
+
+    _lib.call = counting_call
+    ops._lib.call = counting_call
+
+    def step(x, lab=labels):
+        logits, _ = clf(x)                       # HDEN on the full-resolution batch (timed)
+        out, info = router(x, intensity=lab)     # device-side bucketing + the three branches
+        return out, logits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        step(hazy)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches["n"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out, logits = step(hazy)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches_per_step = launches["n"] // max(1, args.steps)
+    _lib.call("adb_kernel_error_flag")
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * B / (ms_step / 1000.0)
+
+    # ---- per-branch ms / image and the conv kernel's roofline (instrumented pass, CUDA events around every conv launch)
+    per_branch, roof = {}, None
+    if rank == 0:
+        per_branch, roof = instrumented_pass(torch, ops, _lib, branches, clf, hazy, args.hden)
+
+    # ---- e2e: pinned host buffers -> H2D -> public API -> D2H, all inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, dist, world, dev, step, hazy, args, B)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, desc = cpu_sample(args.hden, threads=os.cpu_count() or 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc, "seconds": sec}
+
+    if rank == 0:
+        mix = (TFLOP_PER_IMAGE["low"] + TFLOP_PER_IMAGE["medium"] + TFLOP_PER_IMAGE["high"]) / 3 + TFLOP_PER_IMAGE[args.hden]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: adaptive mix HDEN({args.hden}) -> Light/Medium/Complex, {B} images/GPU/step at {Hh}x{Ww}, "
+                                   "beta round-robin {0.03,0.06,0.09}, image-sharded, random-init weights seed 42",
+                       "images_per_gpu_per_step": B, "height": Hh, "width": Ww, "hden": args.hden,
+                       "mix": "labels i%3 injected via HardRouter.forward(x, intensity=labels); HDEN timed",
+                       "l2": f"inputs {B * 3 * Hh * Ww * 4 / 2**30:.1f} GiB per step (> 126 MB L2)",
+                       "algorithmic_tflop_per_image": mix},
+            "clocks": clocks, "gpu_launches": launches_per_step, "per_branch_ms_per_image": per_branch,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "model_tflops_per_gpu": value / world * mix,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
+    """Per-branch device ms per image, and for the dominant kernel (conv_igemm_kernel) the achieved TFLOP/s: true
+    conv FLOPs of every launch / CUDA-event time of that launch, summed over one pass of each branch + HDEN."""
+    from adam_dehaze_b200 import ops as ops_mod
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+        peaks = json.load(fh) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    rec = []
+    orig = ops_mod.conv2d
+
+    def timed_conv(spec, src0, src1=None, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = orig(spec, src0, src1, **kw)
+        b.record()
+        n = kw.get("n") or src0.shape[0]
+        rec.append((a, b, conv_flops(spec, src0, src1, n, kw)))
+        return r
+
+    nimg = min(8, hazy.shape[0])
+    x = hazy[:nimg].contiguous()
+    per_branch = {}
+    import adam_dehaze_b200.engine as eng
+    eng.ops.conv2d = timed_conv
+    ops_mod.conv2d = timed_conv
+    try:
+        for name, m in list(branches.items()) + [(hden, clf)]:
+            m(x)  # warm
+            torch.cuda.synchronize()
+            rec.clear()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); m(x); e.record()
+            torch.cuda.synchronize()
+            conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+            flops = sum(f for _, _, f in rec)
+            per_branch[name] = {"ms": s.elapsed_time(e) / nimg, "conv_ms": conv_ms / nimg, "conv_launches": len(rec),
+                                "conv_tflops": flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                                "tflop_per_image": flops / nimg / 1e12}
+    finally:
+        eng.ops.conv2d = orig
+        ops_mod.conv2d = orig
+    tot_ms = sum(v["conv_ms"] for k, v in per_branch.items() if k in ("low", "medium", "high")) + per_branch[hden]["conv_ms"] * 3
+    tot_fl = sum(v["tflop_per_image"] for k, v in per_branch.items() if k in ("low", "medium", "high")) + per_branch[hden]["tflop_per_image"] * 3
+    achieved = tot_fl / (tot_ms * 1e-3)
+    peak = peaks.get("bf16_tflops_sustained")
+    src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+    if not peak:
+        peak, src = 1400.0, "fallback sustained figure, B200_PROFILING.md (of fallback)"
+    launches = sum(v["conv_launches"] for v in per_branch.values())
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": src,
+            "how": f"sum of true conv FLOPs / sum of CUDA-event durations over the {launches} conv launches of one pass of "
+                   f"Light+Medium+Complex+HDEN on {nimg} images at {hazy.shape[2]}x{hazy.shape[3]} (equal-thirds mix weighting)",
+            "flops_per_launch_avg": tot_fl * 1e12 * nimg / max(1, launches) / 2,
+            "ms_per_launch_avg": tot_ms * nimg / max(1, launches) / 2}
+    return per_branch, roof
+
+
+def conv_flops(spec, src0, src1, n, kw):
+    """True (unpadded) 2*MAC of one launch: stems count their real 3-channel taps, padded channels count nothing."""
+    from adam_dehaze_b200 import _lib
+    _, h, w, p0 = src0.shape
+    cin = (kw.get("c0") or p0) + ((kw.get("c1") or src1.shape[3]) if src1 is not None else 0)
+    if spec.kind == _lib.CONVT_4X4S2:
+        return 2.0 * n * h * w * 16 * cin * spec.cout
+    if spec.kind == _lib.CONV_S2:
+        return 2.0 * n * (h // 2) * (w // 2) * spec.kh * spec.kw * cin * spec.cout
+    k = spec.kh * spec.kw * cin
+    if spec.kw == 1 and spec.kh in (3, 7) and cin in (16, 32):   # horizontally packed stem: real K = kh*kh*3
+        k = spec.kh * spec.kh * 3
+    if spec.kh == 1 and cin == 160:                               # full-im2col stem: real K = 147
+        k = 147
+    return 2.0 * n * h * w * k * spec.cout
+
+
+def run_e2e(torch, dist, world, dev, step, hazy, args, B):
+    """Public-API step from pinned host memory: per chunk H2D -> HDEN + router -> D2H of the dehazed chunk."""
+    chunk = min(B, 32)
+    shape = (B,) + tuple(hazy.shape[1:])
+    try:
+        host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        host_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    except RuntimeError:
+        return {"value": None, "unit": UNIT, "error": "pinned host allocation failed"}
+    host_in.copy_(hazy)
+    x_dev = torch.empty((chunk,) + tuple(hazy.shape[1:]), dtype=torch.float32, device=dev)
+    labels_full = (torch.arange(B, device=dev) % 3)
+
+    def e2e_step():
+        for s in range(0, B, chunk):
+            n = min(chunk, B - s)
+            x_dev[:n].copy_(host_in[s:s + n], non_blocking=True)
+            out, _ = step(x_dev[:n], labels_full[s:s + n])
+            host_out[s:s + n].copy_(out, non_blocking=True)
+
+    for _ in range(max(1, min(2, args.warmup))):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / args.steps
+    nbytes = B * hazy[0].numel() * 4
+    return {"value": world * B / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": nbytes,
+            "d2h_bytes_per_step": nbytes, "chunk_images": chunk,
+            "api": "FogIntensityClassifier.forward + HardRouter.forward(x, intensity=labels) on host-resident batches"}
+
+
+if __name__ == "__main__":
+    main()

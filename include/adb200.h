@@ -131,7 +131,9 @@ ADB_API int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h
  *  2) gate:   gate = sigmoid(fc(avg)+fc(max)) (fc = w2*relu(w1*.)), then per pixel the channel mean and max of
  *             x*gate -> stats[n,h,w,2] fp32                                      (:66-73)
  *  3) apply:  y = x*gate*sigmoid(conv7x7(stats))                                 (:74-78)
- * pool_buf: fp32 [n][2][c] (sum, max) zero/-inf initialised by the call itself. */
+ * pool_buf: caller scratch of adb_pool_scratch_floats(n,h,w,c) floats; its first n*2*c floats end up holding
+ * [n][2][c] (sum, max).  The reduction is deterministic (per-block partials folded in block order by the last block). */
+ADB_API int64_t adb_pool_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c);
 ADB_API int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                   float* pool_buf, void* stream);
 ADB_API int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
@@ -142,7 +144,7 @@ ADB_API int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32
 
 /* Pooling for the HDEN backbones (torchvision resnet/densenet called from models/classifier.py:24-36,91). */
 ADB_API int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, int32_t pitch_out, void* stream);
-ADB_API int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*[n][2][c]*/,
+ADB_API int adb_global_avgpool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, float* scratch /*adb_pool_scratch_floats*/,
                        float* y /*[n][c] fp32*/, void* stream);
 /* DenseNet121 HDEN arm (north_star; torchvision densenet121 — the reference has no DenseNet):
  * pre-activation y = relu(x*scale + shift) on the first c channels of an NHWC bf16 map (norm1/relu1 ahead of conv1),
