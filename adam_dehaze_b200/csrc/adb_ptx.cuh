@@ -47,11 +47,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (error flag set), never as a hung GPU.
+// try_wait itself suspends the thread for a hardware time slice, so the poll count below is seconds, not microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (++polls > (1u << 24)) {
       if (err_flag) atomicExch(err_flag, code);
       __threadfence_system();
       asm volatile("trap;");

@@ -169,8 +169,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ======================================================= TMA producer
+    // The whole warp walks the loop (waits are warp-uniform, no divergent single-lane path); lane 0 issues.
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage_bytes = (uint32_t)P.stage_tx_bytes;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -185,42 +186,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const CUtensorMap* tm = src ? &tmA1 : &tmA0;
           for (int ch = 0; ch < chunks; ++ch) {
             mbar_wait(empty_bar(stage), phase ^ 1u, P.err_flag, 1);
-            mbar_expect_tx(full_bar(stage), stage_bytes);
-            tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, tm, full_bar(stage),
-                        cbase + ch * P.Ck, tc.w0 + e.dw, e.p, tc.h0 + e.dh, tc.img);
-            tma_load_2d(b_base + (uint32_t)stage * P.b_stage_bytes, &tmB, full_bar(stage), kcoord, brow);
+            if (lane == 0) {
+              mbar_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, tm, full_bar(stage),
+                          cbase + ch * P.Ck, tc.w0 + e.dw, e.p, tc.h0 + e.dh, tc.img);
+              tma_load_2d(b_base + (uint32_t)stage * P.b_stage_bytes, &tmB, full_bar(stage), kcoord, brow);
+            }
+            __syncwarp();
             kcoord += P.Ck;
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ======================================================= MMA issuer
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer (whole warp waits, lane 0 issues)
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const int ksteps = P.Ck / 16;
-    const uint32_t sub_bytes = 128u * P.row_bytes;
+    const uint32_t sub_units = (128u * P.row_bytes) >> 4;          // descriptor address units (16 B) per 128-row sub-tile
+    const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, P.err_flag, 2);
       tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)(acc * P.MT * P.bn_cols);
       for (int k = 0; k < kiters; ++k) {
         mbar_wait(full_bar(stage), phase, P.err_flag, 3);
         tc_fence_after();
-        const uint32_t a_s = a_base + (uint32_t)stage * P.a_stage_bytes;
-        const uint32_t b_s = b_base + (uint32_t)stage * P.b_stage_bytes;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t bdesc = make_kmajor_desc(b_s + kk * 32u, P.row_bytes);
-          for (int mt = 0; mt < P.MT; ++mt) {
-            const uint64_t adesc = make_kmajor_desc(a_s + mt * sub_bytes + kk * 32u, P.row_bytes);
-            umma_bf16(tmem_base + (uint32_t)((acc * P.MT + mt) * P.bn_cols), adesc, bdesc, P.idesc,
-                      (k | kk) ? 1u : 0u);
+        if (lane == 0) {
+          const uint64_t a0 = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * P.a_stage_bytes) & 0x3FFFFu) >> 4);
+          const uint64_t b0 = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * P.b_stage_bytes) & 0x3FFFFu) >> 4);
+          for (int kk = 0; kk < ksteps; ++kk) {
+            for (int mt = 0; mt < P.MT; ++mt) {
+              umma_bf16(d_base + (uint32_t)(mt * P.bn_cols), a0 + (uint64_t)(mt * sub_units + kk * 2u),
+                        b0 + (uint64_t)(kk * 2u), P.idesc, (k | kk) ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+          if (k == kiters - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= kEpiWarp0) {

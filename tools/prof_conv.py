@@ -1,0 +1,91 @@
+"""Time (CUDA events) representative adb_conv2d launches of the three branches; optional tuning sweep.
+
+    python tools/prof_conv.py [--sweep] [--reps 5] [--only NAME]
+Prints one line per (shape, tune): ms, TFLOP/s (true FLOPs), fraction of the measured sustained bf16 peak.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from adam_dehaze_b200 import ops  # noqa: E402
+
+SHAPES = [
+    # name, kind, cin(s), cout, k, n, h, w   (h, w = INPUT size)
+    ("light_32_3x3", "s1", (32,), 32, 3, 2, 1024, 2048),
+    ("med_64_3x3", "s1", (64,), 64, 3, 2, 1024, 2048),
+    ("med_128_3x3", "s1", (128,), 128, 3, 4, 512, 1024),
+    ("med_256_3x3", "s1", (256,), 256, 3, 8, 256, 512),
+    ("cpx_96_3x3", "s1", (96,), 96, 3, 2, 1024, 2048),
+    ("cpx_192_3x3", "s1", (192,), 192, 3, 4, 512, 1024),
+    ("cpx_384_3x3", "s1", (384,), 384, 3, 8, 256, 512),
+    ("cpx_cat_192_96", "s1", (96, 96), 96, 3, 2, 1024, 2048),
+    ("cpx_96_48", "s1", (96,), 48, 3, 2, 1024, 2048),
+    ("cpx_down_96_192", "s2", (96,), 192, 4, 2, 1024, 2048),
+    ("cpx_down_192_384", "s2", (192,), 384, 4, 4, 512, 1024),
+    ("cpx_up_384_192", "t", (384,), 192, 4, 8, 256, 512),
+    ("cpx_up_cat_384_96", "t", (192, 192), 96, 4, 4, 512, 1024),
+    ("dense_1x1_512_128", "s1", (512,), 128, 1, 8, 128, 256),
+    ("dense_3x3_128_32", "s1", (128,), 32, 3, 8, 128, 256),
+]
+
+
+def run(shape, tune, reps):
+    name, kind, cins, cout, k, n, h, w = shape
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    srcs = [torch.randn((n, h, w, c), generator=g, device=dev).to(torch.bfloat16) for c in cins]
+    cin = sum(cins)
+    if kind == "t":
+        wt = torch.randn((cin, cout, 4, 4), generator=g, device=dev) / (cin * 4) ** 0.5
+        spec = ops.ConvSpec.from_convT(wt, act=ops.ACT_RELU)
+        flops = 2.0 * n * h * w * 16 * cin * cout
+    else:
+        wt = torch.randn((cout, cin, k, k), generator=g, device=dev) / (cin * k * k) ** 0.5
+        spec = ops.ConvSpec.from_conv(wt, act=ops.ACT_RELU, stride=2 if kind == "s2" else 1, pad=(1 if kind == "s2" else k // 2))
+        oh, ow = (h // 2, w // 2) if kind == "s2" else (h, w)
+        flops = 2.0 * n * oh * ow * k * k * cin * cout
+    src1 = srcs[1] if len(srcs) > 1 else None
+    dst = ops.conv2d(spec, srcs[0], src1, tune=tune)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        ops.conv2d(spec, srcs[0], src1, dst=dst, tune=tune)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return ms, flops / (ms * 1e-3) / 1e12
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    peak = 1414.7
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:
+        pass
+    tunes = [None]
+    if args.sweep:
+        tunes = [None, {"mt": 2}, {"mt": 1, "acc": 1}, {"mt": 2, "acc": 1}, {"stages": 3}, {"mt": 2, "stages": 3}]
+    for shape in SHAPES:
+        if args.only and args.only not in shape[0]:
+            continue
+        for tune in tunes:
+            try:
+                ms, tf = run(shape, tune, args.reps)
+                print(f"{shape[0]:22s} tune={str(tune):28s} {ms:8.3f} ms  {tf:8.1f} TFLOP/s  {tf / peak:6.3f} of sustained", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"{shape[0]:22s} tune={tune} FAILED: {e}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
