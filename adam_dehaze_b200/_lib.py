@@ -38,6 +38,7 @@ class ConvDesc(C.Structure):
         ("img_guidance", C.c_void_p), ("img_alpha", C.c_void_p),
         ("n_dev", C.c_void_p), ("n_start", C.c_int32),
         ("tune_mt", C.c_int32), ("tune_stages", C.c_int32), ("tune_acc_stages", C.c_int32),
+        ("tune_flags", C.c_int32),
     ]
 
 

@@ -1,15 +1,20 @@
 // conv_igemm.cu — implicit-GEMM convolution for sm_100a: TMA-fed, tcgen05.mma into TMEM, fused epilogues.
 //
 // GEMM view:  D[pixel, cout] = sum_k A[pixel, k] * B[cout, k],  k = (tap, input channel).
-//   A: NHWC bf16 feature map(s).  One K step = one filter tap x one chunk of Ck channels; the producer fetches it as a
-//      5-D TMA box {Ck, TW, 1, TH*MT, 1} at the tap-shifted coordinate — out-of-image pixels are zero-filled by the
-//      TMA unit, which is the convolution's zero padding.  Stride-2 convs read the same buffer through a
-//      space-to-depth view {2C, W/2, 2, H/2, N}; ConvTranspose2d(4,2,1) runs as four 2x2 sub-pixel phases whose outputs
-//      are stored through the same view of the destination.  A channel concat is two tensor maps walked back to back.
-//   B: packed weights [cout][k] bf16, K-major, one 2-D TMA box {Ck, BN} per K step.
+//   A: NHWC bf16 feature map(s).  One "A load" = one chunk of Ck channels of the tile's input HALO: a 5-D TMA box
+//      {Ck, TW+ew, 1, TH*MT+eh, 1} fetched ONCE and then read by every filter tap that falls inside it through a
+//      row-shifted UMMA shared-memory descriptor (a 3x3 conv re-uses each halo box for 9 taps instead of re-reading the
+//      input 9x through L2, which is what bounds an implicit GEMM on B200: L2->SM bandwidth for non-replicated data is
+//      ~6.7 TB/s, about HBM speed).  Out-of-image pixels are zero-filled by the TMA unit = the conv's zero padding.
+//      Stride-2 convs read the buffer through a space-to-depth view {2C, W/2, 2, H/2, N} (one A load per row/column
+//      phase); ConvTranspose2d(4,2,1) runs as four 2x2 sub-pixel phases whose outputs are stored through the same view
+//      of the destination.  A channel concat is two tensor maps walked back to back.  When the tile is not one image
+//      row wide (TW < 128) and taps shift columns, every tap becomes its own A load (no halo re-use).
+//   B: packed weights [cout][k] bf16, K-major, one 2-D TMA box {Ck, BN} per (tap, chunk), on its own mbarrier ring and
+//      its own producer warp.
 //   D: fp32 accumulators in TMEM, 128 pixels (lanes) x BN columns; MT sub-tiles share each B box.
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM -> registers -> affine/residual/activation -> swizzled smem -> TMA store, or the fused
+// Roles (256 threads): warp 0 = A (halo) TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 = B (weights)
+// TMA producer, warps 4-7 = epilogue (TMEM -> registers -> affine/residual/activation -> swizzled smem -> TMA store, or the fused
 // image/dot epilogues).  The grid is persistent: one CTA per SM walking tiles round-robin; TMEM accumulators are
 // double buffered when they fit so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -31,11 +36,19 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxGroups = 4;
 constexpr int kMaxStages = 12;
 
-struct Tap {
-  int16_t c_mul;  // A channel coordinate = c_mul * channel_pitch(src) + chunk*Ck   (space-to-depth column phase)
-  int8_t dw;      // A column coordinate = tile w0 + dw
-  int8_t p;       // A row-phase coordinate
-  int8_t dh;      // A row coordinate = tile h0 + dh
+constexpr int kMaxALoads = 16;
+constexpr int kMaxASlots = 8;
+constexpr int kMaxBSlots = 12;
+
+struct ALoad {          // one halo box per (group, phase): coordinates relative to the tile origin
+  int16_t c_mul;        // channel coordinate = c_mul * channel_pitch(src) + chunk*Ck   (space-to-depth column phase)
+  int8_t p;             // row-phase coordinate
+  int8_t dw0, dh0;      // box origin = (w0 + dw0, h0 + dh0)
+  uint8_t tap_begin, tap_count;
+};
+struct TapK {
+  uint16_t shift_px;    // pixel offset of this tap's 128-row view inside the halo box
+  uint16_t kidx;        // position of the tap in the packed-weight K order (r*kw + s)
 };
 
 struct ConvK {
@@ -48,23 +61,29 @@ struct ConvK {
   int tiles_w, tiles_h;
   // K walk
   int Ck, row_bytes;
-  int chunks0, chunks1, pitch0, pitch1;
-  int ntaps, ngroups;
-  Tap taps[kMaxGroups][kMaxTaps];
+  int chunks0, chunks1, pitch0, pitch1, ctot;
+  int ngroups;
+  int n_aloads[kMaxGroups];
+  ALoad aloads[kMaxGroups][kMaxALoads];
+  TapK taps[kMaxGroups][kMaxTaps];
+  int ntaps;               // taps per group (all groups equal)
+  int halo_w;              // TW + ew: pixels per halo row
+  int sub_px;              // pixel offset between the MT sub-tiles inside the halo box (= TH * halo_w)
   // N
   int BN, n_tiles_n, bn_cols, cout_pad;
   // pipeline
-  int stages, acc_stages, tmem_cols;
-  int a_stage_bytes, b_stage_bytes;   // smem slot sizes (1024-aligned)
-  int stage_tx_bytes;                 // bytes the two TMA boxes of one K step deliver
+  int a_slots, b_slots, acc_stages, tmem_cols;
+  int a_slot_bytes, b_slot_bytes;     // smem slot sizes (1024-aligned)
+  int a_tx_bytes, b_tx_bytes;         // bytes one TMA box delivers
   uint32_t idesc;
+  int desc_base_offset;               // experiment knob: put (addr>>7)&7 in the descriptor's base_offset field
   // epilogue
   int epi, act;
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
   int res_pitch;
-  int Cs, n_slabs, slab_bytes;           // FEATURE: output slab channels (TMA store box inner dim)
+  int Cs, n_slabs, slab_bytes, n_slab_bufs;   // FEATURE: output slab channels (TMA store box inner dim), staging ring
   int out_c_off[kMaxGroups];             // 5-D store coordinate 0 base per group
   int out_p[kMaxGroups];                 // 5-D store coordinate 2 per group
   const float* dot_w; float dot_b; float* dot_out;
@@ -78,16 +97,16 @@ struct SmemLayout {
   uint32_t a_off, b_off, slab_off, scale_off, bar_off, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int stages, int a_stage_bytes, int b_stage_bytes, int slab_bytes,
-                                                  int n_slab_bufs, int cout_pad) {
+__host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes, int b_slots, int b_slot_bytes,
+                                                  int slab_bytes, int n_slab_bufs, int cout_pad) {
   SmemLayout L;
   uint32_t off = 0;
-  L.a_off = off; off += (uint32_t)stages * a_stage_bytes;
-  L.b_off = off; off += (uint32_t)stages * b_stage_bytes;
+  L.a_off = off; off += (uint32_t)a_slots * a_slot_bytes;
+  L.b_off = off; off += (uint32_t)b_slots * b_slot_bytes;
   L.slab_off = off; off += (uint32_t)n_slab_bufs * slab_bytes;
   L.scale_off = off; off += (uint32_t)cout_pad * 8;      // scale then shift, fp32
   off = (off + 15u) & ~15u;
-  L.bar_off = off; off += 8u * (2 * kMaxStages + 4) + 16;  // full[], empty[], tmem_full[2], tmem_empty[2], tmem ptr
+  L.bar_off = off; off += 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16;  // fullA, emptyA, fullB, emptyB, tmem full/empty, tmem ptr
   L.total = off;
   return L;
 }
@@ -120,18 +139,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
 
-  const SmemLayout L = smem_layout(P.stages, P.a_stage_bytes, P.b_stage_bytes, P.slab_bytes, 2, P.cout_pad);
+  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
   const uint32_t a_base = base + L.a_off;
   const uint32_t b_base = base + L.b_off;
   const uint32_t slab_base = base + L.slab_off;
   float* s_scale = reinterpret_cast<float*>(base_ptr + L.scale_off);
   float* s_shift = s_scale + P.cout_pad;
   const uint32_t bar_base = base + L.bar_off;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 8u * (2 * kMaxStages + 4));
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (kMaxASlots + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * kMaxASlots + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * kMaxASlots + kMaxBSlots + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,7 +163,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (P.n_dev) n_eff = max(0, min(P.n, *P.n_dev - P.n_start));
   const int tiles_per_img = P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
   const int total_tiles = n_eff * tiles_per_img;
-  const int kiters = P.ntaps * (P.chunks0 + P.chunks1);
+  const int nchunks = P.chunks0 + P.chunks1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -150,7 +172,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < P.a_slots; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < P.b_slots; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     fence_mbar_init();
   }
@@ -169,64 +192,98 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // All three pipeline roles walk the same nest: tile -> channel chunk (src0 then src1) -> A load -> tap.
   if (warp == 0) {
-    // ======================================================= TMA producer
-    // The whole warp walks the loop (waits are warp-uniform, no divergent single-lane path); lane 0 issues.
-    int stage = 0; uint32_t phase = 0;
-    const uint32_t stage_bytes = (uint32_t)P.stage_tx_bytes;
+    // ======================================================= A producer: one halo box per (chunk, A load)
+    int slot = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(P, t);
-      int kcoord = 0;
+      const int nal = P.n_aloads[tc.g];
+      for (int c = 0; c < nchunks; ++c) {
+        const bool s1 = c >= P.chunks0;
+        const int coff = (s1 ? c - P.chunks0 : c) * P.Ck;
+        const int pitch = s1 ? P.pitch1 : P.pitch0;
+        const CUtensorMap* tm = s1 ? &tmA1 : &tmA0;
+        for (int a = 0; a < nal; ++a) {
+          const ALoad al = P.aloads[tc.g][a];
+          mbar_wait(emptyA(slot), phase ^ 1u, P.err_flag, 1);
+          if (lane == 0) {
+            mbar_expect_tx(fullA(slot), (uint32_t)P.a_tx_bytes);
+            tma_load_5d(a_base + (uint32_t)slot * P.a_slot_bytes, tm, fullA(slot), al.c_mul * pitch + coff,
+                        tc.w0 + al.dw0, al.p, tc.h0 + al.dh0, tc.img);
+          }
+          __syncwarp();
+          if (++slot == P.a_slots) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ======================================================= B producer: one weight box per (chunk, tap)
+    int slot = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(P, t);
       const int brow = tc.g * P.cout_pad + tc.nt * P.BN;
-      for (int tap = 0; tap < P.ntaps; ++tap) {
-        const Tap e = P.taps[tc.g][tap];
-        for (int src = 0; src < 2; ++src) {
-          const int chunks = src ? P.chunks1 : P.chunks0;
-          const int cbase = e.c_mul * (src ? P.pitch1 : P.pitch0);
-          const CUtensorMap* tm = src ? &tmA1 : &tmA0;
-          for (int ch = 0; ch < chunks; ++ch) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, P.err_flag, 1);
+      const int nal = P.n_aloads[tc.g];
+      for (int c = 0; c < nchunks; ++c) {
+        const int kc = (c >= P.chunks0 ? P.chunks0 * P.Ck + (c - P.chunks0) * P.Ck : c * P.Ck);   // channel offset in the concat
+        for (int a = 0; a < nal; ++a) {
+          const ALoad al = P.aloads[tc.g][a];
+          for (int j = 0; j < al.tap_count; ++j) {
+            const TapK tk = P.taps[tc.g][al.tap_begin + j];
+            mbar_wait(emptyB(slot), phase ^ 1u, P.err_flag, 5);
             if (lane == 0) {
-              mbar_expect_tx(full_bar(stage), stage_bytes);
-              tma_load_5d(a_base + (uint32_t)stage * P.a_stage_bytes, tm, full_bar(stage),
-                          cbase + ch * P.Ck, tc.w0 + e.dw, e.p, tc.h0 + e.dh, tc.img);
-              tma_load_2d(b_base + (uint32_t)stage * P.b_stage_bytes, &tmB, full_bar(stage), kcoord, brow);
+              mbar_expect_tx(fullB(slot), (uint32_t)P.b_tx_bytes);
+              tma_load_2d(b_base + (uint32_t)slot * P.b_slot_bytes, &tmB, fullB(slot), tk.kidx * P.ctot + kc, brow);
             }
             __syncwarp();
-            kcoord += P.Ck;
-            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+            if (++slot == P.b_slots) { slot = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ======================================================= MMA issuer (whole warp waits, lane 0 issues)
-    int stage = 0; uint32_t phase = 0;
+    int sa = 0; uint32_t pa = 0;
+    int sb = 0; uint32_t pb = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const int ksteps = P.Ck / 16;
-    const uint32_t sub_units = (128u * P.row_bytes) >> 4;          // descriptor address units (16 B) per 128-row sub-tile
     const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(P, t);
+      const int nal = P.n_aloads[tc.g];
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, P.err_flag, 2);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(acc * P.MT * P.bn_cols);
-      for (int k = 0; k < kiters; ++k) {
-        mbar_wait(full_bar(stage), phase, P.err_flag, 3);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint64_t a0 = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * P.a_stage_bytes) & 0x3FFFFu) >> 4);
-          const uint64_t b0 = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * P.b_stage_bytes) & 0x3FFFFu) >> 4);
-          for (int kk = 0; kk < ksteps; ++kk) {
-            for (int mt = 0; mt < P.MT; ++mt) {
-              umma_bf16(d_base + (uint32_t)(mt * P.bn_cols), a0 + (uint64_t)(mt * sub_units + kk * 2u),
-                        b0 + (uint64_t)(kk * 2u), P.idesc, (k | kk) ? 1u : 0u);
+      uint32_t accumulate = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        for (int a = 0; a < nal; ++a) {
+          const ALoad al = P.aloads[tc.g][a];
+          mbar_wait(fullA(sa), pa, P.err_flag, 3);
+          const uint32_t a_slot = a_base + (uint32_t)sa * P.a_slot_bytes;
+          for (int j = 0; j < al.tap_count; ++j) {
+            const TapK tk = P.taps[tc.g][al.tap_begin + j];
+            mbar_wait(fullB(sb), pb, P.err_flag, 6);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t b0 = desc_hi | (uint64_t)(((b_base + (uint32_t)sb * P.b_slot_bytes) & 0x3FFFFu) >> 4);
+              for (int mt = 0; mt < P.MT; ++mt) {
+                const uint32_t a_addr = a_slot + (uint32_t)(mt * P.sub_px + tk.shift_px) * (uint32_t)P.row_bytes;
+                uint64_t a0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
+                if (P.desc_base_offset) a0 |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+                for (int kk = 0; kk < ksteps; ++kk)
+                  umma_bf16(d_base + (uint32_t)(mt * P.bn_cols), a0 + (uint64_t)(kk * 2u), b0 + (uint64_t)(kk * 2u),
+                            P.idesc, (accumulate | (uint32_t)kk) ? 1u : 0u);
+              }
+              umma_commit(emptyB(sb));                                   // weight slot free once these MMAs have read it
+              if (j == al.tap_count - 1) umma_commit(emptyA(sa));        // halo slot free after its last tap
+              if (c == nchunks - 1 && a == nal - 1 && j == al.tap_count - 1) umma_commit(tfull_bar(acc));
             }
+            __syncwarp();
+            accumulate = 1;
+            if (++sb == P.b_slots) { sb = 0; pb ^= 1u; }
           }
-          umma_commit(empty_bar(stage));   // frees the smem slot once these MMAs have read it
-          if (k == kiters - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          if (++sa == P.a_slots) { sa = 0; pa ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
@@ -254,7 +311,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int sl = 0; sl < P.n_slabs; ++sl) {
             const uint32_t sbuf = slab_base + (uint32_t)slab_buf * P.slab_bytes;
             // the TMA store that last read this buffer must have drained
-            if (et == 0) tma_store_wait_read<1>();
+            if (et == 0) { if (P.n_slab_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             named_bar_sync(1, 128);
             for (int c16 = 0; c16 < c16_per_slab; ++c16) {
               const int cl = sl * P.Cs + c16 * 16;   // channel offset inside the N tile
@@ -297,7 +354,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                            tc.h0 + mt * P.TH, tc.img);
               tma_store_commit();
             }
-            slab_buf ^= 1;
+            if (++slab_buf == P.n_slab_bufs) slab_buf = 0;
           }
         } else if (P.epi == ADB_EPI_DOT) {
           float v[16];
@@ -354,7 +411,9 @@ inline int pick_chunk(int c) { return (c % 64 == 0) ? 64 : (c % 32 == 0) ? 32 : 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int pow2_at_least(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
-int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
+struct RawTap { int c_mul, p, dw, dh, kidx; };
+
+int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, int& box_w, int& box_h) {
   memset(&P, 0, sizeof(P));
   ADB_REQUIRE(d != nullptr, "adb_conv2d: null descriptor");
   ADB_REQUIRE(d->src0 && d->c0 > 0 && d->c0_pitch >= d->c0 && d->c0_pitch % 8 == 0, "adb_conv2d: bad src0 (c0=%d pitch=%d)", d->c0, d->c0_pitch);
@@ -370,8 +429,10 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
   P.Ck = Ck; P.row_bytes = Ck * 2;
   P.chunks0 = d->c0 / Ck; P.chunks1 = d->c1 / Ck;
   P.pitch0 = d->c0_pitch; P.pitch1 = d->src1 ? d->c1_pitch : d->c0_pitch;
+  P.ctot = d->c0 + d->c1;
 
-  // ---- taps
+  // ---- raw taps per group: (space-to-depth phases, pixel offsets, position in the packed K order)
+  RawTap raw[kMaxGroups][kMaxTaps];
   if (d->kind == ADB_CONV_S1) {
     ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "adb_conv2d: %dx%d taps unsupported (max %d)", d->kh, d->kw, kMaxTaps);
     // 'same' convolution: the padding is implied by the (odd) kernel extents, so a kh x 1 stem conv pads rows only
@@ -381,10 +442,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
     out_h = d->h_in; out_w = d->w_in;
     P.ngroups = 1; P.ntaps = d->kh * d->kw;
     for (int r = 0; r < d->kh; ++r)
-      for (int s = 0; s < d->kw; ++s) {
-        Tap& t = P.taps[0][r * d->kw + s];
-        t.c_mul = 0; t.dw = (int8_t)(s - pad_w); t.p = 0; t.dh = (int8_t)(r - pad_h);
-      }
+      for (int s = 0; s < d->kw; ++s) raw[0][r * d->kw + s] = {0, 0, s - pad_w, r - pad_h, r * d->kw + s};
     P.grid_h = out_h; P.grid_w = out_w;
   } else if (d->kind == ADB_CONV_S2) {
     ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "adb_conv2d: %dx%d taps unsupported", d->kh, d->kw);
@@ -396,35 +454,24 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
     auto fl2 = [](int u) { return (u >= 0) ? u / 2 : -((-u + 1) / 2); };
     for (int r = 0; r < d->kh; ++r)
       for (int s = 0; s < d->kw; ++s) {
-        Tap& t = P.taps[0][r * d->kw + s];
-        int u = r - d->pad, v = s - d->pad;
-        t.dh = (int8_t)fl2(u); t.p = (int8_t)(u - 2 * fl2(u));
-        t.dw = (int8_t)fl2(v); t.c_mul = (int16_t)(v - 2 * fl2(v));
+        const int u = r - d->pad, v = s - d->pad;
+        raw[0][r * d->kw + s] = {v - 2 * fl2(v), u - 2 * fl2(u), fl2(v), fl2(u), r * d->kw + s};
       }
     P.grid_h = out_h; P.grid_w = out_w;
   } else if (d->kind == ADB_CONVT_4X4S2) {
-    ADB_REQUIRE(d->src1 == nullptr || true, "");
     out_h = d->h_in * 2; out_w = d->w_in * 2;
     P.ngroups = 4; P.ntaps = 4;
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int i = 0; i < 2; ++i)
-          for (int j = 0; j < 2; ++j) {
-            Tap& t = P.taps[a * 2 + b][i * 2 + j];
-            t.c_mul = 0; t.p = 0;
-            t.dh = (int8_t)(a ? 1 - i : -i);
-            t.dw = (int8_t)(b ? 1 - j : -j);
-          }
+          for (int j = 0; j < 2; ++j) raw[a * 2 + b][i * 2 + j] = {0, 0, b ? 1 - j : -j, a ? 1 - i : -i, i * 2 + j};
     P.grid_h = d->h_in; P.grid_w = d->w_in;
   } else {
     return adbh::fail(ADB_ERR_INVALID, "adb_conv2d: unknown kind %d", d->kind);
   }
-  ktot = P.ntaps * (d->c0 + d->c1);
+  ktot = P.ntaps * P.ctot;
 
-  // ---- tiles
-  int TW = 128;
-  while (TW > P.grid_w && TW > 8) TW >>= 1;
-  P.TW = TW; P.TH = 128 / TW;
+  // ---- N tiling
   P.BN = d->cout_pad;
   P.n_tiles_n = 1;
   if (d->cout_pad > 256) {
@@ -434,25 +481,77 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
   ADB_REQUIRE(P.BN % 16 == 0 && P.BN >= 16 && P.BN <= 256, "adb_conv2d: N tile %d invalid", P.BN);
   P.cout_pad = d->cout_pad;
   P.bn_cols = (2 * round_up(P.BN, 32) <= 512) ? round_up(P.BN, 32) : P.BN;
-  int mt = d->tune_mt > 0 ? d->tune_mt : 1;
+
+  // ---- pixel tile
+  int TW = 128;
+  while (TW > P.grid_w && TW > 8) TW >>= 1;
+  P.TW = TW; P.TH = 128 / TW;
+  int mt = d->tune_mt > 0 ? d->tune_mt : (P.bn_cols <= 128 ? 2 : 1);
   ADB_REQUIRE(mt == 1 || mt == 2, "adb_conv2d: tune_mt must be 1 or 2");
   if (mt * P.bn_cols > 512) mt = 1;
-  if (d->epi != ADB_EPI_FEATURE) mt = std::min(mt, 2);
+  if ((long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) < 2LL * 148 * mt) mt = 1;  // keep the SMs busy
   P.MT = mt;
   P.tiles_w = (P.grid_w + TW - 1) / TW;
   P.tiles_h = (P.grid_h + P.TH * mt - 1) / (P.TH * mt);
-  int acc = 512 / (mt * P.bn_cols);
-  acc = std::min(acc, 2);
+  int acc = std::min(512 / (mt * P.bn_cols), 2);
   if (d->tune_acc_stages > 0) acc = std::min(acc, d->tune_acc_stages);
   ADB_REQUIRE(acc >= 1, "adb_conv2d: accumulators do not fit TMEM");
   P.acc_stages = acc;
   P.tmem_cols = pow2_at_least(acc * mt * P.bn_cols);
   P.idesc = make_idesc_bf16(128, (uint32_t)P.BN);
+  P.desc_base_offset = (d->tune_flags & 2) ? 1 : 0;
+
+  // ---- A loads: taps of one (c_mul, p) phase share a halo box when the 128-row views stay contiguous in it
+  //      (tile = one image row, or no column shifts); otherwise each tap is its own box.
+  int eh = 0, ew = 0;
+  for (int g = 0; g < P.ngroups; ++g) {
+    int nal = 0, ntp = 0;
+    bool used[kMaxTaps] = {false};
+    for (int t0 = 0; t0 < P.ntaps; ++t0) {
+      if (used[t0]) continue;
+      const RawTap& f = raw[g][t0];
+      int dw_min = f.dw, dw_max = f.dw, dh_min = f.dh, dh_max = f.dh;
+      int members[kMaxTaps], nm = 0;
+      for (int t1 = t0; t1 < P.ntaps; ++t1) {
+        const RawTap& q = raw[g][t1];
+        if (used[t1] || q.c_mul != f.c_mul || q.p != f.p) continue;
+        members[nm++] = t1;
+        dw_min = std::min(dw_min, q.dw); dw_max = std::max(dw_max, q.dw);
+        dh_min = std::min(dh_min, q.dh); dh_max = std::max(dh_max, q.dh);
+      }
+      const bool can_share = !(d->tune_flags & 1) && (P.TH == 1 || dw_max == dw_min);
+      if (!can_share) { nm = 1; members[0] = t0; dw_min = dw_max = f.dw; dh_min = dh_max = f.dh; }
+      ADB_REQUIRE(nal < kMaxALoads, "adb_conv2d: too many A loads");
+      ALoad& al = P.aloads[g][nal++];
+      al.c_mul = (int16_t)f.c_mul; al.p = (int8_t)f.p; al.dw0 = (int8_t)dw_min; al.dh0 = (int8_t)dh_min;
+      al.tap_begin = (uint8_t)ntp; al.tap_count = (uint8_t)nm;
+      eh = std::max(eh, dh_max - dh_min); ew = std::max(ew, dw_max - dw_min);
+      for (int k = 0; k < nm; ++k) {
+        used[members[k]] = true;
+        // shift is finalised below once the halo width is known; stash (ddh, ddw) for now
+        P.taps[g][ntp].shift_px = (uint16_t)(((raw[g][members[k]].dh - dh_min) << 8) | (raw[g][members[k]].dw - dw_min));
+        P.taps[g][ntp].kidx = (uint16_t)raw[g][members[k]].kidx;
+        ++ntp;
+      }
+    }
+    P.n_aloads[g] = nal;
+  }
+  P.halo_w = P.TW + ew;
+  P.sub_px = P.TH * P.halo_w;
+  for (int g = 0; g < P.ngroups; ++g)
+    for (int t = 0; t < P.ntaps; ++t) {
+      const int ddh = P.taps[g][t].shift_px >> 8, ddw = P.taps[g][t].shift_px & 0xFF;
+      P.taps[g][t].shift_px = (uint16_t)(ddh * P.halo_w + ddw);
+    }
+  box_w = P.halo_w;
+  box_h = P.TH * mt + eh;
+  ADB_REQUIRE(box_w <= 256 && box_h <= 256, "adb_conv2d: halo box %dx%d exceeds the TMA box limit", box_w, box_h);
 
   // ---- smem
-  P.a_stage_bytes = round_up(mt * 128 * P.row_bytes, 1024);
-  P.b_stage_bytes = round_up(P.BN * P.row_bytes, 1024);
-  P.stage_tx_bytes = mt * 128 * P.row_bytes + P.BN * P.row_bytes;
+  P.a_tx_bytes = box_w * box_h * P.row_bytes;
+  P.b_tx_bytes = P.BN * P.row_bytes;
+  P.a_slot_bytes = round_up(P.a_tx_bytes, 1024);
+  P.b_slot_bytes = round_up(P.b_tx_bytes, 1024);
   if (d->epi == ADB_EPI_FEATURE) {
     P.Cs = pick_chunk(P.BN);
     P.n_slabs = P.BN / P.Cs;
@@ -465,13 +564,24 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot) {
   int st = adbh::device_info(&di);
   if (st != ADB_OK) return st;
   const int budget = di.max_smem_optin - 1024;  // alignment slack
-  const int stage_bytes = P.a_stage_bytes + P.b_stage_bytes;
-  const SmemLayout fixed = smem_layout(0, 0, 0, P.slab_bytes, 2, P.cout_pad);
-  int stages = (budget - (int)fixed.total) / stage_bytes;
-  stages = std::min(stages, kMaxStages);
-  if (d->tune_stages > 0) stages = std::min(stages, d->tune_stages);
-  ADB_REQUIRE(stages >= 2, "adb_conv2d: pipeline does not fit shared memory (stage %d B)", stage_bytes);
-  P.stages = stages;
+  // weights ring first (>= 3 boxes), then up to 4 halo slots, then the rest back to the weights ring; the output staging
+  // ring drops from 2 slabs to 1 when that buys the third weight box.
+  int a_slots = 2, b_slots = 0;
+  for (int bufs = 2; bufs >= 1; --bufs) {
+    P.n_slab_bufs = bufs;
+    const SmemLayout fixed = smem_layout(0, 0, 0, 0, P.slab_bytes, bufs, P.cout_pad);
+    const int avail = budget - (int)fixed.total;
+    a_slots = 2;
+    b_slots = (avail - a_slots * P.a_slot_bytes) / P.b_slot_bytes;
+    if (b_slots >= 3 || bufs == 1) {
+      ADB_REQUIRE(b_slots >= 2, "adb_conv2d: pipeline does not fit shared memory (A %d B, B %d B)", P.a_slot_bytes, P.b_slot_bytes);
+      while (a_slots < 4 && (a_slots + 1) * P.a_slot_bytes + 4 * P.b_slot_bytes <= avail) ++a_slots;
+      b_slots = std::min(kMaxBSlots, (avail - a_slots * P.a_slot_bytes) / P.b_slot_bytes);
+      break;
+    }
+  }
+  if (d->tune_stages > 0) { a_slots = std::min(a_slots, std::max(2, d->tune_stages)); b_slots = std::min(b_slots, std::max(2, d->tune_stages)); }
+  P.a_slots = a_slots; P.b_slots = b_slots;
 
   // ---- batch / epilogue
   P.n = d->n; P.n_start = d->n_start; P.n_dev = d->n_dev;
@@ -526,8 +636,8 @@ int make_act_tmap(CUtensorMap* m, const void* base, int pitch, int n, int h, int
 
 extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   ConvK P;
-  int out_h = 0, out_w = 0, ktot = 0;
-  int st = build(d, P, out_h, out_w, ktot);
+  int out_h = 0, out_w = 0, ktot = 0, box_w = 0, box_h = 0;
+  int st = build(d, P, out_h, out_w, ktot, box_w, box_h);
   if (st != ADB_OK) return st;
   adbh::DeviceInfo di;
   st = adbh::device_info(&di);
@@ -537,10 +647,10 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
 
   alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
   const bool s2d_in = d->kind == ADB_CONV_S2;
-  st = make_act_tmap(&tmA0, d->src0, d->c0_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, P.TW, P.TH * P.MT, P.row_bytes);
+  st = make_act_tmap(&tmA0, d->src0, d->c0_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
   if (st != ADB_OK) return st;
   if (d->src1) {
-    st = make_act_tmap(&tmA1, d->src1, d->c1_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, P.TW, P.TH * P.MT, P.row_bytes);
+    st = make_act_tmap(&tmA1, d->src1, d->c1_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
     if (st != ADB_OK) return st;
   } else {
     tmA1 = tmA0;
@@ -559,7 +669,7 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
     tmOut = tmA0;
   }
 
-  const SmemLayout L = smem_layout(P.stages, P.a_stage_bytes, P.b_stage_bytes, P.slab_bytes, 2, P.cout_pad);
+  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
   int smem = (int)L.total + 1024;
   smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
   static int configured_for = 0;

@@ -173,6 +173,7 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     d.n_start = n_start
     if tune:
         d.tune_mt, d.tune_stages, d.tune_acc_stages = tune.get("mt", 0), tune.get("stages", 0), tune.get("acc", 0)
+        d.tune_flags = tune.get("flags", 0)
     _lib.call("adb_conv2d", C.byref(d), _lib.current_stream())
     return ret
 

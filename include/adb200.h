@@ -90,6 +90,7 @@ typedef struct adb_conv_desc {
   const int32_t* n_dev; int32_t n_start;
   /* --- tuning (0 = choose automatically) */
   int32_t tune_mt, tune_stages, tune_acc_stages;
+  int32_t tune_flags;   /* bit 0: one TMA box per tap (no halo re-use); bit 1: descriptor base-offset experiment */
 } adb_conv_desc;
 
 /* Weight packing order expected in w_packed (done on the host side by adam_dehaze_b200/engine.py):

@@ -80,6 +80,12 @@ CONV_CASES = [
     (64, 64, 3, 2, 64, 128, {"mt": 2}),
     (96, 96, 3, 2, 64, 128, {"mt": 2}),
     (64, 64, 3, 2, 64, 128, {"stages": 2, "acc": 1}),
+    (64, 64, 3, 2, 64, 256, None),           # halo re-use path: tile = one image row (TW = 128), 128-byte swizzle
+    (96, 96, 3, 1, 32, 128, None),           # halo path with 64-byte swizzle rows (Ck = 32)
+    (48, 48, 3, 1, 32, 128, None),           # halo path with 32-byte swizzle rows (Ck = 16)
+    (64, 64, 3, 2, 64, 256, {"flags": 1}),   # one TMA box per tap (no halo), same shape
+    (192, 192, 3, 1, 16, 256, None),
+    (256, 256, 3, 1, 8, 128, {"mt": 2}),
 ]
 
 

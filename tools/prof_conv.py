@@ -75,7 +75,7 @@ def main():
         pass
     tunes = [None]
     if args.sweep:
-        tunes = [None, {"mt": 2}, {"mt": 1, "acc": 1}, {"mt": 2, "acc": 1}, {"stages": 3}, {"mt": 2, "stages": 3}]
+        tunes = [None, {"mt": 1}, {"mt": 2}, {"flags": 1}, {"flags": 1, "mt": 1}]
     for shape in SHAPES:
         if args.only and args.only not in shape[0]:
             continue
