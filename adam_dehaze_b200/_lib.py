@@ -50,6 +50,7 @@ SIGNATURES = {
     "adb_device_check": [],
     "adb_kernel_error_flag": [],
     "adb_conv2d": [C.POINTER(ConvDesc), _P],
+    "adb_debug_timeline": [_P, _I],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],

@@ -90,6 +90,7 @@ struct ConvK {
   int img_mode;
   const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
   int* err_flag;
+  long long* dbg;   // optional timeline buffer (tune_flags bit 2): [6 roles][256 events] of clock64() from CTA 0
 };
 
 struct SmemLayout {
@@ -117,6 +118,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ADB_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
   return v;
 }
+// kAct >= 0: compile-time activation (no per-element branches in the hot FEATURE epilogue); kAct < 0: runtime P.act
+template <int kAct>
+__device__ __forceinline__ float act_t(float v, int act_rt) {
+  if (kAct == ADB_ACT_RELU) return fmaxf(v, 0.f);
+  if (kAct == ADB_ACT_NONE) return v;
+  return apply_act(v, act_rt);
+}
+
+#define ADB_DBG(role, idx) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 
 struct TileCoord { int nt, g, w0, h0, img; };
 
@@ -130,6 +140,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t) {
   return c;
 }
 
+template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -195,7 +206,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // All three pipeline roles walk the same nest: tile -> channel chunk (src0 then src1) -> A load -> tap.
   if (warp == 0) {
     // ======================================================= A producer: one halo box per (chunk, A load)
-    int slot = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t phase = 0; int dbg_i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(P, t);
       const int nal = P.n_aloads[tc.g];
@@ -207,7 +218,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int a = 0; a < nal; ++a) {
           const ALoad al = P.aloads[tc.g][a];
           mbar_wait(emptyA(slot), phase ^ 1u, P.err_flag, 1);
-          if (lane == 0) {
+          ADB_DBG(0, dbg_i); ++dbg_i;
+          if (elect_one()) {
             mbar_expect_tx(fullA(slot), (uint32_t)P.a_tx_bytes);
             tma_load_5d(a_base + (uint32_t)slot * P.a_slot_bytes, tm, fullA(slot), al.c_mul * pitch + coff,
                         tc.w0 + al.dw0, al.p, tc.h0 + al.dh0, tc.img);
@@ -219,7 +231,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 3) {
     // ======================================================= B producer: one weight box per (chunk, tap)
-    int slot = 0; uint32_t phase = 0;
+    int slot = 0; uint32_t phase = 0; int dbg_i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(P, t);
       const int brow = tc.g * P.cout_pad + tc.nt * P.BN;
@@ -231,7 +243,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int j = 0; j < al.tap_count; ++j) {
             const TapK tk = P.taps[tc.g][al.tap_begin + j];
             mbar_wait(emptyB(slot), phase ^ 1u, P.err_flag, 5);
-            if (lane == 0) {
+            ADB_DBG(1, dbg_i); ++dbg_i;
+            if (elect_one()) {
               mbar_expect_tx(fullB(slot), (uint32_t)P.b_tx_bytes);
               tma_load_2d(b_base + (uint32_t)slot * P.b_slot_bytes, &tmB, fullB(slot), tk.kidx * P.ctot + kc, brow);
             }
@@ -245,7 +258,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ======================================================= MMA issuer (whole warp waits, lane 0 issues)
     int sa = 0; uint32_t pa = 0;
     int sb = 0; uint32_t pb = 0;
-    int acc = 0; uint32_t acc_phase = 0;
+    int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
     const int ksteps = P.Ck / 16;
     const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -264,7 +277,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const TapK tk = P.taps[tc.g][al.tap_begin + j];
             mbar_wait(fullB(sb), pb, P.err_flag, 6);
             tc_fence_after();
-            if (lane == 0) {
+            ADB_DBG(2, dbg_i);
+            if (elect_one()) {   // elect.sync lets the compiler keep the UTCHMMA stream in straight-line uniform code
               const uint64_t b0 = desc_hi | (uint64_t)(((b_base + (uint32_t)sb * P.b_slot_bytes) & 0x3FFFFu) >> 4);
               for (int mt = 0; mt < P.MT; ++mt) {
                 const uint32_t a_addr = a_slot + (uint32_t)(mt * P.sub_px + tk.shift_px) * (uint32_t)P.row_bytes;
@@ -279,6 +293,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               if (c == nchunks - 1 && a == nal - 1 && j == al.tap_count - 1) umma_commit(tfull_bar(acc));
             }
             __syncwarp();
+            ADB_DBG(3, dbg_i); ++dbg_i;
             accumulate = 1;
             if (++sb == P.b_slots) { sb = 0; pb ^= 1u; }
           }
@@ -292,12 +307,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..127 == TMEM lane == tile row
     const int ew = warp - kEpiWarp0;                    // TMEM sub-partition of this warp
     const int th_l = et / P.TW, tw_l = et % P.TW;
-    int acc = 0; uint32_t acc_phase = 0;
+    int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
     int slab_buf = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(P, t);
       mbar_wait(tfull_bar(acc), acc_phase, P.err_flag, 4);
       tc_fence_after();
+
       const int ch0 = tc.nt * P.BN;   // first output channel of this N tile
       for (int mt = 0; mt < P.MT; ++mt) {
         const int h = tc.h0 + mt * P.TH + th_l;
@@ -305,53 +321,60 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const bool inb = (h < P.grid_h) && (w < P.grid_w);
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * P.MT + mt) * P.bn_cols);
         if (P.epi == ADB_EPI_FEATURE) {
+          // Each epilogue warp owns 32 tile rows end to end: TMEM -> registers -> affine/residual/activation -> its own
+          // swizzled staging quarter -> its own TMA store.  No cross-warp barrier anywhere in the epilogue.
           const size_t pix = ((size_t)tc.img * P.grid_h + h) * P.grid_w + w;
           const __nv_bfloat16* res_row = (P.residual && inb) ? P.residual + pix * P.res_pitch + ch0 : nullptr;
           const int c16_per_slab = P.Cs / 16;
+          const uint32_t span = (uint32_t)(P.Cs * 2);
+          const int q_row0 = ew * 32;                       // first tile row of this warp
+          const int q_th = q_row0 / P.TW, q_tw = q_row0 % P.TW;
           for (int sl = 0; sl < P.n_slabs; ++sl) {
-            const uint32_t sbuf = slab_base + (uint32_t)slab_buf * P.slab_bytes;
-            // the TMA store that last read this buffer must have drained
-            if (et == 0) { if (P.n_slab_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-            named_bar_sync(1, 128);
+            const uint32_t sbuf = slab_base + (uint32_t)(slab_buf * 4 + ew) * (uint32_t)(P.slab_bytes >> 2);
+            // the TMA store of this warp that last read this quarter must have drained
+            if (lane == 0) { if (P.n_slab_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            __syncwarp();
+            if (ew == 0) { ADB_DBG(4, dbg_i); }
             for (int c16 = 0; c16 < c16_per_slab; ++c16) {
               const int cl = sl * P.Cs + c16 * 16;   // channel offset inside the N tile
               float v[16];
               tmem_ld16(taddr + (uint32_t)cl, v);
-              tmem_ld_wait();
-              float r[16];
+              uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
               if (res_row) {
                 const uint4* rp = reinterpret_cast<const uint4*>(res_row + cl);
-                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
-                const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
-                  r[2 * i] = __low2float(b2);
-                  r[2 * i + 1] = __high2float(b2);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = 0.f;
+                q0 = __ldg(rp); q1 = __ldg(rp + 1);
               }
+              const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch0 + cl);
+              const float4* sh4 = reinterpret_cast<const float4*>(s_shift + ch0 + cl);
+              float sc[16], sh[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = sc4[i], b = sh4[i];
+                sc[4 * i] = a.x; sc[4 * i + 1] = a.y; sc[4 * i + 2] = a.z; sc[4 * i + 3] = a.w;
+                sh[4 * i] = b.x; sh[4 * i + 1] = b.y; sh[4 * i + 2] = b.z; sh[4 * i + 3] = b.w;
+              }
+              const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+              tmem_ld_wait();
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int c = ch0 + cl + 2 * i;
-                float y0 = apply_act(fmaf(v[2 * i], s_scale[c], s_shift[c]) + r[2 * i], P.act);
-                float y1 = apply_act(fmaf(v[2 * i + 1], s_scale[c + 1], s_shift[c + 1]) + r[2 * i + 1], P.act);
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
+                const float y0 = act_t<kAct>(fmaf(v[2 * i], sc[2 * i], sh[2 * i]) + __low2float(b2), P.act);
+                const float y1 = act_t<kAct>(fmaf(v[2 * i + 1], sc[2 * i + 1], sh[2 * i + 1]) + __high2float(b2), P.act);
                 pk[i] = pack_bf16x2(y0, y1);
               }
-              const uint32_t row_off = (uint32_t)et * (uint32_t)(P.Cs * 2) + (uint32_t)c16 * 32u;
-              const uint32_t a0 = sbuf + swizzle_addr(row_off, (uint32_t)(P.Cs * 2));
-              const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, (uint32_t)(P.Cs * 2));
+              const uint32_t row_off = (uint32_t)lane * span + (uint32_t)c16 * 32u;
+              const uint32_t a0 = sbuf + swizzle_addr(row_off, span);
+              const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, span);
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
               asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
             }
+            if (ew == 0) { ADB_DBG(5, dbg_i); ++dbg_i; }
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (et == 0) {
-              tma_store_5d(&tmOut, sbuf, P.out_c_off[tc.g] + ch0 + sl * P.Cs, tc.w0, P.out_p[tc.g],
-                           tc.h0 + mt * P.TH, tc.img);
+            __syncwarp();
+            if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
+              tma_store_5d(&tmOut, sbuf, P.out_c_off[tc.g] + ch0 + sl * P.Cs, tc.w0 + q_tw, P.out_p[tc.g],
+                           tc.h0 + mt * P.TH + q_th, tc.img);
               tma_store_commit();
             }
             if (++slab_buf == P.n_slab_bufs) slab_buf = 0;
@@ -398,7 +421,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   // ---------------------------------------------------------- teardown
@@ -634,6 +657,14 @@ int make_act_tmap(CUtensorMap* m, const void* base, int pitch, int n, int h, int
 
 }  // namespace
 
+static long long* g_dbg = nullptr;
+
+extern "C" int adb_debug_timeline(int64_t* host_out, int32_t count) {
+  if (!g_dbg || !host_out || count > 6 * 256) return adbh::fail(ADB_ERR_INVALID, "adb_debug_timeline: no timeline recorded");
+  ADB_CUDA_OK(cudaMemcpy(host_out, g_dbg, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost));
+  return ADB_OK;
+}
+
 extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   ConvK P;
   int out_h = 0, out_w = 0, ktot = 0, box_w = 0, box_h = 0;
@@ -644,6 +675,11 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   if (st != ADB_OK) return st;
   if (di.cc_major != 10) return adbh::fail(ADB_ERR_NO_DEVICE, "adb_conv2d: device sm_%d%d is not sm_100", di.cc_major, di.cc_minor);
   P.err_flag = adbh::kernel_err_flag();
+  if (d->tune_flags & 4) {
+    if (!g_dbg) ADB_CUDA_OK(cudaMalloc(&g_dbg, 6 * 256 * sizeof(long long)));
+    ADB_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 6 * 256 * sizeof(long long), (cudaStream_t)stream));
+    P.dbg = g_dbg;
+  }
 
   alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
   const bool s2d_in = d->kind == ADB_CONV_S2;
@@ -663,7 +699,9 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
     if (st != ADB_OK) return st;
   }
   if (d->epi == ADB_EPI_FEATURE) {
-    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->n, out_h, out_w, d->kind == ADB_CONVT_4X4S2, P.Cs, P.TW, P.TH, P.Cs * 2);
+    // one store box per epilogue warp: its 32 tile rows = 32 pixels of one image row, or 32/TW whole rows of a narrow tile
+    const int qw = std::min(P.TW, 32), qh = 32 / qw;
+    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->n, out_h, out_w, d->kind == ADB_CONVT_4X4S2, P.Cs, qw, qh, P.Cs * 2);
     if (st != ADB_OK) return st;
   } else {
     tmOut = tmA0;
@@ -672,14 +710,19 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
   int smem = (int)L.total + 1024;
   smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
-  static int configured_for = 0;
-  if (configured_for < smem) {
-    ADB_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-    configured_for = di.max_smem_optin;
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvK);
+  KernelFn fn = conv_igemm_kernel<-1>;
+  int which = 2;
+  if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_RELU) { fn = conv_igemm_kernel<ADB_ACT_RELU>; which = 0; }
+  else if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_NONE) { fn = conv_igemm_kernel<ADB_ACT_NONE>; which = 1; }
+  static bool configured[3] = {false, false, false};
+  if (!configured[which]) {
+    ADB_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+    configured[which] = true;
   }
   const long long max_tiles = (long long)d->n * P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
   const int grid = (int)std::min<long long>(max_tiles, di.sm_count);
-  conv_igemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmOut, P);
+  fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmOut, P);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

@@ -182,6 +182,10 @@ ADB_API int adb_mse_bwd(const float* pred, const float* target, int64_t numel, f
 ADB_API int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale,
                    float* loss /*[1]*/, float* grad_logits /*nullable [b][classes]*/, void* stream);
 
+/* Developer aid: copy the clock64() timeline CTA 0 recorded during the last adb_conv2d launched with tune_flags bit 2
+ * ([6 roles][256 events]: A producer, B producer, MMA ready, MMA issued, epilogue start, epilogue end). Synchronises. */
+ADB_API int adb_debug_timeline(int64_t* host_out, int32_t count);
+
 /* Read and clear the device-side kernel error flag (non-zero => a bounded mbarrier wait expired). Synchronises. */
 ADB_API int adb_kernel_error_flag(void);
 

@@ -1,0 +1,28 @@
+"""Dump the in-kernel clock64 timeline of CTA 0 for one conv shape (developer aid)."""
+import ctypes as C
+import sys, os
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from adam_dehaze_b200 import ops, _lib
+import prof_conv
+
+def main():
+    names = sys.argv[1:] or ["med_64_3x3", "med_256_3x3"]
+    for shape in prof_conv.SHAPES:
+        if shape[0] not in names:
+            continue
+        prof_conv.run(shape, None, 2)
+        ms, tf = prof_conv.run(shape, {"flags": 4}, 1)
+        torch.cuda.synchronize()
+        buf = (C.c_int64 * (6 * 256))()
+        _lib.call("adb_debug_timeline", buf, 6 * 256)
+        t = [list(buf[r * 256:(r + 1) * 256]) for r in range(6)]
+        t0 = min(v for r in t for v in r if v > 0)
+        print(f"== {shape[0]}  {ms:.3f} ms {tf:.0f} TF/s")
+        for r, nm in enumerate(["A-prod wait done", "B-prod wait done", "MMA ready", "MMA issued", "epi start", "epi end"]):
+            vals = [v - t0 for v in t[r] if v > 0][:40]
+            print(f"{nm:18s}", " ".join(str(v) for v in vals))
+
+main()
