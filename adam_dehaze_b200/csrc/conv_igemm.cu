@@ -75,6 +75,7 @@ struct ConvK {
   int a_slots, b_slots, acc_stages, tmem_cols;
   int a_slot_bytes, b_slot_bytes;     // smem slot sizes (1024-aligned)
   int a_tx_bytes, b_tx_bytes;         // bytes one TMA box delivers
+  int taps_per_slot, b_tap_stride;    // a weight slot carries up to taps_per_slot tap boxes, b_tap_stride bytes apart
   uint32_t idesc;
   int desc_base_offset;               // experiment knob: put (addr>>7)&7 in the descriptor's base_offset field
   // epilogue
@@ -127,6 +128,18 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 }
 
 #define ADB_DBG(role, idx) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
+
+// One tap's MMAs as a straight-line UTCHMMA run: kKs K-steps of 16 (descriptor start address += 32 B each) for kMt sub-tiles.
+template <int kMt, int kKs>
+__device__ __forceinline__ void issue_mmas(uint32_t d0, uint32_t d1, uint64_t a0, uint64_t a1, uint64_t b0, uint32_t idesc,
+                                           uint32_t first) {
+#pragma unroll
+  for (int kk = 0; kk < kKs; ++kk) {
+    const uint32_t accum = (first | (uint32_t)kk) ? 1u : 0u;
+    umma_bf16(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+    if (kMt == 2) umma_bf16(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+  }
+}
 
 struct TileCoord { int nt, g, w0, h0, img; };
 
@@ -240,13 +253,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int kc = (c >= P.chunks0 ? P.chunks0 * P.Ck + (c - P.chunks0) * P.Ck : c * P.Ck);   // channel offset in the concat
         for (int a = 0; a < nal; ++a) {
           const ALoad al = P.aloads[tc.g][a];
-          for (int j = 0; j < al.tap_count; ++j) {
-            const TapK tk = P.taps[tc.g][al.tap_begin + j];
+          for (int j0 = 0; j0 < al.tap_count; j0 += P.taps_per_slot) {
+            const int nt = min(P.taps_per_slot, (int)al.tap_count - j0);
             mbar_wait(emptyB(slot), phase ^ 1u, P.err_flag, 5);
             ADB_DBG(1, dbg_i); ++dbg_i;
             if (elect_one()) {
-              mbar_expect_tx(fullB(slot), (uint32_t)P.b_tx_bytes);
-              tma_load_2d(b_base + (uint32_t)slot * P.b_slot_bytes, &tmB, fullB(slot), tk.kidx * P.ctot + kc, brow);
+              mbar_expect_tx(fullB(slot), (uint32_t)(nt * P.b_tx_bytes));
+              for (int jj = 0; jj < nt; ++jj) {
+                const TapK tk = P.taps[tc.g][al.tap_begin + j0 + jj];
+                tma_load_2d(b_base + (uint32_t)slot * P.b_slot_bytes + (uint32_t)jj * P.b_tap_stride, &tmB, fullB(slot),
+                            tk.kidx * P.ctot + kc, brow);
+              }
             }
             __syncwarp();
             if (++slot == P.b_slots) { slot = 0; phase ^= 1u; }
@@ -273,24 +290,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const ALoad al = P.aloads[tc.g][a];
           mbar_wait(fullA(sa), pa, P.err_flag, 3);
           const uint32_t a_slot = a_base + (uint32_t)sa * P.a_slot_bytes;
-          for (int j = 0; j < al.tap_count; ++j) {
-            const TapK tk = P.taps[tc.g][al.tap_begin + j];
+          for (int j0 = 0; j0 < al.tap_count; j0 += P.taps_per_slot) {
+            const int nt = min(P.taps_per_slot, (int)al.tap_count - j0);
+            const bool last_of_a = j0 + nt >= al.tap_count;
             mbar_wait(fullB(sb), pb, P.err_flag, 6);
             tc_fence_after();
             ADB_DBG(2, dbg_i);
             if (elect_one()) {   // elect.sync lets the compiler keep the UTCHMMA stream in straight-line uniform code
-              const uint64_t b0 = desc_hi | (uint64_t)(((b_base + (uint32_t)sb * P.b_slot_bytes) & 0x3FFFFu) >> 4);
-              for (int mt = 0; mt < P.MT; ++mt) {
-                const uint32_t a_addr = a_slot + (uint32_t)(mt * P.sub_px + tk.shift_px) * (uint32_t)P.row_bytes;
-                uint64_t a0 = desc_hi | (uint64_t)((a_addr & 0x3FFFFu) >> 4);
-                if (P.desc_base_offset) a0 |= (uint64_t)((a_addr >> 7) & 7u) << 49;
-                for (int kk = 0; kk < ksteps; ++kk)
-                  umma_bf16(d_base + (uint32_t)(mt * P.bn_cols), a0 + (uint64_t)(kk * 2u), b0 + (uint64_t)(kk * 2u),
-                            P.idesc, (accumulate | (uint32_t)kk) ? 1u : 0u);
+              const uint32_t b_slot = b_base + (uint32_t)sb * P.b_slot_bytes;
+              for (int jj = 0; jj < nt; ++jj) {
+                const uint32_t shift = P.taps[tc.g][al.tap_begin + j0 + jj].shift_px;
+                const uint64_t b0 = desc_hi | (uint64_t)(((b_slot + (uint32_t)jj * P.b_tap_stride) & 0x3FFFFu) >> 4);
+                const uint32_t a_addr0 = a_slot + shift * (uint32_t)P.row_bytes;
+                const uint64_t a0 = desc_hi | (uint64_t)((a_addr0 & 0x3FFFFu) >> 4);
+                const uint64_t a1 = a0 + (uint64_t)(((uint32_t)P.sub_px * (uint32_t)P.row_bytes) >> 4);
+                const uint32_t first = accumulate | (uint32_t)jj;
+                const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
+                if (P.MT == 2) {
+                  if (ksteps == 4) issue_mmas<2, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 2) issue_mmas<2, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else issue_mmas<2, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
+                } else {
+                  if (ksteps == 4) issue_mmas<1, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 2) issue_mmas<1, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else issue_mmas<1, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
+                }
               }
               umma_commit(emptyB(sb));                                   // weight slot free once these MMAs have read it
-              if (j == al.tap_count - 1) umma_commit(emptyA(sa));        // halo slot free after its last tap
-              if (c == nchunks - 1 && a == nal - 1 && j == al.tap_count - 1) umma_commit(tfull_bar(acc));
+              if (last_of_a) umma_commit(emptyA(sa));                    // halo slot free after its last tap
+              if (c == nchunks - 1 && a == nal - 1 && last_of_a) umma_commit(tfull_bar(acc));
             }
             __syncwarp();
             ADB_DBG(3, dbg_i); ++dbg_i;
@@ -574,7 +602,17 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   P.a_tx_bytes = box_w * box_h * P.row_bytes;
   P.b_tx_bytes = P.BN * P.row_bytes;
   P.a_slot_bytes = round_up(P.a_tx_bytes, 1024);
-  P.b_slot_bytes = round_up(P.b_tx_bytes, 1024);
+  P.b_tap_stride = round_up(P.b_tx_bytes, 1024);
+  {
+    // small weight boxes are batched: one mbarrier round-trip then covers several taps' worth of MMAs
+    int max_taps = 1;
+    for (int g = 0; g < P.ngroups; ++g)
+      for (int a = 0; a < P.n_aloads[g]; ++a) max_taps = std::max(max_taps, (int)P.aloads[g][a].tap_count);
+    int tb = std::max(1, (16 * 1024) / P.b_tap_stride);
+    if (d->tune_flags & 8) tb = 1;
+    P.taps_per_slot = std::min(tb, max_taps);
+  }
+  P.b_slot_bytes = P.taps_per_slot * P.b_tap_stride;
   if (d->epi == ADB_EPI_FEATURE) {
     P.Cs = pick_chunk(P.BN);
     P.n_slabs = P.BN / P.Cs;
