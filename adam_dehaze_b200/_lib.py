@@ -56,7 +56,7 @@ SIGNATURES = {
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_attn_pool": [_P, _I, _I, _I, _I, _P, _I, _P, _P],
     "adb_attn_gate_stats": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P],
-    "adb_attn_apply": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
+    "adb_attn_apply": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
     "adb_maxpool3x3s2": [_P, _I, _I, _I, _I, _P, _I, _P],
     "adb_global_avgpool": [_P, _I, _I, _I, _I, _P, _P, _P],
     "adb_affine_relu": [_P, _L, _I, _I, _P, _P, _P, _I, _P],

@@ -250,57 +250,60 @@ __global__ void attn_stats_kernel(const __nv_bfloat16* __restrict__ x, int n, lo
   }
 }
 
-// pass 3: y = x * gate * sigmoid(conv7x7(stats)); the LP lanes of a pixel split the 98 stencil taps.
-template <int LP>
-__global__ void attn_apply_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, const int* n_dev,
-                                  int n_start, const float* __restrict__ gate, const float* __restrict__ stats,
-                                  const float* __restrict__ wsp, __nv_bfloat16* __restrict__ y) {
+// pass 3a: spatial gate map sp[n,h,w] = sigmoid(conv7x7(stats)) — a 2-channel stencil over 8 B/pixel, tiled through
+// shared memory (32x16 output pixels + 3-pixel halo per block) so every stats value is read from L2/HBM once.
+constexpr int kSpTW = 32, kSpTH = 16;
+__global__ void attn_spatial_kernel(const float* __restrict__ stats, int n, int h, int w, const int* n_dev, int n_start,
+                                    const float* __restrict__ wsp, float* __restrict__ sp) {
   __shared__ float s_w[98];
-  for (int i = threadIdx.x; i < 98; i += blockDim.x) s_w[i] = wsp[i];
+  __shared__ float2 s_t[kSpTH + 6][kSpTW + 6];
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int img = blockIdx.z;
+  if (img >= n_eff) return;
+  const int tid = threadIdx.y * kSpTW + threadIdx.x;
+  for (int i = tid; i < 98; i += kSpTW * kSpTH) s_w[i] = wsp[i];
+  const int x0 = blockIdx.x * kSpTW - 3, y0 = blockIdx.y * kSpTH - 3;
+  const float2* st = reinterpret_cast<const float2*>(stats) + (size_t)img * h * w;
+  for (int i = tid; i < (kSpTH + 6) * (kSpTW + 6); i += kSpTW * kSpTH) {
+    const int ty = i / (kSpTW + 6), tx = i - ty * (kSpTW + 6);
+    const int yy = y0 + ty, xx = x0 + tx;
+    s_t[ty][tx] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(st + (size_t)yy * w + xx) : make_float2(0.f, 0.f);
+  }
   __syncthreads();
+  const int px = blockIdx.x * kSpTW + threadIdx.x, py = blockIdx.y * kSpTH + threadIdx.y;
+  if (px >= w || py >= h) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const float2 v = s_t[threadIdx.y + dy][threadIdx.x + dx];
+      acc = fmaf(s_w[dy * 7 + dx], v.x, acc);          // channel 0: mean over channels
+      acc = fmaf(s_w[49 + dy * 7 + dx], v.y, acc);     // channel 1: max over channels
+    }
+  sp[((size_t)img * h + py) * w + px] = 1.f / (1.f + __expf(-acc));
+}
+
+// pass 3b: y = x * gate[c] * sp[pixel] — pure streaming, one 16-byte group per thread
+__global__ void attn_scale_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
+                                  int n_start, const float* __restrict__ gate, const float* __restrict__ sp,
+                                  __nv_bfloat16* __restrict__ y) {
   const int n_eff = live_images(n, n_dev, n_start);
   const int G = c / 8;
-  const int sub = threadIdx.x % LP;
-  const long long hw = (long long)h * w;
-  constexpr int PPW = 32 / LP;
-  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long stride = ((long long)gridDim.x * blockDim.x >> 5) * PPW;
-  const long long total = (long long)n_eff * hw;
-  for (long long pw = warp_id * PPW; pw < total; pw += stride) {
-    const long long p = pw + (threadIdx.x & 31) / LP;
-    const bool live = p < total;
-    float acc = 0.f;
-    int img = 0;
-    if (live) {
-      img = (int)(p / hw);
-      const int rem = (int)(p - (long long)img * hw);
-      const int py = rem / w, px = rem - py * w;
-      const float* st = stats + (size_t)img * hw * 2;
-      for (int t = sub; t < 98; t += LP) {
-        const int ch = t / 49, k = t - ch * 49;
-        const int dy = k / 7 - 3, dx = k - (k / 7) * 7 - 3;
-        const int yy = py + dy, xx = px + dx;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc = fmaf(s_w[t], __ldg(st + ((size_t)yy * w + xx) * 2 + ch), acc);
-      }
-    }
+  const long long total = (long long)n_eff * hw * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long p = t / G;
+    const int img = (int)(p / hw);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)p * c + g * 8)), f);
+    const float s = __ldg(sp + p);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c + g * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c + g * 8 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-    for (int o = LP / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (live) {
-      const float sp = 1.f / (1.f + __expf(-acc));
-      const __nv_bfloat16* pxp = x + (size_t)p * c;
-      __nv_bfloat16* pyp = y + (size_t)p * c;
-      const float* gt = gate + (size_t)img * c;
-      for (int g = sub; g < G; g += LP) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(pxp + g * 8)), f);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + g * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + g * 8 + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] = f[q] * gg[q] * sp;
-        *reinterpret_cast<uint4*>(pyp + g * 8) = pack8(f);
-      }
-    }
+    for (int q = 0; q < 8; ++q) f[q] = f[q] * gg[q] * s;
+    *reinterpret_cast<uint4*>(y + (size_t)p * c + g * 8) = pack8(f);
   }
 }
 
@@ -642,17 +645,16 @@ int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
 }
 
 int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
-                   const float* gate, const float* stats, const float* w_spatial, void* y, void* stream) {
-  ADB_REQUIRE(x && gate && stats && w_spatial && y && n > 0 && c % 8 == 0, "adb_attn_apply: bad arguments");
+                   const float* gate, const float* stats, const float* w_spatial, float* spatial, void* y, void* stream) {
+  ADB_REQUIRE(x && gate && stats && w_spatial && spatial && y && n > 0 && c % 8 == 0, "adb_attn_apply: bad arguments");
   const int sms = sm_count();
   if (!sms) return ADB_ERR_NO_DEVICE;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)n * h * w;
-  if (c / 8 <= 16) {
-    attn_apply_kernel<16><<<grid_for(total * 16, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, n_dev, n_start, gate, stats, w_spatial, reinterpret_cast<__nv_bfloat16*>(y));
-  } else {
-    attn_apply_kernel<32><<<grid_for(total * 32, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, n_dev, n_start, gate, stats, w_spatial, reinterpret_cast<__nv_bfloat16*>(y));
-  }
+  dim3 grid((w + kSpTW - 1) / kSpTW, (h + kSpTH - 1) / kSpTH, n), block(kSpTW, kSpTH);
+  attn_spatial_kernel<<<grid, block, 0, st>>>(stats, n, h, w, n_dev, n_start, w_spatial, spatial);
+  const long long total = (long long)n * h * w * (c / 8);
+  attn_scale_kernel<<<grid_for(total, 256, sms, 16), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, (long long)h * w, c,
+                                                                  n_dev, n_start, gate, spatial, reinterpret_cast<__nv_bfloat16*>(y));
   ADB_LAUNCH_OK();
   return ADB_OK;
 }

@@ -107,7 +107,8 @@ class BranchEngine:
 
     # ------------------------------------------------------------------ packing
     def specs(self):
-        if self.S is not None and not self._ver.stale():
+        stale = self._ver.stale()   # always evaluated: it records the signature the packed specs correspond to
+        if self.S is not None and not stale:
             return self.S
         m = self.model
         S = {}
@@ -306,7 +307,8 @@ class BlockEngine:
         self._spec = None
 
     def _get(self, build):
-        if self._spec is None or self._ver.stale():
+        stale = self._ver.stale()
+        if self._spec is None or stale:
             self._spec = build()
         return self._spec
 
@@ -343,7 +345,8 @@ class ResNetEngine:
         self.S = None
 
     def specs(self):
-        if self.S is not None and not self._ver.stale():
+        stale = self._ver.stale()   # always evaluated: it records the signature the packed specs correspond to
+        if self.S is not None and not stale:
             return self.S
         bb = self.clf.backbone
         S = {"stem": None, "layers": []}
@@ -422,7 +425,8 @@ class DenseNetEngine:
         return s, b
 
     def specs(self):
-        if self.S is not None and not self._ver.stale():
+        stale = self._ver.stale()   # always evaluated: it records the signature the packed specs correspond to
+        if self.S is not None and not stale:
             return self.S
         ft = self.clf.backbone.features
         S = {"stem": _stem7x7s2_spec(ft.conv0, ft.norm0), "blocks": [], "trans": []}

@@ -235,6 +235,7 @@ def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
         pool = scratch[("pool", nb, h, w, c)] = torch.empty(pool_scratch_floats(nb, h, w, c), dtype=torch.float32, device=dev)
     gate = scratch.setdefault(("gate", nb, c), torch.empty((nb, c), dtype=torch.float32, device=dev))
     stats = scratch.setdefault(("stats", nb, h, w), torch.empty((nb, h, w, 2), dtype=torch.float32, device=dev))
+    spatial = scratch.setdefault(("spatial", nb, h, w), torch.empty((nb, h, w), dtype=torch.float32, device=dev))
     if out is None:
         out = torch.empty_like(x)
     st = _lib.current_stream()
@@ -243,7 +244,7 @@ def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
     _lib.call("adb_attn_gate_stats", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(pool), _lib.ptr(ap.w1),
               _lib.ptr(ap.w2), ap.c_red, _lib.ptr(gate), _lib.ptr(stats), st)
     _lib.call("adb_attn_apply", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(gate), _lib.ptr(stats),
-              _lib.ptr(ap.wsp), _lib.ptr(out), st)
+              _lib.ptr(ap.wsp), _lib.ptr(spatial), _lib.ptr(out), st)
     return out
 
 

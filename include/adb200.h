@@ -131,7 +131,7 @@ ADB_API int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h
  *  1) pool:   sum_c, max_c over h*w per (image, channel)                        (avg_pool/max_pool, :64-66)
  *  2) gate:   gate = sigmoid(fc(avg)+fc(max)) (fc = w2*relu(w1*.)), then per pixel the channel mean and max of
  *             x*gate -> stats[n,h,w,2] fp32                                      (:66-73)
- *  3) apply:  y = x*gate*sigmoid(conv7x7(stats))                                 (:74-78)
+ *  3) apply:  spatial = sigmoid(conv7x7(stats)) (smem-tiled stencil, fp32 [n,h,w] scratch), y = x*gate*spatial (:74-78)
  * pool_buf: caller scratch of adb_pool_scratch_floats(n,h,w,c) floats; its first n*2*c floats end up holding
  * [n][2][c] (sum, max).  The reduction is deterministic (per-block partials folded in block order by the last block). */
 ADB_API int64_t adb_pool_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c);
@@ -141,7 +141,8 @@ ADB_API int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, 
                         const float* pool_buf, const float* w1 /*[c/r][c]*/, const float* w2 /*[c][c/r]*/, int32_t c_red,
                         float* gate /*[n][c]*/, float* stats /*[n,h,w,2]*/, void* stream);
 ADB_API int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
-                   const float* gate, const float* stats, const float* w_spatial /*[2][7][7]*/, void* y, void* stream);
+                   const float* gate, const float* stats, const float* w_spatial /*[2][7][7]*/, float* spatial /*[n,h,w]*/,
+                   void* y, void* stream);
 
 /* Pooling for the HDEN backbones (torchvision resnet/densenet called from models/classifier.py:24-36,91). */
 ADB_API int adb_maxpool3x3s2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, int32_t pitch_out, void* stream);
