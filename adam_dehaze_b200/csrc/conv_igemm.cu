@@ -59,6 +59,7 @@ struct ConvK {
   int grid_h, grid_w;      // extent of the pixel grid tiles cover (output H/W; input H/W for ConvTranspose phases)
   int TW, TH, MT;
   int tiles_w, tiles_h;
+  int ncta;                // 1, or 2 = CTA-pair mode (cluster of 2, tcgen05 cta_group::2): a tile spans both CTAs' sub-tiles
   // K walk
   int Ck, row_bytes;
   int chunks0, chunks1, pitch0, pitch1, ctot;
@@ -130,30 +131,36 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 #define ADB_DBG(role, idx) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 
 // One tap's MMAs as a straight-line UTCHMMA run: kKs K-steps of 16 (descriptor start address += 32 B each) for kMt sub-tiles.
-template <int kMt, int kKs>
+template <bool kPair, int kMt, int kKs>
 __device__ __forceinline__ void issue_mmas(uint32_t d0, uint32_t d1, uint64_t a0, uint64_t a1, uint64_t b0, uint32_t idesc,
                                            uint32_t first) {
 #pragma unroll
   for (int kk = 0; kk < kKs; ++kk) {
     const uint32_t accum = (first | (uint32_t)kk) ? 1u : 0u;
-    umma_bf16(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
-    if (kMt == 2) umma_bf16(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+    if (kPair) {
+      umma_bf16_pair(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+      if (kMt == 2) umma_bf16_pair(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+    } else {
+      umma_bf16(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+      if (kMt == 2) umma_bf16(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+    }
   }
 }
 
 struct TileCoord { int nt, g, w0, h0, img; };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t) {
+// `rank` = this CTA's rank in its pair (0 when ncta == 1): a pair's tile is two row-adjacent sub-tiles, one per CTA.
+__device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t, int rank) {
   TileCoord c;
   c.nt = t % P.n_tiles_n; t /= P.n_tiles_n;
   c.g = t % P.ngroups;    t /= P.ngroups;
   c.w0 = (t % P.tiles_w) * P.TW; t /= P.tiles_w;
-  c.h0 = (t % P.tiles_h) * (P.TH * P.MT);
+  c.h0 = ((t % P.tiles_h) * P.ncta + rank) * (P.TH * P.MT);
   c.img = t / P.tiles_h;
   return c;
 }
 
-template <int kAct>
+template <int kAct, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -181,6 +188,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA-pair mode: the two CTAs of a cluster walk the same tile sequence; rank 0 (the leader) issues the MMAs.
+  const int rank = kPair ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nunits = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // the leader's barrier block as a shared::cluster address (TMA complete_tx / remote arrives of the peer go there)
+  const uint32_t lead_bar_base = kPair ? mapa_shared(bar_base, 0) : bar_base;
+  auto fullA_lead = [&](int s) { return lead_bar_base + 8u * s; };
+  auto fullB_lead = [&](int s) { return lead_bar_base + 8u * (2 * kMaxASlots + s); };
+  auto tempty_lead = [&](int a) { return lead_bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 2 + a); };
 
   // live image count of this launch (routed buckets carry it on the device)
   int n_eff = P.n;
@@ -198,12 +215,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P.a_slots; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < P.b_slots; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPair ? 8 : 4); }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)P.tmem_cols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(smem_u32((const void*)tmem_ptr_smem), (uint32_t)P.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)P.tmem_cols);
+      tmem_relinquish();
+    }
   }
   if (warp >= kEpiWarp0) {
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.cout_pad; i += 128) {
@@ -212,7 +234,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -220,8 +242,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     // ======================================================= A producer: one halo box per (chunk, A load)
     int slot = 0; uint32_t phase = 0; int dbg_i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(P, t);
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = decode_tile(P, t, rank);
       const int nal = P.n_aloads[tc.g];
       for (int c = 0; c < nchunks; ++c) {
         const bool s1 = c >= P.chunks0;
@@ -233,9 +255,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_wait(emptyA(slot), phase ^ 1u, P.err_flag, 1);
           ADB_DBG(0, dbg_i); ++dbg_i;
           if (elect_one()) {
-            mbar_expect_tx(fullA(slot), (uint32_t)P.a_tx_bytes);
-            tma_load_5d(a_base + (uint32_t)slot * P.a_slot_bytes, tm, fullA(slot), al.c_mul * pitch + coff,
-                        tc.w0 + al.dw0, al.p, tc.h0 + al.dh0, tc.img);
+            if (kPair) {   // both CTAs' halo boxes are counted on the leader's barrier
+              if (leader) mbar_expect_tx(fullA(slot), 2u * (uint32_t)P.a_tx_bytes);
+              tma_load_5d_pair(a_base + (uint32_t)slot * P.a_slot_bytes, tm, fullA_lead(slot), al.c_mul * pitch + coff,
+                               tc.w0 + al.dw0, al.p, tc.h0 + al.dh0, tc.img);
+            } else {
+              mbar_expect_tx(fullA(slot), (uint32_t)P.a_tx_bytes);
+              tma_load_5d(a_base + (uint32_t)slot * P.a_slot_bytes, tm, fullA(slot), al.c_mul * pitch + coff,
+                          tc.w0 + al.dw0, al.p, tc.h0 + al.dh0, tc.img);
+            }
           }
           __syncwarp();
           if (++slot == P.a_slots) { slot = 0; phase ^= 1u; }
@@ -245,9 +273,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp == 3) {
     // ======================================================= B producer: one weight box per (chunk, tap)
     int slot = 0; uint32_t phase = 0; int dbg_i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(P, t);
-      const int brow = tc.g * P.cout_pad + tc.nt * P.BN;
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = decode_tile(P, t, rank);
+      const int brow = tc.g * P.cout_pad + tc.nt * P.BN + rank * (P.BN / P.ncta);   // pair: each CTA holds half of the N rows
       const int nal = P.n_aloads[tc.g];
       for (int c = 0; c < nchunks; ++c) {
         const int kc = (c >= P.chunks0 ? P.chunks0 * P.Ck + (c - P.chunks0) * P.Ck : c * P.Ck);   // channel offset in the concat
@@ -258,11 +286,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_wait(emptyB(slot), phase ^ 1u, P.err_flag, 5);
             ADB_DBG(1, dbg_i); ++dbg_i;
             if (elect_one()) {
-              mbar_expect_tx(fullB(slot), (uint32_t)(nt * P.b_tx_bytes));
+              if (kPair) { if (leader) mbar_expect_tx(fullB(slot), 2u * (uint32_t)(nt * P.b_tx_bytes)); }
+              else mbar_expect_tx(fullB(slot), (uint32_t)(nt * P.b_tx_bytes));
               for (int jj = 0; jj < nt; ++jj) {
                 const TapK tk = P.taps[tc.g][al.tap_begin + j0 + jj];
-                tma_load_2d(b_base + (uint32_t)slot * P.b_slot_bytes + (uint32_t)jj * P.b_tap_stride, &tmB, fullB(slot),
-                            tk.kidx * P.ctot + kc, brow);
+                const uint32_t dst = b_base + (uint32_t)slot * P.b_slot_bytes + (uint32_t)jj * P.b_tap_stride;
+                if (kPair) tma_load_2d_pair(dst, &tmB, fullB_lead(slot), tk.kidx * P.ctot + kc, brow);
+                else tma_load_2d(dst, &tmB, fullB(slot), tk.kidx * P.ctot + kc, brow);
               }
             }
             __syncwarp();
@@ -271,15 +301,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================================================= MMA issuer (whole warp waits, lane 0 issues)
+  } else if (warp == 1 && leader) {
+    // ======================================================= MMA issuer (whole warp waits, one elected lane issues; pair: leader CTA only)
     int sa = 0; uint32_t pa = 0;
     int sb = 0; uint32_t pb = 0;
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
     const int ksteps = P.Ck / 16;
     const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(P, t);
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = decode_tile(P, t, 0);
       const int nal = P.n_aloads[tc.g];
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, P.err_flag, 2);
       tc_fence_after();
@@ -307,18 +337,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 const uint32_t first = accumulate | (uint32_t)jj;
                 const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
                 if (P.MT == 2) {
-                  if (ksteps == 4) issue_mmas<2, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 2) issue_mmas<2, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else issue_mmas<2, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  if (ksteps == 4) issue_mmas<kPair, 2, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 2) issue_mmas<kPair, 2, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else issue_mmas<kPair, 2, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
                 } else {
-                  if (ksteps == 4) issue_mmas<1, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 2) issue_mmas<1, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else issue_mmas<1, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  if (ksteps == 4) issue_mmas<kPair, 1, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 2) issue_mmas<kPair, 1, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else issue_mmas<kPair, 1, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
                 }
               }
-              umma_commit(emptyB(sb));                                   // weight slot free once these MMAs have read it
-              if (last_of_a) umma_commit(emptyA(sa));                    // halo slot free after its last tap
-              if (c == nchunks - 1 && a == nal - 1 && last_of_a) umma_commit(tfull_bar(acc));
+              const bool tile_done = c == nchunks - 1 && a == nal - 1 && last_of_a;
+              if (kPair) {   // multicast commits: the slot / accumulator barriers of BOTH CTAs
+                umma_commit_pair(emptyB(sb));
+                if (last_of_a) umma_commit_pair(emptyA(sa));
+                if (tile_done) umma_commit_pair(tfull_bar(acc));
+              } else {
+                umma_commit(emptyB(sb));                                   // weight slot free once these MMAs have read it
+                if (last_of_a) umma_commit(emptyA(sa));                    // halo slot free after its last tap
+                if (tile_done) umma_commit(tfull_bar(acc));
+              }
             }
             __syncwarp();
             ADB_DBG(3, dbg_i); ++dbg_i;
@@ -337,8 +374,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int th_l = et / P.TW, tw_l = et % P.TW;
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
     int slab_buf = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(P, t);
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = decode_tile(P, t, rank);
       mbar_wait(tfull_bar(acc), acc_phase, P.err_flag, 4);
       tc_fence_after();
 
@@ -446,7 +483,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // accumulator stage fully read -> hand it back to the MMA issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty_lead(acc)); else mbar_arrive(tempty_bar(acc)); }
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -454,8 +491,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   // ---------------------------------------------------------- teardown
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  if (kPair) cluster_sync_all(); else __syncthreads();   // pair: neither CTA may retire while its peer can still signal it
+  if (warp == 2) { if (kPair) tmem_dealloc_pair(tmem_base, (uint32_t)P.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
 }
 
 inline int pick_chunk(int c) { return (c % 64 == 0) ? 64 : (c % 32 == 0) ? 32 : (c % 16 == 0) ? 16 : 0; }
@@ -540,16 +577,24 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   int mt = d->tune_mt > 0 ? d->tune_mt : (P.bn_cols <= 128 ? 2 : 1);
   ADB_REQUIRE(mt == 1 || mt == 2, "adb_conv2d: tune_mt must be 1 or 2");
   if (mt * P.bn_cols > 512) mt = 1;
-  if ((long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) < 2LL * 148 * mt) mt = 1;  // keep the SMs busy
+  const long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
+  if (sub_tiles < 2LL * 148 * mt) mt = 1;  // keep the SMs busy
   P.MT = mt;
+  // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA; worth it once the weights are a real share
+  // of the shared-memory traffic (N tile >= 48) and there are enough tiles to fill 74 pairs.  tune_flags bit 4 forces it
+  // on, bit 5 forces it off.
+  int ncta = (P.BN >= 48 && sub_tiles >= 4LL * 148 * mt) ? 2 : 1;
+  if (d->tune_flags & 16) ncta = 2;
+  if (d->tune_flags & 32) ncta = 1;
+  P.ncta = ncta;
   P.tiles_w = (P.grid_w + TW - 1) / TW;
-  P.tiles_h = (P.grid_h + P.TH * mt - 1) / (P.TH * mt);
+  P.tiles_h = (P.grid_h + P.TH * mt * ncta - 1) / (P.TH * mt * ncta);
   int acc = std::min(512 / (mt * P.bn_cols), 2);
   if (d->tune_acc_stages > 0) acc = std::min(acc, d->tune_acc_stages);
   ADB_REQUIRE(acc >= 1, "adb_conv2d: accumulators do not fit TMEM");
   P.acc_stages = acc;
   P.tmem_cols = pow2_at_least(acc * mt * P.bn_cols);
-  P.idesc = make_idesc_bf16(128, (uint32_t)P.BN);
+  P.idesc = make_idesc_bf16(128u * (uint32_t)P.ncta, (uint32_t)P.BN);
   P.desc_base_offset = (d->tune_flags & 2) ? 1 : 0;
 
   // ---- A loads: taps of one (c_mul, p) phase share a halo box when the 128-row views stay contiguous in it
@@ -600,7 +645,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
 
   // ---- smem
   P.a_tx_bytes = box_w * box_h * P.row_bytes;
-  P.b_tx_bytes = P.BN * P.row_bytes;
+  P.b_tx_bytes = (P.BN / P.ncta) * P.row_bytes;     // pair: each CTA loads (and holds) half of the N rows
   P.a_slot_bytes = round_up(P.a_tx_bytes, 1024);
   P.b_tap_stride = round_up(P.b_tx_bytes, 1024);
   {
@@ -732,7 +777,7 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)P.ngroups * d->cout_pad};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
-    uint32_t box[2] = {(uint32_t)P.Ck, (uint32_t)P.BN};
+    uint32_t box[2] = {(uint32_t)P.Ck, (uint32_t)(P.BN / P.ncta)};
     st = adbh::make_tmap_bf16(&tmB, d->w_packed, 2, dims, strides, box, P.row_bytes);
     if (st != ADB_OK) return st;
   }
@@ -749,19 +794,41 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   int smem = (int)L.total + 1024;
   smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvK);
-  KernelFn fn = conv_igemm_kernel<-1>;
+  const bool pair = P.ncta == 2;
+  KernelFn fn = pair ? conv_igemm_kernel<-1, true> : conv_igemm_kernel<-1, false>;
   int which = 2;
-  if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_RELU) { fn = conv_igemm_kernel<ADB_ACT_RELU>; which = 0; }
-  else if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_NONE) { fn = conv_igemm_kernel<ADB_ACT_NONE>; which = 1; }
-  static bool configured[3] = {false, false, false};
+  if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_RELU) { fn = pair ? conv_igemm_kernel<ADB_ACT_RELU, true> : conv_igemm_kernel<ADB_ACT_RELU, false>; which = 0; }
+  else if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_NONE) { fn = pair ? conv_igemm_kernel<ADB_ACT_NONE, true> : conv_igemm_kernel<ADB_ACT_NONE, false>; which = 1; }
+  which = which * 2 + (pair ? 1 : 0);
+  static bool configured[6] = {false, false, false, false, false, false};
+  static int max_pairs[6] = {0, 0, 0, 0, 0, 0};
   if (!configured[which]) {
     ADB_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
     configured[which] = true;
   }
   const long long max_tiles = (long long)d->n * P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
-  const int grid = (int)std::min<long long>(max_tiles, di.sm_count);
-  fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, tmOut, P);
-  ADB_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  if (pair) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_pairs[which] == 0) {   // how many CTA pairs the device can hold at once (each CTA owns a whole SM)
+      cfg.gridDim = dim3(2 * (di.sm_count / 2), 1, 1);
+      int nclusters = 0;
+      ADB_CUDA_OK(cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg));
+      ADB_REQUIRE(nclusters >= 1, "adb_conv2d: no CTA pair fits the device");
+      max_pairs[which] = std::min(nclusters, di.sm_count / 2);
+    }
+    cfg.gridDim = dim3(2 * (unsigned)std::min<long long>(max_tiles, max_pairs[which]), 1, 1);
+  } else {
+    cfg.gridDim = dim3((unsigned)std::min<long long>(max_tiles, di.sm_count), 1, 1);
+  }
+  ADB_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tmA0, tmA1, tmB, tmOut, P));
   return ADB_OK;
 }
 

@@ -86,6 +86,17 @@ CONV_CASES = [
     (64, 64, 3, 2, 64, 256, {"flags": 1}),   # one TMA box per tap (no halo), same shape
     (192, 192, 3, 1, 16, 256, None),
     (256, 256, 3, 1, 8, 128, {"mt": 2}),
+    # CTA-pair mode (cluster of 2, tcgen05 cta_group::2) forced on: flags bit 4
+    (64, 64, 3, 2, 64, 128, {"flags": 16}),
+    (64, 64, 3, 4, 128, 256, {"flags": 16}),          # many pair-tiles per cluster: ring / accumulator phase wrap
+    (96, 96, 3, 2, 64, 128, {"flags": 16, "mt": 2}),
+    (128, 128, 3, 1, 24, 40, {"flags": 16}),          # ragged: the peer's sub-tile partly / wholly outside the image
+    (192, 192, 3, 1, 16, 256, {"flags": 16}),
+    (256, 256, 3, 2, 16, 128, {"flags": 16}),
+    (384, 384, 3, 1, 16, 32, {"flags": 16}),          # two N tiles of 192
+    (64, 48, 3, 1, 32, 32, {"flags": 16}),            # N = 48: 24 weight rows per CTA
+    (64, 64, 3, 1, 6, 128, {"flags": 16, "mt": 1}),   # 3 pair-rows: odd row count
+    (512, 128, 1, 2, 16, 32, {"flags": 16}),          # 1x1 (DenseNet bottleneck shape)
 ]
 
 
@@ -104,14 +115,15 @@ def test_conv_s1(cin, cout, k, n, h, w, tune):
         assert y[..., cout:].float().abs().max().item() == 0.0
 
 
-def test_conv_bias_residual():
+@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
+def test_conv_bias_residual(tune):
     ops = _ops()
     x = _rand_fm(2, 64, 32, 48, 4)
     res = _rand_fm(2, 64, 32, 48, 5)
     wt = _rand_w((64, 64, 3, 3), 6, 576)
     bias = torch.randn(64, device="cuda") * 0.1
     spec = ops.ConvSpec.from_conv(wt, bias=bias, act=ops.ACT_RELU)
-    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), residual=ops.nchw_to_nhwc(res))
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), residual=ops.nchw_to_nhwc(res), tune=tune)
     ref = F.relu(F.conv2d(x, wt, bias, padding=1) + res)
     _close(ops.nhwc_to_nchw(y), ref)
 
@@ -127,42 +139,45 @@ def test_conv_activations(act):
     _close(ops.nhwc_to_nchw(y), fn(F.conv2d(x, wt, padding=1)))
 
 
+@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
 @pytest.mark.parametrize("cin,cout,k,pad,n,h,w", [(64, 128, 4, 1, 1, 32, 32), (96, 192, 4, 1, 2, 64, 64),
                                                   (64, 128, 3, 1, 1, 32, 64), (64, 128, 1, 0, 1, 32, 32)])
-def test_conv_s2(cin, cout, k, pad, n, h, w):
+def test_conv_s2(cin, cout, k, pad, n, h, w, tune):
     ops = _ops()
     x = _rand_fm(n, cin, h, w, 9)
     wt = _rand_w((cout, cin, k, k), 10, cin * k * k)
     bn = _bn(cout, 11)
     spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU, stride=2, pad=pad)
-    y = ops.conv2d(spec, ops.nchw_to_nhwc(x))
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), tune=tune)
     ref = F.relu(_bn_ref(F.conv2d(x, wt, stride=2, padding=pad), bn))
     assert y.shape[1:3] == ref.shape[2:]
     _close(ops.nhwc_to_nchw(y, cout), ref)
 
 
+@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
 @pytest.mark.parametrize("cin,cout,n,h,w", [(128, 64, 1, 16, 16), (384, 192, 1, 16, 32), (256, 64, 2, 32, 32)])
-def test_conv_transpose(cin, cout, n, h, w):
+def test_conv_transpose(cin, cout, n, h, w, tune):
     ops = _ops()
     x = _rand_fm(n, cin, h, w, 12)
     wt = _rand_w((cin, cout, 4, 4), 13, cin * 4)
     bias = torch.randn(cout, device="cuda") * 0.1
     bn = _bn(cout, 14)
     spec = ops.ConvSpec.from_convT(wt, bias=bias, bn=bn, act=ops.ACT_RELU)
-    y = ops.conv2d(spec, ops.nchw_to_nhwc(x))
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), tune=tune)
     ref = F.relu(_bn_ref(F.conv_transpose2d(x, wt, bias, stride=2, padding=1), bn))
     assert tuple(y.shape[1:3]) == (2 * h, 2 * w)
     _close(ops.nhwc_to_nchw(y, cout), ref)
 
 
+@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
 @pytest.mark.parametrize("c0,c1,cout", [(64, 64, 64), (96, 96, 96), (192, 192, 96)])
-def test_conv_concat_sources(c0, c1, cout):
+def test_conv_concat_sources(c0, c1, cout, tune):
     ops = _ops()
     a = _rand_fm(1, c0, 32, 32, 15)
     b = _rand_fm(1, c1, 32, 32, 16)
     wt = _rand_w((cout, c0 + c1, 3, 3), 17, (c0 + c1) * 9)
     spec = ops.ConvSpec.from_conv(wt, act=ops.ACT_RELU)
-    y = ops.conv2d(spec, ops.nchw_to_nhwc(a), ops.nchw_to_nhwc(b))
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(a), ops.nchw_to_nhwc(b), tune=tune)
     ref = F.relu(F.conv2d(torch.cat([a, b], 1), wt, padding=1))
     _close(ops.nhwc_to_nchw(y, cout), ref)
 
@@ -241,14 +256,15 @@ def test_image_epilogue(mode):
     assert out[untouched].abs().max().item() == 0.0
 
 
-def test_dynamic_bucket_count():
+@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
+def test_dynamic_bucket_count(tune):
     """n_dev < n: images beyond the live count are not touched (routed bucket without a host round-trip)."""
     ops = _ops()
     x = _rand_fm(4, 64, 16, 32, 29)
     wt = _rand_w((64, 64, 3, 3), 30, 576)
     n_dev = torch.tensor([5], dtype=torch.int32, device="cuda")   # bucket holds 5 images, this launch covers [3, 7)
     dst = torch.full((4, 16, 32, 64), 7.0, dtype=torch.bfloat16, device="cuda")
-    ops.conv2d(ops.ConvSpec.from_conv(wt), ops.nchw_to_nhwc(x), dst=dst, n_dev=n_dev, n_start=3)
+    ops.conv2d(ops.ConvSpec.from_conv(wt), ops.nchw_to_nhwc(x), dst=dst, n_dev=n_dev, n_start=3, tune=tune)
     ref = F.conv2d(x, wt, padding=1)
     _close(ops.nhwc_to_nchw(dst)[:2], ref[:2])
     assert (dst[2:].float() == 7.0).all()

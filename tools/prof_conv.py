@@ -75,7 +75,7 @@ def main():
         pass
     tunes = [None]
     if args.sweep:
-        tunes = [None, {"mt": 1}, {"mt": 2}, {"flags": 1}, {"flags": 1, "mt": 1}]
+        tunes = [{"flags": 32}, {"flags": 16}, {"flags": 16, "mt": 1}, {"flags": 16, "mt": 2}, {"flags": 32, "mt": 1}, {"flags": 32, "mt": 2}]
     for shape in SHAPES:
         if args.only and args.only not in shape[0]:
             continue
