@@ -574,19 +574,22 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   int TW = 128;
   while (TW > P.grid_w && TW > 8) TW >>= 1;
   P.TW = TW; P.TH = 128 / TW;
-  int mt = d->tune_mt > 0 ? d->tune_mt : (P.bn_cols <= 128 ? 2 : 1);
-  ADB_REQUIRE(mt == 1 || mt == 2, "adb_conv2d: tune_mt must be 1 or 2");
-  if (mt * P.bn_cols > 512) mt = 1;
   const long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
-  if (sub_tiles < 2LL * 148 * mt) mt = 1;  // keep the SMs busy
-  P.MT = mt;
-  // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA; worth it once the weights are a real share
-  // of the shared-memory traffic (N tile >= 48) and there are enough tiles to fill 74 pairs.  tune_flags bit 4 forces it
-  // on, bit 5 forces it off.
-  int ncta = (P.BN >= 48 && sub_tiles >= 4LL * 148 * mt) ? 2 : 1;
+  // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA (operand reads and TMA fill), which is what
+  // bounds the 1-CTA kernel.  Worth it once the weights are a real share of the shared-memory traffic
+  // (N tile >= 48, more than one tap) and there are enough tiles to fill 74 pairs for a few waves.
+  // tune_flags bit 4 forces it on, bit 5 forces it off.
+  int ncta = (P.BN >= 48 && P.ntaps > 1 && sub_tiles >= 8LL * 148) ? 2 : 1;
   if (d->tune_flags & 16) ncta = 2;
   if (d->tune_flags & 32) ncta = 1;
   P.ncta = ncta;
+  // sub-tiles per CTA: two share every weight box when their accumulators fit TMEM; measured (profiles/r1_pair_sweep.txt):
+  // pairs prefer MT = 2 even single-buffered (N = 192), except at N = 256 where double buffering wins.
+  int mt = d->tune_mt > 0 ? d->tune_mt : (ncta == 2 ? (P.bn_cols <= 192 ? 2 : 1) : (P.bn_cols <= 128 ? 2 : 1));
+  ADB_REQUIRE(mt == 1 || mt == 2, "adb_conv2d: tune_mt must be 1 or 2");
+  if (mt * P.bn_cols > 512) mt = 1;
+  if (sub_tiles < 2LL * 148 * mt * ncta) mt = 1;  // keep the SMs busy
+  P.MT = mt;
   P.tiles_w = (P.grid_w + TW - 1) / TW;
   P.tiles_h = (P.grid_h + P.TH * mt * ncta - 1) / (P.TH * mt * ncta);
   int acc = std::min(512 / (mt * P.bn_cols), 2);

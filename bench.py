@@ -90,7 +90,7 @@ def synth_batch_on_device(n, h, w, dev, seed):
 
 
 # --------------------------------------------------------------------------- CPU leg (oracle port of the reference path)
-def cpu_sample(hden, h=256, w=512, threads=None, repeats=1, warm=0):
+def cpu_sample(hden, h=512, w=1024, threads=None, repeats=1, warm=0):
     """One image per branch + HDEN on the three, fp32 on the host cores, through the oracle (a port of the reference
     arithmetic).  Returns (images/s scaled to 1024x2048, seconds per sample, description).  FLOPs are linear in pixels
     (SURVEY.md §8), so the rate at h x w is scaled by (h*w)/(1024*2048)."""
@@ -283,8 +283,9 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, desc = cpu_sample(args.hden, threads=os.cpu_count() or 1)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc, "seconds": sec}
+        v, sec, desc = cpu_sample(args.hden, threads=os.cpu_count() or 1, repeats=3, warm=1)   # ~10-15 s of host work
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + ", mean of 3 after 1 warm-up",
+               "seconds": sec}
 
     if rank == 0:
         mix = (TFLOP_PER_IMAGE["low"] + TFLOP_PER_IMAGE["medium"] + TFLOP_PER_IMAGE["high"]) / 3 + TFLOP_PER_IMAGE[args.hden]
