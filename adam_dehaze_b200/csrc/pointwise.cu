@@ -75,6 +75,62 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, const int* __restr
   }
 }
 
+// Tiled variant for the shapes the models use (compile-time geometry, so the tap index math is constant-divisor):
+// a block stages the 3-channel input footprint of PX consecutive output pixels of one output row in shared memory with
+// coalesced loads (every input element is read from global once per block), then writes the packed operand with
+// 16-byte stores in memory order (thread -> (pixel, channel group), group fastest).
+template <int KH, int KW, int STRIDE, int KP>
+__global__ void __launch_bounds__(256) stem_pack_tiled_kernel(const float* __restrict__ x, const int* __restrict__ index,
+                                                              const int* n_dev, int n_start, int n, int h, int w, int ho, int wo,
+                                                              int pad, __nv_bfloat16* __restrict__ out) {
+  constexpr int PX = STRIDE == 1 ? 128 : 64;
+  constexpr int COLS = (PX - 1) * STRIDE + KW;
+  constexpr int G = KP / 8;
+  constexpr int TAPS = KH * KW;
+  constexpr int SH = KH > 1 ? STRIDE : 1;
+  __shared__ float tile[3][KH][COLS];
+  const int ph = KH > 1 ? pad : 0;
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int segs = (wo + PX - 1) / PX;
+  const long long units = (long long)n_eff * ho * segs;
+  const size_t plane = (size_t)h * w;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const int seg = (int)(u % segs);
+    long long q = u / segs;
+    const int yo = (int)(q % ho);
+    const int i = (int)(q / ho);
+    const int pos = n_start + i;
+    const size_t row = index ? (size_t)index[pos] : (size_t)pos;
+    const float* xi = x + row * 3 * plane;
+    const int x0 = seg * PX;
+    const int xin0 = x0 * STRIDE - pad;
+    for (int e = threadIdx.x; e < 3 * KH * COLS; e += blockDim.x) {
+      const int col = e % COLS;
+      const int r = (e / COLS) % KH;
+      const int c = e / (COLS * KH);
+      const int yy = yo * SH + r - ph;
+      const int xx = xin0 + col;
+      tile[c][r][col] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + c * plane + (size_t)yy * w + xx) : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16* orow = out + (((size_t)i * ho + yo) * wo + x0) * KP;
+    const int npx = min(PX, wo - x0);
+    for (int t = threadIdx.x; t < npx * G; t += blockDim.x) {
+      const int g = t % G, p = t / G;
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = g * 8 + k;
+        const int tap = j / 3, c = j - 3 * tap;
+        const int r = tap / KW, s2 = tap - r * KW;
+        f[k] = tap < TAPS ? tile[c][r][p * STRIDE + s2] : 0.f;
+      }
+      *reinterpret_cast<uint4*>(orow + (size_t)t * 8) = pack8(f);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ layout converters
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int h, int w, int pitch,
                                     __nv_bfloat16* __restrict__ out) {
@@ -145,11 +201,23 @@ __global__ void attn_pool_kernel(const __nv_bfloat16* __restrict__ x, int n, lon
   const long long p1 = min(hw, p0 + pix_per_block);
   if (py < PY) {
     const __nv_bfloat16* base = x + (size_t)img * hw * c + g * 8;
-    for (long long p = p0 + py; p < p1; p += PY) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)p * c)), f);
+    // four independent 16-byte loads in flight per thread; the accumulation order over pixels is fixed (deterministic)
+    for (long long p = p0 + py; p < p1; p += 4LL * PY) {
+      uint4 v[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { s[q] += f[q]; m[q] = fmaxf(m[q], f[q]); }
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p + (long long)u * PY;
+        v[u] = pp < p1 ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)pp * c)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + (long long)u * PY < p1) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { s[q] += f[q]; m[q] = fmaxf(m[q], f[q]); }
+        }
+      }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -210,9 +278,10 @@ __global__ void attn_gate_kernel(const float* __restrict__ pool, int n, float in
   }
 }
 
-// pass 2: per pixel, mean and max over channels of x*gate.  LP lanes share a pixel (LP = 16 or 32), each lane owns
-// 16-byte channel groups l, l+LP, ...; a segmented shuffle tree finishes the reduction.
-template <int LP>
+// pass 2: per pixel, mean and max over channels of x*gate.  LP lanes share a pixel, each lane owns the 16-byte channel
+// groups sub, sub+LP, ... (at most ML of them, all loaded before any is used: ML independent loads in flight per lane);
+// a segmented shuffle tree finishes the reduction.
+template <int LP, int ML>
 __global__ void attn_stats_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
                                   int n_start, const float* __restrict__ gate, float* __restrict__ stats) {
   const int n_eff = live_images(n, n_dev, n_start);
@@ -231,14 +300,24 @@ __global__ void attn_stats_kernel(const __nv_bfloat16* __restrict__ x, int n, lo
       const int img = (int)(p / hw);
       const __nv_bfloat16* px = x + (size_t)p * c;
       const float* gt = gate + (size_t)img * c;
-      for (int g = sub; g < G; g += LP) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(px + g * 8)), f);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + g * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + g * 8 + 4));
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      uint4 v[ML];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const float v = f[q] * gg[q]; s += v; m = fmaxf(m, v); }
+      for (int k = 0; k < ML; ++k) {
+        const int g = sub + k * LP;
+        v[k] = g < G ? __ldg(reinterpret_cast<const uint4*>(px + g * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        const int g = sub + k * LP;
+        if (g < G) {
+          float f[8];
+          unpack8(v[k], f);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gt + g * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gt + g * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const float t = f[q] * gg[q]; s += t; m = fmaxf(m, t); }
+        }
       }
     }
 #pragma unroll
@@ -558,8 +637,22 @@ int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, in
   const int wo = (w + 2 * pad - kw) / stride + 1;
   const int ho = kh > 1 ? (h + 2 * pad - kh) / stride + 1 : h;
   const long long total = (long long)n * ho * wo * (kp / 8);
-  stem_pack_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
-      x, index, n_dev, n_start, n, h, w, ho, wo, kh, kw, pad, stride, kp, reinterpret_cast<__nv_bfloat16*>(out));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  cudaStream_t st = (cudaStream_t)stream;
+#define ADB_STEM_TILED(KH_, KW_, S_, KP_)                                                                                \
+  do {                                                                                                                   \
+    const int px = (S_) == 1 ? 128 : 64;                                                                                 \
+    const long long units = (long long)n * ho * ((wo + px - 1) / px);                                                    \
+    stem_pack_tiled_kernel<KH_, KW_, S_, KP_><<<(int)std::min<long long>(units, (long long)sms * 16), 256, 0, st>>>(     \
+        x, index, n_dev, n_start, n, h, w, ho, wo, pad, o);                                                              \
+    ADB_LAUNCH_OK();                                                                                                     \
+    return ADB_OK;                                                                                                       \
+  } while (0)
+  if (kh == 1 && stride == 1 && kw == 3 && kp == 16) ADB_STEM_TILED(1, 3, 1, 16);
+  if (kh == 1 && stride == 1 && kw == 7 && kp == 32) ADB_STEM_TILED(1, 7, 1, 32);
+  if (kh == 7 && stride == 2 && kw == 7 && kp == 160) ADB_STEM_TILED(7, 7, 2, 160);
+#undef ADB_STEM_TILED
+  stem_pack_kernel<<<grid_for(total, 256, sms, 16), 256, 0, st>>>(x, index, n_dev, n_start, n, h, w, ho, wo, kh, kw, pad, stride, kp, o);
   ADB_LAUNCH_OK();
   return ADB_OK;
 }
@@ -586,8 +679,10 @@ int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h, int32_
 
 static void pool_geometry(int n, int h, int w, int sms, long long* chunks, int* ppb) {
   const long long hw = (long long)h * w;
-  // enough blocks for ~4 waves over the SMs, at least 256 pixels each
-  long long ch = std::max<long long>(1, std::min<long long>((hw + 255) / 256, (4LL * sms + n - 1) / n));
+  // enough blocks to fill the device even when a single image of the launch is live (a routed bucket's live count is
+  // only known on the device), at least 256 pixels each; n is deliberately not used
+  (void)n;
+  long long ch = std::max<long long>(1, std::min<long long>((hw + 255) / 256, 2LL * sms));
   *ppb = (int)((hw + ch - 1) / ch);
   *chunks = (hw + *ppb - 1) / *ppb;
 }
@@ -635,11 +730,16 @@ int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   ADB_LAUNCH_OK();
   const int G = c / 8;
   const long long total = (long long)n * hw;
-  if (G <= 16) {
-    attn_stats_kernel<16><<<grid_for(total * 16, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, gate, stats);
-  } else {
-    attn_stats_kernel<32><<<grid_for(total * 32, 256, sms, 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, hw, c, n_dev, n_start, gate, stats);
-  }
+  ADB_REQUIRE(G <= 256, "adb_attn_gate_stats: channels %d > 2048", c);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+#define ADB_STATS(LP_, ML_) attn_stats_kernel<LP_, ML_><<<grid_for(total * (LP_), 256, sms, 8), 256, 0, st>>>(xb, n, hw, c, n_dev, n_start, gate, stats)
+  if (G <= 8) ADB_STATS(4, 2);
+  else if (G <= 16) ADB_STATS(8, 2);
+  else if (G <= 24) ADB_STATS(8, 3);
+  else if (G <= 48) ADB_STATS(8, 6);
+  else if (G <= 128) ADB_STATS(32, 4);
+  else ADB_STATS(32, 8);
+#undef ADB_STATS
   ADB_LAUNCH_OK();
   return ADB_OK;
 }

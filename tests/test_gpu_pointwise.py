@@ -127,3 +127,30 @@ def test_losses():
     (0.2 * ref).backward()
     assert torch.allclose(loss[0], ref.detach(), rtol=1e-5, atol=1e-6)
     assert torch.allclose(grad, logits.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("kh,kw,pad,stride,kp,h,w", [(1, 3, 1, 1, 16, 9, 300), (1, 7, 3, 1, 32, 5, 257), (7, 7, 3, 2, 160, 64, 160),
+                                                     (1, 5, 2, 1, 16, 8, 40)])   # last one: the generic (untiled) kernel
+def test_stem_pack_bit_exact(kh, kw, pad, stride, kp, h, w):
+    """adb_stem_pack against an unfold-based restatement (bf16 rounding of the same fp32 pixels -> bit-exact), with a
+    routed index list and a live count below n."""
+    import torch.nn.functional as F
+    from adam_dehaze_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    xb = torch.rand(5, 3, h, w, generator=g).cuda()
+    index = torch.tensor([3, 0, 4, 1], dtype=torch.int32, device="cuda")
+    n_dev = torch.tensor([3], dtype=torch.int32, device="cuda")
+    wo = (w + 2 * pad - kw) // stride + 1
+    ho = (h + 2 * pad - kh) // stride + 1 if kh > 1 else h
+    out = torch.full((4, ho, wo, kp), -1.0, dtype=torch.bfloat16, device="cuda")
+    ops.stem_pack(xb, kw, pad, kp, stride=stride, kh=kh, index=index, n_dev=n_dev, n=4, out=out)
+    xs = xb[index[:3].long()]
+    if kh == 1:
+        cols = F.unfold(xs, (1, kw), padding=(0, pad), stride=(1, stride))          # [n, 3*kw, h*wo], channel-major (c, s)
+        cols = cols.view(3, 3, 1, kw, ho, wo)
+    else:
+        cols = F.unfold(xs, (kh, kw), padding=pad, stride=stride).view(3, 3, kh, kw, ho, wo)
+    ref = cols.permute(0, 4, 5, 2, 3, 1).reshape(3, ho, wo, kh * kw * 3)             # j = (r*kw + s)*3 + c
+    assert torch.equal(out[:3, ..., :kh * kw * 3].float(), ref.to(torch.bfloat16).float())
+    assert out[:3, ..., kh * kw * 3:].float().abs().max().item() == 0.0
+    assert (out[3].float() == -1.0).all()
