@@ -75,59 +75,98 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, const int* __restr
   }
 }
 
-// Tiled variant for the shapes the models use (compile-time geometry, so the tap index math is constant-divisor):
-// a block stages the 3-channel input footprint of PX consecutive output pixels of one output row in shared memory with
-// coalesced loads (every input element is read from global once per block), then writes the packed operand with
-// 16-byte stores in memory order (thread -> (pixel, channel group), group fastest).
-template <int KH, int KW, int STRIDE, int KP>
+// Tiled variant for the shapes the models use.  All geometry is compile-time, so the tap index math folds to immediate
+// shared-memory offsets (the generic kernel above spends ~20 integer instructions per bf16 it writes and is
+// instruction-bound at ~0.25 of HBM speed).  Per unit (RO output rows x PX pixels of one image):
+//   1. stage the 3-channel input footprint in shared memory, coalesced, eight independent loads in flight per thread;
+//   2. thread = (pixel, part): build the pixel's channel groups of this part (compile-time taps) and park them in a
+//      padded shared tile (row stride KP*2+16 bytes: conflict-free 16-byte stores);
+//   3. copy the tile out in memory order with 16-byte stores (a warp writes 512 contiguous bytes).
+template <int KH, int KW, int STRIDE, int KP, int RO, int PARTS>
 __global__ void __launch_bounds__(256) stem_pack_tiled_kernel(const float* __restrict__ x, const int* __restrict__ index,
                                                               const int* n_dev, int n_start, int n, int h, int w, int ho, int wo,
                                                               int pad, __nv_bfloat16* __restrict__ out) {
   constexpr int PX = STRIDE == 1 ? 128 : 64;
   constexpr int COLS = (PX - 1) * STRIDE + KW;
   constexpr int G = KP / 8;
+  constexpr int GPP = G / PARTS;                  // groups per part
   constexpr int TAPS = KH * KW;
   constexpr int SH = KH > 1 ? STRIDE : 1;
-  __shared__ float tile[3][KH][COLS];
+  constexpr int TR = (RO - 1) * SH + KH;          // input rows staged per unit
+  constexpr int NE = 3 * TR * COLS;
+  constexpr int PIX = RO * PX;
+  constexpr int OSTRIDE = KP * 2 + 16;            // bytes per pixel in the padded output tile
+  static_assert(PIX * PARTS == 256 && G % PARTS == 0, "one thread per (pixel, part)");
+  __shared__ float tile[NE];                      // [3][TR][COLS]
+  __shared__ __align__(16) unsigned char otile[PIX * OSTRIDE];
   const int ph = KH > 1 ? pad : 0;
   const int n_eff = live_images(n, n_dev, n_start);
   const int segs = (wo + PX - 1) / PX;
-  const long long units = (long long)n_eff * ho * segs;
+  const int rgroups = (ho + RO - 1) / RO;
+  const long long units = (long long)n_eff * rgroups * segs;
   const size_t plane = (size_t)h * w;
+  const int pp = threadIdx.x % PIX, part = threadIdx.x / PIX;     // part is warp-uniform (PIX is a multiple of 32)
+  const int p = pp % PX, ro = pp / PX;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const int seg = (int)(u % segs);
     long long q = u / segs;
-    const int yo = (int)(q % ho);
-    const int i = (int)(q / ho);
+    const int yo0 = (int)(q % rgroups) * RO;
+    const int i = (int)(q / rgroups);
     const int pos = n_start + i;
     const size_t row = index ? (size_t)index[pos] : (size_t)pos;
     const float* xi = x + row * 3 * plane;
     const int x0 = seg * PX;
     const int xin0 = x0 * STRIDE - pad;
-    for (int e = threadIdx.x; e < 3 * KH * COLS; e += blockDim.x) {
-      const int col = e % COLS;
-      const int r = (e / COLS) % KH;
-      const int c = e / (COLS * KH);
-      const int yy = yo * SH + r - ph;
-      const int xx = xin0 + col;
-      tile[c][r][col] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + c * plane + (size_t)yy * w + xx) : 0.f;
-    }
-    __syncthreads();
-    __nv_bfloat16* orow = out + (((size_t)i * ho + yo) * wo + x0) * KP;
-    const int npx = min(PX, wo - x0);
-    for (int t = threadIdx.x; t < npx * G; t += blockDim.x) {
-      const int g = t % G, p = t / G;
-      float f[8];
+    const int yin0 = yo0 * SH - ph;
+    for (int e0 = threadIdx.x; e0 < NE; e0 += 256 * 8) {
+      float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int j = g * 8 + k;
-        const int tap = j / 3, c = j - 3 * tap;
-        const int r = tap / KW, s2 = tap - r * KW;
-        f[k] = tap < TAPS ? tile[c][r][p * STRIDE + s2] : 0.f;
+        const int e = e0 + k * 256;
+        const int col = e % COLS;
+        const int r = (e / COLS) % TR;
+        const int c = e / (COLS * TR);
+        const int yy = yin0 + r, xx = xin0 + col;
+        v[k] = (e < NE && yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + c * plane + (size_t)yy * w + xx) : 0.f;
       }
-      *reinterpret_cast<uint4*>(orow + (size_t)t * 8) = pack8(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + k * 256;
+        if (e < NE) tile[e] = v[k];
+      }
     }
     __syncthreads();
+    const float* tp = tile + ro * SH * COLS + p * STRIDE;
+#pragma unroll
+    for (int pt = 0; pt < PARTS; ++pt) {
+      if (part == pt) {
+#pragma unroll
+        for (int gg = 0; gg < GPP; ++gg) {
+          const int g = pt * GPP + gg;            // compile-time after unrolling
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int j = g * 8 + k;
+            const int tap = j / 3, c = j - 3 * tap;
+            const int r = tap / KW, s2 = tap - r * KW;
+            f[k] = tap < TAPS ? tp[(c * TR + r) * COLS + s2] : 0.f;
+          }
+          *reinterpret_cast<uint4*>(otile + pp * OSTRIDE + g * 16) = pack8(f);
+        }
+      }
+    }
+    __syncthreads();
+    const int npx = min(PX, wo - x0);
+    const int nro = min(RO, ho - yo0);
+    for (int t = threadIdx.x; t < nro * npx * G; t += 256) {
+      const int g = t % G;
+      const int q2 = t / G;
+      const int px = q2 % npx, rr = q2 / npx;
+      const uint4 val = *reinterpret_cast<const uint4*>(otile + (rr * PX + px) * OSTRIDE + g * 16);
+      *reinterpret_cast<uint4*>(out + ((((size_t)i * ho + yo0 + rr) * wo + x0 + px) * KP) + g * 8) = val;
+    }
+    // the next iteration's staging writes `tile` (last read before the barrier above) and its packing writes `otile`
+    // after another barrier, so no third barrier is needed here
   }
 }
 
@@ -639,18 +678,18 @@ int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, in
   const long long total = (long long)n * ho * wo * (kp / 8);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   cudaStream_t st = (cudaStream_t)stream;
-#define ADB_STEM_TILED(KH_, KW_, S_, KP_)                                                                                \
+#define ADB_STEM_TILED(KH_, KW_, S_, KP_, RO_, PARTS_)                                                                   \
   do {                                                                                                                   \
     const int px = (S_) == 1 ? 128 : 64;                                                                                 \
-    const long long units = (long long)n * ho * ((wo + px - 1) / px);                                                    \
-    stem_pack_tiled_kernel<KH_, KW_, S_, KP_><<<(int)std::min<long long>(units, (long long)sms * 16), 256, 0, st>>>(     \
+    const long long units = (long long)n * ((ho + (RO_) - 1) / (RO_)) * ((wo + px - 1) / px);                            \
+    stem_pack_tiled_kernel<KH_, KW_, S_, KP_, RO_, PARTS_><<<(int)std::min<long long>(units, (long long)sms * 16), 256, 0, st>>>( \
         x, index, n_dev, n_start, n, h, w, ho, wo, pad, o);                                                              \
     ADB_LAUNCH_OK();                                                                                                     \
     return ADB_OK;                                                                                                       \
   } while (0)
-  if (kh == 1 && stride == 1 && kw == 3 && kp == 16) ADB_STEM_TILED(1, 3, 1, 16);
-  if (kh == 1 && stride == 1 && kw == 7 && kp == 32) ADB_STEM_TILED(1, 7, 1, 32);
-  if (kh == 7 && stride == 2 && kw == 7 && kp == 160) ADB_STEM_TILED(7, 7, 2, 160);
+  if (kh == 1 && stride == 1 && kw == 3 && kp == 16) ADB_STEM_TILED(1, 3, 1, 16, 2, 1);
+  if (kh == 1 && stride == 1 && kw == 7 && kp == 32) ADB_STEM_TILED(1, 7, 1, 32, 2, 1);
+  if (kh == 7 && stride == 2 && kw == 7 && kp == 160) ADB_STEM_TILED(7, 7, 2, 160, 1, 4);
 #undef ADB_STEM_TILED
   stem_pack_kernel<<<grid_for(total, 256, sms, 16), 256, 0, st>>>(x, index, n_dev, n_start, n, h, w, ho, wo, kh, kw, pad, stride, kp, o);
   ADB_LAUNCH_OK();
@@ -734,8 +773,9 @@ int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t 
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
 #define ADB_STATS(LP_, ML_) attn_stats_kernel<LP_, ML_><<<grid_for(total * (LP_), 256, sms, 8), 256, 0, st>>>(xb, n, hw, c, n_dev, n_start, gate, stats)
   if (G <= 8) ADB_STATS(4, 2);
-  else if (G <= 16) ADB_STATS(8, 2);
-  else if (G <= 24) ADB_STATS(8, 3);
+  else if (G <= 12) ADB_STATS(4, 3);
+  else if (G <= 16) ADB_STATS(4, 4);
+  else if (G <= 24) ADB_STATS(4, 6);
   else if (G <= 48) ADB_STATS(8, 6);
   else if (G <= 128) ADB_STATS(32, 4);
   else ADB_STATS(32, 8);
