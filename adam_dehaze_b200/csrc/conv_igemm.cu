@@ -30,7 +30,7 @@ namespace {
 
 using namespace adb;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;         // 4 role warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;          // first epilogue warp
 constexpr int kMaxTaps = 16;
 constexpr int kMaxGroups = 4;
@@ -93,6 +93,7 @@ struct ConvK {
   const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
   int* err_flag;
   long long* dbg;   // optional timeline buffer (tune_flags bit 2): [6 roles][256 events] of clock64() from CTA 0
+  int dbg_detail;   // tune_flags bit 6: the buffer instead holds a flat sequence of epilogue sub-step stamps (warp 4, lane 0)
 };
 
 struct SmemLayout {
@@ -128,7 +129,9 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
   return apply_act(v, act_rt);
 }
 
-#define ADB_DBG(role, idx) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
+#define ADB_DBG(role, idx) do { if (P.dbg && !P.dbg_detail && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
+// epilogue sub-step stamp: tag in the top byte, clock below (flat sequence, warp 4 lane 0 of CTA 0)
+#define ADB_DBGE(tag) do { if (P.dbg && P.dbg_detail && blockIdx.x == 0 && ew == 0 && lane == 0 && e_i < 6 * 256) P.dbg[e_i++] = ((long long)(tag) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFLL); } while (0)
 
 // One tap's MMAs as a straight-line UTCHMMA run: kKs K-steps of 16 (descriptor start address += 32 B each) for kMt sub-tiles.
 template <bool kPair, int kMt, int kKs>
@@ -147,6 +150,59 @@ __device__ __forceinline__ void issue_mmas(uint32_t d0, uint32_t d1, uint64_t a0
   }
 }
 
+// Epilogue building blocks.  An epilogue warp handles "slabs": 32 tile rows x CS16*16 channels.  The residual row of the
+// NEXT slab is requested while the current one is computed, and all TMEM columns of a slab are requested before the
+// single tcgen05.wait::ld, so a slab exposes neither a global-load latency nor one TMEM round trip per 16 channels.
+template <int CS16>
+__device__ __forceinline__ void load_residual(const __nv_bfloat16* res_ptr, uint4 (&q)[CS16 * 2]) {
+  if (res_ptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(res_ptr);
+#pragma unroll
+    for (int i = 0; i < CS16 * 2; ++i) q[i] = __ldg(rp + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CS16 * 2; ++i) q[i] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// TMEM -> registers -> affine / residual / activation -> bf16 -> the warp's swizzled staging buffer (TMA-store source).
+template <int kAct, int CS16>
+__device__ __forceinline__ void compute_slab(uint32_t taddr, const uint4 (&q)[CS16 * 2], const float* sc_ptr,
+                                             const float* sh_ptr, uint32_t sbuf, int lane, int act_rt) {
+  constexpr uint32_t span = CS16 * 32;
+  float v[CS16 * 16];
+#pragma unroll
+  for (int c = 0; c < CS16; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v + c * 16);
+  tmem_ld_wait();
+#pragma unroll
+  for (int c16 = 0; c16 < CS16; ++c16) {
+    const float4* sc4 = reinterpret_cast<const float4*>(sc_ptr + c16 * 16);
+    const float4* sh4 = reinterpret_cast<const float4*>(sh_ptr + c16 * 16);
+    float sc[16], sh[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 a = sc4[i], b = sh4[i];
+      sc[4 * i] = a.x; sc[4 * i + 1] = a.y; sc[4 * i + 2] = a.z; sc[4 * i + 3] = a.w;
+      sh[4 * i] = b.x; sh[4 * i + 1] = b.y; sh[4 * i + 2] = b.z; sh[4 * i + 3] = b.w;
+    }
+    const uint4 q0 = q[2 * c16], q1 = q[2 * c16 + 1];
+    const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
+      const float y0 = act_t<kAct>(fmaf(v[c16 * 16 + 2 * i], sc[2 * i], sh[2 * i]) + __low2float(b2), act_rt);
+      const float y1 = act_t<kAct>(fmaf(v[c16 * 16 + 2 * i + 1], sc[2 * i + 1], sh[2 * i + 1]) + __high2float(b2), act_rt);
+      pk[i] = pack_bf16x2(y0, y1);
+    }
+    const uint32_t row_off = (uint32_t)lane * span + (uint32_t)c16 * 32u;
+    const uint32_t a0 = sbuf + swizzle_addr(row_off, span);
+    const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, span);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+  }
+}
+
 struct TileCoord { int nt, g, w0, h0, img; };
 
 // `rank` = this CTA's rank in its pair (0 when ncta == 1): a pair's tile is two row-adjacent sub-tiles, one per CTA.
@@ -160,7 +216,53 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t, int rank
   return c;
 }
 
-template <int kAct, bool kPair>
+// FEATURE epilogue of one tile for one epilogue warp.  The tile's work items are its (sub-tile, slab) pairs in order; the two
+// warps that share a TMEM lane quarter (`half` 0 / 1) take alternate items.  Each warp owns one staging buffer and one
+// TMA-store bulk group stream; no cross-warp barrier anywhere.
+template <int kAct, int CS16>
+__device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* tmOut, const TileCoord& tc, uint32_t tfull,
+                                             uint32_t tfull_phase, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
+                                             const float* s_shift, int ew, int half, int lane) {
+  constexpr int Cs = CS16 * 16;
+  const int items = P.MT * P.n_slabs;
+  const int ch0 = tc.nt * P.BN;                        // first output channel of this N tile
+  const int row = ew * 32 + lane;                      // tile row == TMEM lane
+  const int th_l = row / P.TW, tw_l = row % P.TW;
+  const int q_row0 = ew * 32;                          // first tile row of this warp
+  const int q_th = q_row0 / P.TW, q_tw = q_row0 % P.TW;
+  auto res_ptr = [&](int j) -> const __nv_bfloat16* {
+    if (!P.residual || j >= items) return nullptr;
+    const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
+    const int h = tc.h0 + mt * P.TH + th_l, w = tc.w0 + tw_l;
+    if (h >= P.grid_h || w >= P.grid_w) return nullptr;
+    return P.residual + (((size_t)tc.img * P.grid_h + h) * P.grid_w + w) * P.res_pitch + ch0 + sl * Cs;
+  };
+  uint4 qn[CS16 * 2];
+  load_residual<CS16>(res_ptr(half), qn);              // does not depend on the accumulator: overlaps this tile's main loop
+  mbar_wait(tfull, tfull_phase, P.err_flag, 4);
+  tc_fence_after();
+#pragma unroll 1
+  for (int j = half; j < items; j += 2) {
+    uint4 q[CS16 * 2];
+#pragma unroll
+    for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i];
+    load_residual<CS16>(res_ptr(j + 2), qn);           // next item's residual rides under this item's arithmetic
+    const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
+    const int cl = sl * Cs;                            // channel offset of the slab inside the N tile
+    // this warp's previous TMA store must have finished reading the staging buffer
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+    compute_slab<kAct, CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), q, s_scale + ch0 + cl, s_shift + ch0 + cl, sbuf, lane, P.act);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
+      tma_store_5d(tmOut, sbuf, P.out_c_off[tc.g] + ch0 + cl, tc.w0 + q_tw, P.out_p[tc.g], tc.h0 + mt * P.TH + q_th, tc.img);
+      tma_store_commit();
+    }
+  }
+}
+
+template <int kAct, bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -215,7 +317,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P.a_slots; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < P.b_slots; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPair ? 8 : 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPair ? 16 : 8); }   // 8 epilogue warps per CTA
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -228,7 +330,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   }
   if (warp >= kEpiWarp0) {
-    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.cout_pad; i += 128) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.cout_pad; i += 256) {
       s_scale[i] = P.scale[i];
       s_shift[i] = P.shift[i];
     }
@@ -368,119 +470,81 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================================================= epilogue (128 threads, thread = pixel row)
-    const int et = threadIdx.x - kEpiWarp0 * 32;        // 0..127 == TMEM lane == tile row
-    const int ew = warp - kEpiWarp0;                    // TMEM sub-partition of this warp
+    // ======================================================= epilogue (8 warps; thread = pixel row of the tile)
+    // Warps 4-7 and 8-11 both cover the four TMEM lane quarters (a warp may only read lanes 32*(warp%4)..+31); the two
+    // warps of a quarter split the tile's work items, which doubles the instruction throughput of an otherwise
+    // latency-bound single-warp-per-scheduler epilogue.
+    const int ewi = warp - kEpiWarp0;                   // 0..7
+    const int ew = ewi & 3;                             // TMEM lane quarter
+    const int half = ewi >> 2;                          // which alternate work items of a tile this warp takes
+    const int et = ew * 32 + lane;                      // 0..127 == TMEM lane == tile row
     const int th_l = et / P.TW, tw_l = et % P.TW;
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
-    int slab_buf = 0;
+    const uint32_t sbuf = slab_base + (uint32_t)ewi * (uint32_t)(P.slab_bytes >> 2);   // this warp's staging buffer
+    float dotw[16];
+    if (kEpi == ADB_EPI_DOT) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dotw[i] = __ldg(P.dot_w + i);
+    }
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, rank);
-      mbar_wait(tfull_bar(acc), acc_phase, P.err_flag, 4);
-      tc_fence_after();
-
-      const int ch0 = tc.nt * P.BN;   // first output channel of this N tile
-      for (int mt = 0; mt < P.MT; ++mt) {
+      const uint32_t tmem_tile = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * P.MT * P.bn_cols);
+      if (kEpi == ADB_EPI_FEATURE) {
+        if (P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
+        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
+        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
+        if (ewi == 0) { ADB_DBG(4, dbg_i); }
+      } else {
+        // DOT / IMAGE: one work item per sub-tile; `half` takes sub-tile `half`
+        const int mt = half;
         const int h = tc.h0 + mt * P.TH + th_l;
         const int w = tc.w0 + tw_l;
-        const bool inb = (h < P.grid_h) && (w < P.grid_w);
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((acc * P.MT + mt) * P.bn_cols);
-        if (P.epi == ADB_EPI_FEATURE) {
-          // Each epilogue warp owns 32 tile rows end to end: TMEM -> registers -> affine/residual/activation -> its own
-          // swizzled staging quarter -> its own TMA store.  No cross-warp barrier anywhere in the epilogue.
-          const size_t pix = ((size_t)tc.img * P.grid_h + h) * P.grid_w + w;
-          const __nv_bfloat16* res_row = (P.residual && inb) ? P.residual + pix * P.res_pitch + ch0 : nullptr;
-          const int c16_per_slab = P.Cs / 16;
-          const uint32_t span = (uint32_t)(P.Cs * 2);
-          const int q_row0 = ew * 32;                       // first tile row of this warp
-          const int q_th = q_row0 / P.TW, q_tw = q_row0 % P.TW;
-          for (int sl = 0; sl < P.n_slabs; ++sl) {
-            const uint32_t sbuf = slab_base + (uint32_t)(slab_buf * 4 + ew) * (uint32_t)(P.slab_bytes >> 2);
-            // the TMA store of this warp that last read this quarter must have drained
-            if (lane == 0) { if (P.n_slab_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-            __syncwarp();
-            if (ew == 0) { ADB_DBG(4, dbg_i); }
-            for (int c16 = 0; c16 < c16_per_slab; ++c16) {
-              const int cl = sl * P.Cs + c16 * 16;   // channel offset inside the N tile
-              float v[16];
-              tmem_ld16(taddr + (uint32_t)cl, v);
-              uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-              if (res_row) {
-                const uint4* rp = reinterpret_cast<const uint4*>(res_row + cl);
-                q0 = __ldg(rp); q1 = __ldg(rp + 1);
-              }
-              const float4* sc4 = reinterpret_cast<const float4*>(s_scale + ch0 + cl);
-              const float4* sh4 = reinterpret_cast<const float4*>(s_shift + ch0 + cl);
-              float sc[16], sh[16];
+        const bool inb = mt < P.MT && (h < P.grid_h) && (w < P.grid_w);
+        // IMAGE: the hazy pixels / guidance this thread combines with its accumulator row do not depend on the MMAs: fetch
+        // them before waiting for the accumulator so their latency hides under this tile's main loop.
+        float xin[3] = {0.f, 0.f, 0.f};
+        float gd = 1.f, alpha = 0.f;
+        size_t img_o = 0;
+        const size_t plane = (size_t)P.grid_h * P.grid_w;
+        if (kEpi == ADB_EPI_IMAGE && inb) {
+          const int pos = P.n_start + tc.img;
+          const size_t row = P.img_index ? (size_t)__ldg(P.img_index + pos) : (size_t)pos;
+          if (P.img_mode == ADB_IMG_BLEND) alpha = __ldg(P.img_alpha);
+          img_o = row * 3 * plane + (size_t)h * P.grid_w + w;
+          if (P.img_mode == ADB_IMG_GUIDED) gd = __ldg(P.img_guidance + ((size_t)tc.img * P.grid_h + h) * P.grid_w + w);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 a = sc4[i], b = sh4[i];
-                sc[4 * i] = a.x; sc[4 * i + 1] = a.y; sc[4 * i + 2] = a.z; sc[4 * i + 3] = a.w;
-                sh[4 * i] = b.x; sh[4 * i + 1] = b.y; sh[4 * i + 2] = b.z; sh[4 * i + 3] = b.w;
-              }
-              const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-              tmem_ld_wait();
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
-                const float y0 = act_t<kAct>(fmaf(v[2 * i], sc[2 * i], sh[2 * i]) + __low2float(b2), P.act);
-                const float y1 = act_t<kAct>(fmaf(v[2 * i + 1], sc[2 * i + 1], sh[2 * i + 1]) + __high2float(b2), P.act);
-                pk[i] = pack_bf16x2(y0, y1);
-              }
-              const uint32_t row_off = (uint32_t)lane * span + (uint32_t)c16 * 32u;
-              const uint32_t a0 = sbuf + swizzle_addr(row_off, span);
-              const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, span);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-            }
-            if (ew == 0) { ADB_DBG(5, dbg_i); ++dbg_i; }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
-              tma_store_5d(&tmOut, sbuf, P.out_c_off[tc.g] + ch0 + sl * P.Cs, tc.w0 + q_tw, P.out_p[tc.g],
-                           tc.h0 + mt * P.TH + q_th, tc.img);
-              tma_store_commit();
-            }
-            if (++slab_buf == P.n_slab_bufs) slab_buf = 0;
-          }
-        } else if (P.epi == ADB_EPI_DOT) {
+          for (int c = 0; c < 3; ++c) xin[c] = __ldg(P.img_x + img_o + c * plane);
+        }
+        mbar_wait(tfull_bar(acc), acc_phase, P.err_flag, 4);
+        tc_fence_after();
+        if (ewi == 0) { ADB_DBG(4, dbg_i); }
+        if (mt < P.MT) {
           float v[16];
-          tmem_ld16(taddr, v);
+          tmem_ld16(tmem_tile + (uint32_t)(mt * P.bn_cols), v);
           tmem_ld_wait();
-          float g = P.dot_b;
+          if (kEpi == ADB_EPI_DOT) {
+            float g = P.dot_b;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float y = apply_act(fmaf(v[i], s_scale[i], s_shift[i]), P.act);
-            g = fmaf(y, __ldg(P.dot_w + i), g);
-          }
-          g = 1.f / (1.f + __expf(-g));
-          if (inb) P.dot_out[((size_t)tc.img * P.grid_h + h) * P.grid_w + w] = g;
-        } else {  // ADB_EPI_IMAGE
-          float v[16];
-          tmem_ld16(taddr, v);
-          tmem_ld_wait();
-          if (inb) {
-            const int pos = P.n_start + tc.img;
-            const size_t row = P.img_index ? (size_t)P.img_index[pos] : (size_t)pos;
-            const size_t plane = (size_t)P.grid_h * P.grid_w;
-            const size_t o = row * 3 * plane + (size_t)h * P.grid_w + w;
-            float gd = 1.f, alpha = 0.f;
-            if (P.img_mode == ADB_IMG_GUIDED) gd = P.img_guidance[((size_t)tc.img * P.grid_h + h) * P.grid_w + w];
-            if (P.img_mode == ADB_IMG_BLEND) alpha = __ldg(P.img_alpha);
+            for (int i = 0; i < 16; ++i) {
+              float y = apply_act(fmaf(v[i], s_scale[i], s_shift[i]), P.act);
+              g = fmaf(y, dotw[i], g);
+            }
+            g = 1.f / (1.f + __expf(-g));
+            if (inb) P.dot_out[((size_t)tc.img * P.grid_h + h) * P.grid_w + w] = g;
+          } else if (inb) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const float y = apply_act(fmaf(v[c], s_scale[c], s_shift[c]), P.act);
-              const float x = __ldg(P.img_x + o + c * plane);
               float out;
-              if (P.img_mode == ADB_IMG_BLEND) out = (1.f - alpha) * x + alpha * y;
-              else out = fminf(fmaxf(x + y * gd, 0.f), 1.f);
-              P.img_out[o + c * plane] = out;
+              if (P.img_mode == ADB_IMG_BLEND) out = (1.f - alpha) * xin[c] + alpha * y;
+              else out = fminf(fmaxf(xin[c] + y * gd, 0.f), 1.f);
+              P.img_out[img_o + c * plane] = out;
             }
           }
         }
       }
-      // accumulator stage fully read -> hand it back to the MMA issuer
+      // accumulator stage fully read by this warp -> hand it back to the MMA issuer (8 arrivals per CTA complete the phase)
+      if (ewi == 0) { ADB_DBG(5, dbg_i); ++dbg_i; }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty_lead(acc)); else mbar_arrive(tempty_bar(acc)); }
@@ -673,21 +737,24 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   int st = adbh::device_info(&di);
   if (st != ADB_OK) return st;
   const int budget = di.max_smem_optin - 1024;  // alignment slack
-  // weights ring first (>= 3 boxes), then up to 4 halo slots, then the rest back to the weights ring; the output staging
-  // ring drops from 2 slabs to 1 when that buys the third weight box.
+  // Output staging: one buffer of 32 rows x Cs channels per epilogue warp (8 warps = 2 slabs).  Weights ring first
+  // (>= 3 boxes), then up to 4 halo slots, then the rest back to the weights ring; the slab narrows from 64 to 32 channels
+  // when that buys the third weight box.
+  P.n_slab_bufs = 2;
   int a_slots = 2, b_slots = 0;
-  for (int bufs = 2; bufs >= 1; --bufs) {
-    P.n_slab_bufs = bufs;
-    const SmemLayout fixed = smem_layout(0, 0, 0, 0, P.slab_bytes, bufs, P.cout_pad);
+  for (int pass = 0; pass < 2; ++pass) {
+    const SmemLayout fixed = smem_layout(0, 0, 0, 0, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
     const int avail = budget - (int)fixed.total;
     a_slots = 2;
     b_slots = (avail - a_slots * P.a_slot_bytes) / P.b_slot_bytes;
-    if (b_slots >= 3 || bufs == 1) {
+    const bool can_narrow = pass == 0 && d->epi == ADB_EPI_FEATURE && P.Cs == 64;
+    if (b_slots >= 3 || !can_narrow) {
       ADB_REQUIRE(b_slots >= 2, "adb_conv2d: pipeline does not fit shared memory (A %d B, B %d B)", P.a_slot_bytes, P.b_slot_bytes);
       while (a_slots < 4 && (a_slots + 1) * P.a_slot_bytes + 4 * P.b_slot_bytes <= avail) ++a_slots;
       b_slots = std::min(kMaxBSlots, (avail - a_slots * P.a_slot_bytes) / P.b_slot_bytes);
       break;
     }
+    P.Cs = 32; P.n_slabs = P.BN / 32; P.slab_bytes = 128 * 32 * 2;
   }
   if (d->tune_stages > 0) { a_slots = std::min(a_slots, std::max(2, d->tune_stages)); b_slots = std::min(b_slots, std::max(2, d->tune_stages)); }
   P.a_slots = a_slots; P.b_slots = b_slots;
@@ -761,10 +828,11 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   if (st != ADB_OK) return st;
   if (di.cc_major != 10) return adbh::fail(ADB_ERR_NO_DEVICE, "adb_conv2d: device sm_%d%d is not sm_100", di.cc_major, di.cc_minor);
   P.err_flag = adbh::kernel_err_flag();
-  if (d->tune_flags & 4) {
+  if (d->tune_flags & (4 | 64)) {
     if (!g_dbg) ADB_CUDA_OK(cudaMalloc(&g_dbg, 6 * 256 * sizeof(long long)));
     ADB_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 6 * 256 * sizeof(long long), (cudaStream_t)stream));
     P.dbg = g_dbg;
+    P.dbg_detail = (d->tune_flags & 64) ? 1 : 0;
   }
 
   alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
@@ -798,13 +866,26 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvK);
   const bool pair = P.ncta == 2;
-  KernelFn fn = pair ? conv_igemm_kernel<-1, true> : conv_igemm_kernel<-1, false>;
-  int which = 2;
-  if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_RELU) { fn = pair ? conv_igemm_kernel<ADB_ACT_RELU, true> : conv_igemm_kernel<ADB_ACT_RELU, false>; which = 0; }
-  else if (d->epi == ADB_EPI_FEATURE && d->act == ADB_ACT_NONE) { fn = pair ? conv_igemm_kernel<ADB_ACT_NONE, true> : conv_igemm_kernel<ADB_ACT_NONE, false>; which = 1; }
-  which = which * 2 + (pair ? 1 : 0);
-  static bool configured[6] = {false, false, false, false, false, false};
-  static int max_pairs[6] = {0, 0, 0, 0, 0, 0};
+  KernelFn fn = nullptr;
+  int which = 0;
+  if (d->epi == ADB_EPI_FEATURE) {
+    const int a = d->act == ADB_ACT_RELU ? 0 : (d->act == ADB_ACT_NONE ? 1 : 2);
+    which = a * 2 + (pair ? 1 : 0);
+    switch (which) {
+      case 0: fn = conv_igemm_kernel<ADB_ACT_RELU, false, ADB_EPI_FEATURE>; break;
+      case 1: fn = conv_igemm_kernel<ADB_ACT_RELU, true, ADB_EPI_FEATURE>; break;
+      case 2: fn = conv_igemm_kernel<ADB_ACT_NONE, false, ADB_EPI_FEATURE>; break;
+      case 3: fn = conv_igemm_kernel<ADB_ACT_NONE, true, ADB_EPI_FEATURE>; break;
+      case 4: fn = conv_igemm_kernel<-1, false, ADB_EPI_FEATURE>; break;
+      default: fn = conv_igemm_kernel<-1, true, ADB_EPI_FEATURE>; break;
+    }
+  } else {
+    ADB_REQUIRE(!pair, "adb_conv2d: the DOT / IMAGE epilogues run in 1-CTA mode only");
+    if (d->epi == ADB_EPI_DOT) { fn = conv_igemm_kernel<-1, false, ADB_EPI_DOT>; which = 6; }
+    else { fn = conv_igemm_kernel<-1, false, ADB_EPI_IMAGE>; which = 7; }
+  }
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  static int max_pairs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (!configured[which]) {
     ADB_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
     configured[which] = true;

@@ -29,6 +29,13 @@ SHAPES = [
     ("cpx_down_192_384", "s2", (192,), 384, 4, 4, 512, 1024),
     ("cpx_up_384_192", "t", (384,), 192, 4, 8, 256, 512),
     ("cpx_up_cat_384_96", "t", (192, 192), 96, 4, 4, 512, 1024),
+    ("med_out_32_3_img", "img", (32,), 3, 3, 2, 1024, 2048),
+    ("cpx_out_48_3_img", "img", (48,), 3, 3, 2, 1024, 2048),
+    ("cpx_det_16_16_dot", "dot", (16,), 16, 3, 2, 1024, 2048),
+    ("cpx_stem_7x1_32_96", "stem7", (32,), 96, 7, 2, 1024, 2048),
+    ("light_stem_3x1_16_32", "stem3", (16,), 32, 3, 2, 1024, 2048),
+    ("med_64_3x3_res", "res", (64,), 64, 3, 2, 1024, 2048),
+    ("cpx_192_3x3_res", "res", (192,), 192, 3, 4, 512, 1024),
     ("dense_1x1_512_128", "s1", (512,), 128, 1, 8, 128, 256),
     ("dense_3x3_128_32", "s1", (128,), 32, 3, 8, 128, 256),
 ]
@@ -40,22 +47,41 @@ def run(shape, tune, reps):
     g = torch.Generator(device=dev).manual_seed(0)
     srcs = [torch.randn((n, h, w, c), generator=g, device=dev).to(torch.bfloat16) for c in cins]
     cin = sum(cins)
+    kwargs = {}
     if kind == "t":
         wt = torch.randn((cin, cout, 4, 4), generator=g, device=dev) / (cin * 4) ** 0.5
         spec = ops.ConvSpec.from_convT(wt, act=ops.ACT_RELU)
         flops = 2.0 * n * h * w * 16 * cin * cout
+    elif kind in ("stem7", "stem3"):
+        kk = 7 if kind == "stem7" else 3
+        wt = torch.randn((cout, 3, kk, kk), generator=g, device=dev) / (3 * kk * kk) ** 0.5
+        spec = ops.ConvSpec.from_stem(wt, cin, act=ops.ACT_RELU)
+        flops = 2.0 * n * h * w * kk * kk * 3 * cout
     else:
         wt = torch.randn((cout, cin, k, k), generator=g, device=dev) / (cin * k * k) ** 0.5
-        spec = ops.ConvSpec.from_conv(wt, act=ops.ACT_RELU, stride=2 if kind == "s2" else 1, pad=(1 if kind == "s2" else k // 2))
+        act = ops.ACT_TANH if kind == "img" else ops.ACT_RELU
+        spec = ops.ConvSpec.from_conv(wt, act=act, stride=2 if kind == "s2" else 1, pad=(1 if kind == "s2" else k // 2))
         oh, ow = (h // 2, w // 2) if kind == "s2" else (h, w)
         flops = 2.0 * n * oh * ow * k * k * cin * cout
+        if kind == "img":
+            xb = torch.rand((n, 3, h, w), device=dev)
+            kwargs = dict(epi=ops.EPI_IMAGE, image=dict(mode=ops.IMG_RESIDUAL, x=xb, out=torch.empty_like(xb),
+                                                        index=torch.arange(n, dtype=torch.int32, device=dev)))
+        elif kind == "dot":
+            kwargs = dict(epi=ops.EPI_DOT, dot=(torch.randn(16, device=dev), 0.1, torch.empty((n, h, w), device=dev)))
+        elif kind == "res":
+            kwargs = dict(residual=torch.randn((n, h, w, cout), generator=g, device=dev).to(torch.bfloat16))
     src1 = srcs[1] if len(srcs) > 1 else None
-    dst = ops.conv2d(spec, srcs[0], src1, tune=tune)
+    if kwargs.get("epi") is None:
+        dst = ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
+        kwargs["dst"] = dst
+    else:
+        ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        ops.conv2d(spec, srcs[0], src1, dst=dst, tune=tune)
+        ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
