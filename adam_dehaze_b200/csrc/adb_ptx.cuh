@@ -145,8 +145,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Relaxed arrives: used where the data hand-off is ordered by other means (TMEM reads by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync).  A release arrive compiles to MEMBAR + ERRBAR, which also waits for every global
+// load the thread has in flight (the epilogue's prefetched residual rows) - thousands of cycles per tile.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are counted on the mbarrier
 // `bar` given as a shared::cluster address (the leader CTA's barrier).

@@ -40,6 +40,22 @@ constexpr int kMaxALoads = 16;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 12;
 
+// Division by a launch constant as one multiply-high (tile decode runs once per tile in every role's loop).
+// q = umulhi(n, floor(2^32/d) + 1) is exact for n * d < 2^32 (checked on the host against the tile count).
+struct FastDiv {
+  uint32_t d, mul;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.mul = d <= 1 ? 0u : (uint32_t)(((unsigned long long)1 << 32) / (unsigned long long)d) + 1u;
+  return f;
+}
+__device__ __forceinline__ void fast_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = f.d == 1 ? n : __umulhi(n, f.mul);
+  r = n - q * f.d;
+}
+
 struct ALoad {          // one halo box per (group, phase): coordinates relative to the tile origin
   int16_t c_mul;        // channel coordinate = c_mul * channel_pitch(src) + chunk*Ck   (space-to-depth column phase)
   int8_t p;             // row-phase coordinate
@@ -59,6 +75,8 @@ struct ConvK {
   int grid_h, grid_w;      // extent of the pixel grid tiles cover (output H/W; input H/W for ConvTranspose phases)
   int TW, TH, MT;
   int tiles_w, tiles_h;
+  FastDiv fd_nt, fd_g, fd_tw, fd_th;   // decode_tile divisors: n_tiles_n, ngroups, tiles_w, tiles_h
+  int tw_shift;            // log2(TW)
   int ncta;                // 1, or 2 = CTA-pair mode (cluster of 2, tcgen05 cta_group::2): a tile spans both CTAs' sub-tiles
   // K walk
   int Ck, row_bytes;
@@ -131,7 +149,7 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 
 #define ADB_DBG(role, idx) do { if (P.dbg && !P.dbg_detail && blockIdx.x == 0 && lane == 0 && (idx) < 256) P.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 // epilogue sub-step stamp: tag in the top byte, clock below (flat sequence, warp 4 lane 0 of CTA 0)
-#define ADB_DBGE(tag) do { if (P.dbg && P.dbg_detail && blockIdx.x == 0 && ew == 0 && lane == 0 && e_i < 6 * 256) P.dbg[e_i++] = ((long long)(tag) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFLL); } while (0)
+#define ADB_DBGE(tag) do { if (P.dbg && P.dbg_detail && blockIdx.x == 0 && ew == 0 && half == 0 && lane == 0 && e_i < 6 * 256) P.dbg[e_i++] = ((long long)(tag) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFLL); } while (0)
 
 // One tap's MMAs as a straight-line UTCHMMA run: kKs K-steps of 16 (descriptor start address += 32 B each) for kMt sub-tiles.
 template <bool kPair, int kMt, int kKs>
@@ -150,29 +168,55 @@ __device__ __forceinline__ void issue_mmas(uint32_t d0, uint32_t d1, uint64_t a0
   }
 }
 
+struct TileCoord { int nt, g, w0, h0, img; };
+
 // Epilogue building blocks.  An epilogue warp handles "slabs": 32 tile rows x CS16*16 channels.  The residual row of the
 // NEXT slab is requested while the current one is computed, and all TMEM columns of a slab are requested before the
 // single tcgen05.wait::ld, so a slab exposes neither a global-load latency nor one TMEM round trip per 16 channels.
 template <int CS16>
-__device__ __forceinline__ void load_residual(const __nv_bfloat16* res_ptr, uint4 (&q)[CS16 * 2]) {
-  if (res_ptr) {
-    const uint4* rp = reinterpret_cast<const uint4*>(res_ptr);
+__device__ __forceinline__ void load_residual(const ConvK& P, const TileCoord& tc, int j, int items, int ew, int lane,
+                                              uint4 (&q)[CS16 * 2]) {
+  constexpr int CPR = CS16 * 2;                      // 16-byte chunks per slab row
+  constexpr int Cs = CS16 * 16;
+  if (!P.residual || j >= items) return;             // (q is not read when there is no residual)
+  const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
+  const int ch = tc.nt * P.BN + sl * Cs + (lane % CPR) * 8;
 #pragma unroll
-    for (int i = 0; i < CS16 * 2; ++i) q[i] = __ldg(rp + i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < CS16 * 2; ++i) q[i] = make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < CPR; ++i) {
+    const int row = ew * 32 + i * (32 / CPR) + lane / CPR;          // tile row this lane fetches in load i
+    const int h = tc.h0 + mt * P.TH + (row >> P.tw_shift), w = tc.w0 + (row & (P.TW - 1));
+    q[i] = (h < P.grid_h && w < P.grid_w)
+               ? __ldg(reinterpret_cast<const uint4*>(P.residual + (((size_t)tc.img * P.grid_h + h) * P.grid_w + w) * P.res_pitch + ch))
+               : make_uint4(0, 0, 0, 0);
   }
 }
 
 // TMEM -> registers -> affine / residual / activation -> bf16 -> the warp's swizzled staging buffer (TMA-store source).
 template <int kAct, int CS16>
-__device__ __forceinline__ void compute_slab(uint32_t taddr, const uint4 (&q)[CS16 * 2], const float* sc_ptr,
+__device__ __forceinline__ void compute_slab(uint32_t taddr, uint4 (&q)[CS16 * 2], bool has_res, const float* sc_ptr,
                                              const float* sh_ptr, uint32_t sbuf, int lane, int act_rt) {
   constexpr uint32_t span = CS16 * 32;
+  constexpr int CPR = CS16 * 2;                      // 16-byte chunks per slab row
   float v[CS16 * 16];
 #pragma unroll
   for (int c = 0; c < CS16; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v + c * 16);
+  if (has_res) {
+    // q holds the residual lane-transposed (load i, lane l = row i*(32/CPR) + l/CPR, chunk l%CPR: coalesced global
+    // reads).  Bounce it through the (free) staging buffer so every lane ends up with its own row.
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const uint32_t r = (uint32_t)(i * (32 / CPR) + lane / CPR), c = (uint32_t)(lane % CPR);
+      const uint32_t a = sbuf + swizzle_addr(r * span + c * 16u, span);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const uint32_t a = sbuf + swizzle_addr((uint32_t)lane * span + (uint32_t)i * 16u, span);
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w) : "r"(a) : "memory");
+    }
+    __syncwarp();
+  }
   tmem_ld_wait();
 #pragma unroll
   for (int c16 = 0; c16 < CS16; ++c16) {
@@ -203,16 +247,16 @@ __device__ __forceinline__ void compute_slab(uint32_t taddr, const uint4 (&q)[CS
   }
 }
 
-struct TileCoord { int nt, g, w0, h0, img; };
 
 // `rank` = this CTA's rank in its pair (0 when ncta == 1): a pair's tile is two row-adjacent sub-tiles, one per CTA.
 __device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t, int rank) {
   TileCoord c;
-  c.nt = t % P.n_tiles_n; t /= P.n_tiles_n;
-  c.g = t % P.ngroups;    t /= P.ngroups;
-  c.w0 = (t % P.tiles_w) * P.TW; t /= P.tiles_w;
-  c.h0 = ((t % P.tiles_h) * P.ncta + rank) * (P.TH * P.MT);
-  c.img = t / P.tiles_h;
+  uint32_t q = (uint32_t)t, r;
+  fast_divmod(q, P.fd_nt, q, r); c.nt = (int)r;
+  fast_divmod(q, P.fd_g, q, r);  c.g = (int)r;
+  fast_divmod(q, P.fd_tw, q, r); c.w0 = (int)r * P.TW;
+  fast_divmod(q, P.fd_th, q, r); c.h0 = ((int)r * P.ncta + rank) * (P.TH * P.MT);
+  c.img = (int)q;
   return c;
 }
 
@@ -222,43 +266,43 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t, int rank
 template <int kAct, int CS16>
 __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* tmOut, const TileCoord& tc, uint32_t tfull,
                                              uint32_t tfull_phase, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
-                                             const float* s_shift, int ew, int half, int lane) {
+                                             const float* s_shift, int ew, int half, int lane, int& e_i) {
   constexpr int Cs = CS16 * 16;
   const int items = P.MT * P.n_slabs;
   const int ch0 = tc.nt * P.BN;                        // first output channel of this N tile
-  const int row = ew * 32 + lane;                      // tile row == TMEM lane
-  const int th_l = row / P.TW, tw_l = row % P.TW;
   const int q_row0 = ew * 32;                          // first tile row of this warp
-  const int q_th = q_row0 / P.TW, q_tw = q_row0 % P.TW;
-  auto res_ptr = [&](int j) -> const __nv_bfloat16* {
-    if (!P.residual || j >= items) return nullptr;
-    const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
-    const int h = tc.h0 + mt * P.TH + th_l, w = tc.w0 + tw_l;
-    if (h >= P.grid_h || w >= P.grid_w) return nullptr;
-    return P.residual + (((size_t)tc.img * P.grid_h + h) * P.grid_w + w) * P.res_pitch + ch0 + sl * Cs;
-  };
+  const int q_th = q_row0 >> P.tw_shift, q_tw = q_row0 & (P.TW - 1);
+  const bool has_res = P.residual != nullptr;
   uint4 qn[CS16 * 2];
-  load_residual<CS16>(res_ptr(half), qn);              // does not depend on the accumulator: overlaps this tile's main loop
+#pragma unroll
+  for (int i = 0; i < CS16 * 2; ++i) qn[i] = make_uint4(0, 0, 0, 0);
+  ADB_DBGE(1);
+  load_residual<CS16>(P, tc, half, items, ew, lane, qn);   // independent of the accumulator: overlaps this tile's main loop
   mbar_wait(tfull, tfull_phase, P.err_flag, 4);
   tc_fence_after();
+  ADB_DBGE(2);
 #pragma unroll 1
   for (int j = half; j < items; j += 2) {
     uint4 q[CS16 * 2];
 #pragma unroll
     for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i];
-    load_residual<CS16>(res_ptr(j + 2), qn);           // next item's residual rides under this item's arithmetic
+    load_residual<CS16>(P, tc, j + 2, items, ew, lane, qn);   // next item's residual rides under this item's arithmetic
     const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
     const int cl = sl * Cs;                            // channel offset of the slab inside the N tile
     // this warp's previous TMA store must have finished reading the staging buffer
     if (lane == 0) tma_store_wait_read<0>();
     __syncwarp();
-    compute_slab<kAct, CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), q, s_scale + ch0 + cl, s_shift + ch0 + cl, sbuf, lane, P.act);
+    ADB_DBGE(3);
+    compute_slab<kAct, CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), q, has_res, s_scale + ch0 + cl, s_shift + ch0 + cl, sbuf, lane, P.act);
+    ADB_DBGE(4);
     fence_proxy_async_smem();
     __syncwarp();
+    ADB_DBGE(5);
     if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
       tma_store_5d(tmOut, sbuf, P.out_c_off[tc.g] + ch0 + cl, tc.w0 + q_tw, P.out_p[tc.g], tc.h0 + mt * P.TH + q_th, tc.img);
       tma_store_commit();
     }
+    ADB_DBGE(6);
   }
 }
 
@@ -478,8 +522,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int ew = ewi & 3;                             // TMEM lane quarter
     const int half = ewi >> 2;                          // which alternate work items of a tile this warp takes
     const int et = ew * 32 + lane;                      // 0..127 == TMEM lane == tile row
-    const int th_l = et / P.TW, tw_l = et % P.TW;
-    int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
+    const int th_l = et >> P.tw_shift, tw_l = et & (P.TW - 1);
+    int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0; int e_i = 0;
     const uint32_t sbuf = slab_base + (uint32_t)ewi * (uint32_t)(P.slab_bytes >> 2);   // this warp's staging buffer
     float dotw[16];
     if (kEpi == ADB_EPI_DOT) {
@@ -488,11 +532,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, rank);
+      ADB_DBGE(12);
       const uint32_t tmem_tile = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * P.MT * P.bn_cols);
       if (kEpi == ADB_EPI_FEATURE) {
-        if (P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
-        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
-        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane);
+        if (P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
+        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
+        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
         if (ewi == 0) { ADB_DBG(4, dbg_i); }
       } else {
         // DOT / IMAGE: one work item per sub-tile; `half` takes sub-tile `half`
@@ -545,9 +590,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       // accumulator stage fully read by this warp -> hand it back to the MMA issuer (8 arrivals per CTA complete the phase)
       if (ewi == 0) { ADB_DBG(5, dbg_i); ++dbg_i; }
+      ADB_DBGE(9);
       tc_fence_before();
+      ADB_DBGE(10);
       __syncwarp();
-      if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty_lead(acc)); else mbar_arrive(tempty_bar(acc)); }
+      if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty_lead(acc)); else mbar_arrive_relaxed(tempty_bar(acc)); }
+      ADB_DBGE(11);
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -641,9 +689,9 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   const long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
   // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA (operand reads and TMA fill), which is what
   // bounds the 1-CTA kernel.  Worth it once the weights are a real share of the shared-memory traffic
-  // (N tile >= 48, more than one tap) and there are enough tiles to fill 74 pairs for a few waves.
+  // (N tile >= 48, or >= 32 with a deep K; more than one tap) and there are enough tiles to fill 74 pairs for a few waves.
   // tune_flags bit 4 forces it on, bit 5 forces it off.
-  int ncta = (P.BN >= 48 && P.ntaps > 1 && sub_tiles >= 8LL * 148) ? 2 : 1;
+  int ncta = ((P.BN >= 48 || (P.BN >= 32 && P.ctot >= 128)) && P.ntaps > 1 && sub_tiles >= 8LL * 148) ? 2 : 1;
   if (d->tune_flags & 16) ncta = 2;
   if (d->tune_flags & 32) ncta = 1;
   P.ncta = ncta;
@@ -656,6 +704,15 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   P.MT = mt;
   P.tiles_w = (P.grid_w + TW - 1) / TW;
   P.tiles_h = (P.grid_h + P.TH * mt * ncta - 1) / (P.TH * mt * ncta);
+  P.fd_nt = make_fastdiv(P.n_tiles_n); P.fd_g = make_fastdiv(P.ngroups);
+  P.fd_tw = make_fastdiv(P.tiles_w); P.fd_th = make_fastdiv(P.tiles_h);
+  {
+    const unsigned long long all_tiles = (unsigned long long)d->n * P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
+    const unsigned long long dmax = (unsigned long long)std::max(std::max(P.tiles_w, P.tiles_h), 4);
+    ADB_REQUIRE(all_tiles * dmax < (1ULL << 32), "adb_conv2d: %llu tiles exceed the tile-decode range; split the batch", all_tiles);
+  }
+  P.tw_shift = 0;
+  while ((1 << P.tw_shift) < TW) ++P.tw_shift;
   int acc = std::min(512 / (mt * P.bn_cols), 2);
   if (d->tune_acc_stages > 0) acc = std::min(acc, d->tune_acc_stages);
   ADB_REQUIRE(acc >= 1, "adb_conv2d: accumulators do not fit TMEM");

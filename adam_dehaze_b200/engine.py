@@ -378,7 +378,7 @@ class ResNetEngine:
         S = self.specs()
         # bound the activation footprint: the stem operand is 320 B per stem-output pixel
         per_img = (h // 2) * (w // 2) * (320 + 2 * 128) + (h // 4) * (w // 4) * 3 * 128
-        chunk = chunk or max(1, min(b, (8 << 30) // max(1, per_img)))
+        chunk = chunk or max(1, min(b, (24 << 30) // max(1, per_img)))
         feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
         for s in range(0, b, chunk):
             n = min(chunk, b - s)
@@ -456,7 +456,7 @@ class DenseNetEngine:
             raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
         S = self.specs()
         per_img = (h // 2) * (w // 2) * (320 + 128) + (h // 4) * (w // 4) * 2 * (256 + 256 + 128)
-        chunk = chunk or max(1, min(b, (8 << 30) // max(1, per_img)))
+        chunk = chunk or max(1, min(b, (24 << 30) // max(1, per_img)))
         feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
         dev = x.device
         for s in range(0, b, chunk):

@@ -36,6 +36,10 @@ SHAPES = [
     ("light_stem_3x1_16_32", "stem3", (16,), 32, 3, 2, 1024, 2048),
     ("med_64_3x3_res", "res", (64,), 64, 3, 2, 1024, 2048),
     ("cpx_192_3x3_res", "res", (192,), 192, 3, 4, 512, 1024),
+    ("med_64_3x3_resin", "resin", (64,), 64, 3, 2, 1024, 2048),
+    ("cpx_192_3x3_resin", "resin", (192,), 192, 3, 4, 512, 1024),
+    ("med_64_3x3_resdst", "resdst", (64,), 64, 3, 2, 1024, 2048),
+    ("cpx_192_3x3_resdst", "resdst", (192,), 192, 3, 4, 512, 1024),
     ("dense_1x1_512_128", "s1", (512,), 128, 1, 8, 128, 256),
     ("dense_3x3_128_32", "s1", (128,), 32, 3, 8, 128, 256),
 ]
@@ -71,10 +75,15 @@ def run(shape, tune, reps):
             kwargs = dict(epi=ops.EPI_DOT, dot=(torch.randn(16, device=dev), 0.1, torch.empty((n, h, w), device=dev)))
         elif kind == "res":
             kwargs = dict(residual=torch.randn((n, h, w, cout), generator=g, device=dev).to(torch.bfloat16))
+        elif kind == "resin":      # residual = the conv's own input (L2-hot rows): separates DRAM traffic from access cost
+            kwargs = dict(residual=srcs[0])
+        elif kind == "resdst":     # in place, like ResidualBlock.conv2 in the engine: dst == residual
+            r = torch.randn((n, h, w, cout), generator=g, device=dev).to(torch.bfloat16)
+            kwargs = dict(residual=r, dst=r)
     src1 = srcs[1] if len(srcs) > 1 else None
     if kwargs.get("epi") is None:
         dst = ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
-        kwargs["dst"] = dst
+        kwargs.setdefault("dst", dst)
     else:
         ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
     torch.cuda.synchronize()
