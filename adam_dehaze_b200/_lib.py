@@ -61,6 +61,8 @@ SIGNATURES = {
     "adb_global_avgpool": [_P, _I, _I, _I, _I, _P, _P, _P],
     "adb_affine_relu": [_P, _L, _I, _I, _P, _P, _P, _I, _P],
     "adb_avgpool2x2": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "adb_maxpool_kxk": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "adb_upsample_bilinear": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P],
     "adb_head_mlp": [_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
     "adb_linear": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "adb_route": [_P, _P, _I, _I, _P, _P, _P, _P, _P],

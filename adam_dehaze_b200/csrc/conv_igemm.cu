@@ -525,10 +525,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int th_l = et >> P.tw_shift, tw_l = et & (P.TW - 1);
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0; int e_i = 0;
     const uint32_t sbuf = slab_base + (uint32_t)ewi * (uint32_t)(P.slab_bytes >> 2);   // this warp's staging buffer
-    float dotw[16];
+    float dotw[32];                                     // DOT: the 1x1 head's weights over the (<= 32) conv channels
     if (kEpi == ADB_EPI_DOT) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dotw[i] = __ldg(P.dot_w + i);
+      for (int i = 0; i < 32; ++i) dotw[i] = i < P.BN ? __ldg(P.dot_w + i) : 0.f;
     }
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, rank);
@@ -573,6 +573,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             for (int i = 0; i < 16; ++i) {
               float y = apply_act(fmaf(v[i], s_scale[i], s_shift[i]), P.act);
               g = fmaf(y, dotw[i], g);
+            }
+            if (P.BN > 16) {                            // second 16-column group (24- / 32-channel heads)
+              tmem_ld16(tmem_tile + (uint32_t)(mt * P.bn_cols + 16), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float y = apply_act(fmaf(v[i], s_scale[16 + i], s_shift[16 + i]), P.act);
+                g = fmaf(y, dotw[16 + i], g);
+              }
             }
             g = 1.f / (1.f + __expf(-g));
             if (inb) P.dot_out[((size_t)tc.img * P.grid_h + h) * P.grid_w + w] = g;
@@ -787,7 +796,8 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
     P.n_slabs = P.BN / P.Cs;
     P.slab_bytes = 128 * P.Cs * 2;
   } else {
-    ADB_REQUIRE(P.BN == 16 && P.n_tiles_n == 1, "adb_conv2d: DOT/IMAGE epilogues need cout_pad == 16");
+    ADB_REQUIRE((P.BN == 16 || (d->epi == ADB_EPI_DOT && P.BN == 32)) && P.n_tiles_n == 1,
+                "adb_conv2d: the IMAGE epilogue needs cout_pad == 16, the DOT epilogue cout_pad 16 or 32 (got %d)", P.BN);
     P.Cs = 16; P.n_slabs = 0; P.slab_bytes = 1024;
   }
   adbh::DeviceInfo di;

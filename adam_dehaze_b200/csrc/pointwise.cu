@@ -455,6 +455,74 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int n, 
   }
 }
 
+// k x k / stride k max pool (nn.MaxPool2d(k, k): medium_intensity.py:144,149; high_intensity.py:164,167), NHWC bf16.
+// One thread per (output pixel, 8-channel group): k*k independent 16-byte loads, coalesced along channels.
+template <int K>
+__global__ void maxpool_kxk_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, const int* n_dev,
+                                   int n_start, __nv_bfloat16* __restrict__ y) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int G = c / 8, ho = h / K, wo = w / K;
+  const long long total = (long long)n_eff * ho * wo * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int i = (int)(p / ho);
+    uint4 v[K * K];
+#pragma unroll
+    for (int r = 0; r < K; ++r)
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+        v[r * K + q] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)i * h + yo * K + r) * w + xo * K + q) * c + g * 8));
+    float m[8];
+    unpack8(v[0], m);
+#pragma unroll
+    for (int k = 1; k < K * K; ++k) {
+      float f[8];
+      unpack8(v[k], f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * c + g * 8) = pack8(m);
+  }
+}
+
+// nn.UpsamplingBilinear2d(scale_factor=S) == interpolate(mode='bilinear', align_corners=True) (medium_intensity.py:146,151;
+// high_intensity.py:171,173), NHWC bf16 -> channels [c_off, c_off+c) of a [n, h*S, w*S, pitch] buffer (so the multi-scale
+// concat of COrunInspiredModel is never materialised).  Source index arithmetic as in ATen: src = dst * (in-1)/(out-1) in
+// fp32, i0 = (int)src, lambda = src - i0, i1 = i0 + (i0 < in-1).
+__global__ void upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int scale,
+                                         const int* n_dev, int n_start, __nv_bfloat16* __restrict__ y, int pitch, int c_off) {
+  const int n_eff = live_images(n, n_dev, n_start);
+  const int G = c / 8, ho = h * scale, wo = w * scale;
+  const float rh = ho > 1 ? (float)(h - 1) / (float)(ho - 1) : 0.f;
+  const float rw = wo > 1 ? (float)(w - 1) / (float)(wo - 1) : 0.f;
+  const long long total = (long long)n_eff * ho * wo * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int i = (int)(p / ho);
+    const float sy = rh * (float)yo, sx = rw * (float)xo;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const __nv_bfloat16* base = x + (size_t)i * h * w * c + g * 8;
+    const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x0) * c));
+    const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * w + x1) * c));
+    const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x0) * c));
+    const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * w + x1) * c));
+    float a[8], b[8], cc[8], d[8], o[8];
+    unpack8(q00, a); unpack8(q01, b); unpack8(q10, cc); unpack8(q11, d);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = hy * (hx * a[q] + lx * b[q]) + ly * (hx * cc[q] + lx * d[q]);
+    *reinterpret_cast<uint4*>(y + (((size_t)i * ho + yo) * wo + xo) * pitch + c_off + g * 8) = pack8(o);
+  }
+}
+
 // y[p, 0:c] = relu(x[p, 0:c] * scale + shift) — DenseNet pre-activation (norm -> relu ahead of a conv), NHWC bf16
 __global__ void affine_relu_kernel(const __nv_bfloat16* __restrict__ x, long long pixels, int c, int pitch_in,
                                    const float* __restrict__ scale, const float* __restrict__ shift,
@@ -818,6 +886,34 @@ int adb_affine_relu(const void* x, int64_t pixels, int32_t c, int32_t pitch_in, 
   if (!sms) return ADB_ERR_NO_DEVICE;
   affine_relu_kernel<<<grid_for(pixels * (c / 8), 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), pixels, c, pitch_in, scale, shift, reinterpret_cast<__nv_bfloat16*>(y), pitch_out);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_maxpool_kxk(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, const int32_t* n_dev, int32_t n_start,
+                    void* y, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && (k == 2 || k == 4) && h % k == 0 && w % k == 0,
+              "adb_maxpool_kxk: k must be 2 or 4 and divide H and W, channels a multiple of 8 (k=%d h=%d w=%d c=%d)", k, h, w, c);
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const long long total = (long long)n * (h / k) * (w / k) * (c / 8);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+  if (k == 2) maxpool_kxk_kernel<2><<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(xb, n, h, w, c, n_dev, n_start, yb);
+  else maxpool_kxk_kernel<4><<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(xb, n, h, w, c, n_dev, n_start, yb);
+  ADB_LAUNCH_OK();
+  return ADB_OK;
+}
+
+int adb_upsample_bilinear(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t scale, const int32_t* n_dev,
+                          int32_t n_start, void* y, int32_t pitch_out, int32_t c_off, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && scale >= 1 && pitch_out % 8 == 0 && c_off % 8 == 0 && c_off + c <= pitch_out,
+              "adb_upsample_bilinear: bad arguments (c=%d scale=%d pitch=%d c_off=%d)", c, scale, pitch_out, c_off);
+  const int sms = sm_count();
+  if (!sms) return ADB_ERR_NO_DEVICE;
+  const long long total = (long long)n * h * scale * w * scale * (c / 8);
+  upsample_bilinear_kernel<<<grid_for(total, 256, sms, 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), n, h, w, c, scale, n_dev, n_start, reinterpret_cast<__nv_bfloat16*>(y), pitch_out, c_off);
   ADB_LAUNCH_OK();
   return ADB_OK;
 }

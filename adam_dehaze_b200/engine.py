@@ -98,7 +98,7 @@ class BranchEngine:
     """Runs LightweightDehazeModel / MediumIntensityDehazeModel / HighIntensityDehazeModel forwards."""
 
     def __init__(self, model, kind):
-        assert kind in ("light", "unet", "unet_attn")
+        assert kind in ("light", "unet", "unet_attn", "low_unet", "corun", "dual")
         self.model, self.kind = model, kind
         self._ver = _Versioned(model)
         self.S = None
@@ -117,6 +117,45 @@ class BranchEngine:
             S["res"] = [_res_specs(rb) for rb in m.residual_blocks]
             S["out0"] = _conv_block_spec(m.output_conv[0])
             S["out1"] = ConvSpec.from_conv(m.output_conv[1].weight, bias=m.output_conv[1].bias, act=ACT_SIGMOID)
+        elif self.kind == "low_unet":      # LowIntensityDehazeModel, low_intensity.py:56-125
+            S["init"] = _conv_block_spec(m.init_conv, stem_kp=16)
+            S["down"] = _conv_block_spec(m.down1[0])
+            S["res"] = [_res_specs(m.down1[1])] + [_res_specs(rb) for rb in m.bottleneck]
+            S["up"] = ConvSpec.from_convT(m.up1[0].weight, bias=m.up1[0].bias, bn=bn_args(m.up1[1]), act=ACT_RELU)
+            S["out0"] = _conv_block_spec(m.output_conv[0])
+            S["out1"] = _conv_block_spec(m.output_conv[1])
+            # clamp(x + (sigmoid(z) - 0.5) * 2) == clamp(x + tanh(z / 2)): halve the epilogue affine, use the tanh/residual epilogue
+            sp = ConvSpec.from_conv(m.output_conv[2].weight, bias=m.output_conv[2].bias, act=ACT_TANH)
+            sp.scale, sp.shift = (sp.scale * 0.5).contiguous(), (sp.shift * 0.5).contiguous()
+            S["out2"] = sp
+        elif self.kind == "corun":         # COrunInspiredModel, medium_intensity.py:128-199
+            S["init"] = _conv_block_spec(m.init_conv, stem_kp=32)
+            S["scale1"] = _conv_block_spec(m.scale1_conv)
+            S["scale2"] = _conv_block_spec(m.scale2_conv[1])
+            S["scale3"] = _conv_block_spec(m.scale3_conv[1])
+            S["fusion"] = _conv_block_spec(m.fusion_conv)
+            S["res"] = [_res_specs(rb) for rb in m.residual_blocks]
+            S["out0"] = _conv_block_spec(m.output_conv[0])
+            S["out1"] = ConvSpec.from_conv(m.output_conv[1].weight, bias=m.output_conv[1].bias, act=ACT_TANH)
+        elif self.kind == "dual":          # DualBranchAttentionModel, high_intensity.py:149-223
+            gb, lb, tb, fc = m.global_branch, m.local_branch, m.transmission_branch, m.fusion_conv
+            S["g_init"] = _conv_block_spec(gb[0], stem_kp=32)
+            S["g_res"] = [_res_specs(gb[2]), _res_specs(gb[5]), _res_specs(gb[7]), _res_specs(gb[9])]
+            S["g_attn"] = [_attn_params(gb[3]), _attn_params(gb[6])]
+            S["g_out"] = _conv_block_spec(gb[11])
+            S["l_init"] = _conv_block_spec(lb[0], stem_kp=16)
+            S["l_res"] = [_res_specs(lb[1]), _res_specs(lb[2])]
+            S["l_out"] = _conv_block_spec(lb[3])
+            S["t0"] = _conv_block_spec(tb[0])
+            S["t1"] = _conv_block_spec(tb[1])
+            # (1 - sigmoid(w.f + b)) == sigmoid(-(w.f + b)): the 1x1 head rides in the DOT epilogue with negated weights
+            cp = S["t1"].cout_pad
+            w = tb[2].weight.detach().float().reshape(-1)
+            dot_w = torch.zeros(cp, dtype=torch.float32, device=w.device)
+            dot_w[:w.numel()] = -w
+            S["t_dot"] = (dot_w.contiguous(), -float(tb[2].bias.detach().float().item()))
+            S["f0"] = _conv_block_spec(fc[0])
+            S["f1"] = ConvSpec.from_conv(fc[1].weight, bias=fc[1].bias, act=ACT_TANH)
         else:
             attn = self.kind == "unet_attn"
             S["init"] = _conv_block_spec(m.init_conv, stem_kp=32)
@@ -158,6 +197,12 @@ class BranchEngine:
         px = h * w
         if self.kind == "light":
             return px * (16 + 3 * c) * 2
+        if self.kind == "low_unet":
+            return px * (16 + 3 * c) * 2 + (px // 4) * 2 * 2 * c * 2
+        if self.kind == "corun":
+            return px * (32 + c + 7 * c + 2 * 2 * c + c) * 2 + (px // 4) * 3 * c * 2 + (px // 16) * 5 * c * 2
+        if self.kind == "dual":
+            return px * (32 + 16 + c + 4 * (c // 2) + 2 * (c // 2)) * 2 + px * 4 + (px // 4) * 3 * c * 2 + (px // 16) * 2 * c * 2
         # stem operand + full-res maps (f0, x2, tmp, head) + half/quarter-res pyramids + guidance path
         full = px * (32 + 4 * c + 16 + 2 * 16) * 2 + px * 4
         return full + (px // 4) * 3 * 2 * c * 2 + (px // 16) * 2 * 4 * c * 2
@@ -186,14 +231,16 @@ class BranchEngine:
         require_inference(self.model, type(self.model).__name__)
         x = x.contiguous()
         b, _, h, w = x.shape
-        if self.kind != "light" and (h % 4 or w % 4):
-            raise ValueError(f"{type(self.model).__name__}: H and W must be multiples of 4 on the B200 path (got {h}x{w})")
+        need = {"light": 1, "low_unet": 2}.get(self.kind, 4)
+        if h % need or w % need:
+            raise ValueError(f"{type(self.model).__name__}: H and W must be multiples of {need} on the B200 path (got {h}x{w})")
         if out is None:
             out = torch.empty_like(x)
         upper = b if count is None else int(count)
         S = self.specs()
         mb = self.micro_batch(h, w, upper)
-        run = self._run_light if self.kind == "light" else self._run_unet
+        run = {"light": self._run_light, "low_unet": self._run_low_unet, "corun": self._run_corun,
+               "dual": self._run_dual}.get(self.kind, self._run_unet)
         for start in range(0, upper, mb):
             run(S, x, out, index, n_dev, start, min(mb, upper - start), mb)
         return out
@@ -225,6 +272,107 @@ class BranchEngine:
         ops.conv2d(S["out0"], f, dst=t, **kw)
         ops.conv2d(S["out1"], t, epi=EPI_IMAGE,
                    image=dict(mode=IMG_BLEND, x=x, out=out, index=index, alpha=self.model.skip_alpha), **kw)
+
+    def _run_low_unet(self, S, x, out, index, n_dev, n_start, n, cap):
+        """LowIntensityDehazeModel.forward, low_intensity.py:96-115."""
+        dev = x.device
+        _, _, h, w = x.shape
+        c, c2 = S["init"].cout_pad, S["down"].cout_pad
+        kw = self._kw(n_dev, n_start, n)
+        x3 = self._buf("x3", (cap, h, w, 16), dev)
+        f0 = self._buf("f0", (cap, h, w, c), dev)
+        f1 = self._buf("f1", (cap, h // 2, w // 2, c2), dev)
+        t1 = self._buf("t1", (cap, h // 2, w // 2, c2), dev)
+        up = self._buf("up", (cap, h, w, c), dev)
+        t0 = self._buf("t0", (cap, h, w, c), dev)
+        ops.stem_pack(x, 3, 1, 16, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x3)
+        ops.conv2d(S["init"], x3, dst=f0, **kw)
+        ops.conv2d(S["down"], f0, dst=f1, **kw)
+        for specs in S["res"]:
+            self._res(specs, f1, t1, kw)
+        ops.conv2d(S["up"], f1, dst=up, **kw)
+        ops.conv2d(S["out0"], up, f0, dst=t0, **kw)            # cat([up, init_features]) never materialised
+        ops.conv2d(S["out1"], t0, dst=up, **kw)
+        ops.conv2d(S["out2"], up, epi=EPI_IMAGE, image=dict(mode=IMG_RESIDUAL, x=x, out=out, index=index), **kw)
+
+    def _run_corun(self, S, x, out, index, n_dev, n_start, n, cap):
+        """COrunInspiredModel.forward, medium_intensity.py:170-190."""
+        dev = x.device
+        _, _, h, w = x.shape
+        c = S["init"].cout_pad
+        c2, c4 = S["scale2"].cout_pad, S["scale3"].cout_pad
+        cf = S["fusion"].cout_pad
+        kw = self._kw(n_dev, n_start, n)
+        nd = dict(n=n, n_dev=n_dev, n_start=n_start)
+        x7 = self._buf("x7", (cap, h, w, 32), dev)
+        f0 = self._buf("f0", (cap, h, w, c), dev)
+        fused = self._buf("fused", (cap, h, w, c + c2 + c4), dev)
+        ops.stem_pack(x, 7, 3, 32, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x7)
+        ops.conv2d(S["init"], x7, dst=f0, **kw)
+        ops.conv2d(S["scale1"], f0, dst=fused, dst_c_off=0, **kw)
+        p2 = ops.maxpool_kxk(f0, 2, out=self._buf("p2", (cap, h // 2, w // 2, c), dev), **nd)
+        s2 = ops.conv2d(S["scale2"], p2, dst=self._buf("s2", (cap, h // 2, w // 2, c2), dev), **kw)
+        ops.upsample_bilinear(s2, 2, out=fused, c_off=c, **nd)
+        p4 = ops.maxpool_kxk(f0, 4, out=self._buf("p4", (cap, h // 4, w // 4, c), dev), **nd)
+        s4 = ops.conv2d(S["scale3"], p4, dst=self._buf("s4", (cap, h // 4, w // 4, c4), dev), **kw)
+        ops.upsample_bilinear(s4, 4, out=fused, c_off=c + c2, **nd)
+        g = self._buf("g", (cap, h, w, cf), dev)
+        t = self._buf("t", (cap, h, w, cf), dev)
+        ops.conv2d(S["fusion"], fused, dst=g, **kw)
+        for specs in S["res"]:
+            self._res(specs, g, t, kw)
+        ops.conv2d(S["out0"], g, dst=f0, **kw)
+        ops.conv2d(S["out1"], f0, epi=EPI_IMAGE, image=dict(mode=IMG_RESIDUAL, x=x, out=out, index=index), **kw)
+
+    def _run_dual(self, S, x, out, index, n_dev, n_start, n, cap):
+        """DualBranchAttentionModel.forward, high_intensity.py:203-223."""
+        dev = x.device
+        _, _, h, w = x.shape
+        c = S["g_init"].cout_pad
+        ch = S["g_out"].cout_pad
+        kw = self._kw(n_dev, n_start, n)
+        nd = dict(n=n, n_dev=n_dev, n_start=n_start)
+        scratch = self._bufs.setdefault(("attn_scratch", cap, str(dev)), {})
+
+        def attend(ap, f):
+            return ops.attention(f, ap, n=n, n_dev=n_dev, n_start=n_start, out=f, scratch=scratch)
+
+        # global branch
+        x7 = self._buf("x7", (cap, h, w, 32), dev)
+        gf = self._buf("gf", (cap, h, w, c), dev)
+        ops.stem_pack(x, 7, 3, 32, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x7)
+        ops.conv2d(S["g_init"], x7, dst=gf, **kw)
+        g1 = ops.maxpool_kxk(gf, 2, out=self._buf("g1", (cap, h // 2, w // 2, c), dev), **nd)
+        t1 = self._buf("gt1", tuple(g1.shape), dev)
+        self._res(S["g_res"][0], g1, t1, kw)
+        attend(S["g_attn"][0], g1)
+        g2 = ops.maxpool_kxk(g1, 2, out=self._buf("g2", (cap, h // 4, w // 4, c), dev), **nd)
+        t2 = self._buf("gt2", tuple(g2.shape), dev)
+        self._res(S["g_res"][1], g2, t2, kw)
+        attend(S["g_attn"][1], g2)
+        self._res(S["g_res"][2], g2, t2, kw)
+        ops.upsample_bilinear(g2, 2, out=g1, **nd)
+        self._res(S["g_res"][3], g1, t1, kw)
+        ops.upsample_bilinear(g1, 2, out=gf, **nd)
+        G = self._buf("G", (cap, h, w, ch), dev)
+        ops.conv2d(S["g_out"], gf, dst=G, **kw)
+        # local branch
+        x3 = self._buf("x3", (cap, h, w, 16), dev)
+        lf = self._buf("lf", (cap, h, w, ch), dev)
+        lt = self._buf("lt", (cap, h, w, ch), dev)
+        ops.stem_pack(x, 3, 1, 16, index=index, n_dev=n_dev, n_start=n_start, n=n, out=x3)
+        ops.conv2d(S["l_init"], x3, dst=lf, **kw)
+        for specs in S["l_res"]:
+            self._res(specs, lf, lt, kw)
+        L = self._buf("L", (cap, h, w, ch), dev)
+        ops.conv2d(S["l_out"], lf, dst=L, **kw)
+        # transmission: (1 - t) as fp32 [n,h,w]; fusion: residual, out = clamp(x + (1 - t) * residual)
+        ops.conv2d(S["t0"], G, L, dst=lt, **kw)                # cat([global, local]) never materialised
+        one_minus_t = self._buf("omt", (cap, h, w), dev, torch.float32)
+        dot_w, dot_b = S["t_dot"]
+        ops.conv2d(S["t1"], lt, epi=EPI_DOT, dot=(dot_w, dot_b, one_minus_t), **kw)
+        ops.conv2d(S["f0"], G, L, dst=lf, **kw)
+        ops.conv2d(S["f1"], lf, epi=EPI_IMAGE, image=dict(mode=IMG_GUIDED, x=x, out=out, index=index, guidance=one_minus_t), **kw)
 
     def _run_unet(self, S, x, out, index, n_dev, n_start, n, cap):
         dev = x.device

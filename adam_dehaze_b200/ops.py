@@ -14,7 +14,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, 
 
 __all__ = [
     "pad16", "fold_bn", "pack_conv_weight", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
-    "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "head_mlp",
+    "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "maxpool_kxk", "upsample_bilinear", "head_mlp",
     "linear", "route", "blend3", "l1_mse", "cross_entropy",
 ]
 
@@ -281,6 +281,26 @@ def avgpool2x2(x, c=None, out=None):
     if out is None:
         out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
     _lib.call("adb_avgpool2x2", _lib.ptr(x), n, h, w, c, p, _lib.ptr(out), out.shape[3], _lib.current_stream())
+    return out
+
+
+def maxpool_kxk(x, k, *, n=None, n_dev=None, n_start=0, out=None):
+    """nn.MaxPool2d(k, k), k in {2, 4}, NHWC bf16."""
+    nb, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((nb, h // k, w // k, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_maxpool_kxk", _lib.ptr(x), nb if n is None else n, h, w, c, k, _lib.ptr(n_dev), n_start, _lib.ptr(out),
+              _lib.current_stream())
+    return out
+
+
+def upsample_bilinear(x, scale, *, n=None, n_dev=None, n_start=0, out=None, c_off=0):
+    """nn.UpsamplingBilinear2d(scale_factor=scale) (align_corners=True) into channels [c_off, c_off+c) of `out`."""
+    nb, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((nb, h * scale, w * scale, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("adb_upsample_bilinear", _lib.ptr(x), nb if n is None else n, h, w, c, scale, _lib.ptr(n_dev), n_start,
+              _lib.ptr(out), out.shape[3], c_off, _lib.current_stream())
     return out
 
 

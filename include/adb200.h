@@ -52,7 +52,8 @@ enum {
 /* epilogue kinds */
 enum {
   ADB_EPI_FEATURE = 0, /* y = act(acc*scale + shift (+ residual)) -> NHWC bf16 feature map (ConvBlock/ResidualBlock, base_model.py:23,36-41) */
-  ADB_EPI_DOT = 1,     /* g = sigmoid(dot(act(acc*scale+shift), dot_w) + dot_b) -> fp32 [n,h,w] (detail_branch tail, high:84-89) */
+  ADB_EPI_DOT = 1,     /* g = sigmoid(dot(act(acc*scale+shift), dot_w) + dot_b) -> fp32 [n,h,w]; cout_pad 16 or 32, dot_w fp32[cout_pad]
+                          (detail_branch tail, high:84-89; transmission_branch tail, high:184-189) */
   ADB_EPI_IMAGE = 2    /* final 3-channel head fused with the output arithmetic, NCHW fp32 out (low:45; medium:117; high:135-138) */
 };
 
@@ -155,6 +156,14 @@ ADB_API int adb_affine_relu(const void* x, int64_t pixels, int32_t c, int32_t pi
                     void* y, int32_t pitch_out, void* stream);
 ADB_API int adb_avgpool2x2(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pitch_in, void* y,
                    int32_t pitch_out, void* stream);
+/* Non-default branch variants: nn.MaxPool2d(k, k) for k in {2, 4} (medium_intensity.py:144,149;
+ * high_intensity.py:164,167) and nn.UpsamplingBilinear2d(scale_factor) == bilinear with align_corners=True
+ * (medium_intensity.py:146,151; high_intensity.py:171,173) on NHWC bf16 maps.  The upsampler writes channels
+ * [c_off, c_off+c) of a wider buffer so COrunInspiredModel's three-scale concat is never materialised. */
+ADB_API int adb_maxpool_kxk(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, const int32_t* n_dev,
+                            int32_t n_start, void* y, void* stream);
+ADB_API int adb_upsample_bilinear(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t scale,
+                                  const int32_t* n_dev, int32_t n_start, void* y, int32_t pitch_out, int32_t c_off, void* stream);
 /* Classifier head, fp32: logits = W2*relu(W1*f + b1) + b2 (models/classifier.py:72-78, eval mode: dropout = identity). */
 ADB_API int adb_head_mlp(const float* feat, int32_t n, int32_t f, const float* w1, const float* b1, int32_t hidden,
                  const float* w2, const float* b2, int32_t classes, float* logits, void* stream);

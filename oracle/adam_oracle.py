@@ -120,7 +120,60 @@ def complex_forward(sd, x):
     return torch.clamp(x + _unet_forward(sd, x, attention=True) * g, 0, 1)
 
 
-BRANCH_FORWARD = {"low": light_forward, "medium": medium_forward, "high": complex_forward}
+# --------------------------------------------------------------------------- non-default variants
+def low_unet_forward(sd, x):
+    """LowIntensityDehazeModel.forward, low_intensity.py:96-115 (n_blocks - 1 bottleneck blocks, read from the keys)."""
+    f0 = conv_block(sd, "init_conv", x)
+    f = residual_block(sd, "down1.1", conv_block(sd, "down1.0", f0, stride=2, padding=1))
+    i = 0
+    while f"bottleneck.{i}.conv1.block.0.weight" in sd:
+        f = residual_block(sd, f"bottleneck.{i}", f)
+        i += 1
+    up = _up_block(sd, "up1", f)
+    r = conv_block(sd, "output_conv.0", torch.cat([up, f0], dim=1))
+    r = conv_block(sd, "output_conv.1", r)
+    out = torch.sigmoid(F.conv2d(r, sd["output_conv.2.weight"], sd["output_conv.2.bias"], padding=1))
+    return torch.clamp(x + (out - 0.5) * 2, 0, 1)
+
+
+def corun_forward(sd, x):
+    """COrunInspiredModel.forward, medium_intensity.py:170-190.  nn.UpsamplingBilinear2d == bilinear, align_corners=True."""
+    f0 = conv_block(sd, "init_conv", x, padding=3)
+    s1 = conv_block(sd, "scale1_conv", f0)
+    s2 = F.interpolate(conv_block(sd, "scale2_conv.1", F.max_pool2d(f0, 2, 2)), scale_factor=2, mode="bilinear", align_corners=True)
+    s3 = F.interpolate(conv_block(sd, "scale3_conv.1", F.max_pool2d(f0, 4, 4)), scale_factor=4, mode="bilinear", align_corners=True)
+    f = conv_block(sd, "fusion_conv", torch.cat([s1, s2, s3], dim=1), padding=0)
+    i = 0
+    while f"residual_blocks.{i}.conv1.block.0.weight" in sd:
+        f = residual_block(sd, f"residual_blocks.{i}", f)
+        i += 1
+    r = conv_block(sd, "output_conv.0", f)
+    r = torch.tanh(F.conv2d(r, sd["output_conv.1.weight"], sd["output_conv.1.bias"], padding=1))
+    return torch.clamp(x + r, 0, 1)
+
+
+def dual_branch_forward(sd, x):
+    """DualBranchAttentionModel.forward, high_intensity.py:203-223."""
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)   # noqa: E731
+    g = conv_block(sd, "global_branch.0", x, padding=3)
+    g = attention_block(sd, "global_branch.3", residual_block(sd, "global_branch.2", F.max_pool2d(g, 2, 2)))
+    g = attention_block(sd, "global_branch.6", residual_block(sd, "global_branch.5", F.max_pool2d(g, 2, 2)))
+    g = up(residual_block(sd, "global_branch.7", g))
+    g = up(residual_block(sd, "global_branch.9", g))
+    g = conv_block(sd, "global_branch.11", g)
+    l = conv_block(sd, "local_branch.0", x)
+    l = residual_block(sd, "local_branch.2", residual_block(sd, "local_branch.1", l))
+    l = conv_block(sd, "local_branch.3", l)
+    cat = torch.cat([g, l], dim=1)
+    t = conv_block(sd, "transmission_branch.1", conv_block(sd, "transmission_branch.0", cat))
+    t = torch.sigmoid(F.conv2d(t, sd["transmission_branch.2.weight"], sd["transmission_branch.2.bias"]))
+    r = conv_block(sd, "fusion_conv.0", cat)
+    r = torch.tanh(F.conv2d(r, sd["fusion_conv.1.weight"], sd["fusion_conv.1.bias"], padding=1))
+    return torch.clamp(x + (1 - t) * r, 0, 1)
+
+
+BRANCH_FORWARD = {"low": light_forward, "medium": medium_forward, "high": complex_forward,
+                  "low_unet": low_unet_forward, "corun": corun_forward, "dual_branch": dual_branch_forward}
 
 
 # --------------------------------------------------------------------------- classifier (HDEN)

@@ -105,6 +105,21 @@ def main():
         torch.save(gold, os.path.join(OUT, f"branch_{name}.pt"))
         print(name, gold["fingerprint"][:16], len(gold["keys"]), "tensors")
 
+    # --- non-default variants: the factories select them through model_type
+    vcfg = {"low_unet": ("low", "enhanced", create_low_intensity_model), "corun": ("medium", "corun", create_medium_intensity_model),
+            "dual_branch": ("high", "dual_branch", create_high_intensity_model)}
+    for name, (lvl, mtype, mk) in vcfg.items():
+        cfg = {**CONFIG, "dehazing": {**CONFIG["dehazing"], lvl: {**CONFIG["dehazing"][lvl], "model_type": mtype}}}
+        seed_everything(SEED)
+        m = mk(cfg).eval()
+        gold = {"fingerprint": fingerprint(m.state_dict()), "keys": list(m.state_dict().keys()), "info": m.get_info(),
+                "model_type": mtype, "level": lvl, "cases": []}
+        for (n, h, w, s) in [(2, 64, 64, 11), (1, 32, 96, 12)]:
+            x = rand_image(n, h, w, s)
+            gold["cases"].append({"shape": (n, h, w), "seed": s, "out": m(x).clone()})
+        torch.save(gold, os.path.join(OUT, f"branch_{name}.pt"))
+        print(name, gold["fingerprint"][:16], len(gold["keys"]), "tensors")
+
     # --- building blocks (base_model.py)
     seed_everything(SEED)
     rb = ResidualBlock(32).eval()

@@ -48,9 +48,16 @@ def make_branch(name, seed=SEED):
     from adam_dehaze_b200.models.dehazing.low_intensity import create_low_intensity_model
     from adam_dehaze_b200.models.dehazing.medium_intensity import create_medium_intensity_model
     from adam_dehaze_b200.models.dehazing.high_intensity import create_high_intensity_model
-    mk = {"low": create_low_intensity_model, "medium": create_medium_intensity_model, "high": create_high_intensity_model}[name]
+    mk = {"low": create_low_intensity_model, "medium": create_medium_intensity_model, "high": create_high_intensity_model}
+    # non-default variants are selected through the reference's own config key `model_type`
+    variants = {"low_unet": ("low", "enhanced"), "corun": ("medium", "corun"), "dual_branch": ("high", "dual_branch")}
+    cfg = CONFIG
+    if name in variants:
+        lvl, mtype = variants[name]
+        cfg = {**CONFIG, "dehazing": {**CONFIG["dehazing"], lvl: {**CONFIG["dehazing"][lvl], "model_type": mtype}}}
+        name = lvl
     torch.manual_seed(seed)
-    return mk(CONFIG).eval()
+    return mk[name](cfg).eval()
 
 
 def make_classifier(model="resnet18", seed=SEED):

@@ -32,7 +32,7 @@ def _check_image(out, ref):
     return err, p
 
 
-@pytest.mark.parametrize("name", ["low", "medium", "high"])
+@pytest.mark.parametrize("name", ["low", "medium", "high", "low_unet", "corun", "dual_branch"])
 def test_branch_vs_golden_fixture(name):
     """The committed reference outputs (tests/golden) at the fixture sizes, incl. config 1 (Light, 1x3x256x256)."""
     g = golden(f"branch_{name}.pt")
@@ -44,7 +44,8 @@ def test_branch_vs_golden_fixture(name):
 
 
 @pytest.mark.parametrize("name,n,h,w", [("low", 3, 128, 256), ("medium", 2, 128, 192), ("high", 2, 128, 192),
-                                        ("high", 1, 256, 512)])
+                                        ("high", 1, 256, 512), ("low_unet", 2, 128, 256), ("corun", 2, 128, 192),
+                                        ("dual_branch", 2, 128, 192), ("dual_branch", 1, 256, 512)])
 def test_branch_vs_oracle_trained_like_stats(name, n, h, w):
     """Non-trivial BN statistics (folding exercised) and synthetic hazy inputs; oracle runs in fp32 on the same GPU."""
     m = randomize_bn(make_branch(name)).cuda()

@@ -154,3 +154,26 @@ def test_stem_pack_bit_exact(kh, kw, pad, stride, kp, h, w):
     assert torch.equal(out[:3, ..., :kh * kw * 3].float(), ref.to(torch.bfloat16).float())
     assert out[:3, ..., kh * kw * 3:].float().abs().max().item() == 0.0
     assert (out[3].float() == -1.0).all()
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_maxpool_kxk_bit_exact(k):
+    import torch.nn.functional as F
+    from adam_dehaze_b200 import ops
+    x = torch.randn(3, 24, 16, 40, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16).float().cuda()
+    y = ops.maxpool_kxk(ops.nchw_to_nhwc(x), k)
+    assert torch.equal(ops.nhwc_to_nchw(y), F.max_pool2d(x, k, k))
+
+
+@pytest.mark.parametrize("scale", [2, 4])
+def test_upsample_bilinear_align_corners(scale):
+    """nn.UpsamplingBilinear2d(scale_factor) into a channel slice of a wider buffer; fp32 interpolation of bf16 inputs,
+    bf16 output: |err| <= 1 bf16 ulp of the largest magnitude (2^-8 relative)."""
+    from adam_dehaze_b200 import ops
+    x = torch.randn(2, 16, 9, 13, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).float().cuda()
+    out = torch.full((2, 9 * scale, 13 * scale, 40), 3.0, dtype=torch.bfloat16, device="cuda")
+    ops.upsample_bilinear(ops.nchw_to_nhwc(x), scale, out=out, c_off=8)
+    ref = torch.nn.UpsamplingBilinear2d(scale_factor=scale)(x)
+    got = ops.nhwc_to_nchw(out)[:, 8:24]
+    assert (got - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -8
+    assert (out[..., :8].float() == 3.0).all() and (out[..., 24:].float() == 3.0).all()

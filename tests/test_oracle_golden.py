@@ -11,7 +11,7 @@ import adam_oracle as oracle
 torch.set_grad_enabled(False)
 
 
-@pytest.mark.parametrize("name", ["low", "medium", "high"])
+@pytest.mark.parametrize("name", ["low", "medium", "high", "low_unet", "corun", "dual_branch"])
 def test_branch_oracle_matches_reference(name):
     g = golden(f"branch_{name}.pt")
     m = make_branch(name)
