@@ -42,6 +42,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("grad", C.c_void_p), ("cg", C.c_int32), ("cg_pitch", C.c_int32), ("cg_true", C.c_int32),
+        ("act0", C.c_void_p), ("c0", C.c_int32), ("c0_pitch", C.c_int32),
+        ("act1", C.c_void_p), ("c1", C.c_int32), ("c1_pitch", C.c_int32),
+        ("n", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
+        ("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("dw", C.c_void_p), ("layout", C.c_int32), ("stem_kw", C.c_int32), ("accumulate", C.c_int32),
+    ]
+
+
+WG_OIHW, WG_STEM = 0, 1
+
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> argtypes (all return int status unless listed in _SPECIAL)
@@ -51,6 +65,7 @@ SIGNATURES = {
     "adb_kernel_error_flag": [],
     "adb_conv2d": [C.POINTER(ConvDesc), _P],
     "adb_debug_timeline": [_P, _I],
+    "adb_wgrad": [C.POINTER(WgradDesc), _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
@@ -76,6 +91,8 @@ _SPECIAL = {
     "adb_last_error": ([], C.c_char_p),
     "adb_conv2d_flops": ([C.POINTER(ConvDesc)], C.c_double),
     "adb_pool_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
+    "adb_wgrad_workspace_bytes": ([C.POINTER(WgradDesc)], C.c_int64),
+    "adb_wgrad_flops": ([C.POINTER(WgradDesc)], C.c_double),
 }
 EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

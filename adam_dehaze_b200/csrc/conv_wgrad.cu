@@ -1,0 +1,459 @@
+// conv_wgrad.cu — weight gradient of the implicit-GEMM convolutions for sm_100a (training step).
+//
+// GEMM view:  dW[m, (tap, c)] = sum_pixels S[pixel, m] * L[pixel + tap, c]
+//   S ("small" map): the gradient w.r.t. the conv output (nn.Conv2d), or the layer INPUT of a ConvTranspose2d(4,2,1);
+//   L ("large" map): the conv input (one or two concatenated sources), or the output gradient of a ConvTranspose2d.
+// The reduction (K) dimension is the PIXEL index, so both operands sit in shared memory exactly as TMA delivers an NHWC
+// box — 128-byte rows of 64 channels, one row per pixel — and are consumed as MN-major UMMA operands (instruction
+// descriptor a_major = b_major = 1).  One K step of 16 = 16 consecutive pixels of a tile row.
+//   M = 128 S-channels (two 64-channel boxes), N = 64 * gpu L-channels, one TMEM accumulator per filter tap of the unit.
+// Work unit = (M tile, source, tap set, channel chunk); a tap set is the taps of one filter row (same row/column phase
+// of the space-to-depth view for stride 2), which all read ONE halo box {64, TW+ew, 1, TH, 1} through pixel-shifted
+// descriptors.  Each unit's pixel range is cut `splits` ways over the grid; a CTA accumulates its range in TMEM and
+// writes one fp32 partial [m][k] slab; adb_wgrad's second kernel folds the slabs (deterministic order) into the
+// parameter's own layout ([O][I][kh][kw] fp32, the .grad tensor of nn.Conv2d / nn.ConvTranspose2d).
+//
+// Reference arithmetic replaced: the weight-gradient half of loss.backward() for every nn.Conv2d / nn.ConvTranspose2d
+// of models/dehazing/*.py (training/train_dehazing.py:90-92, training/train_joint.py:148-150).
+#include "adb_ptx.cuh"
+#include "adb_host.h"
+#include <algorithm>
+#include <string.h>
+
+namespace {
+
+using namespace adb;
+
+constexpr int kWgThreads = 192;     // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+constexpr int kWgMaxSets = 16;
+constexpr int kWgMaxSetTaps = 5;
+constexpr int kWgMaxStages = 6;
+
+struct WgSet {          // taps of one filter row / phase: one halo box, pixel-shifted views
+  int16_t c_mul;        // space-to-depth column phase (channel coordinate += c_mul * pitch)
+  int8_t p;             // row phase coordinate
+  int8_t dh, dw0;       // halo box origin relative to the tile origin
+  uint8_t ntaps;
+  uint8_t ddw[kWgMaxSetTaps];     // column shift of each tap inside the halo box
+  uint8_t kidx[kWgMaxSetTaps];    // r*kw + s of each tap
+};
+
+struct WgK {
+  int n, grid_h, grid_w;          // K space: n images of grid_h x grid_w S pixels
+  int TW, TH, tiles_w, tiles_h, tw_shift;
+  int total_tiles, splits;
+  int m_tiles;
+  int nsets;
+  WgSet sets[kWgMaxSets];
+  int chunks0, chunks1;           // channel chunks (of gpu*64 channels) per source
+  int c0, c1, pitch0, pitch1;
+  int gpu;                        // 64-channel groups per unit (N = 64*gpu)
+  int halo_w;
+  int s_group_bytes, l_group_bytes, stage_bytes, stages;
+  int tmem_cols;
+  uint32_t idesc;
+  int cs;                         // S channels (rows of dW)
+  int ktot;                       // taps * (c0 + c1)
+  int m_pad;                      // m_tiles * 128
+  float* ws;                      // [splits][m_pad][ktot]
+  int* err_flag;
+};
+
+// MN-major SWIZZLE_128B operand descriptor: 64 channels (128 B) contiguous per pixel row, 8-pixel groups SBO apart,
+// 64-channel groups LBO apart (cute UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmL0,
+                  const __grid_constant__ CUtensorMap tmL1, const __grid_constant__ WgK P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t bar_base = base + (uint32_t)P.stages * (uint32_t)P.stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kWgMaxStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kWgMaxStages);
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + (size_t)P.stages * P.stage_bytes + 8u * (2 * kWgMaxStages + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work item: blockIdx.x = unit * splits + split ; unit = ((m_tile * nsets + set) * chunks + chunk)
+  const int split = (int)(blockIdx.x % (unsigned)P.splits);
+  int unit = (int)(blockIdx.x / (unsigned)P.splits);
+  const int nchunks = P.chunks0 + P.chunks1;
+  const int chunk = unit % nchunks; unit /= nchunks;
+  const int set_i = unit % P.nsets;
+  const int m_tile = unit / P.nsets;
+  const WgSet S = P.sets[set_i];
+  const bool src1 = chunk >= P.chunks0;
+  const int ch_base = (src1 ? chunk - P.chunks0 : chunk) * P.gpu * 64;   // first L channel of this unit inside its source
+  const int c_src = src1 ? P.c1 : P.c0;
+  const int pitch = src1 ? P.pitch1 : P.pitch0;
+  const CUtensorMap* tmL = src1 ? &tmL1 : &tmL0;
+  const int N = P.gpu * 64;
+  // contiguous tile range of this split
+  const int per = (P.total_tiles + P.splits - 1) / P.splits;
+  const int t_begin = min(P.total_tiles, split * per), t_end = min(P.total_tiles, t_begin + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(tmL);
+    for (int s = 0; s < P.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_ptr_smem), (uint32_t)P.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ======================================================= producer: S boxes (2 x 64 channels) + L halo boxes (gpu x 64)
+    int slot = 0; uint32_t phase = 0;
+    const uint32_t tx = 2u * (uint32_t)(128 * 128) + (uint32_t)P.gpu * (uint32_t)(P.halo_w * P.TH * 128);
+    for (int t = t_begin; t < t_end; ++t) {
+      int q = t;
+      const int tw = q % P.tiles_w; q /= P.tiles_w;
+      const int th = q % P.tiles_h;
+      const int img = q / P.tiles_h;
+      const int w0 = tw * P.TW, h0 = th * P.TH;
+      mbar_wait(empty_bar(slot), phase ^ 1u, P.err_flag, 11);
+      if (elect_one()) {
+        const uint32_t sbase = base + (uint32_t)slot * (uint32_t)P.stage_bytes;
+        mbar_expect_tx(full_bar(slot), tx);
+        tma_load_5d(sbase, &tmS, full_bar(slot), m_tile * 128, w0, 0, h0, img);
+        tma_load_5d(sbase + (uint32_t)P.s_group_bytes, &tmS, full_bar(slot), m_tile * 128 + 64, w0, 0, h0, img);
+        const uint32_t lbase = sbase + 2u * (uint32_t)P.s_group_bytes;
+        for (int g = 0; g < P.gpu; ++g)
+          tma_load_5d(lbase + (uint32_t)g * (uint32_t)P.l_group_bytes, tmL, full_bar(slot), S.c_mul * pitch + ch_base + g * 64,
+                      w0 + S.dw0, S.p, h0 + S.dh, img);
+      }
+      __syncwarp();
+      if (++slot == P.stages) { slot = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer
+    int slot = 0; uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(full_bar(slot), phase, P.err_flag, 12);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sbase = base + (uint32_t)slot * (uint32_t)P.stage_bytes;
+        const uint32_t lbase = sbase + 2u * (uint32_t)P.s_group_bytes;
+#pragma unroll 1
+        for (int kk = 0; kk < 8; ++kk) {
+          const int px = kk * 16;
+          const int r = px >> P.tw_shift, c = px & (P.TW - 1);
+          const uint64_t a = make_mnmajor_desc(sbase + (uint32_t)px * 128u, (uint32_t)P.s_group_bytes, 1024u);
+          const uint32_t l_row = (uint32_t)(r * P.halo_w + c);
+          for (int j = 0; j < S.ntaps; ++j) {
+            const uint64_t b = make_mnmajor_desc(lbase + (l_row + S.ddw[j]) * 128u, (uint32_t)P.l_group_bytes, 1024u);
+            umma_bf16(tmem_base + (uint32_t)(j * N), a, b, P.idesc, accumulate | (uint32_t)kk);
+          }
+        }
+        umma_commit(empty_bar(slot));
+        if (t == t_end - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++slot == P.stages) { slot = 0; phase ^= 1u; }
+    }
+  } else {
+    // ======================================================= epilogue: TMEM -> fp32 partial slab
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int m = m_tile * 128 + q * 32 + lane;
+    float* row = P.ws + ((size_t)split * P.m_pad + m) * P.ktot;
+    const int ctot = P.c0 + P.c1;
+    const int k_src = src1 ? P.c0 : 0;
+    if (t_end > t_begin) {
+      mbar_wait(done_bar, 0, P.err_flag, 13);
+      tc_fence_after();
+    }
+    for (int j = 0; j < S.ntaps; ++j) {
+      float* dst = row + (size_t)S.kidx[j] * ctot + k_src + ch_base;
+      for (int c16 = 0; c16 < N / 16; ++c16) {
+        if (ch_base + c16 * 16 >= c_src) break;     // (warp-uniform) columns past the source's channels
+        float v[16];
+        if (t_end > t_begin) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * N + c16 * 16), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (m < P.cs) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(dst + c16 * 16 + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+// Fold the per-split slabs and scatter into the parameter layout.
+//  layout 0 (OIHW): dw[(m*ctot + c)*taps + tap]                     <- ws[.][m][tap*ctot + c]
+//  layout 1 (STEM): the L operand is an adb_stem_pack operand (kp channels = kw_img taps x 3 colours, kh row taps):
+//                   dw[((m*3 + c)*kh + r)*kw_img + s]               <- ws[.][m][r*kp + s*3 + c]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int m_pad, int cs, int ktot, int ctot, int taps,
+                                    int layout, int kw_img, int accumulate, float* __restrict__ dw) {
+  const long long total = (long long)cs * ktot;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / ktot), k = (int)(i - (long long)m * ktot);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[((size_t)s * m_pad + m) * ktot + k];
+    long long o;
+    if (layout == 0) {
+      const int tap = k / ctot, c = k - tap * ctot;
+      o = ((long long)m * ctot + c) * taps + tap;
+    } else {
+      const int r = k / ctot, j = k - r * ctot;       // ctot == kp
+      const int s = j / 3, c = j - 3 * s;
+      if (s >= kw_img) continue;
+      o = (((long long)m * 3 + c) * taps + r) * kw_img + s;
+    }
+    dw[o] = accumulate ? dw[o] + acc : acc;
+  }
+}
+
+inline int wg_round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct WgPlan {
+  WgK P;
+  int box_w, box_h;
+  int units;
+  int smem;
+  size_t ws_bytes;
+};
+
+int wg_plan(const adb_wgrad_desc* d, WgPlan& pl, int sm_count, int max_smem) {
+  WgK& P = pl.P;
+  memset(&P, 0, sizeof(P));
+  ADB_REQUIRE(d != nullptr, "adb_wgrad: null descriptor");
+  ADB_REQUIRE(d->grad && d->cg > 0 && d->cg_pitch >= d->cg && d->cg_pitch % 8 == 0 && d->cg % 16 == 0,
+              "adb_wgrad: bad small map (cg=%d pitch=%d)", d->cg, d->cg_pitch);
+  ADB_REQUIRE(d->act0 && d->c0 > 0 && d->c0 % 16 == 0 && d->c0_pitch >= d->c0 && d->c0_pitch % 8 == 0,
+              "adb_wgrad: bad act0 (c0=%d pitch=%d)", d->c0, d->c0_pitch);
+  ADB_REQUIRE((d->act1 == nullptr) == (d->c1 == 0), "adb_wgrad: act1/c1 mismatch");
+  if (d->act1) ADB_REQUIRE(d->c1 % 16 == 0 && d->c1_pitch >= d->c1 && d->c1_pitch % 8 == 0, "adb_wgrad: bad act1 (c1=%d pitch=%d)", d->c1, d->c1_pitch);
+  ADB_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in > 0, "adb_wgrad: bad n/h/w");
+  ADB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 64, "adb_wgrad: %dx%d taps unsupported", d->kh, d->kw);
+
+  struct Raw { int c_mul, p, dw, dh, kidx; };
+  Raw raw[64];
+  const int ntaps = d->kh * d->kw;
+  if (d->kind == ADB_CONV_S1) {
+    ADB_REQUIRE(d->kh % 2 == 1 && d->kw % 2 == 1, "adb_wgrad: stride-1 convs need odd kernel extents");
+    const int pad_h = (d->kh - 1) / 2, pad_w = (d->kw - 1) / 2;
+    ADB_REQUIRE(d->pad == std::max(pad_h, pad_w), "adb_wgrad: stride-1 convs must be 'same'");
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) raw[r * d->kw + s] = {0, 0, s - pad_w, r - pad_h, r * d->kw + s};
+    P.grid_h = d->h_in; P.grid_w = d->w_in;
+  } else if (d->kind == ADB_CONV_S2) {
+    ADB_REQUIRE(d->h_in % 2 == 0 && d->w_in % 2 == 0, "adb_wgrad: stride-2 convs need even H/W");
+    ADB_REQUIRE((d->h_in + 2 * d->pad - d->kh) / 2 + 1 == d->h_in / 2 && (d->w_in + 2 * d->pad - d->kw) / 2 + 1 == d->w_in / 2,
+                "adb_wgrad: stride-2 conv must halve H/W");
+    auto fl2 = [](int u) { return (u >= 0) ? u / 2 : -((-u + 1) / 2); };
+    for (int r = 0; r < d->kh; ++r)
+      for (int s = 0; s < d->kw; ++s) {
+        const int u = r - d->pad, v = s - d->pad;
+        raw[r * d->kw + s] = {v - 2 * fl2(v), u - 2 * fl2(u), fl2(v), fl2(u), r * d->kw + s};
+      }
+    P.grid_h = d->h_in / 2; P.grid_w = d->w_in / 2;
+  } else {
+    return adbh::fail(ADB_ERR_INVALID, "adb_wgrad: kind %d unsupported (a ConvTranspose2d gradient is the stride-2 form with the maps swapped)", d->kind);
+  }
+
+  // ---- tap sets: same (c_mul, p, dh)
+  bool used[64] = {false};
+  int ew = 0;
+  P.nsets = 0;
+  for (int t0 = 0; t0 < ntaps; ++t0) {
+    if (used[t0]) continue;
+    int members[64], nm = 0, dw_min = raw[t0].dw, dw_max = raw[t0].dw;
+    for (int t1 = t0; t1 < ntaps; ++t1) {
+      if (used[t1] || raw[t1].c_mul != raw[t0].c_mul || raw[t1].p != raw[t0].p || raw[t1].dh != raw[t0].dh) continue;
+      members[nm++] = t1;
+      dw_min = std::min(dw_min, raw[t1].dw); dw_max = std::max(dw_max, raw[t1].dw);
+    }
+    for (int b = 0; b < nm; b += kWgMaxSetTaps) {     // wide filter rows are cut into sets of <= kWgMaxSetTaps taps
+      ADB_REQUIRE(P.nsets < kWgMaxSets, "adb_wgrad: too many tap sets");
+      WgSet& s = P.sets[P.nsets++];
+      const int cnt = std::min(kWgMaxSetTaps, nm - b);
+      int lo = raw[members[b]].dw, hi = lo;
+      for (int k = 0; k < cnt; ++k) { lo = std::min(lo, raw[members[b + k]].dw); hi = std::max(hi, raw[members[b + k]].dw); }
+      s.c_mul = (int16_t)raw[t0].c_mul; s.p = (int8_t)raw[t0].p; s.dh = (int8_t)raw[t0].dh; s.dw0 = (int8_t)lo;
+      s.ntaps = (uint8_t)cnt;
+      for (int k = 0; k < cnt; ++k) {
+        s.ddw[k] = (uint8_t)(raw[members[b + k]].dw - lo);
+        s.kidx[k] = (uint8_t)raw[members[b + k]].kidx;
+        used[members[b + k]] = true;
+      }
+      ew = std::max(ew, hi - lo);
+    }
+  }
+  int max_set_taps = 1;
+  for (int i = 0; i < P.nsets; ++i) max_set_taps = std::max(max_set_taps, (int)P.sets[i].ntaps);
+
+  // ---- K tiles: 128 S pixels = TH rows x TW columns, TW >= 16 so a K step of 16 pixels stays inside one row
+  int TW = 128;
+  while (TW > P.grid_w && TW > 16) TW >>= 1;
+  ADB_REQUIRE(P.grid_w >= 16, "adb_wgrad: maps narrower than 16 pixels are unsupported (got %d)", P.grid_w);
+  P.TW = TW; P.TH = 128 / TW;
+  P.tw_shift = 0;
+  while ((1 << P.tw_shift) < TW) ++P.tw_shift;
+  P.tiles_w = (P.grid_w + TW - 1) / TW;
+  P.tiles_h = (P.grid_h + P.TH - 1) / P.TH;
+  const long long tt = (long long)d->n * P.tiles_w * P.tiles_h;
+  ADB_REQUIRE(tt < (1LL << 30), "adb_wgrad: too many pixel tiles");
+  P.total_tiles = (int)tt;
+  P.n = d->n;
+  P.halo_w = TW + ew;
+
+  // ---- N: 64-channel groups per unit
+  P.c0 = d->c0; P.c1 = d->c1; P.pitch0 = d->c0_pitch; P.pitch1 = d->act1 ? d->c1_pitch : d->c0_pitch;
+  const int g0 = (d->c0 + 63) / 64, g1 = (d->c1 + 63) / 64;
+  int gpu = std::min(4, 512 / (max_set_taps * 64));
+  gpu = std::max(1, std::min(gpu, std::max(g0, g1)));
+  P.gpu = gpu;
+  P.chunks0 = (g0 + gpu - 1) / gpu;
+  P.chunks1 = (g1 + gpu - 1) / gpu;
+  const int N = 64 * gpu;
+  int cols = 32;
+  while (cols < max_set_taps * N) cols <<= 1;
+  ADB_REQUIRE(cols <= 512, "adb_wgrad: accumulators do not fit TMEM");
+  P.tmem_cols = cols;
+  P.idesc = make_idesc_bf16(128u, (uint32_t)N) | (1u << 15) | (1u << 16);   // A and B MN-major
+
+  P.cs = d->cg;
+  P.m_tiles = (d->cg + 127) / 128;
+  P.m_pad = P.m_tiles * 128;
+  P.ktot = ntaps * (d->c0 + d->c1);
+
+  // ---- smem
+  P.s_group_bytes = 128 * 128;
+  P.l_group_bytes = wg_round_up(P.halo_w * P.TH * 128, 1024);
+  P.stage_bytes = 2 * P.s_group_bytes + gpu * P.l_group_bytes;
+  const int bar_bytes = 8 * (2 * kWgMaxStages + 1) + 16;
+  int stages = (max_smem - 1024 - bar_bytes) / P.stage_bytes;
+  stages = std::min(stages, kWgMaxStages);
+  ADB_REQUIRE(stages >= 2, "adb_wgrad: pipeline does not fit shared memory");
+  P.stages = stages;
+  pl.smem = stages * P.stage_bytes + bar_bytes + 1024;
+  pl.box_w = P.halo_w; pl.box_h = P.TH;
+
+  // ---- split the pixel range so the grid fills the device for ~2 waves, bounded by the workspace the caller gave
+  pl.units = P.m_tiles * P.nsets * (P.chunks0 + P.chunks1);
+  int splits = std::max(1, (2 * sm_count + pl.units - 1) / pl.units);
+  splits = std::min(splits, std::max(1, P.total_tiles / 4));
+  splits = std::min(splits, P.total_tiles);
+  const size_t slab = (size_t)P.m_pad * P.ktot * sizeof(float);
+  if (d->workspace_bytes > 0) {
+    const long long fit = (long long)(d->workspace_bytes / (long long)slab);
+    splits = (int)std::max<long long>(0, std::min<long long>(splits, fit));
+  }
+  P.splits = splits;
+  pl.ws_bytes = (size_t)std::max(splits, 1) * slab;
+  return ADB_OK;
+}
+
+// 5-D view {C, W, P, H, N} of an NHWC bf16 buffer (same convention as conv_igemm.cu)
+int wg_act_tmap(CUtensorMap* m, const void* base, int c_dim, int pitch, int n, int h, int w, bool s2d, int box_w, int box_h) {
+  uint64_t dims[5], strides[4];
+  uint32_t box[5] = {64u, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
+  const uint64_t px = (uint64_t)pitch * 2;
+  if (!s2d) {
+    dims[0] = c_dim; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
+    strides[0] = px; strides[1] = px * w; strides[2] = px * w; strides[3] = px * w * h;
+  } else {
+    dims[0] = 2 * (uint64_t)pitch; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n;
+    strides[0] = 2 * px; strides[1] = px * w; strides[2] = 2 * px * w; strides[3] = px * w * h;
+  }
+  return adbh::make_tmap_bf16(m, base, 5, dims, strides, box, 128);
+}
+
+}  // namespace
+
+extern "C" int64_t adb_wgrad_workspace_bytes(const adb_wgrad_desc* d) {
+  WgPlan pl;
+  adbh::DeviceInfo di;
+  int sm = 148, smem = 227 * 1024;
+  if (adbh::device_info(&di) == ADB_OK) { sm = di.sm_count; smem = di.max_smem_optin; }
+  adb_wgrad_desc q = *d;
+  q.workspace_bytes = 0;
+  if (wg_plan(&q, pl, sm, smem) != ADB_OK) return -1;
+  return (int64_t)pl.ws_bytes;
+}
+
+extern "C" int adb_wgrad(const adb_wgrad_desc* d, void* stream) {
+  adbh::DeviceInfo di;
+  int st = adbh::device_info(&di);
+  if (st != ADB_OK) return st;
+  if (di.cc_major != 10) return adbh::fail(ADB_ERR_NO_DEVICE, "adb_wgrad: device sm_%d%d is not sm_100", di.cc_major, di.cc_minor);
+  WgPlan pl;
+  st = wg_plan(d, pl, di.sm_count, di.max_smem_optin);
+  if (st != ADB_OK) return st;
+  WgK& P = pl.P;
+  ADB_REQUIRE(d->workspace && d->dw, "adb_wgrad: null workspace / dw");
+  ADB_REQUIRE(P.splits >= 1, "adb_wgrad: workspace of %lld bytes cannot hold one %d x %d fp32 slab", (long long)d->workspace_bytes, P.m_pad, P.ktot);
+  ADB_REQUIRE(d->layout == ADB_WG_OIHW || (d->layout == ADB_WG_STEM && d->kw == 1 && d->act1 == nullptr && d->stem_kw >= 1 && 3 * d->stem_kw <= d->c0),
+              "adb_wgrad: bad output layout %d", d->layout);
+  P.ws = d->workspace;
+  P.err_flag = adbh::kernel_err_flag();
+
+  alignas(64) CUtensorMap tmS, tmL0, tmL1;
+  st = wg_act_tmap(&tmS, d->grad, d->cg_pitch, d->cg_pitch, d->n, P.grid_h, P.grid_w, false, P.TW, P.TH);
+  if (st != ADB_OK) return st;
+  const bool s2d = d->kind == ADB_CONV_S2;
+  st = wg_act_tmap(&tmL0, d->act0, d->c0_pitch, d->c0_pitch, d->n, d->h_in, d->w_in, s2d, pl.box_w, pl.box_h);
+  if (st != ADB_OK) return st;
+  if (d->act1) {
+    st = wg_act_tmap(&tmL1, d->act1, d->c1_pitch, d->c1_pitch, d->n, d->h_in, d->w_in, s2d, pl.box_w, pl.box_h);
+    if (st != ADB_OK) return st;
+  } else {
+    tmL1 = tmL0;
+  }
+  static bool configured = false;
+  if (!configured) {
+    ADB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+    configured = true;
+  }
+  const int smem = std::max(pl.smem, 120 * 1024);   // one CTA per SM: the CTA owns the SM's TMEM
+  const long long grid = (long long)pl.units * P.splits;
+  ADB_REQUIRE(grid < (1LL << 31), "adb_wgrad: grid too large");
+  conv_wgrad_kernel<<<(unsigned)grid, kWgThreads, smem, (cudaStream_t)stream>>>(tmS, tmL0, tmL1, P);
+  ADB_CUDA_OK(cudaGetLastError());
+  const long long total = (long long)P.cs * P.ktot;
+  const int rgrid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)di.sm_count * 8));
+  const int ctot = d->c0 + d->c1;
+  wgrad_reduce_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(P.ws, P.splits, P.m_pad, (d->cg_true > 0 ? d->cg_true : d->cg), P.ktot, ctot,
+                                                                  d->layout == ADB_WG_STEM ? d->kh : d->kh * d->kw, d->layout,
+                                                                  d->stem_kw, d->accumulate, d->dw);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+extern "C" double adb_wgrad_flops(const adb_wgrad_desc* d) {
+  if (!d) return 0.0;
+  const double oh = d->kind == ADB_CONV_S2 ? d->h_in / 2 : d->h_in, ow = d->kind == ADB_CONV_S2 ? d->w_in / 2 : d->w_in;
+  return 2.0 * d->n * oh * ow * d->kh * d->kw * ((double)d->c0 + d->c1) * (d->cg_true > 0 ? d->cg_true : d->cg);
+}

@@ -10,12 +10,12 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, CONVT_4X4S2, EPI_DOT, EPI_FEATURE,
-                   EPI_IMAGE, IMG_BLEND, IMG_GUIDED, IMG_RESIDUAL, ConvDesc)
+                   EPI_IMAGE, IMG_BLEND, IMG_GUIDED, IMG_RESIDUAL, WG_OIHW, WG_STEM, ConvDesc, WgradDesc)
 
 __all__ = [
     "pad16", "fold_bn", "pack_conv_weight", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
     "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "maxpool_kxk", "upsample_bilinear", "head_mlp",
-    "linear", "route", "blend3", "l1_mse", "cross_entropy",
+    "linear", "route", "blend3", "l1_mse", "cross_entropy", "wgrad",
 ]
 
 
@@ -176,6 +176,52 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
         d.tune_flags = tune.get("flags", 0)
     _lib.call("adb_conv2d", C.byref(d), _lib.current_stream())
     return ret
+
+
+_WG_WS = {}
+
+
+def _wgrad_workspace(nbytes, device):
+    """One grow-only fp32 scratch per device for the wgrad partial slabs (stream-ordered re-use)."""
+    key = str(device)
+    t = _WG_WS.get(key)
+    if t is None or t.numel() * 4 < nbytes:
+        t = _WG_WS[key] = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+    return t
+
+
+def wgrad(small, large0, large1=None, *, kind=CONV_S1, kh=3, kw=3, pad=1, cs=None, cs_true=None, c0=None, c1=None, n=None,
+          out=None, layout=WG_OIHW, stem_kw=0, accumulate=False):
+    """Weight gradient of one conv: out[m][c][r][s] (+)= sum small[.., m] * large[.. + tap, c]  (see adb_wgrad in adb200.h).
+
+    small: NHWC bf16 [n, hs, ws, pitch]; large0/large1: NHWC bf16 [n, h, w, pitch] (concat sources).
+    Returns the fp32 gradient in the parameter layout ([cs_true][c0+c1][kh][kw], or [cs_true][3][kh][stem_kw] for STEM)."""
+    assert small.dtype == torch.bfloat16 and large0.dtype == torch.bfloat16 and small.is_contiguous() and large0.is_contiguous()
+    nb, h, w, p0 = large0.shape
+    d = WgradDesc()
+    d.grad, d.cg, d.cg_pitch = small.data_ptr(), (cs or small.shape[3]), small.shape[3]
+    d.cg_true = cs_true or 0
+    d.act0, d.c0, d.c0_pitch = large0.data_ptr(), (c0 or p0), p0
+    if large1 is not None:
+        assert large1.is_contiguous() and large1.shape[:3] == large0.shape[:3]
+        d.act1, d.c1, d.c1_pitch = large1.data_ptr(), (c1 or large1.shape[3]), large1.shape[3]
+    d.n, d.h_in, d.w_in = (nb if n is None else n), h, w
+    d.kind, d.kh, d.kw, d.pad = kind, kh, kw, pad
+    d.layout, d.stem_kw, d.accumulate = layout, stem_kw, int(bool(accumulate))
+    rows = d.cg_true or d.cg
+    if out is None:
+        shape = (rows, 3, kh, stem_kw) if layout == WG_STEM else (rows, d.c0 + d.c1, kh, kw)
+        out = torch.empty(shape, dtype=torch.float32, device=small.device)
+        assert not accumulate
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    need = int(_lib.load().adb_wgrad_workspace_bytes(C.byref(d)))
+    if need < 0:
+        raise _lib.AdbError(f"adb_wgrad_workspace_bytes: {_lib.last_error()}")
+    ws = _wgrad_workspace(min(need, 256 << 20), small.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    d.dw = out.data_ptr()
+    _lib.call("adb_wgrad", C.byref(d), _lib.current_stream())
+    return out
 
 
 def stem_pack(x, kw, pad, kp, *, stride=1, kh=1, index=None, n_dev=None, n_start=0, n=None, out=None):

@@ -192,6 +192,37 @@ ADB_API int adb_mse_bwd(const float* pred, const float* target, int64_t numel, f
 ADB_API int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale,
                    float* loss /*[1]*/, float* grad_logits /*nullable [b][classes]*/, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step (training/train_dehazing.py:71-96, training/train_joint.py:129-154: forward in train() mode,
+ * loss.backward(), optimizer.step()).  Data gradients (dgrad) re-use adb_conv2d with transformed weights
+ * (adam_dehaze_b200/training/autograd.py); the entry points below are the rest of backward.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of one convolution as a pixel-reduction implicit GEMM on tcgen05 (MN-major operands straight from the
+ * NHWC TMA boxes), fp32 accumulate:
+ *     dw[m][c][r][s] (+)= sum_{n,y,x} small[n,y,x,m] * large[n, y*stride + r - pad, x*stride + s - pad, c]
+ *  - nn.Conv2d:             small = dL/d(conv output) (cg channels), large = the conv input ([act0 | act1] concat);
+ *                           dw is conv.weight.grad, [cout][cin][kh][kw]
+ *  - nn.ConvTranspose2d(4,2,1): small = the layer INPUT, large = dL/d(output), kind = ADB_CONV_S2, kh = kw = 4, pad = 1;
+ *                           dw is weight.grad, [cin][cout][4][4]
+ * layout ADB_WG_STEM: `act0` is an adb_stem_pack operand (kh x 1 conv over c0 = kp channels holding stem_kw x 3 values);
+ *                           dw is the 3-channel stem's weight.grad [cout][3][kh][stem_kw].
+ * workspace: adb_wgrad_workspace_bytes(desc) bytes of fp32 scratch (per-split partial slabs, folded in a fixed order:
+ * the result is deterministic).  A smaller workspace (>= one slab) is accepted and lowers the split count. */
+enum { ADB_WG_OIHW = 0, ADB_WG_STEM = 1 };
+typedef struct adb_wgrad_desc {
+  const void* grad; int32_t cg; int32_t cg_pitch; int32_t cg_true;   /* small map: channels (multiple of 16) / pitch / rows of dw written (0 = cg) */
+  const void* act0; int32_t c0; int32_t c0_pitch;                    /* large map source(s), NHWC bf16 */
+  const void* act1; int32_t c1; int32_t c1_pitch;
+  int32_t n, h_in, w_in;                                             /* of the large map */
+  int32_t kind, kh, kw, pad;                                         /* ADB_CONV_S1 ('same') or ADB_CONV_S2 (halving) */
+  float* workspace; int64_t workspace_bytes;
+  float* dw; int32_t layout; int32_t stem_kw; int32_t accumulate;    /* accumulate != 0: dw += result */
+} adb_wgrad_desc;
+ADB_API int64_t adb_wgrad_workspace_bytes(const adb_wgrad_desc* desc);
+ADB_API int adb_wgrad(const adb_wgrad_desc* desc, void* stream);
+ADB_API double adb_wgrad_flops(const adb_wgrad_desc* desc);
+
 /* Developer aid: copy the clock64() timeline CTA 0 recorded during the last adb_conv2d launched with tune_flags bit 2
  * ([6 roles][256 events]: A producer, B producer, MMA ready, MMA issued, epilogue start, epilogue end). Synchronises. */
 ADB_API int adb_debug_timeline(int64_t* host_out, int32_t count);
