@@ -66,6 +66,16 @@ SIGNATURES = {
     "adb_conv2d": [C.POINTER(ConvDesc), _P],
     "adb_debug_timeline": [_P, _I],
     "adb_wgrad": [C.POINTER(WgradDesc), _P],
+    "adb_bn_train_stats": [_P, _L, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "adb_affine_act": [_P, _I, _L, _I, _P, _P, _P, _I, _I, _P, _I, _P],
+    "adb_bn_bwd": [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P],
+    "adb_add_bf16": [_P, _I, _P, _I, _L, _I, _P],
+    "adb_img_head_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "adb_img_head_bwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "adb_dot_head_fwd": [_P, _I, _I, _P, _P, _L, _P, _P],
+    "adb_dot_head_bwd": [_P, _P, _P, _I, _I, _P, _L, _P, _I, _P, _P],
+    "adb_attn_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
@@ -92,6 +102,8 @@ _SPECIAL = {
     "adb_conv2d_flops": ([C.POINTER(ConvDesc)], C.c_double),
     "adb_pool_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
     "adb_wgrad_workspace_bytes": ([C.POINTER(WgradDesc)], C.c_int64),
+    "adb_bn_scratch_floats": ([_L, _I], C.c_int64),
+    "adb_attn_bwd_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
     "adb_wgrad_flops": ([C.POINTER(WgradDesc)], C.c_double),
 }
 EXPORTED_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))

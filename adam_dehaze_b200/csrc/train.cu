@@ -1,0 +1,803 @@
+// train.cu — the HBM-bound kernels of the training step: batch-statistics BatchNorm forward/backward,
+// activation backward, the image / guidance heads forward+backward, AttentionBlock backward, pooling backward.
+// All stream NHWC bf16 maps with 16-byte accesses; per-channel reductions publish per-block partials that a finalize
+// kernel folds in block order in fp64 (deterministic).
+//
+// Reference arithmetic replaced: what autograd runs for nn.BatchNorm2d(train) / ReLU / Tanh / Sigmoid / clamp / the
+// AttentionBlock inside loss.backward() (training/train_dehazing.py:90-92) on the modules of models/dehazing/*.py.
+#include "adb_ptx.cuh"
+#include "adb_host.h"
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    f[2 * i] = __low2float(b);
+    f[2 * i + 1] = __high2float(b);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  q.x = adb::pack_bf16x2(f[0], f[1]); q.y = adb::pack_bf16x2(f[2], f[3]);
+  q.z = adb::pack_bf16x2(f[4], f[5]); q.w = adb::pack_bf16x2(f[6], f[7]);
+  return q;
+}
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float act_grad(float y, int act) {
+  if (act == ADB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ADB_ACT_TANH) return 1.f - y * y;
+  if (act == ADB_ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == ADB_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ADB_ACT_TANH) return tanhf(v);
+  if (act == ADB_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+inline int grid_for(long long work_items, int threads, int sm_count, int waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)sm_count * waves;
+  return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+inline int sm_count() {
+  adbh::DeviceInfo di;
+  return adbh::device_info(&di) == ADB_OK ? di.sm_count : 148;
+}
+
+constexpr int kRedThreads = 256;
+inline int red_blocks(long long pixels, int c, int sms) {
+  const int G = c / 8, PY = std::max(1, kRedThreads / G);
+  return (int)std::max<long long>(1, std::min<long long>((pixels + PY * 8 - 1) / (PY * 8), (long long)sms * 4));
+}
+
+// ------------------------------------------------------------------ per-channel reductions over a map
+// block = G x PY threads (G = c/8), thread (py, g) streams 8 channels down the pixels py, py + PY*gridDim, ...
+// MODE 0: a = sum z, b = sum z^2                                    (BatchNorm batch statistics)
+// MODE 1: g = dy * act'(y); a = sum g, b = sum g * xhat; writes g   (BatchNorm / bias backward; xhat = (z-mean)*rstd)
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads)
+chan_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, const __nv_bfloat16* __restrict__ dy, int pitch_dy,
+                   const __nv_bfloat16* __restrict__ y, int pitch_y, long long pixels, int c, int act,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ g_out,
+                   int pitch_g, float* __restrict__ partials) {
+  const int G = c / 8;
+  const int PY = blockDim.x / G;
+  const int g = threadIdx.x % G, py = threadIdx.x / G;
+  extern __shared__ float sm[];   // [PY][2][c]
+  float a[8], b[8], mu[8], rs[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a[q] = 0.f; b[q] = 0.f; mu[q] = 0.f; rs[q] = 0.f; }
+  if (py < PY) {
+    if (MODE == 1 && z) { load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); }
+    for (long long p = (long long)blockIdx.x * PY + py; p < pixels; p += (long long)gridDim.x * PY) {
+      if (MODE == 0) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { a[q] += f[q]; b[q] = fmaf(f[q], f[q], b[q]); }
+      } else {
+        float d[8], yy[8], zz[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)), d);
+        if (y) unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch_y + g * 8)), yy);
+        if (z) unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), zz);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float gg = y ? d[q] * act_grad(yy[q], act) : d[q];
+          d[q] = gg;
+          a[q] += gg;
+          if (z) b[q] = fmaf(gg, (zz[q] - mu[q]) * rs[q], b[q]);
+        }
+        if (g_out) *reinterpret_cast<uint4*>(g_out + (size_t)p * pitch_g + g * 8) = pack8(d);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sm[(py * 2 + 0) * c + g * 8 + q] = a[q];
+      sm[(py * 2 + 1) * c + g * 8 + q] = b[q];
+    }
+  }
+  __syncthreads();
+  float* mine = partials + (size_t)blockIdx.x * 2 * c;
+  for (int ch = threadIdx.x; ch < 2 * c; ch += blockDim.x) {
+    const int which = ch / c, cc = ch - which * c;
+    float s = 0.f;
+    for (int r = 0; r < PY; ++r) s += sm[(r * 2 + which) * c + cc];
+    mine[ch] = s;
+  }
+}
+
+// BatchNorm2d(train) statistics -> the epilogue affine, plus the running-statistics update (momentum, unbiased variance).
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int c, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, long long* num_batches_tracked,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (ch >= c) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nblocks; ++k) { s += partials[(size_t)k * 2 * c + ch]; ss += partials[(size_t)k * 2 * c + c + ch]; }
+  const double m = s / count;
+  double var = ss / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[ch] = (float)m;
+  rstd[ch] = r;
+  const float sc = gamma[ch] * r;
+  scale[ch] = sc;
+  shift[ch] = beta[ch] - (float)m * sc;
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+// y = act(z*scale + shift (+ residual))
+__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, long long pixels, int c,
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const __nv_bfloat16* __restrict__ res, int pitch_r, int act, __nv_bfloat16* __restrict__ y,
+                                  int pitch_y) {
+  const int G = c / 8;
+  const long long total = pixels * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long p = t / G;
+    float f[8], sc[8], sh[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), f);
+    load8f(scale + g * 8, sc); load8f(shift + g * 8, sh);
+    if (res) unpack8(__ldg(reinterpret_cast<const uint4*>(res + (size_t)p * pitch_r + g * 8)), r);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = act_fwd(fmaf(f[q], sc[q], sh[q]) + (res ? r[q] : 0.f), act);
+    *reinterpret_cast<uint4*>(y + (size_t)p * pitch_y + g * 8) = pack8(f);
+  }
+}
+
+// BatchNorm backward coefficients: dz = A*g + B*z + C per channel; dgamma = sum g*xhat, dbeta = sum g.
+// gamma == NULL: bias-only layer -> only dbeta (the conv bias gradient) is produced.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int c, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, int accumulate, float* dgamma, float* dbeta,
+                                       float* __restrict__ coef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int k = 0; k < nblocks; ++k) { sg += partials[(size_t)k * 2 * c + ch]; sgx += partials[(size_t)k * 2 * c + c + ch]; }
+  if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + (float)sg;
+  if (!gamma) return;
+  if (dgamma) dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)sgx;
+  const double k = (double)gamma[ch] * (double)rstd[ch];
+  const double mg = sg / count, mgx = sgx / count;
+  const double B = -k * mgx * (double)rstd[ch];
+  coef[ch] = (float)k;
+  coef[c + ch] = (float)B;
+  coef[2 * c + ch] = (float)(-k * mg - B * (double)mean[ch]);
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, int pitch_g, const __nv_bfloat16* __restrict__ z,
+                                    int pitch_z, long long pixels, int c, const float* __restrict__ coef,
+                                    __nv_bfloat16* __restrict__ dz, int pitch_dz) {
+  const int G = c / 8;
+  const long long total = pixels * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(t % G);
+    const long long p = t / G;
+    float gg[8], zz[8], A[8], B[8], Cc[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(g + (size_t)p * pitch_g + gi * 8)), gg);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + gi * 8)), zz);
+    load8f(coef + gi * 8, A); load8f(coef + c + gi * 8, B); load8f(coef + 2 * c + gi * 8, Cc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) gg[q] = fmaf(A[q], gg[q], fmaf(B[q], zz[q], Cc[q]));
+    *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + gi * 8) = pack8(gg);
+  }
+}
+
+__global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ a, int pitch_a, const __nv_bfloat16* __restrict__ b, int pitch_b,
+                                long long pixels, int c) {
+  const int G = c / 8;
+  const long long total = pixels * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long p = t / G;
+    float x[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + (size_t)p * pitch_a + g * 8), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + (size_t)p * pitch_b + g * 8)), y);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) x[q] += y[q];
+    *reinterpret_cast<uint4*>(a + (size_t)p * pitch_a + g * 8) = pack8(x);
+  }
+}
+
+// ------------------------------------------------------------------ image head (low:45, medium:117, high:135-138)
+// v = act(z[..., c]) per colour; BLEND: out = (1-alpha) x + alpha v; RESIDUAL: clamp(x + v); GUIDED: clamp(x + v*guidance)
+__global__ void img_head_fwd_kernel(const __nv_bfloat16* __restrict__ z, int pitch, const float* __restrict__ x,
+                                    const float* __restrict__ guidance, const float* __restrict__ alpha_p, int mode, int act,
+                                    int n, long long hw, float* __restrict__ out) {
+  const long long total = (long long)n * hw;
+  const float alpha = mode == ADB_IMG_BLEND ? __ldg(alpha_p) : 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long img = p / hw, q = p - img * hw;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(z + (size_t)p * pitch));
+    const __nv_bfloat162 b01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float zz[3] = {__low2float(b01), __high2float(b01), __low2float(b23)};
+    const float gd = mode == ADB_IMG_GUIDED ? __ldg(guidance + p) : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = ((size_t)img * 3 + c) * hw + q;
+      const float xv = __ldg(x + o), v = act_fwd(zz[c], act);
+      out[o] = mode == ADB_IMG_BLEND ? (1.f - alpha) * xv + alpha * v : fminf(fmaxf(xv + v * gd, 0.f), 1.f);
+    }
+  }
+}
+
+// red[0..2] += dbias, red[3] += dalpha  (block partial + one atomic per block and value)
+__global__ void img_head_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ z, int pitch,
+                                    const float* __restrict__ x, const float* __restrict__ guidance,
+                                    const float* __restrict__ alpha_p, int mode, int act, int n, long long hw,
+                                    __nv_bfloat16* __restrict__ dz, float* __restrict__ dguidance, float* __restrict__ red) {
+  const long long total = (long long)n * hw;
+  const float alpha = mode == ADB_IMG_BLEND ? __ldg(alpha_p) : 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long img = p / hw, q = p - img * hw;
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(z + (size_t)p * pitch));
+    const __nv_bfloat162 b01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 b23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float zz[3] = {__low2float(b01), __high2float(b01), __low2float(b23)};
+    const float gd = mode == ADB_IMG_GUIDED ? __ldg(guidance + p) : 1.f;
+    float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dgd = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const size_t o = ((size_t)img * 3 + c) * hw + q;
+      const float xv = __ldg(x + o), v = act_fwd(zz[c], act), go = __ldg(dout + o);
+      float dv;
+      if (mode == ADB_IMG_BLEND) {
+        dv = alpha * go;
+        acc[3] += go * (v - xv);
+      } else {
+        const float pre = xv + v * gd;
+        const float m = (pre >= 0.f && pre <= 1.f) ? go : 0.f;   // torch.clamp passes the gradient on the closed interval
+        dv = m * gd;
+        dgd += m * v;
+      }
+      d[c] = dv * act_grad(v, act);
+      acc[c] += d[c];
+    }
+    uint4* o16 = reinterpret_cast<uint4*>(dz + (size_t)p * pitch);
+    o16[0] = pack8(d);
+    for (int k = 1; k < pitch / 8; ++k) o16[k] = make_uint4(0, 0, 0, 0);
+    if (dguidance) dguidance[p] = dgd;
+  }
+  __shared__ float s_red[4][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_red[threadIdx.x][w];
+    atomicAdd(red + threadIdx.x, v);
+  }
+}
+
+// ------------------------------------------------------------------ 1x1 sigmoid head (detail_branch tail, high:87-89)
+// g = sigmoid(dot(y[..., :c], w) + b) ; backward: dpre = dg * g(1-g); dy = dpre * w; red[0..c) += dpre*y, red[c] += dpre
+__global__ void dot_head_fwd_kernel(const __nv_bfloat16* __restrict__ y, int pitch, int c, const float* __restrict__ w,
+                                    const float* __restrict__ b, long long pixels, float* __restrict__ g) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    float acc = __ldg(b);
+    for (int k = 0; k < c / 8; ++k) {
+      float f[8], ww[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch + k * 8)), f);
+      load8f(w + k * 8, ww);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(f[q], ww[q], acc);
+    }
+    g[p] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+template <int C>
+__global__ void dot_head_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                    int pitch, const float* __restrict__ w, long long pixels, __nv_bfloat16* __restrict__ dy,
+                                    int pitch_dy, float* __restrict__ red) {
+  float acc[C + 1];
+#pragma unroll
+  for (int i = 0; i <= C; ++i) acc[i] = 0.f;
+  float ww[C];
+#pragma unroll
+  for (int i = 0; i < C; ++i) ww[i] = __ldg(w + i);
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    const float gv = __ldg(g + p);
+    const float dpre = __ldg(dg + p) * gv * (1.f - gv);
+    acc[C] += dpre;
+#pragma unroll
+    for (int k = 0; k < C / 8; ++k) {
+      float f[8], d[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch + k * 8)), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { acc[k * 8 + q] = fmaf(dpre, f[q], acc[k * 8 + q]); d[q] = dpre * ww[k * 8 + q]; }
+      *reinterpret_cast<uint4*>(dy + (size_t)p * pitch_dy + k * 8) = pack8(d);
+    }
+  }
+  __shared__ float s_red[C + 1][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k <= C; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x <= C) {
+    float v = 0.f;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) v += s_red[threadIdx.x][wi];
+    atomicAdd(red + threadIdx.x, v);
+  }
+}
+
+// ------------------------------------------------------------------ AttentionBlock backward (base_model.py:64-78)
+// forward: cg = sigmoid(fc(avg)+fc(max)) [n,c]; u = x*cg; stats = (mean_c u, max_c u); sg = sigmoid(conv7x7(stats)); y = u*sg
+// pass 1 (per pixel): d_pre[p] = (sum_c dy*u) * sg(1-sg);  amax[p] = first argmax_c u
+template <int LP, int ML>
+__global__ void attn_bwd_pixel_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int n,
+                                      long long hw, int c, const float* __restrict__ gate, const float* __restrict__ sg,
+                                      float* __restrict__ d_pre, int* __restrict__ amax) {
+  const int G = c / 8;
+  const int sub = threadIdx.x % LP;
+  constexpr int PPW = 32 / LP;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long stride = ((long long)gridDim.x * blockDim.x >> 5) * PPW;
+  const long long total = (long long)n * hw;
+  for (long long pw = warp_id * PPW; pw < total; pw += stride) {
+    const long long p = pw + (threadIdx.x & 31) / LP;
+    const bool live = p < total;
+    float s = 0.f, m = -INFINITY;
+    int mi = 0x7fffffff;
+    if (live) {
+      const int img = (int)(p / hw);
+      const float* gt = gate + (size_t)img * c;
+#pragma unroll
+      for (int k = 0; k < ML; ++k) {
+        const int g = sub + k * LP;
+        if (g < G) {
+          float f[8], d[8], gg[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)p * c + g * 8)), f);
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * c + g * 8)), d);
+          load8f(gt + g * 8, gg);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float u = f[q] * gg[q];
+            s = fmaf(d[q], u, s);
+            if (u > m) { m = u; mi = g * 8 + q; }     // ascending channel order within the lane: first max wins
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LP / 2; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    }
+    if (live && sub == 0) {
+      const float sv = __ldg(sg + p);
+      d_pre[p] = s * sv * (1.f - sv);
+      amax[p] = mi;
+    }
+  }
+}
+
+// pass 2 (stencil transpose): d_stats[ch][q] = sum_off wsp[ch][off] * d_pre[q - off];  dwsp[ch][off] += sum_p d_pre[p] * stats[ch][p + off]
+constexpr int kBwTW = 32, kBwTH = 16;
+__global__ void attn_bwd_stencil_kernel(const float* __restrict__ d_pre, const float* __restrict__ stats, int h, int w,
+                                        const float* __restrict__ wsp, float* __restrict__ d_stats, float* __restrict__ dwsp) {
+  __shared__ float s_w[98];
+  __shared__ float s_d[kBwTH + 6][kBwTW + 6];
+  __shared__ float2 s_t[kBwTH + 6][kBwTW + 6];
+  __shared__ float s_acc[98];
+  const int img = blockIdx.z;
+  const int tid = threadIdx.y * kBwTW + threadIdx.x;
+  for (int i = tid; i < 98; i += kBwTW * kBwTH) { s_w[i] = wsp[i]; s_acc[i] = 0.f; }
+  const int x0 = blockIdx.x * kBwTW - 3, y0 = blockIdx.y * kBwTH - 3;
+  const float* dp = d_pre + (size_t)img * h * w;
+  const float2* st = reinterpret_cast<const float2*>(stats) + (size_t)img * h * w;
+  for (int i = tid; i < (kBwTH + 6) * (kBwTW + 6); i += kBwTW * kBwTH) {
+    const int ty = i / (kBwTW + 6), tx = i - ty * (kBwTW + 6);
+    const int yy = y0 + ty, xx = x0 + tx;
+    const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+    s_d[ty][tx] = in ? __ldg(dp + (size_t)yy * w + xx) : 0.f;
+    s_t[ty][tx] = in ? __ldg(st + (size_t)yy * w + xx) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int px = blockIdx.x * kBwTW + threadIdx.x, py = blockIdx.y * kBwTH + threadIdx.y;
+  const bool live = px < w && py < h;
+  // d_stats at q = (py, px): forward pre[p] = sum_off w[off] * stats[p + off - 3]  =>  d_stats[q] = sum_off w[off] * d_pre[q - off + 3]
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const float v = s_d[threadIdx.y + 6 - dy][threadIdx.x + 6 - dx];
+      a0 = fmaf(s_w[dy * 7 + dx], v, a0);
+      a1 = fmaf(s_w[49 + dy * 7 + dx], v, a1);
+    }
+  if (live) *reinterpret_cast<float2*>(d_stats + (((size_t)img * h + py) * w + px) * 2) = make_float2(a0, a1);
+  // dwsp: this thread's pixel p contributes d_pre[p] * stats[p + off - 3]
+  const float dcen = live ? s_d[threadIdx.y + 3][threadIdx.x + 3] : 0.f;
+  const int lane = tid & 31;
+  for (int off = 0; off < 49; ++off) {
+    const int dy = off / 7, dx = off - dy * 7;
+    const float2 v = s_t[threadIdx.y + dy][threadIdx.x + dx];
+    float c0 = dcen * v.x, c1 = dcen * v.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); }
+    if (lane == 0) { atomicAdd(&s_acc[off], c0); atomicAdd(&s_acc[49 + off], c1); }
+  }
+  __syncthreads();
+  for (int i = tid; i < 98; i += kBwTW * kBwTH) atomicAdd(dwsp + i, s_acc[i]);
+}
+
+// pass 3: du = dy*sg + d_mean/C + d_max*[c == amax];  dx = du*cg (bf16);  per-block partial of dgate[n][c] = sum_p du*x;
+//         pos[n][c] = min pixel index with x == max (AdaptiveMaxPool2d's winner), for pass 5.
+// grid = (chunks, n); block = G x PY
+__global__ void __launch_bounds__(kRedThreads)
+attn_bwd_main_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, long long hw, int c,
+                     const float* __restrict__ gate, const float* __restrict__ sg, const float* __restrict__ d_stats,
+                     const int* __restrict__ amax, const float* __restrict__ pool, __nv_bfloat16* __restrict__ dx,
+                     float* __restrict__ partials, int* __restrict__ pos) {
+  const int img = blockIdx.y, chunks = gridDim.x;
+  const int G = c / 8;
+  const int PY = blockDim.x / G;
+  const int g = threadIdx.x % G, py = threadIdx.x / G;
+  extern __shared__ float sm[];   // [PY][c]
+  float a[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a[q] = 0.f;
+  if (py < PY) {
+    float gg[8], mx[8];
+    load8f(gate + (size_t)img * c + g * 8, gg);
+    load8f(pool + ((size_t)img * 2 + 1) * c + g * 8, mx);
+    const float inv_c = 1.f / (float)c;
+    int best[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) best[q] = 0x7fffffff;
+    for (long long p = (long long)blockIdx.x * PY + py; p < hw; p += (long long)chunks * PY) {
+      const size_t gp = (size_t)img * hw + p;
+      float f[8], d[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + gp * c + g * 8)), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + gp * c + g * 8)), d);
+      const float sv = __ldg(sg + gp);
+      const float2 ds = __ldg(reinterpret_cast<const float2*>(d_stats) + gp);
+      const int am = __ldg(amax + gp);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float du = fmaf(d[q], sv, ds.x * inv_c);
+        if (am == g * 8 + q) du += ds.y;
+        a[q] = fmaf(du, f[q], a[q]);
+        d[q] = du * gg[q];
+        if (f[q] == mx[q] && (int)p < best[q]) best[q] = (int)p;
+      }
+      *reinterpret_cast<uint4*>(dx + gp * c + g * 8) = pack8(d);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sm[py * c + g * 8 + q] = a[q];
+      if (best[q] != 0x7fffffff) atomicMin(pos + (size_t)img * c + g * 8 + q, best[q]);
+    }
+  }
+  __syncthreads();
+  float* mine = partials + ((size_t)img * chunks + blockIdx.x) * c;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < PY; ++r) s += sm[r * c + ch];
+    mine[ch] = s;
+  }
+}
+
+// pass 4 (one block per image): dgate -> through sigmoid and the shared MLP (fc = W2 relu(W1 .)) for the avg and max inputs.
+// d_avg[n][c] (already divided by hw), d_max[n][c]; dw1[cr][c], dw2[c][cr] accumulate over images with atomics.
+__global__ void attn_bwd_gate_kernel(const float* __restrict__ partials, int chunks, const float* __restrict__ pool, float inv_hw,
+                                     int c, int cr, const float* __restrict__ gate, const float* __restrict__ w1,
+                                     const float* __restrict__ w2, float* __restrict__ d_avg, float* __restrict__ d_max,
+                                     float* __restrict__ dw1, float* __restrict__ dw2) {
+  const int img = blockIdx.x;
+  extern __shared__ float sm[];   // avg[c], mx[c], dpre[c], ha[cr], hm[cr], dha[cr], dhm[cr]
+  float* avg = sm; float* mx = sm + c; float* dpre = sm + 2 * c;
+  float* ha = sm + 3 * c; float* hm = ha + cr; float* dha = hm + cr; float* dhm = dha + cr;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    avg[ch] = pool[((size_t)img * 2 + 0) * c + ch] * inv_hw;
+    mx[ch] = pool[((size_t)img * 2 + 1) * c + ch];
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += partials[((size_t)img * chunks + k) * c + ch];
+    const float gv = gate[(size_t)img * c + ch];
+    dpre[ch] = s * gv * (1.f - gv);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < cr; j += nwarps) {          // hidden pre-activations and their gradients
+    float a = 0.f, b = 0.f, dh = 0.f;
+    for (int ch = lane; ch < c; ch += 32) {
+      const float wv = w1[(size_t)j * c + ch];
+      a = fmaf(wv, avg[ch], a); b = fmaf(wv, mx[ch], b);
+      dh = fmaf(w2[(size_t)ch * cr + j], dpre[ch], dh);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); dh += __shfl_xor_sync(0xffffffffu, dh, o);
+    }
+    if (lane == 0) { ha[j] = fmaxf(a, 0.f); hm[j] = fmaxf(b, 0.f); dha[j] = a > 0.f ? dh : 0.f; dhm[j] = b > 0.f ? dh : 0.f; }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float da = 0.f, dm = 0.f;
+    for (int j = 0; j < cr; ++j) {
+      const float wv = w1[(size_t)j * c + ch];
+      da = fmaf(wv, dha[j], da); dm = fmaf(wv, dhm[j], dm);
+      atomicAdd(dw1 + (size_t)j * c + ch, dha[j] * avg[ch] + dhm[j] * mx[ch]);
+      atomicAdd(dw2 + (size_t)ch * cr + j, dpre[ch] * (ha[j] + hm[j]));
+    }
+    d_avg[(size_t)img * c + ch] = da * inv_hw;
+    d_max[(size_t)img * c + ch] = dm;
+  }
+}
+
+// pass 5: dx[p][c] += d_avg[n][c] + d_max[n][c] * [p == pos[n][c]]
+__global__ void attn_bwd_pool_kernel(__nv_bfloat16* __restrict__ dx, int n, long long hw, int c, const float* __restrict__ d_avg,
+                                     const float* __restrict__ d_max, const int* __restrict__ pos) {
+  const int G = c / 8;
+  const long long total = (long long)n * hw * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long gp = t / G;
+    const int img = (int)(gp / hw);
+    const int p = (int)(gp - (long long)img * hw);
+    float f[8], da[8], dm[8];
+    unpack8(*reinterpret_cast<const uint4*>(dx + (size_t)gp * c + g * 8), f);
+    load8f(d_avg + (size_t)img * c + g * 8, da);
+    load8f(d_max + (size_t)img * c + g * 8, dm);
+    const int4 p0 = __ldg(reinterpret_cast<const int4*>(pos + (size_t)img * c + g * 8));
+    const int4 p1 = __ldg(reinterpret_cast<const int4*>(pos + (size_t)img * c + g * 8 + 4));
+    const int pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] += da[q] + (pp[q] == p ? dm[q] : 0.f);
+    *reinterpret_cast<uint4*>(dx + (size_t)gp * c + g * 8) = pack8(f);
+  }
+}
+
+__global__ void fill_int_kernel(int* p, long long n, int v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------ Adam (torch.optim.Adam semantics: L2 weight decay added to the gradient)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    const float gr = fmaf(wd, w, g[i] * grad_scale);
+    const float mm = fmaf(b1, m[i], (1.f - b1) * gr);
+    const float vv = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+    m[i] = mm; v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    p[i] = w - (lr / bc1) * (mm / denom);
+  }
+}
+
+}  // namespace
+
+#define ADB_BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define ADB_BFM(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+extern "C" {
+
+int64_t adb_bn_scratch_floats(int64_t pixels, int32_t c) {
+  return (int64_t)red_blocks(pixels, c, sm_count()) * 2 * c + 3 * (int64_t)c;
+}
+
+int adb_bn_train_stats(const void* z, int64_t pixels, int32_t c, int32_t pitch, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scratch,
+                       float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  ADB_REQUIRE(z && gamma && beta && scratch && mean && rstd && scale && shift, "adb_bn_train_stats: null pointer");
+  ADB_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0 && c <= 2048 && pitch >= c && pitch % 8 == 0, "adb_bn_train_stats: bad shape (pixels=%lld c=%d pitch=%d)", (long long)pixels, c, pitch);
+  const int sms = sm_count();
+  const int nb = red_blocks(pixels, c, sms);
+  const int G = c / 8, PY = std::max(1, kRedThreads / G);
+  cudaStream_t st = (cudaStream_t)stream;
+  chan_reduce_kernel<0><<<nb, kRedThreads, (size_t)PY * 2 * c * sizeof(float), st>>>(ADB_BF(z), pitch, nullptr, 0, nullptr, 0, pixels, c, 0,
+                                                                                   nullptr, nullptr, nullptr, 0, scratch);
+  ADB_CUDA_OK(cudaGetLastError());
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, nb, c, (double)pixels, gamma, beta, eps, momentum, running_mean, running_var,
+                                                      reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_affine_act(const void* z, int32_t pitch_z, int64_t pixels, int32_t c, const float* scale, const float* shift,
+                   const void* residual, int32_t pitch_r, int32_t act, void* y, int32_t pitch_y, void* stream) {
+  ADB_REQUIRE(z && scale && shift && y, "adb_affine_act: null pointer");
+  ADB_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0 && pitch_z % 8 == 0 && pitch_y % 8 == 0 && (!residual || pitch_r % 8 == 0), "adb_affine_act: bad shape");
+  affine_act_kernel<<<grid_for(pixels * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(z), pitch_z, pixels, c, scale, shift, ADB_BF(residual), pitch_r, act, ADB_BFM(y), pitch_y);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t pitch_y, const void* z, int32_t pitch_z, int64_t pixels,
+               int32_t c, int32_t act, const float* gamma, const float* mean, const float* rstd, float* scratch, void* g_out,
+               int32_t pitch_g, void* dz, int32_t pitch_dz, float* dgamma, float* dbeta, int32_t accumulate, void* stream) {
+  ADB_REQUIRE(dy && scratch && g_out, "adb_bn_bwd: null pointer");
+  ADB_REQUIRE((gamma != nullptr) == (z != nullptr), "adb_bn_bwd: gamma and z go together (both NULL for a bias-only layer)");
+  ADB_REQUIRE(!gamma || (mean && rstd && dz), "adb_bn_bwd: BatchNorm backward needs mean/rstd/dz");
+  ADB_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0 && c <= 2048, "adb_bn_bwd: bad shape");
+  const int sms = sm_count();
+  const int nb = red_blocks(pixels, c, sms);
+  const int G = c / 8, PY = std::max(1, kRedThreads / G);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* coef = scratch + (size_t)nb * 2 * c;
+  chan_reduce_kernel<1><<<nb, kRedThreads, (size_t)PY * 2 * c * sizeof(float), st>>>(ADB_BF(z), pitch_z, ADB_BF(dy), pitch_dy, ADB_BF(y), pitch_y,
+                                                                                   pixels, c, act, mean, rstd, ADB_BFM(g_out), pitch_g, scratch);
+  ADB_CUDA_OK(cudaGetLastError());
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
+  ADB_CUDA_OK(cudaGetLastError());
+  if (gamma) {
+    bn_bwd_apply_kernel<<<grid_for(pixels * G, 256, sms, 16), 256, 0, st>>>(ADB_BF(g_out), pitch_g, ADB_BF(z), pitch_z, pixels, c, coef,
+                                                                            ADB_BFM(dz), pitch_dz);
+    ADB_CUDA_OK(cudaGetLastError());
+  }
+  return ADB_OK;
+}
+
+int adb_add_bf16(void* a, int32_t pitch_a, const void* b, int32_t pitch_b, int64_t pixels, int32_t c, void* stream) {
+  ADB_REQUIRE(a && b && pixels > 0 && c % 8 == 0 && pitch_a % 8 == 0 && pitch_b % 8 == 0, "adb_add_bf16: bad arguments");
+  add_bf16_kernel<<<grid_for(pixels * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(ADB_BFM(a), pitch_a, ADB_BF(b), pitch_b, pixels, c);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_img_head_fwd(const void* z, int32_t pitch, const float* x, const float* guidance, const float* alpha, int32_t mode,
+                     int32_t act, int32_t n, int32_t h, int32_t w, float* out, void* stream) {
+  ADB_REQUIRE(z && x && out && pitch >= 8 && pitch % 8 == 0, "adb_img_head_fwd: bad arguments");
+  ADB_REQUIRE(mode != ADB_IMG_GUIDED || guidance, "adb_img_head_fwd: GUIDED needs guidance");
+  ADB_REQUIRE(mode != ADB_IMG_BLEND || alpha, "adb_img_head_fwd: BLEND needs alpha");
+  const long long hw = (long long)h * w;
+  img_head_fwd_kernel<<<grid_for((long long)n * hw, 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(ADB_BF(z), pitch, x, guidance, alpha, mode, act, n, hw, out);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_img_head_bwd(const float* dout, const void* z, int32_t pitch, const float* x, const float* guidance, const float* alpha,
+                     int32_t mode, int32_t act, int32_t n, int32_t h, int32_t w, void* dz, float* dguidance, float* red4,
+                     void* stream) {
+  ADB_REQUIRE(dout && z && x && dz && red4 && pitch >= 8 && pitch % 8 == 0, "adb_img_head_bwd: bad arguments");
+  ADB_REQUIRE(mode != ADB_IMG_GUIDED || (guidance && dguidance), "adb_img_head_bwd: GUIDED needs guidance/dguidance");
+  ADB_REQUIRE(mode != ADB_IMG_BLEND || alpha, "adb_img_head_bwd: BLEND needs alpha");
+  const long long hw = (long long)h * w;
+  cudaStream_t st = (cudaStream_t)stream;
+  ADB_CUDA_OK(cudaMemsetAsync(red4, 0, 4 * sizeof(float), st));
+  img_head_bwd_kernel<<<grid_for((long long)n * hw, 256, sm_count(), 8), 256, 0, st>>>(dout, ADB_BF(z), pitch, x, guidance, alpha, mode, act, n, hw,
+                                                                                        ADB_BFM(dz), dguidance, red4);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_dot_head_fwd(const void* y, int32_t pitch, int32_t c, const float* w, const float* b, int64_t pixels, float* g, void* stream) {
+  ADB_REQUIRE(y && w && b && g && c % 8 == 0 && pitch >= c, "adb_dot_head_fwd: bad arguments");
+  dot_head_fwd_kernel<<<grid_for(pixels, 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(ADB_BF(y), pitch, c, w, b, pixels, g);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_dot_head_bwd(const float* dg, const float* g, const void* y, int32_t pitch, int32_t c, const float* w, int64_t pixels, void* dy,
+                     int32_t pitch_dy, float* red /*[c+1]*/, void* stream) {
+  ADB_REQUIRE(dg && g && y && w && dy && red, "adb_dot_head_bwd: null pointer");
+  ADB_REQUIRE(c == 16 || c == 32, "adb_dot_head_bwd: c must be 16 or 32 (got %d)", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  ADB_CUDA_OK(cudaMemsetAsync(red, 0, (size_t)(c + 1) * sizeof(float), st));
+  const int grid = grid_for(pixels, 256, sm_count(), 4);
+  if (c == 16) dot_head_bwd_kernel<16><<<grid, 256, 0, st>>>(dg, g, ADB_BF(y), pitch, w, pixels, ADB_BFM(dy), pitch_dy, red);
+  else dot_head_bwd_kernel<32><<<grid, 256, 0, st>>>(dg, g, ADB_BF(y), pitch, w, pixels, ADB_BFM(dy), pitch_dy, red);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+static int attn_chunks(long long hw, int c, int n, int sms) {
+  const int G = c / 8, PY = std::max(1, kRedThreads / G);
+  long long chunks = (hw + PY * 8 - 1) / (PY * 8);
+  chunks = std::min<long long>(chunks, std::max(1, sms * 4 / std::max(1, n)));
+  return (int)std::max<long long>(1, chunks);
+}
+
+int64_t adb_attn_bwd_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c) {
+  const long long hw = (long long)h * w;
+  // d_pre[n*hw] | amax[n*hw] (int) | d_stats[n*hw*2] | partials[n*chunks*c] | d_avg[n*c] | d_max[n*c] | pos[n*c] (int)
+  return (int64_t)n * hw * 4 + (int64_t)n * attn_chunks(hw, c, n, sm_count()) * c + 3LL * n * c;
+}
+
+int adb_attn_bwd(const void* dy, const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* pool, const float* gate,
+                 const float* stats, const float* spatial, const float* w1, const float* w2, int32_t c_red, const float* w_spatial,
+                 float* scratch, void* dx, float* dw1, float* dw2, float* dw_spatial, void* stream) {
+  ADB_REQUIRE(dy && x && pool && gate && stats && spatial && w1 && w2 && w_spatial && scratch && dx && dw1 && dw2 && dw_spatial,
+              "adb_attn_bwd: null pointer");
+  ADB_REQUIRE(n > 0 && h > 0 && w > 0 && c % 8 == 0 && c <= 2048 && c_red > 0, "adb_attn_bwd: bad shape");
+  const long long hw = (long long)h * w;
+  ADB_REQUIRE(hw < (1LL << 31), "adb_attn_bwd: map too large");
+  const int sms = sm_count();
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = attn_chunks(hw, c, n, sms);
+  float* d_pre = scratch;
+  int* amax = reinterpret_cast<int*>(scratch + (size_t)n * hw);
+  float* d_stats = scratch + 2 * (size_t)n * hw;
+  float* partials = scratch + 4 * (size_t)n * hw;
+  float* d_avg = partials + (size_t)n * chunks * c;
+  float* d_max = d_avg + (size_t)n * c;
+  int* pos = reinterpret_cast<int*>(d_max + (size_t)n * c);
+  const int G = c / 8;
+  const long long total = (long long)n * hw;
+#define ADB_BWPIX(LP_, ML_) attn_bwd_pixel_kernel<LP_, ML_><<<grid_for(total * (LP_), 256, sms, 8), 256, 0, st>>>( \
+    ADB_BF(dy), ADB_BF(x), n, hw, c, gate, spatial, d_pre, amax)
+  if (G <= 4) ADB_BWPIX(4, 1);
+  else if (G <= 8) ADB_BWPIX(8, 1);
+  else if (G <= 16) ADB_BWPIX(16, 1);
+  else if (G <= 32) ADB_BWPIX(32, 1);
+  else if (G <= 64) ADB_BWPIX(32, 2);
+  else if (G <= 128) ADB_BWPIX(32, 4);
+  else ADB_BWPIX(32, 8);
+#undef ADB_BWPIX
+  ADB_CUDA_OK(cudaGetLastError());
+  ADB_CUDA_OK(cudaMemsetAsync(dw_spatial, 0, 98 * sizeof(float), st));
+  {
+    dim3 block(kBwTW, kBwTH), grid((w + kBwTW - 1) / kBwTW, (h + kBwTH - 1) / kBwTH, n);
+    attn_bwd_stencil_kernel<<<grid, block, 0, st>>>(d_pre, stats, h, w, w_spatial, d_stats, dw_spatial);
+    ADB_CUDA_OK(cudaGetLastError());
+  }
+  fill_int_kernel<<<grid_for((long long)n * c, 256, sms, 1), 256, 0, st>>>(pos, (long long)n * c, 0x7fffffff);
+  {
+    const int PY = std::max(1, kRedThreads / G);
+    dim3 grid(chunks, n);
+    attn_bwd_main_kernel<<<grid, kRedThreads, (size_t)PY * c * sizeof(float), st>>>(ADB_BF(dy), ADB_BF(x), hw, c, gate, spatial, d_stats, amax, pool,
+                                                                                   ADB_BFM(dx), partials, pos);
+    ADB_CUDA_OK(cudaGetLastError());
+  }
+  ADB_CUDA_OK(cudaMemsetAsync(dw1, 0, (size_t)c_red * c * sizeof(float), st));
+  ADB_CUDA_OK(cudaMemsetAsync(dw2, 0, (size_t)c_red * c * sizeof(float), st));
+  attn_bwd_gate_kernel<<<n, 256, (size_t)(3 * c + 4 * c_red) * sizeof(float), st>>>(partials, chunks, pool, 1.f / (float)hw, c, c_red, gate, w1, w2,
+                                                                                    d_avg, d_max, dw1, dw2);
+  ADB_CUDA_OK(cudaGetLastError());
+  attn_bwd_pool_kernel<<<grid_for(total * G, 256, sms, 16), 256, 0, st>>>(ADB_BFM(dx), n, hw, c, d_avg, d_max, pos);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+  ADB_REQUIRE(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "adb_adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(numel, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
+                                                                                     weight_decay, bc1, sqrtf(bc2), grad_scale);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+}  // extern "C"

@@ -104,6 +104,7 @@ class BranchEngine:
         self.S = None
         self._bufs = {}
         self.tune = None
+        self.train_cache = None   # bf16 weight packings of the training path (training/autograd.py)
 
     # ------------------------------------------------------------------ packing
     def specs(self):
@@ -228,7 +229,8 @@ class BranchEngine:
         (index int32[>=count], n_dev device int) only bucket rows index[0:*n_dev] are read and their outputs scattered
         to the same rows of `out`; `count` is the host-side upper bound of the bucket size (default: batch size)."""
         require_cuda(x, type(self.model).__name__)
-        require_inference(self.model, type(self.model).__name__)
+        if self.model.training:
+            return self._forward_train(x, out, index)
         x = x.contiguous()
         b, _, h, w = x.shape
         need = {"light": 1, "low_unet": 2}.get(self.kind, 4)
@@ -244,6 +246,23 @@ class BranchEngine:
         for start in range(0, upper, mb):
             run(S, x, out, index, n_dev, start, min(mb, upper - start), mb)
         return out
+
+    def _forward_train(self, x, out, index):
+        """train() mode: batch-statistics BatchNorm forward on a tape + kernel-built backward (training/autograd.py)."""
+        from .training import autograd as _ag
+        name = type(self.model).__name__
+        if index is not None or out is not None:
+            raise NotImplementedError(f"{name}: routed buckets are an inference path; train() mode takes a plain batch")
+        if self.kind not in ("light", "unet", "unet_attn"):
+            raise NotImplementedError(f"{name}: training on the B200 path covers the default branch models; call .eval() "
+                                      "for inference — there is no torch fallback")
+        b, _, h, w = x.shape
+        need, wmin = (1, 16) if self.kind == "light" else (4, 64)
+        if h % need or w % need or w < wmin:
+            raise ValueError(f"{name}: train() mode needs H, W multiples of {need} and W >= {wmin} (got {h}x{w})")
+        if self.train_cache is None:
+            self.train_cache = _ag._WeightCache()
+        return _ag.train_forward(self, x.contiguous())
 
     def _kw(self, n_dev, n_start, n):
         kw = {"n": n, "n_dev": n_dev, "n_start": n_start}

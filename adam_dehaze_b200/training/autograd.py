@@ -1,0 +1,370 @@
+"""Training-mode execution of the branch models: forward with batch-statistics BatchNorm, and a reverse-mode tape whose
+backward is built from libadb200 kernels only (reference: model.train(); loss.backward() in
+training/train_dehazing.py:66-92 and training/train_joint.py:129-150).
+
+Data gradients re-use the tcgen05 implicit-GEMM forward kernel (adb_conv2d) with transformed weights:
+  * k x k stride-1 conv  -> the same conv with the kernel rotated by 180 degrees and in/out channels swapped;
+  * 4x4 stride-2 conv    -> ConvTranspose2d(4,2,1) with the weight as is (the kernel's four sub-pixel phases);
+  * ConvTranspose2d(4,2,1) -> 4x4 stride-2 conv with the weight as is.
+Weight gradients run on adb_wgrad (pixel-reduction GEMM), BatchNorm/activation/attention/head backward on the
+HBM-bound kernels of csrc/train.cu.  Activations and their gradients are NHWC bf16; parameter gradients fp32 in the
+parameter's own layout, handed to autograd by `BranchTrainFn` so optimizers/DDP hooks see ordinary `.grad`s.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib, ops
+from ..ops import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, CONVT_4X4S2, IMG_BLEND, IMG_GUIDED,
+                   IMG_RESIDUAL, WG_OIHW, WG_STEM, ConvSpec)
+
+
+def _f32(n, dev):
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+class Node:
+    """An activation on the tape: NHWC bf16 tensor (or fp32 [n,h,w] for the guidance map) + its accumulated gradient."""
+    __slots__ = ("t", "c", "grad")
+
+    def __init__(self, t, c=None):
+        self.t, self.c, self.grad = t, (t.shape[-1] if c is None else c), None
+
+    def accumulate(self, g):
+        if self.grad is None:
+            self.grad = g
+        else:
+            n, h, w, p = self.grad.shape
+            _lib.call("adb_add_bf16", _lib.ptr(self.grad), p, _lib.ptr(g), g.shape[3], n * h * w, self.c, _lib.current_stream())
+
+    def accumulate_conv(self, spec, src):
+        """grad += conv(src) with the accumulation fused into the conv epilogue where the kernel allows it."""
+        if self.grad is None:
+            self.grad = ops.conv2d(spec, src)
+        elif spec.kind == CONVT_4X4S2:       # the sub-pixel store path has no residual input
+            self.accumulate(ops.conv2d(spec, src))
+        else:
+            ops.conv2d(spec, src, dst=self.grad, residual=self.grad)
+
+
+class _WeightCache:
+    """bf16 packings of a parameter for the forward and the data-gradient launches, rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, key, params, build):
+        sig = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        hit = self._c.get(key)
+        if hit is None or hit[0] != sig:
+            hit = (sig, build())
+            self._c[key] = hit
+        return hit[1]
+
+
+def _pad_rows16(w):
+    co = w.shape[0]
+    cp = ops.pad16(co)
+    if cp == co:
+        return w
+    out = torch.zeros((cp,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+    out[:co] = w
+    return out
+
+
+def _dgrad_spec_s1(w):
+    """W [co][ci][k][k] -> spec of dX = conv(dZ, rot180(W)^T); dZ carries pad16(co) channels."""
+    wd = _pad_rows16(w.detach().float()).flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    return ConvSpec.from_conv(wd, stride=1, pad=w.shape[2] // 2)
+
+
+class Tape:
+    def __init__(self, model_cache):
+        self.back = []
+        self.pg = {}
+        self.wc = model_cache
+
+    # ------------------------------------------------------------------ helpers
+    def _bn_forward(self, z, c, bn, act, residual=None):
+        n, h, w, pitch = z.shape
+        dev = z.device
+        px = n * h * w
+        scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
+        stats = _f32(4 * c, dev)
+        mean, rstd, scale, shift = stats[:c], stats[c:2 * c], stats[2 * c:3 * c], stats[3 * c:]
+        st = _lib.current_stream()
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        _lib.call("adb_bn_train_stats", _lib.ptr(z), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
+                  _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
+                  _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        y = torch.empty_like(z)
+        _lib.call("adb_affine_act", _lib.ptr(z), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift),
+                  _lib.ptr(residual), 0 if residual is None else residual.shape[3], act, _lib.ptr(y), pitch, st)
+        return y, mean, rstd
+
+    def _bn_backward(self, dy, y, z, c, act, bn, mean, rstd, keep_g):
+        """Returns (g, dz).  g = dy*act'(y) (written over dy); dz aliases g unless keep_g."""
+        n, h, w, pitch = dy.shape
+        px = n * h * w
+        dev = dy.device
+        scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
+        dz = torch.empty_like(dy) if keep_g else dy
+        dgamma, dbeta = _f32(c, dev), _f32(c, dev)
+        _lib.call("adb_bn_bwd", _lib.ptr(dy), pitch, _lib.ptr(y), 0 if y is None else y.shape[3], _lib.ptr(z), z.shape[3], px, c, act,
+                  _lib.ptr(bn.weight), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scratch), _lib.ptr(dy), pitch, _lib.ptr(dz), pitch,
+                  _lib.ptr(dgamma), _lib.ptr(dbeta), 0, _lib.current_stream())
+        self.pg[bn.weight], self.pg[bn.bias] = dgamma, dbeta
+        return dy, dz
+
+    # ------------------------------------------------------------------ layers
+    def stem(self, x, kw, pad, kp):
+        return Node(ops.stem_pack(x, kw, pad, kp))
+
+    def conv_bn_act(self, conv, bn, act, srcs, residual=None, stem_kp=None):
+        """nn.Conv2d (stride 1 'same' or 4x4 stride 2) [+bias] -> BatchNorm2d(train) -> act, optional residual add before
+        the activation (ResidualBlock, base_model.py:36-41).  srcs: one or two Nodes read as a channel concat."""
+        w, b = conv.weight, conv.bias
+        stride = conv.stride[0]
+        if stem_kp:
+            fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_stem(w, stem_kp, bias=b))
+        else:
+            fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_conv(w, bias=b, stride=stride, pad=conv.padding[0]))
+        a = srcs[0]
+        bsrc = srcs[1] if len(srcs) > 1 else None
+        z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        c = fspec.cout_pad
+        assert c == fspec.cout, "BatchNorm layers have channel counts that are multiples of 16"
+        y, mean, rstd = self._bn_forward(z, c, bn, act, None if residual is None else residual.t)
+        out = Node(y, c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            g, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=residual is not None)
+            if residual is not None:
+                residual.accumulate(g)
+            self._conv_backward(conv, dz, c, srcs, stem_kp)
+        self.back.append(backward)
+        return out
+
+    def _conv_backward(self, conv, dz, cz, srcs, stem_kp=None, cz_true=None):
+        """Weight gradient + data gradients of a Conv2d given dL/d(conv output) `dz` (NHWC bf16, cz channels)."""
+        w = conv.weight
+        co, ci, kh, kw = w.shape
+        stride = conv.stride[0]
+        a = srcs[0]
+        bsrc = srcs[1] if len(srcs) > 1 else None
+        if stem_kp:
+            self.pg[w] = ops.wgrad(dz, a.t, kh=kh, kw=1, pad=kh // 2, cs=cz, cs_true=cz_true, layout=WG_STEM, stem_kw=kw)
+            return
+        kind = CONV_S1 if stride == 1 else CONV_S2
+        self.pg[w] = ops.wgrad(dz, a.t, None if bsrc is None else bsrc.t, kind=kind, kh=kh, kw=kw, pad=conv.padding[0], cs=cz,
+                               cs_true=cz_true, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        off = 0
+        for i, s in enumerate(srcs):
+            lo, hi = off, off + s.c
+            off = hi
+            if stride == 1:
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: _dgrad_spec_s1(w[:, lo:hi]))
+            else:   # 4x4 stride-2 conv: dX = ConvTranspose2d(dZ, W)
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_convT(_pad_rows16(w.detach()[:, lo:hi])))
+            s.accumulate_conv(spec, dz)
+
+    def convT_bn_act(self, convT, bn, act, srcs):
+        """nn.ConvTranspose2d(4,2,1) + bias -> BatchNorm2d(train) -> act (decoder `up`, medium:53-55,63-65; high:57-59,68-70)."""
+        w, b = convT.weight, convT.bias
+        fspec = self.wc.get(("f", id(convT)), (w, b), lambda: ConvSpec.from_convT(w, bias=b))
+        a = srcs[0]
+        bsrc = srcs[1] if len(srcs) > 1 else None
+        z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        c = fspec.cout_pad
+        y, mean, rstd = self._bn_forward(z, c, bn, act)
+        out = Node(y, c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            _, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=False)
+            gw = torch.empty_like(w, dtype=torch.float32)
+            off = 0
+            for i, s in enumerate(srcs):
+                lo, hi = off, off + s.c
+                off = hi
+                # dWt[ci][co][r][s]: the stride-2 form with the maps swapped (small = layer input, large = dz)
+                ops.wgrad(s.t, dz, kind=CONV_S2, kh=4, kw=4, pad=1, cs=s.c, c0=c, out=gw[lo:hi])
+                spec = self.wc.get(("d", id(convT), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_conv(w.detach()[lo:hi], stride=2, pad=1))
+                s.accumulate_conv(spec, dz)
+            self.pg[w] = gw
+            if b is not None:
+                # the bias feeds a batch-statistics BatchNorm: its gradient is sum(dz) == 0 identically
+                self.pg[b] = torch.zeros_like(b, dtype=torch.float32)
+        self.back.append(backward)
+        return out
+
+    def res_block(self, rb, x):
+        t = self.conv_bn_act(rb.conv1.block[0], rb.conv1.block[1], ACT_RELU, [x])
+        return self.conv_bn_act(rb.conv2.block[0], rb.conv2.block[1], ACT_RELU, [t], residual=x)
+
+    def conv_block(self, cb, srcs, stem_kp=None):
+        mods = list(cb.block)
+        act = ACT_RELU if any(isinstance(m, torch.nn.ReLU) for m in mods) else ACT_NONE
+        if len(mods) < 2 or not isinstance(mods[1], torch.nn.BatchNorm2d):
+            raise NotImplementedError("training a ConvBlock without BatchNorm is not part of the default branch models")
+        return self.conv_bn_act(mods[0], mods[1], act, srcs, stem_kp=stem_kp)
+
+    def attention(self, ab, x):
+        ap = self.wc.get(("attn", id(ab)), (ab.fc[0].weight, ab.fc[2].weight, ab.conv_spatial.weight),
+                         lambda: ops.AttnParams(ab.fc[0].weight, ab.fc[2].weight, ab.conv_spatial.weight))
+        keep = {}
+        y = ops.attention(x.t, ap, scratch=keep)
+        out = Node(y, x.c)
+        n, h, w, c = x.t.shape
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dev = dy.device
+            pool = keep[("pool", n, h, w, c)]
+            gate, stats, spatial = keep[("gate", n, c)], keep[("stats", n, h, w)], keep[("spatial", n, h, w)]
+            scratch = _f32(int(_lib.load().adb_attn_bwd_scratch_floats(n, h, w, c)), dev)
+            dx = torch.empty_like(dy)
+            dw1, dw2, dws = _f32(ap.c_red * c, dev), _f32(c * ap.c_red, dev), _f32(98, dev)
+            _lib.call("adb_attn_bwd", _lib.ptr(dy), _lib.ptr(x.t), n, h, w, c, _lib.ptr(pool), _lib.ptr(gate), _lib.ptr(stats),
+                      _lib.ptr(spatial), _lib.ptr(ap.w1), _lib.ptr(ap.w2), ap.c_red, _lib.ptr(ap.wsp), _lib.ptr(scratch), _lib.ptr(dx),
+                      _lib.ptr(dw1), _lib.ptr(dw2), _lib.ptr(dws), _lib.current_stream())
+            self.pg[ab.fc[0].weight] = dw1.view_as(ab.fc[0].weight)
+            self.pg[ab.fc[2].weight] = dw2.view_as(ab.fc[2].weight)
+            self.pg[ab.conv_spatial.weight] = dws.view_as(ab.conv_spatial.weight)
+            x.accumulate(dx)
+        self.back.append(backward)
+        return out
+
+    def dot_head(self, conv1x1, src):
+        """nn.Conv2d(c, 1, 1) + Sigmoid -> fp32 [n,h,w] guidance map (detail_branch tail, high:87-89)."""
+        n, h, w, pitch = src.t.shape
+        c = src.c
+        wv = conv1x1.weight.detach().float().reshape(-1).contiguous()
+        bv = conv1x1.bias.detach().float().reshape(-1).contiguous()
+        g = torch.empty((n, h, w), dtype=torch.float32, device=src.t.device)
+        _lib.call("adb_dot_head_fwd", _lib.ptr(src.t), pitch, c, _lib.ptr(wv), _lib.ptr(bv), n * h * w, _lib.ptr(g), _lib.current_stream())
+        out = Node(g, 1)
+
+        def backward():
+            dg = out.grad
+            out.grad = None
+            dy = torch.empty_like(src.t)
+            red = _f32(c + 1, g.device)
+            _lib.call("adb_dot_head_bwd", _lib.ptr(dg), _lib.ptr(g), _lib.ptr(src.t), pitch, c, _lib.ptr(wv), n * h * w, _lib.ptr(dy),
+                      pitch, _lib.ptr(red), _lib.current_stream())
+            self.pg[conv1x1.weight] = red[:c].view_as(conv1x1.weight)
+            self.pg[conv1x1.bias] = red[c:c + 1].view_as(conv1x1.bias)
+            src.accumulate(dy)
+        self.back.append(backward)
+        return out
+
+    def image_head(self, conv, src, x, mode, act, guidance=None, alpha=None):
+        """Final nn.Conv2d(c, 3, 3, padding=1) + act + the output arithmetic -> NCHW fp32 (low:45, medium:117, high:135-138)."""
+        w, b = conv.weight, conv.bias
+        fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_conv(w, bias=b, pad=conv.padding[0]))
+        z = ops.conv2d(fspec, src.t, c0=src.c)
+        n, h, wd, pitch = z.shape
+        out = torch.empty_like(x)
+        gptr = None if guidance is None else guidance.t
+        aval = None if alpha is None else alpha.detach().float().reshape(1)
+        _lib.call("adb_img_head_fwd", _lib.ptr(z), pitch, _lib.ptr(x), _lib.ptr(gptr), _lib.ptr(aval), mode, act, n, h, wd,
+                  _lib.ptr(out), _lib.current_stream())
+
+        def backward(dout):
+            dz = torch.empty_like(z)
+            red = _f32(4, z.device)
+            dgd = torch.empty_like(guidance.t) if guidance is not None else None
+            _lib.call("adb_img_head_bwd", _lib.ptr(dout), _lib.ptr(z), pitch, _lib.ptr(x), _lib.ptr(gptr), _lib.ptr(aval), mode, act,
+                      n, h, wd, _lib.ptr(dz), _lib.ptr(dgd), _lib.ptr(red), _lib.current_stream())
+            self.pg[b] = red[:3].view_as(b)
+            if alpha is not None:
+                self.pg[alpha] = red[3:4].reshape(alpha.shape)
+            if guidance is not None:
+                guidance.grad = dgd
+            self._conv_backward(conv, dz, pitch, [src], cz_true=3)
+        self.head_backward = backward
+        return out
+
+    # ------------------------------------------------------------------ reverse sweep
+    def backward(self, dout):
+        self.head_backward(dout)
+        for fn in reversed(self.back):
+            fn()
+        self.back = []
+        return self.pg
+
+
+# ---------------------------------------------------------------------- branch forwards (train mode)
+def forward_light(t, m, x):
+    """LightweightDehazeModel.forward, low_intensity.py:33-45."""
+    f = t.conv_block(m.init_conv, [t.stem(x, 3, 1, 16)], stem_kp=16)
+    for rb in m.residual_blocks:
+        f = t.res_block(rb, f)
+    f = t.conv_block(m.output_conv[0], [f])
+    return t.image_head(m.output_conv[1], f, x, IMG_BLEND, ACT_SIGMOID, alpha=m.skip_alpha)
+
+
+def forward_unet(t, m, x, attn):
+    """MediumIntensityDehazeModel.forward (medium_intensity.py:78-117) / HighIntensityDehazeModel.forward (high:92-138)."""
+    guidance = None
+    if attn:
+        g = t.conv_block(m.detail_branch[0], [t.stem(x, 3, 1, 16)], stem_kp=16)
+        g = t.conv_block(m.detail_branch[1], [g])
+        guidance = t.dot_head(m.detail_branch[2], g)
+    f0 = t.conv_block(m.init_conv, [t.stem(x, 7, 3, 32)], stem_kp=32)
+    feats = [f0]
+    for e in m.encoder:
+        f = t.conv_block(e[0], [feats[-1]])
+        f = t.res_block(e[1], f)
+        f = t.res_block(e[2], f)
+        if attn:
+            f = t.attention(e[3], f)
+        feats.append(f)
+    b = feats[-1]
+    for mod in m.bottleneck:
+        b = t.attention(mod, b) if type(mod).__name__ == "AttentionBlock" else t.res_block(mod, b)
+    d0, d1 = m.decoder[0], m.decoder[1]
+    x1 = t.convT_bn_act(d0[0], d0[1], ACT_RELU, [b])
+    x1 = t.res_block(d0[3], x1)
+    if attn:
+        x1 = t.attention(d0[4], x1)
+    x2 = t.convT_bn_act(d1[0], d1[1], ACT_RELU, [x1, feats[1]])
+    x2 = t.res_block(d1[3], x2)
+    if attn:
+        x2 = t.attention(d1[4], x2)
+    r = t.conv_block(m.output_conv[0], [x2, f0])
+    r = t.conv_block(m.output_conv[1], [r])
+    return t.image_head(m.output_conv[2], r, x, IMG_GUIDED if attn else IMG_RESIDUAL, ACT_TANH, guidance=guidance)
+
+
+class BranchTrainFn(torch.autograd.Function):
+    """autograd node of one branch forward in train() mode: the parameters are inputs so `.grad` accumulates as usual."""
+
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        tape = Tape(engine.train_cache)
+        if engine.kind == "light":
+            out = forward_light(tape, engine.model, x)
+        elif engine.kind in ("unet", "unet_attn"):
+            out = forward_unet(tape, engine.model, x, engine.kind == "unet_attn")
+        else:
+            raise NotImplementedError(
+                f"{type(engine.model).__name__}: training on the B200 path covers the default branch models "
+                "(LightweightDehazeModel, MediumIntensityDehazeModel, HighIntensityDehazeModel); there is no torch fallback")
+        ctx.tape, ctx.params = tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pg = ctx.tape.backward(dout.contiguous().float())
+        ctx.tape = None
+        return (None, None) + tuple(pg.get(p) for p in ctx.params)
+
+
+def train_forward(engine, x):
+    params = tuple(engine.model.parameters())
+    return BranchTrainFn.apply(engine, x, *params)

@@ -223,6 +223,58 @@ ADB_API int64_t adb_wgrad_workspace_bytes(const adb_wgrad_desc* desc);
 ADB_API int adb_wgrad(const adb_wgrad_desc* desc, void* stream);
 ADB_API double adb_wgrad_flops(const adb_wgrad_desc* desc);
 
+/* BatchNorm2d in train() mode (base_model.py:15-16 under model.train(), train_dehazing.py:66) on a raw conv output z
+ * (NHWC bf16, `pixels` = n*h*w rows of `c` channels, channel pitch `pitch`):
+ *   mean/var over pixels (biased variance normalises, the unbiased one updates running_var with `momentum`),
+ *   mean[c], rstd[c] are kept for backward, scale = gamma*rstd and shift = beta - mean*scale feed adb_affine_act.
+ * scratch: adb_bn_scratch_floats(pixels, c) floats.  running_* / num_batches_tracked are nullable. */
+ADB_API int64_t adb_bn_scratch_floats(int64_t pixels, int32_t c);
+ADB_API int adb_bn_train_stats(const void* z, int64_t pixels, int32_t c, int32_t pitch, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* scratch, float* mean, float* rstd, float* scale,
+                               float* shift, void* stream);
+/* y = act(z*scale + shift (+ residual)) — the normalise/activate pass of ConvBlock / ResidualBlock in train() mode. */
+ADB_API int adb_affine_act(const void* z, int32_t pitch_z, int64_t pixels, int32_t c, const float* scale, const float* shift,
+                           const void* residual, int32_t pitch_r, int32_t act, void* y, int32_t pitch_y, void* stream);
+/* Backward of y = act(BN(z) (+ residual)):  g = dy * act'(y) is written to g_out (it is also the gradient of the
+ * residual input; g_out may alias dy), dgamma = sum g*xhat, dbeta = sum g, dz = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)).
+ * gamma == NULL (and z == NULL): bias-only layer — g_out is dz and dbeta is the conv bias gradient.  y == NULL: no activation. */
+ADB_API int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t pitch_y, const void* z, int32_t pitch_z,
+                       int64_t pixels, int32_t c, int32_t act, const float* gamma, const float* mean, const float* rstd,
+                       float* scratch, void* g_out, int32_t pitch_g, void* dz, int32_t pitch_dz, float* dgamma, float* dbeta,
+                       int32_t accumulate, void* stream);
+/* a[..., :c] += b[..., :c] (gradient accumulation at a fan-out: skip connections, concat sources). */
+ADB_API int adb_add_bf16(void* a, int32_t pitch_a, const void* b, int32_t pitch_b, int64_t pixels, int32_t c, void* stream);
+
+/* The image heads un-fused for training: z = the 3-channel head conv's raw output (NHWC bf16, first 3 channels of `pitch`);
+ * forward = the ADB_EPI_IMAGE arithmetic (img_mode, act); backward turns dL/d(out) (NCHW fp32) into dz (bf16, padding
+ * channels zeroed), dguidance (fp32 [n,h,w], GUIDED) and red4 = {dbias[0..2], dalpha} (low:45, medium:117, high:135-138). */
+ADB_API int adb_img_head_fwd(const void* z, int32_t pitch, const float* x, const float* guidance, const float* alpha,
+                             int32_t mode, int32_t act, int32_t n, int32_t h, int32_t w, float* out, void* stream);
+ADB_API int adb_img_head_bwd(const float* dout, const void* z, int32_t pitch, const float* x, const float* guidance,
+                             const float* alpha, int32_t mode, int32_t act, int32_t n, int32_t h, int32_t w, void* dz,
+                             float* dguidance, float* red4, void* stream);
+/* 1x1 conv to one channel + sigmoid (detail_branch tail, high_intensity.py:87-89) forward / backward;
+ * red = {dw[0..c), dbias}. */
+ADB_API int adb_dot_head_fwd(const void* y, int32_t pitch, int32_t c, const float* w, const float* b, int64_t pixels, float* g,
+                             void* stream);
+ADB_API int adb_dot_head_bwd(const float* dg, const float* g, const void* y, int32_t pitch, int32_t c, const float* w,
+                             int64_t pixels, void* dy, int32_t pitch_dy, float* red, void* stream);
+
+/* AttentionBlock backward (base_model.py:64-78) from the tensors its forward kept (pool_buf [n][2][c], gate [n][c],
+ * stats [n,h,w,2], spatial [n,h,w]): dx (NHWC bf16) and the gradients of fc.0 / fc.2 / conv_spatial (fp32, overwritten).
+ * scratch: adb_attn_bwd_scratch_floats(n,h,w,c) floats. */
+ADB_API int64_t adb_attn_bwd_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c);
+ADB_API int adb_attn_bwd(const void* dy, const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const float* pool,
+                         const float* gate, const float* stats, const float* spatial, const float* w1, const float* w2,
+                         int32_t c_red, const float* w_spatial, float* scratch, void* dx, float* dw1, float* dw2,
+                         float* dw_spatial, void* stream);
+
+/* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
+ * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
+ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
 /* Developer aid: copy the clock64() timeline CTA 0 recorded during the last adb_conv2d launched with tune_flags bit 2
  * ([6 roles][256 events]: A producer, B producer, MMA ready, MMA issued, epilogue start, epilogue end). Synchronises. */
 ADB_API int adb_debug_timeline(int64_t* host_out, int32_t count);

@@ -19,8 +19,26 @@ EPS = 1e-5  # nn.BatchNorm2d default
 
 
 # --------------------------------------------------------------------------- building blocks (base_model.py)
+_TRAIN_BN = False
+
+
+class train_mode:
+    """`with train_mode():` — BatchNorm layers use batch statistics, as under model.train() (train_dehazing.py:66).
+    The functional state_dict is not updated (running statistics are a side effect the caller can compute itself)."""
+
+    def __enter__(self):
+        global _TRAIN_BN
+        self._old, _TRAIN_BN = _TRAIN_BN, True
+
+    def __exit__(self, *a):
+        global _TRAIN_BN
+        _TRAIN_BN = self._old
+
+
 def _bn(sd, p, x):
-    """nn.BatchNorm2d in eval mode (running statistics), base_model.py:15-16."""
+    """nn.BatchNorm2d, base_model.py:15-16: running statistics in eval mode, batch statistics inside train_mode()."""
+    if _TRAIN_BN:
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.1, EPS)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         False, 0.0, EPS)
 

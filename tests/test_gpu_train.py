@@ -113,3 +113,257 @@ def test_wgrad_accumulate():
     out = ops.wgrad(dzs, xs)
     ops.wgrad(dzs, xs, out=out, accumulate=True)
     _close(out, 2 * ref, 2e-3, 1e-4)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Branch models in train() mode: forward (batch-statistics BatchNorm) + backward through an L1 loss, against the fp32
+# oracle under torch autograd on the same weights and inputs (north_star: loss values and gradients
+# within a relative tolerance of 1e-2).  Activations and their gradients travel as bf16 on the B200 path, so a single
+# weight-gradient TENSOR is compared in relative L2 norm: ||g - g_ref|| <= 2e-2 ||g_ref|| per parameter (bf16 rounding
+# noise of ~4e-3 per hop accumulates over up to 50 layers), and the loss value to 1e-2 relative.
+def _train_case(name, n, h, w, seed=5):
+    from helpers import make_branch, rand_image   # (puts oracle/ on sys.path)
+    import adam_oracle as oracle
+    from adam_dehaze_b200.training.loss import DehazingLoss
+    m = make_branch(name).cuda().train()
+    x = rand_image(n, h, w, seed).cuda()
+    tgt = rand_image(n, h, w, seed + 1).cuda()
+    sd = {k: v.detach().clone().float().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
+    fwd = {"low": oracle.light_forward, "medium": oracle.medium_forward, "high": oracle.complex_forward}[name]
+    with oracle.train_mode():
+        ref_out = fwd(sd, x)
+    ref_loss = (ref_out - tgt).abs().mean()
+    names = [k for k, _ in m.named_parameters()]
+    ref_grads = dict(zip(names, torch.autograd.grad(ref_loss, [sd[k] for k in names], allow_unused=True)))
+
+    crit = DehazingLoss(lambda_l1=1.0, lambda_content=0.0, lambda_perceptual=0.0)
+    rm_before = {k: v.clone() for k, v in m.state_dict().items() if k.endswith("running_mean")}
+    out = m(x)
+    loss, parts = crit(out, tgt)
+    loss.backward()
+    torch.cuda.synchronize()
+    return m, out, loss, ref_out.detach(), ref_loss.detach(), ref_grads, rm_before
+
+
+@pytest.mark.parametrize("name,n,h,w", [("low", 2, 32, 48), ("medium", 2, 64, 64), ("high", 2, 64, 64)])
+def test_branch_train_step_matches_oracle(name, n, h, w):
+    m, out, loss, ref_out, ref_loss, ref_grads, rm_before = _train_case(name, n, h, w)
+    assert (out - ref_out).abs().max().item() <= 2e-2
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
+    worst = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None, f"{k}: no gradient"
+        g, r = p.grad.float(), ref_grads[k]
+        assert g.shape == r.shape
+        rel = ((g - r).norm() / (r.norm() + 1e-12)).item()
+        worst.append((rel, k, r.norm().item()))
+    worst.sort(reverse=True)
+    # ConvTranspose biases feed a batch-statistics BatchNorm: their true gradient is 0 (the oracle holds float noise)
+    bad = [(rel, k, rn) for rel, k, rn in worst if rel > 2e-2 and rn > 1e-7]
+    assert not bad, f"gradient mismatch (rel L2, name, |ref|): {bad[:8]}"
+    # running statistics were updated with momentum 0.1 (model.train() side effect)
+    sd = m.state_dict()
+    assert any((sd[k] - v).abs().max().item() > 0 for k, v in rm_before.items())
+    assert int(sd[[k for k in sd if k.endswith("num_batches_tracked")][0]].item()) == 1
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Unit parity of the HBM-bound training kernels against torch autograd (fp32) on bf16-representable inputs.
+def _nhwc(x, pitch=None):
+    return _ops().nchw_to_nhwc(x, pitch or x.shape[1])
+
+
+def _nchw(t, c):
+    return _ops().nhwc_to_nchw(t, c)
+
+
+def _ptr(t):
+    from adam_dehaze_b200 import _lib
+    return _lib.ptr(t)
+
+
+def _call(name, *a):
+    from adam_dehaze_b200 import _lib
+    _lib.call(name, *a, _lib.current_stream())
+
+
+@pytest.mark.parametrize("c,act,with_res", [(32, 1, False), (96, 1, True), (64, 0, False), (384, 1, True)])
+def test_bn_train_forward_backward(c, act, with_res):
+    from adam_dehaze_b200 import _lib
+    n, h, w = 2, 12, 20
+    z = (_fm(n, c, h, w, 20) * 1.5 + 0.3).to(torch.bfloat16).float()
+    res = _fm(n, c, h, w, 21) if with_res else None
+    dy = _fm(n, c, h, w, 22)
+    g = torch.Generator().manual_seed(23)
+    gamma = (torch.rand(c, generator=g) + 0.5).cuda().requires_grad_(True)
+    beta = (torch.randn(c, generator=g) * 0.1).cuda().requires_grad_(True)
+    rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    zr = z.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if with_res else None
+    yref = F.batch_norm(zr, rm.clone(), rv.clone(), gamma, beta, True, 0.1, 1e-5)
+    if with_res:
+        yref = yref + rr
+    if act:
+        yref = F.relu(yref)
+    grads = torch.autograd.grad(yref, [zr, gamma, beta] + ([rr] if with_res else []), dy)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    F.batch_norm(z, rm_ref, rv_ref, None, None, True, 0.1, 1e-5)
+
+    px = n * h * w
+    zt = _nhwc(z)
+    scratch = torch.empty(int(_lib.load().adb_bn_scratch_floats(px, c)), device="cuda")
+    mean, rstd, scale, shift = (torch.empty(c, device="cuda") for _ in range(4))
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    _call("adb_bn_train_stats", _ptr(zt), px, c, c, _ptr(gamma.detach()), _ptr(beta.detach()), 1e-5, 0.1, _ptr(rm), _ptr(rv), _ptr(nbt),
+          _ptr(scratch), _ptr(mean), _ptr(rstd), _ptr(scale), _ptr(shift))
+    rt = _nhwc(res) if with_res else None
+    yt = torch.empty_like(zt)
+    _call("adb_affine_act", _ptr(zt), c, px, c, _ptr(scale), _ptr(shift), _ptr(rt), c, act, _ptr(yt), c)
+    _close(_nchw(yt, c), yref.detach(), 1e-2, 1e-3)
+    _close(rm, rm_ref, 1e-4, 1e-6)
+    _close(rv, rv_ref, 1e-4, 1e-6)
+    assert int(nbt.item()) == 1
+    # backward from the exact fp32 y (rounded to bf16 like the tape keeps it)
+    yk = _nhwc(yref.detach())
+    dyt = _nhwc(dy)
+    gt, dzt = torch.empty_like(dyt), torch.empty_like(dyt)
+    dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    _call("adb_bn_bwd", _ptr(dyt), c, _ptr(yk) if act else None, c, _ptr(zt), c, px, c, act, _ptr(gamma.detach()), _ptr(mean), _ptr(rstd),
+          _ptr(scratch), _ptr(gt), c, _ptr(dzt), c, _ptr(dgamma), _ptr(dbeta), 0)
+    _close(_nchw(dzt, c), grads[0], 1e-2, 1e-3)
+    _close(dgamma, grads[1], 5e-3, 1e-3)
+    _close(dbeta, grads[2], 5e-3, 1e-3)
+    if with_res:
+        _close(_nchw(gt, c), grads[3], 1e-2, 1e-3)
+
+
+@pytest.mark.parametrize("mode,act", [(0, 3), (1, 2), (2, 2)])
+def test_img_head_forward_backward(mode, act):
+    n, h, w = 2, 20, 36
+    g = torch.Generator().manual_seed(30 + mode)
+    z = (torch.randn(n, 3, h, w, generator=g)).to(torch.bfloat16).float().cuda()
+    x = torch.rand(n, 3, h, w, generator=g).cuda()
+    gd = torch.rand(n, 1, h, w, generator=g).cuda()
+    alpha = torch.tensor(0.1).cuda()
+    dout = torch.randn(n, 3, h, w, generator=g).cuda()
+    zr, gr, ar = z.clone().requires_grad_(True), gd.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
+    v = torch.sigmoid(zr) if act == 3 else torch.tanh(zr)
+    if mode == 0:
+        ref = (1 - ar) * x + ar * v
+    elif mode == 1:
+        ref = torch.clamp(x + v, 0, 1)
+    else:
+        ref = torch.clamp(x + v * gr, 0, 1)
+    ins = [zr] + ([ar] if mode == 0 else []) + ([gr] if mode == 2 else [])
+    grads = torch.autograd.grad(ref, ins, dout)
+    zt = _nhwc(z, 16)
+    out = torch.empty_like(x)
+    gflat = gd.reshape(n, h, w).contiguous()
+    _call("adb_img_head_fwd", _ptr(zt), 16, _ptr(x), _ptr(gflat) if mode == 2 else None, _ptr(alpha.reshape(1)) if mode == 0 else None,
+          mode, act, n, h, w, _ptr(out))
+    _close(out, ref.detach(), 1e-5, 1e-5)
+    dz = torch.full_like(zt, 7.0)
+    dgd = torch.empty_like(gflat)
+    red = torch.empty(4, device="cuda")
+    _call("adb_img_head_bwd", _ptr(dout), _ptr(zt), 16, _ptr(x), _ptr(gflat) if mode == 2 else None,
+          _ptr(alpha.reshape(1)) if mode == 0 else None, mode, act, n, h, w, _ptr(dz), _ptr(dgd) if mode == 2 else None, _ptr(red))
+    _close(_nchw(dz, 3), grads[0], 1e-2, 1e-4)
+    assert dz[..., 3:].abs().max().item() == 0
+    _close(red[:3], grads[0].sum(dim=(0, 2, 3)), 1e-2, 1e-3)
+    if mode == 0:
+        _close(red[3:4], grads[1].reshape(1), 1e-3, 1e-3)
+    if mode == 2:
+        _close(dgd, grads[1].reshape(n, h, w), 1e-4, 1e-5)
+
+
+def test_dot_head_forward_backward():
+    n, h, w, c = 2, 16, 24, 16
+    y = _fm(n, c, h, w, 40)
+    g = torch.Generator().manual_seed(41)
+    wv = (torch.randn(c, generator=g) * 0.3).cuda().requires_grad_(True)
+    bv = torch.tensor([0.2]).cuda().requires_grad_(True)
+    dg = torch.randn(n, h, w, generator=g).cuda()
+    yr = y.clone().requires_grad_(True)
+    ref = torch.sigmoid(F.conv2d(yr, wv.view(1, c, 1, 1), bv)).reshape(n, h, w)
+    grads = torch.autograd.grad(ref, [yr, wv, bv], dg)
+    yt = _nhwc(y)
+    out = torch.empty(n, h, w, device="cuda")
+    _call("adb_dot_head_fwd", _ptr(yt), c, c, _ptr(wv.detach()), _ptr(bv.detach()), n * h * w, _ptr(out))
+    _close(out, ref.detach(), 1e-4, 1e-5)
+    dy = torch.empty_like(yt)
+    red = torch.empty(c + 1, device="cuda")
+    _call("adb_dot_head_bwd", _ptr(dg), _ptr(out), _ptr(yt), c, c, _ptr(wv.detach()), n * h * w, _ptr(dy), c, _ptr(red))
+    _close(_nchw(dy, c), grads[0], 1e-2, 1e-4)
+    _close(red[:c], grads[1], 1e-3, 1e-3)
+    _close(red[c:], grads[2], 1e-3, 1e-3)
+
+
+@pytest.mark.parametrize("c,h,w", [(96, 24, 40), (192, 16, 16), (384, 8, 24)])
+def test_attention_backward(c, h, w):
+    import adam_dehaze_b200.ops as ops
+    from adam_dehaze_b200 import _lib
+    n, cr = 2, c // 16
+    x = _fm(n, c, h, w, 50).relu()
+    dy = _fm(n, c, h, w, 51)
+    g = torch.Generator().manual_seed(52)
+    w1 = (torch.randn(cr, c, 1, 1, generator=g) / c ** 0.5).cuda().requires_grad_(True)
+    w2 = (torch.randn(c, cr, 1, 1, generator=g) / cr ** 0.5).cuda().requires_grad_(True)
+    ws = (torch.randn(1, 2, 7, 7, generator=g) * 0.1).cuda().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+
+    def fc(v):
+        return F.conv2d(F.relu(F.conv2d(v, w1)), w2)
+    gate = torch.sigmoid(fc(F.adaptive_avg_pool2d(xr, 1)) + fc(F.adaptive_max_pool2d(xr, 1)))
+    u = xr * gate
+    stats = torch.cat([u.mean(1, keepdim=True), u.max(1, keepdim=True)[0]], 1)
+    ref = u * torch.sigmoid(F.conv2d(stats, ws, padding=3))
+    grads = torch.autograd.grad(ref, [xr, w1, w2, ws], dy)
+
+    ap = ops.AttnParams(w1.detach(), w2.detach(), ws.detach())
+    keep = {}
+    xt = _nhwc(x)
+    yt = ops.attention(xt, ap, scratch=keep)
+    _close(_nchw(yt, c), ref.detach(), 1e-2, 1e-3)
+    scratch = torch.empty(int(_lib.load().adb_attn_bwd_scratch_floats(n, h, w, c)), device="cuda")
+    dx = torch.empty_like(xt)
+    dw1, dw2, dws = torch.empty(cr * c, device="cuda"), torch.empty(c * cr, device="cuda"), torch.empty(98, device="cuda")
+    _call("adb_attn_bwd", _ptr(_nhwc(dy)), _ptr(xt), n, h, w, c, _ptr(keep[("pool", n, h, w, c)]), _ptr(keep[("gate", n, c)]),
+          _ptr(keep[("stats", n, h, w)]), _ptr(keep[("spatial", n, h, w)]), _ptr(ap.w1), _ptr(ap.w2), cr, _ptr(ap.wsp), _ptr(scratch),
+          _ptr(dx), _ptr(dw1), _ptr(dw2), _ptr(dws))
+    _close(_nchw(dx, c), grads[0], 1e-2, 1e-3)
+    _close(dw1.view_as(w1), grads[1], 1e-2, 1e-4)
+    _close(dw2.view_as(w2), grads[2], 1e-2, 1e-4)
+    _close(dws.view_as(ws), grads[3], 1e-2, 1e-4)
+
+
+@pytest.mark.parametrize("kind", ["s1", "s1_head", "s2", "convT"])
+def test_dgrad_through_forward_kernel(kind):
+    """Data gradients = adb_conv2d with transformed weights (training/autograd.py)."""
+    import adam_dehaze_b200.ops as ops
+    from adam_dehaze_b200.training import autograd as ag
+    n, h, w = 2, 16, 32
+    g = torch.Generator().manual_seed(60)
+    if kind in ("s1", "s1_head"):
+        ci, co = (64, 96) if kind == "s1" else (32, 3)
+        wt = (torch.randn(co, ci, 3, 3, generator=g) / (9 * ci) ** 0.5).to(torch.bfloat16).float().cuda()
+        x = _fm(n, ci, h, w, 61).requires_grad_(True)
+        y = F.conv2d(x, wt, padding=1)
+        dz = _fm(n, co, h, w, 62)
+        spec = ag._dgrad_spec_s1(wt)
+        got = ops.conv2d(spec, _nhwc(dz, ops.pad16(co)))
+    elif kind == "s2":
+        ci, co = 64, 128
+        wt = (torch.randn(co, ci, 4, 4, generator=g) / (16 * ci) ** 0.5).to(torch.bfloat16).float().cuda()
+        x = _fm(n, ci, h, w, 61).requires_grad_(True)
+        y = F.conv2d(x, wt, stride=2, padding=1)
+        dz = _fm(n, co, h // 2, w // 2, 62)
+        got = ops.conv2d(ops.ConvSpec.from_convT(wt), _nhwc(dz))
+    else:
+        ci, co = 128, 64
+        wt = (torch.randn(ci, co, 4, 4, generator=g) / (16 * ci) ** 0.5).to(torch.bfloat16).float().cuda()
+        x = _fm(n, ci, h, w, 61).requires_grad_(True)
+        y = F.conv_transpose2d(x, wt, stride=2, padding=1)
+        dz = _fm(n, co, 2 * h, 2 * w, 62)
+        got = ops.conv2d(ops.ConvSpec.from_conv(wt, stride=2, pad=1), _nhwc(dz))
+    (ref,) = torch.autograd.grad(y, x, dz)
+    _close(_nchw(got, ci), ref, 1e-2, 1e-3)
