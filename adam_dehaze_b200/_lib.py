@@ -75,6 +75,7 @@ SIGNATURES = {
     "adb_dot_head_fwd": [_P, _I, _I, _P, _P, _L, _P, _P],
     "adb_dot_head_bwd": [_P, _P, _P, _I, _I, _P, _L, _P, _I, _P, _P],
     "adb_attn_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "adb_blend3_bwd": [_P, _P, _P, _P, _P, _F, _I, _L, _P, _P, _P, _P, _P, _P],
     "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],

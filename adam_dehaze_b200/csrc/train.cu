@@ -585,6 +585,54 @@ __global__ void attn_bwd_pool_kernel(__nv_bfloat16* __restrict__ dx, int n, long
   }
 }
 
+// ------------------------------------------------------------------ soft/gated blend backward (routing.py:111-127)
+// out = sum_k w[b][k] y_k :  dy_k = w[b][k] * dout ;  dwt[b][k] = sum_chw dout * y_k  (block partial + atomics)
+__global__ void blend3_bwd_kernel(const float4* __restrict__ dout, const float4* __restrict__ y0, const float4* __restrict__ y1,
+                                  const float4* __restrict__ y2, const float* __restrict__ wts, long long chw4,
+                                  float4* __restrict__ d0, float4* __restrict__ d1, float4* __restrict__ d2, float* __restrict__ dwt) {
+  const int b = blockIdx.y;
+  const float w0 = __ldg(wts + b * 3), w1 = __ldg(wts + b * 3 + 1), w2 = __ldg(wts + b * 3 + 2);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  const size_t base = (size_t)b * chw4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < chw4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g = __ldg(dout + base + i);
+    const float4 p = __ldg(y0 + base + i), q = __ldg(y1 + base + i), r = __ldg(y2 + base + i);
+    a0 += g.x * p.x + g.y * p.y + g.z * p.z + g.w * p.w;
+    a1 += g.x * q.x + g.y * q.y + g.z * q.z + g.w * q.w;
+    a2 += g.x * r.x + g.y * r.y + g.z * r.z + g.w * r.w;
+    d0[base + i] = make_float4(w0 * g.x, w0 * g.y, w0 * g.z, w0 * g.w);
+    d1[base + i] = make_float4(w1 * g.x, w1 * g.y, w1 * g.z, w1 * g.w);
+    d2[base + i] = make_float4(w2 * g.x, w2 * g.y, w2 * g.z, w2 * g.w);
+  }
+  __shared__ float s_red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[3] = {a0, a1, a2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) s_red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += s_red[threadIdx.x][wi];
+    atomicAdd(dwt + b * 3 + threadIdx.x, t);
+  }
+}
+// softmax(l / T) backward: dl_k = w_k (dw_k - sum_j w_j dw_j) / T
+__global__ void softmax3_bwd_kernel(const float* __restrict__ wts, const float* __restrict__ dwt, float inv_t, int b,
+                                    float* __restrict__ dlogits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const float w0 = wts[i * 3], w1 = wts[i * 3 + 1], w2 = wts[i * 3 + 2];
+  const float g0 = dwt[i * 3], g1 = dwt[i * 3 + 1], g2 = dwt[i * 3 + 2];
+  const float dot = w0 * g0 + w1 * g1 + w2 * g2;
+  dlogits[i * 3] = w0 * (g0 - dot) * inv_t;
+  dlogits[i * 3 + 1] = w1 * (g1 - dot) * inv_t;
+  dlogits[i * 3 + 2] = w2 * (g2 - dot) * inv_t;
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -786,6 +834,27 @@ int adb_attn_bwd(const void* dy, const void* x, int32_t n, int32_t h, int32_t w,
   ADB_CUDA_OK(cudaGetLastError());
   attn_bwd_pool_kernel<<<grid_for(total * G, 256, sms, 16), 256, 0, st>>>(ADB_BFM(dx), n, hw, c, d_avg, d_max, pos);
   ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_blend3_bwd(const float* dout, const float* y0, const float* y1, const float* y2, const float* weights, float temperature,
+                   int32_t b, int64_t chw, float* dy0, float* dy1, float* dy2, float* dweights /*[b][3]*/, float* dlogits /*nullable*/,
+                   void* stream) {
+  ADB_REQUIRE(dout && y0 && y1 && y2 && weights && dy0 && dy1 && dy2 && dweights, "adb_blend3_bwd: null pointer");
+  ADB_REQUIRE(b > 0 && chw > 0 && chw % 4 == 0, "adb_blend3_bwd: chw must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  ADB_CUDA_OK(cudaMemsetAsync(dweights, 0, (size_t)b * 3 * sizeof(float), st));
+  const long long chw4 = chw / 4;
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((chw4 + 255) / 256, (long long)sm_count() * 8 / std::max(1, b) + 1)), (unsigned)b);
+  blend3_bwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y0),
+                                          reinterpret_cast<const float4*>(y1), reinterpret_cast<const float4*>(y2), weights, chw4,
+                                          reinterpret_cast<float4*>(dy0), reinterpret_cast<float4*>(dy1), reinterpret_cast<float4*>(dy2), dweights);
+  ADB_CUDA_OK(cudaGetLastError());
+  if (dlogits) {
+    ADB_REQUIRE(temperature > 0.f, "adb_blend3_bwd: dlogits needs temperature > 0");
+    softmax3_bwd_kernel<<<(b + 127) / 128, 128, 0, st>>>(weights, dweights, 1.f / temperature, b, dlogits);
+    ADB_CUDA_OK(cudaGetLastError());
+  }
   return ADB_OK;
 }
 

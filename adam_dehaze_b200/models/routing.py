@@ -47,6 +47,39 @@ class HardRouter(nn.Module):
         return outputs, {"intensity": inten, "low_mask": masks[0], "medium_mask": masks[1], "high_mask": masks[2]}
 
 
+class _Blend3Fn(torch.autograd.Function):
+    """sum_k softmax(logits/T)[:,k] * y_k with a kernel-built backward (dy_k and dlogits), routing.py:111-127."""
+
+    @staticmethod
+    def forward(ctx, y0, y1, y2, logits, temperature):
+        y0, y1, y2 = y0.contiguous(), y1.contiguous(), y2.contiguous()
+        blend, weights = ops.blend3(y0, y1, y2, logits, temperature)
+        ctx.save_for_backward(y0, y1, y2, weights)
+        ctx.temperature = temperature
+        ctx.mark_non_differentiable(weights)
+        return blend, weights
+
+    @staticmethod
+    def backward(ctx, dout, _dw):
+        from .. import _lib
+        y0, y1, y2, weights = ctx.saved_tensors
+        dout = dout.contiguous().float()
+        b, chw = y0.shape[0], y0[0].numel()
+        d0, d1, d2 = torch.empty_like(y0), torch.empty_like(y1), torch.empty_like(y2)
+        dwt = torch.empty((b, 3), dtype=torch.float32, device=y0.device)
+        dlog = torch.empty((b, 3), dtype=torch.float32, device=y0.device)
+        _lib.call("adb_blend3_bwd", _lib.ptr(dout), _lib.ptr(y0), _lib.ptr(y1), _lib.ptr(y2), _lib.ptr(weights),
+                  float(ctx.temperature), b, chw, _lib.ptr(d0), _lib.ptr(d1), _lib.ptr(d2), _lib.ptr(dwt), _lib.ptr(dlog),
+                  _lib.current_stream())
+        return d0, d1, d2, dlog, None
+
+
+def _blend(y0, y1, y2, logits, temperature):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (y0, y1, y2, logits)):
+        return _Blend3Fn.apply(y0, y1, y2, logits.contiguous().float(), temperature)
+    return ops.blend3(y0, y1, y2, logits, temperature)
+
+
 class SoftRouter(nn.Module):
     def __init__(self, models, classifier=None, temperature=1.0, device="cuda"):
         super().__init__()
@@ -67,7 +100,7 @@ class SoftRouter(nn.Module):
         outs = {name: self.models[name](x) for name in _NAMES if name in self.models}
         if len(outs) != 3:
             raise NotImplementedError("SoftRouter on the B200 path blends exactly the three branches low/medium/high")
-        blend, weights = ops.blend3(outs["low"], outs["medium"], outs["high"], logits, self.temperature)
+        blend, weights = _blend(outs["low"], outs["medium"], outs["high"], logits, self.temperature)
         return blend, {"weights": weights, "individual_outputs": outs}
 
 

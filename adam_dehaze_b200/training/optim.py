@@ -1,0 +1,93 @@
+"""Optimizer step and gradient exchange of the training drivers (train_dehazing.py:33-37,91-92; train_joint.py:84-88,149-150).
+
+`FlatAdam` keeps every parameter as a view of ONE fp32 buffer, so a step is: gather the .grad tensors into the flat
+gradient buffer, one NCCL all-reduce over NVLink when torch.distributed is initialised (replicas + one
+gradient all-reduce per step, mean), and ONE adb_adam_step launch with torch.optim.Adam's arithmetic
+(weight_decay = L2 added to the gradient).  There is no torch fallback: the step runs on the CUDA device only.
+"""
+import torch
+
+from .. import _lib
+
+
+def _bump_versions(params):
+    """The step writes parameter memory from a libadb200 kernel; tell torch (and the weight-packing caches keyed on
+    `_version`) that the tensors changed."""
+    setter = getattr(torch._C._autograd, "_unsafe_set_version_counter", None)
+    if setter is not None:
+        try:
+            for p in params:
+                setter(p, p._version + 1)
+            return
+        except (TypeError, RuntimeError):
+            pass
+    with torch.no_grad():
+        torch._foreach_mul_(list(params), 1.0)
+
+
+class FlatAdam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, process_group=None):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatAdam: empty parameter list")
+        dev = self.params[0].device
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.group = process_group
+        self.step_count = 0
+        sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + (s + 3) // 4 * 4)     # 16-byte aligned views
+        total = self.offsets[-1]
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                if p.dtype != torch.float32:
+                    raise TypeError("FlatAdam: fp32 master parameters expected")
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+
+    @property
+    def param_groups(self):
+        return [{"params": self.params, "lr": self.lr}]
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    def world_size(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def reduce_gradients(self):
+        """Gather the .grad tensors into the flat bucket and sum it over the ranks (one collective per step).
+        Returns the world size (the Adam kernel folds the 1/world mean into its gradient read)."""
+        with torch.no_grad():
+            have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+            none = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+            if none:       # parameters that saw no sample on this rank still take part in the collective (zeros)
+                torch._foreach_zero_(none)
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        world = self.world_size()
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, group=self.group)
+        return world
+
+    def step(self):
+        if self.flat.device.type != "cuda":
+            raise RuntimeError("FlatAdam.step: parameters must live on the CUDA device (no CPU path)")
+        self.step_count += 1
+        world = self.reduce_gradients()
+        b1, b2 = self.betas
+        _lib.call("adb_adam_step", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                  self.flat.numel(), float(self.lr), float(b1), float(b2), float(self.eps), float(self.weight_decay),
+                  self.step_count, 1.0 / world, _lib.current_stream())
+        _bump_versions(self.params)

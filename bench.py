@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: BASELINE configs[4], the joint training step (batch 16/GPU at 512x512, gradient all-reduce)")
     return ap.parse_args()
 
 
@@ -196,6 +198,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist
@@ -307,6 +311,184 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- training step (BASELINE configs[4])
+TRAIN_METRIC = "training samples/sec, joint step (SoftRouter over Light/Medium/Complex, DehazingLoss, Adam) @512x512"
+
+
+def run_train(args):
+    """One step = train_joint.py:129-150 on 16 synthetic samples per GPU at 512x512: HDEN logits, SoftRouter forward of the
+    three branches in train() mode (batch-statistics BatchNorm), DehazingLoss, backward (dgrad + wgrad kernels), one NCCL
+    all-reduce of the flat gradient bucket, one fused Adam launch.  Prints ONE JSON line (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from adam_dehaze_b200 import _lib, ops
+    from adam_dehaze_b200.models.routing import SoftRouter
+    from adam_dehaze_b200.training.loss import DehazingLoss
+    from adam_dehaze_b200.training.optim import FlatAdam
+    import adam_dehaze_b200.training.autograd as ag
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().adb_device_check(), "adb_device_check")
+    B = 16 if args.batch == 256 else args.batch
+    Hh, Ww = (512, 512) if (args.height, args.width) == (H, W) else (args.height, args.width)
+    cfg = dict(CFG, classifier=dict(CFG["classifier"], model=args.hden), routing={"type": "soft", "temperature": 0.5})
+    branches, clf = build_models(cfg, device=dev)
+    router = SoftRouter(branches, classifier=None, temperature=0.5).to(dev).train()
+    crit = DehazingLoss(lambda_l1=1.0, lambda_content=TRAIN_LAMBDAS[0], lambda_perceptual=TRAIN_LAMBDAS[1]).to(dev)
+    opt = FlatAdam(router.parameters(), lr=1e-4, weight_decay=1e-4)
+    nparams = sum(p.numel() for p in router.parameters())
+    hazy, labels = synth_batch_on_device(B, Hh, Ww, dev, seed=42 + rank)
+    clear = torch.rand((B, 3, Hh, Ww), generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev)
+
+    counts = {"n": 0}
+    inner = _lib.call
+
+    def counting(name, *a):
+        counts["n"] += 1
+        return inner(name, *a)
+
+    def set_call(fn):
+        _lib.call = fn
+        ops._lib.call = fn
+        ag._lib.call = fn
+
+    def step():
+        opt.zero_grad()
+        with torch.no_grad():
+            logits, _ = clf(hazy)                      # HDEN (eval): its logits weight the blend
+        out, info = router(hazy, logits)
+        loss, parts = crit(out, clear)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    set_call(counting)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    torch.cuda.nvtx.range_push("adb_timed")
+    for _ in range(args.steps):
+        loss = step()
+    torch.cuda.nvtx.range_pop()
+    e1.record()
+    barrier()
+    set_call(inner)
+    clocks = sampler.stop()
+    _lib.call("adb_kernel_error_flag")
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * B / (ms_step / 1000.0)
+
+    # ---- e2e: the same step with the batch (hazy + clear) copied from pinned host memory and the loss read back
+    host_h = torch.empty(hazy.shape, dtype=torch.float32, pin_memory=True).copy_(hazy)
+    host_c = torch.empty(clear.shape, dtype=torch.float32, pin_memory=True).copy_(clear)
+
+    def e2e_step():
+        hazy.copy_(host_h, non_blocking=True)
+        clear.copy_(host_c, non_blocking=True)
+        return step().item()                           # train_dehazing.py:95 reads the loss every step
+
+    e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    barrier()
+    t2 = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = t2.item() / args.steps
+
+    # ---- instrumented step (rank 0): CUDA events around every C-ABI call -> tensor-pipe kernels' achieved TFLOP/s
+    detail = None
+    if rank == 0:
+        calls = []
+
+        def timed(name, *a):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            r = inner(name, *a)
+            eb.record()
+            fl = 0.0
+            if name == "adb_conv2d":
+                fl = float(_lib.load().adb_conv2d_flops(a[0]))
+            elif name == "adb_wgrad":
+                fl = float(_lib.load().adb_wgrad_flops(a[0]))
+            calls.append((name, ea, eb, fl))
+            return r
+        set_call(timed)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); step(); s1.record()
+        torch.cuda.synchronize()
+        set_call(inner)
+        by, fl = {}, {}
+        for nm, ea, eb, f in calls:
+            by[nm] = by.get(nm, 0.0) + ea.elapsed_time(eb)
+            fl[nm] = fl.get(nm, 0.0) + f
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        mma_ms = by.get("adb_conv2d", 0.0) + by.get("adb_wgrad", 0.0)
+        mma_fl = fl.get("adb_conv2d", 0.0) + fl.get("adb_wgrad", 0.0)
+        detail = {
+            "step_ms_instrumented": s0.elapsed_time(s1),
+            "ms_by_entry_point": {k.replace("adb_", ""): round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])},
+            "conv2d_fwd_dgrad_tflops": fl.get("adb_conv2d", 0.0) / max(1e-9, by.get("adb_conv2d", 0.0) * 1e-3) / 1e12,
+            "wgrad_tflops": fl.get("adb_wgrad", 0.0) / max(1e-9, by.get("adb_wgrad", 0.0) * 1e-3) / 1e12,
+            "launch_flops_tflop_per_step": mma_fl / 1e12,
+        }
+        n_mma = sum(1 for nm, *_ in calls if nm in ("adb_conv2d", "adb_wgrad"))
+        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_wgrad_kernel", "achieved": mma_fl / max(1e-9, mma_ms * 1e-3) / 1e12,
+                "peak": peak, "unit": "TFLOP/s", "frac": mma_fl / max(1e-9, mma_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                "how": f"launch FLOPs (padded-channel 2*MAC of every conv fwd/dgrad/wgrad launch) / CUDA-event time over the {n_mma} tensor-pipe launches of one step",
+                "flops_per_launch_avg": mma_fl / max(1, n_mma), "ms_per_launch_avg": mma_ms / max(1, n_mma)}
+        line = {
+            "metric": TRAIN_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: joint training step, {B} samples/GPU at {Hh}x{Ww}, SoftRouter(T=0.5) over "
+                                   f"Light+Medium+Complex in train() mode, HDEN({args.hden}) logits (eval), DehazingLoss "
+                                   f"lambdas (1.0, {TRAIN_LAMBDAS[0]}, {TRAIN_LAMBDAS[1]}), FlatAdam(lr 1e-4, wd 1e-4), one flat "
+                                   f"{nparams * 4 / 2**20:.0f} MiB gradient all-reduce per step",
+                       "samples_per_gpu_per_step": B, "height": Hh, "width": Ww, "trainable_params": nparams,
+                       "l2": f"activations {B}x{Hh}x{Ww} per layer (> 126 MB L2 for every full-resolution map)"},
+            "clocks": clocks, "gpu_launches": counts["n"] // max(1, args.steps), "loss": float(loss.item()),
+            "roofline": roof, "train_detail": detail, "cpu_baseline": None,
+            "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "samples/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 2 * B * 3 * Hh * Ww * 4, "d2h_bytes_per_step": 4,
+                    "api": "SoftRouter.forward + DehazingLoss + loss.backward() + FlatAdam.step() from pinned host batches; loss.item() per step"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+TRAIN_LAMBDAS = (0.0, 0.0)   # (content, perceptual) terms of DehazingLoss in the training bench
 
 
 def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):

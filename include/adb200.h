@@ -270,6 +270,12 @@ ADB_API int adb_attn_bwd(const void* dy, const void* x, int32_t n, int32_t h, in
                          int32_t c_red, const float* w_spatial, float* scratch, void* dx, float* dw1, float* dw2,
                          float* dw_spatial, void* stream);
 
+/* Backward of adb_blend3 (SoftRouter / GatedRouter under train_joint.py:141-150): dy_k = w[:,k] * dout,
+ * dweights[b][k] = sum dout * y_k, and (dlogits non-NULL) the softmax(logits/T) backward. */
+ADB_API int adb_blend3_bwd(const float* dout, const float* y0, const float* y1, const float* y2, const float* weights,
+                           float temperature, int32_t b, int64_t chw, float* dy0, float* dy1, float* dy2, float* dweights,
+                           float* dlogits, void* stream);
+
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

@@ -83,3 +83,35 @@ def randomize_bn(module, seed=7):
                 m.weight.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
                 m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.1)
     return module
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def oracle_bf16_storage(fn, *args):
+    """Run an oracle forward with every conv / BatchNorm output (and the gradient flowing back through it) rounded to
+    bf16 and conv weights rounded to bf16 — the fp32 oracle restricted to the storage format the north_star prescribes
+    (bf16 tensors, fp32 accumulate).  Used to bound what ANY bf16-storage implementation can achieve against fp32."""
+    import torch.nn.functional as F
+    orig_conv, orig_convt, orig_bn = F.conv2d, F.conv_transpose2d, F.batch_norm
+
+    def conv2d(inp, w, b=None, **kw):
+        return _RoundBf16.apply(orig_conv(_RoundBf16.apply(inp), w.to(torch.bfloat16).float(), b, **kw))
+
+    def convt(inp, w, b=None, **kw):
+        return _RoundBf16.apply(orig_convt(_RoundBf16.apply(inp), w.to(torch.bfloat16).float(), b, **kw))
+
+    def bn(inp, *a, **kw):
+        return _RoundBf16.apply(orig_bn(inp, *a, **kw))
+    F.conv2d, F.conv_transpose2d, F.batch_norm = conv2d, convt, bn
+    try:
+        return fn(*args)
+    finally:
+        F.conv2d, F.conv_transpose2d, F.batch_norm = orig_conv, orig_convt, orig_bn

@@ -262,3 +262,48 @@ def test_sharding_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+_GLOO_GRAD_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ADB_ROOT"])
+from adam_dehaze_b200.training.optim import FlatAdam
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["ADB_PORT"], rank=rank, world_size=2)
+torch.manual_seed(0)
+params = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(()))]
+before = [p.detach().clone() for p in params]
+opt = FlatAdam(params, lr=1e-3, weight_decay=1e-4)
+assert all(torch.equal(p.detach(), b) for p, b in zip(params, before))          # flattening keeps the values
+assert all(p.data_ptr() == opt.flat.data_ptr() + 4 * o for p, o in zip(params, opt.offsets))   # views of ONE buffer
+params[0].grad = torch.full((3, 5), float(rank + 1))
+params[2].grad = torch.tensor(10.0 * (rank + 1))
+# params[1] saw no sample on this rank: it must still take part in the collective with zeros
+world = opt.reduce_gradients()
+assert world == 2
+assert torch.equal(opt.grad_views[0], torch.full((3, 5), 3.0)), opt.grad_views[0]
+assert torch.equal(opt.grad_views[1], torch.zeros(7))
+assert opt.grad_views[2].item() == 30.0
+try:
+    opt.step()
+    raise SystemExit("FlatAdam.step ran on CPU tensors")
+except RuntimeError as e:
+    assert "no CPU path" in str(e)
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_gradient_bucket_allreduce_world2_gloo(tmp_path):
+    """Training multi-GPU path: one flat gradient bucket, one sum all-reduce per step; ranks whose shard
+    missed a branch contribute zeros so collectives stay matched."""
+    script = tmp_path / "g.py"
+    script.write_text(_GLOO_GRAD_WORKER)
+    port = str(31000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), ADB_ROOT=ROOT, ADB_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
