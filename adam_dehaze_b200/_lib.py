@@ -76,6 +76,12 @@ SIGNATURES = {
     "adb_dot_head_bwd": [_P, _P, _P, _I, _I, _P, _L, _P, _I, _P, _P],
     "adb_attn_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "adb_blend3_bwd": [_P, _P, _P, _P, _P, _F, _I, _L, _P, _P, _P, _P, _P, _P],
+    "adb_image_affine": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "adb_maxpool_fwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "adb_maxpool_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "adb_mse_feat": [_P, _P, _L, _F, _P, _P, _P],
+    "adb_lpips_tap": [_P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P],
+    "adb_stem_unpack": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],

@@ -32,11 +32,11 @@ using namespace adb;
 
 constexpr int kThreads = 384;         // 4 role warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;          // first epilogue warp
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 25;        // up to 5x5 (AlexNet conv2 inside LPIPS, loss.py:91)
 constexpr int kMaxGroups = 4;
 constexpr int kMaxStages = 12;
 
-constexpr int kMaxALoads = 16;
+constexpr int kMaxALoads = 25;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxBSlots = 12;
 

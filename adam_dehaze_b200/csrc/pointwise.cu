@@ -738,7 +738,7 @@ extern "C" {
 int adb_stem_pack(const float* x, const int32_t* index, const int32_t* n_dev, int32_t n_start, int32_t n, int32_t h,
                   int32_t w, int32_t kh, int32_t kw, int32_t pad, int32_t stride, int32_t kp, void* out, void* stream) {
   ADB_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && kh >= 1 && kw >= 1, "adb_stem_pack: bad arguments");
-  ADB_REQUIRE(kp % 8 == 0 && kp >= kh * kw * 3 && (stride == 1 || stride == 2), "adb_stem_pack: kp %d must be a multiple of 8 >= 3*kh*kw", kp);
+  ADB_REQUIRE(kp % 8 == 0 && kp >= kh * kw * 3 && stride >= 1 && stride <= 4, "adb_stem_pack: kp %d must be a multiple of 8 >= 3*kh*kw, stride 1..4", kp);
   const int sms = sm_count();
   if (!sms) return ADB_ERR_NO_DEVICE;
   const int wo = (w + 2 * pad - kw) / stride + 1;

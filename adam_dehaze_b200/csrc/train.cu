@@ -633,6 +633,221 @@ __global__ void softmax3_bwd_kernel(const float* __restrict__ wts, const float* 
   dlogits[i * 3 + 2] = w2 * (g2 - dot) * inv_t;
 }
 
+// ------------------------------------------------------------------ perceptual losses (loss.py:47-108)
+// per-colour affine of an NCHW fp32 image batch: y = x*scale[c] + shift[c]  (ImageNet / LPIPS input normalisation)
+__global__ void image_affine_kernel(const float* __restrict__ x, long long hw, long long total, float s0, float s1, float s2,
+                                    float b0, float b1, float b2, float* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / hw) % 3);
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), sh = c == 0 ? b0 : (c == 1 ? b1 : b2);
+    y[i] = fmaf(x[i], sc, sh);
+  }
+}
+
+// nn.MaxPool2d(k, stride, pad) on NHWC bf16 (VGG: 2,2,0; AlexNet: 3,2,0; ResNet stem: 3,2,1), forward and backward.
+// Backward is a gather: every input pixel visits the (<= 4) windows that contain it and takes dy where it is the
+// window's FIRST maximum in scan order (ties resolved like the reference's CPU kernel; never double counted).
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int k, int stride, int pad,
+                                   int ho, int wo, __nv_bfloat16* __restrict__ y) {
+  const int G = c / 8;
+  const long long total = (long long)n * ho * wo * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int img = (int)(p / ho);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const int yy = yo * stride - pad + r;
+      if (yy < 0 || yy >= h) continue;
+      for (int s = 0; s < k; ++s) {
+        const int xx = xo * stride - pad + s;
+        if (xx < 0 || xx >= w) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)img * h + yy) * w + xx) * c + g * 8)), f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = fmaxf(m[q], f[q]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)img * ho + yo) * wo + xo) * c + g * 8) = pack8(m);
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                   const __nv_bfloat16* __restrict__ y, int n, int h, int w, int c, int k, int stride, int pad,
+                                   int ho, int wo, __nv_bfloat16* __restrict__ dx) {
+  const int G = c / 8;
+  const long long total = (long long)n * h * w * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xi = (int)(p % w); p /= w;
+    const int yi = (int)(p % h);
+    const int img = (int)(p / h);
+    float me[8], acc[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)img * h + yi) * w + xi) * c + g * 8)), me);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    // windows (yo, xo) with yo*stride - pad <= yi < yo*stride - pad + k
+    const int yo_hi = min(ho - 1, (yi + pad) / stride), xo_hi = min(wo - 1, (xi + pad) / stride);
+    for (int yo = yo_hi; yo >= 0 && yo * stride - pad + k > yi; --yo) {
+      for (int xo = xo_hi; xo >= 0 && xo * stride - pad + k > xi; --xo) {
+        float mx[8], d[8];
+        const size_t o = (((size_t)img * ho + yo) * wo + xo) * c + g * 8;
+        unpack8(__ldg(reinterpret_cast<const uint4*>(y + o)), mx);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), d);
+        bool cand[8];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { cand[q] = me[q] == mx[q]; any |= cand[q]; }
+        if (!any) continue;
+        // earlier elements of the window (scan order) holding the same maximum win the tie
+        const int y0 = yo * stride - pad, x0 = xo * stride - pad;
+        for (int r = 0; r < k; ++r) {
+          const int yy = y0 + r;
+          if (yy < 0 || yy >= h || yy > yi) continue;
+          for (int s2 = 0; s2 < k; ++s2) {
+            const int xx = x0 + s2;
+            if (xx < 0 || xx >= w) continue;
+            if (yy == yi && xx >= xi) break;
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((size_t)img * h + yy) * w + xx) * c + g * 8)), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) if (f[q] == mx[q]) cand[q] = false;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (cand[q]) acc[q] += d[q];
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (((size_t)img * h + yi) * w + xi) * c + g * 8) = pack8(acc);
+  }
+}
+
+// mean((a-b)^2) over two NHWC bf16 maps (F.mse_loss on VGG features, loss.py:81): out[0] += sum (a-b)^2 * inv_numel;
+// da = grad_scale * 2 (a-b) * inv_numel  (bf16; NULL to skip)
+__global__ void mse_feat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n8,
+                                float inv_numel, float grad_scale, float* __restrict__ out, __nv_bfloat16* __restrict__ da) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const float d = x[q] - y[q]; acc = fmaf(d, d, acc); x[q] = 2.f * d * inv_numel * grad_scale; }
+    if (da) reinterpret_cast<uint4*>(da)[i] = pack8(x);
+  }
+  __shared__ float s_red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) t += s_red[wi];
+    atomicAdd(out, t * inv_numel);
+  }
+}
+
+// LPIPS tap (lpips.py normalize_tensor / spatial_average / lin): per pixel na = fa/(|fa|+eps), nb likewise,
+// v = sum_c w_c (na_c - nb_c)^2;  out[img] += v / hw;  dfa = grad_scale/hw * d v / d fa  (bf16; NULL to skip).
+// One warp per pixel, lanes stride the 16-byte channel groups.
+__global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ fa, const __nv_bfloat16* __restrict__ fb, int n, long long hw,
+                                 int c, const float* __restrict__ lin_w, float grad_scale, float* __restrict__ out,
+                                 __nv_bfloat16* __restrict__ dfa) {
+  const int G = c / 8;
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)n * hw;
+  const float inv_hw = 1.f / (float)hw;
+  for (long long p = warp_id; p < total; p += nwarps) {
+    const int img = (int)(p / hw);
+    float sa = 0.f, sb = 0.f;
+    for (int g = lane; g < G; g += 32) {
+      float x[8], y[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(fa + (size_t)p * c + g * 8)), x);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(fb + (size_t)p * c + g * 8)), y);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { sa = fmaf(x[q], x[q], sa); sb = fmaf(y[q], y[q], sb); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    const float ra = sqrtf(sa), rb = sqrtf(sb);
+    const float ia = 1.f / (ra + 1e-10f), ib = 1.f / (rb + 1e-10f);
+    float v = 0.f, dot = 0.f;      // dot = sum_c q_c fa_c, q_c = 2 w_c d_c
+    for (int g = lane; g < G; g += 32) {
+      float x[8], y[8], wv[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(fa + (size_t)p * c + g * 8)), x);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(fb + (size_t)p * c + g * 8)), y);
+      load8f(lin_w + g * 8, wv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float d = x[q] * ia - y[q] * ib;
+        v = fmaf(wv[q] * d, d, v);
+        dot = fmaf(2.f * wv[q] * d, x[q], dot);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); dot += __shfl_xor_sync(0xffffffffu, dot, o); }
+    if (lane == 0) atomicAdd(out + img, v * inv_hw);
+    if (dfa) {
+      const float k2 = ra > 0.f ? dot * ia * ia / ra : 0.f;     // (sum q.fa) / (r s^2)
+      const float gs = grad_scale * inv_hw;
+      for (int g = lane; g < G; g += 32) {
+        float x[8], y[8], wv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(fa + (size_t)p * c + g * 8)), x);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(fb + (size_t)p * c + g * 8)), y);
+        load8f(lin_w + g * 8, wv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float d = x[q] * ia - y[q] * ib;
+          x[q] = gs * (2.f * wv[q] * d * ia - x[q] * k2);
+        }
+        *reinterpret_cast<uint4*>(dfa + (size_t)p * c + g * 8) = pack8(x);
+      }
+    }
+  }
+}
+
+// Transpose of adb_stem_pack: dx[i,c,y,x] (+)= scale[c] * sum_{r,s} dcols[i, yo, xo, (r*kw+s)*3+c] over the output
+// positions (yo, xo) whose tap (r, s) reads input pixel (y, x).  kh == 1: horizontal taps only (yo = y).
+__global__ void stem_unpack_kernel(const __nv_bfloat16* __restrict__ dcols, int n, int h, int w, int ho, int wo, int kh, int kw,
+                                   int pad, int stride, int kp, float s0, float s1, float s2, int accumulate,
+                                   float* __restrict__ dx) {
+  const long long total = (long long)n * h * w;
+  const int sh = kh > 1 ? stride : 1, ph = kh > 1 ? pad : 0;
+  const size_t plane = (size_t)h * w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int xi = (int)(t % w);
+    const int yi = (int)((t / w) % h);
+    const int img = (int)(t / ((long long)w * h));
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int r = 0; r < kh; ++r) {
+      const int ynum = yi + ph - r;
+      if (ynum < 0 || ynum % sh) continue;
+      const int yo = ynum / sh;
+      if (yo >= ho) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int xnum = xi + pad - s;
+        if (xnum < 0 || xnum % stride) continue;
+        const int xo = xnum / stride;
+        if (xo >= wo) continue;
+        const __nv_bfloat16* q = dcols + (((size_t)img * ho + yo) * wo + xo) * kp + (r * kw + s) * 3;
+        acc[0] += __bfloat162float(q[0]); acc[1] += __bfloat162float(q[1]); acc[2] += __bfloat162float(q[2]);
+      }
+    }
+    float* o = dx + (size_t)img * 3 * plane + (size_t)yi * w + xi;
+    const float sc[3] = {s0, s1, s2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * plane] = (accumulate ? o[c * plane] : 0.f) + acc[c] * sc[c];
+  }
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -855,6 +1070,65 @@ int adb_blend3_bwd(const float* dout, const float* y0, const float* y1, const fl
     softmax3_bwd_kernel<<<(b + 127) / 128, 128, 0, st>>>(weights, dweights, 1.f / temperature, b, dlogits);
     ADB_CUDA_OK(cudaGetLastError());
   }
+  return ADB_OK;
+}
+
+int adb_image_affine(const float* x, int32_t n, int32_t h, int32_t w, const float* scale3_host, const float* shift3_host, float* y,
+                     void* stream) {
+  ADB_REQUIRE(x && y && scale3_host && shift3_host && n > 0, "adb_image_affine: bad arguments");
+  const long long hw = (long long)h * w, total = 3LL * n * hw;
+  image_affine_kernel<<<grid_for(total, 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(x, hw, total, scale3_host[0], scale3_host[1],
+                                                                                           scale3_host[2], shift3_host[0], shift3_host[1], shift3_host[2], y);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_maxpool_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad, void* y, void* stream) {
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && k >= 2 && k <= 3 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_fwd: bad arguments");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  ADB_REQUIRE(ho > 0 && wo > 0, "adb_maxpool_fwd: empty output");
+  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(x), n, h, w, c, k, stride, pad, ho, wo, ADB_BFM(y));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_maxpool_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride,
+                    int32_t pad, void* dx, void* stream) {
+  ADB_REQUIRE(dy && x && y && dx && n > 0 && c % 8 == 0 && k >= 2 && k <= 3 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_bwd: bad arguments");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(dy), ADB_BF(x), ADB_BF(y), n, h, w, c, k, stride, pad, ho, wo, ADB_BFM(dx));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_mse_feat(const void* a, const void* b, int64_t numel, float grad_scale, float* out /* += */, void* da, void* stream) {
+  ADB_REQUIRE(a && b && out && numel > 0 && numel % 8 == 0, "adb_mse_feat: numel must be a positive multiple of 8");
+  mse_feat_kernel<<<grid_for(numel / 8, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(ADB_BF(a), ADB_BF(b), numel / 8, 1.f / (float)numel,
+                                                                                          grad_scale, out, ADB_BFM(da));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_lpips_tap(const void* fa, const void* fb, int32_t n, int32_t h, int32_t w, int32_t c, const float* lin_w, float grad_scale,
+                  float* out /*[n] += */, void* dfa, void* stream) {
+  ADB_REQUIRE(fa && fb && lin_w && out && n > 0 && c % 8 == 0, "adb_lpips_tap: bad arguments");
+  const long long hw = (long long)h * w;
+  lpips_tap_kernel<<<grid_for((long long)n * hw * 32, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(ADB_BF(fa), ADB_BF(fb), n, hw, c, lin_w,
+                                                                                                        grad_scale, out, ADB_BFM(dfa));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_stem_unpack(const void* dcols, int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t pad, int32_t stride, int32_t kp,
+                    const float* scale3_host, int32_t accumulate, float* dx, void* stream) {
+  ADB_REQUIRE(dcols && dx && scale3_host && n > 0 && kp % 8 == 0 && kp >= 3 * kh * (kh > 1 ? kw : 1) && kp >= 3 * kw, "adb_stem_unpack: bad arguments");
+  const int wo = (w + 2 * pad - kw) / stride + 1;
+  const int ho = kh > 1 ? (h + 2 * pad - kh) / stride + 1 : h;
+  stem_unpack_kernel<<<grid_for((long long)n * h * w, 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(dcols), n, h, w, ho, wo, kh > 1 ? kh : 1, kw, pad, stride, kp, scale3_host[0], scale3_host[1], scale3_host[2], accumulate, dx);
+  ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }
 

@@ -1,17 +1,24 @@
-"""Drop-in for training/loss.py (reference loss.py:110-241): DehazingLoss, JointLoss and their factories.
+"""Drop-in for training/loss.py (reference loss.py:7-241): ContentLoss, PerceptualLoss, DehazingLoss, JointLoss and their
+factories.
 
-Built on the B200 path so far: the L1 reconstruction term and the cross-entropy term, forward AND backward, as fused
-warp-shuffle reductions (adb_l1_mse_fwd / adb_l1_bwd / adb_ce_fwd_bwd) wrapped in torch.autograd.Function so the
-reference's `loss.backward()` call keeps working.  The VGG16 content term (loss.py:47-84) and the LPIPS term
-(loss.py:86-108) need the conv dgrad kernels and are not built yet: with their lambdas non-zero the forward raises
-NotImplementedError instead of silently dropping a term.  Pass lambda_content=0, lambda_perceptual=0 to train on
-L1 (+CE) only.
+Every term runs on libadb200 kernels, forward AND backward, wrapped in torch.autograd.Function so the reference's
+`loss.backward()` keeps working:
+  * L1 / cross-entropy: fused warp-shuffle reductions (adb_l1_mse_fwd / adb_l1_bwd / adb_ce_fwd_bwd);
+  * ContentLoss (VGG16 features at indices 9/16/23) and PerceptualLoss (LPIPS-alex): frozen conv trunks on the tcgen05
+    conv kernel, data gradients back to `pred` (training/perceptual.py).
+Pretrained VGG16 / AlexNet / LPIPS-lin weights cannot be downloaded here; when the torch hub cache does not hold them
+the trunks keep torchvision's random init (seeded by the caller) and a one-line notice is printed — the arithmetic is
+the same, load real weights with load_state_dict (the sub-module names follow torchvision / lpips).
 """
 import torch
 import torch.nn as nn
 
+import os
+from collections import OrderedDict
+
 from .. import ops
 from .. import _lib
+from . import perceptual as _perc
 
 
 class _L1Mean(torch.autograd.Function):
@@ -52,22 +59,115 @@ def _need_cuda(t, what):
         raise RuntimeError(f"{what}: expected CUDA tensors — this package runs on B200 (sm_100a) only and has no CPU path")
 
 
+def _hub_file(name):
+    path = os.path.join(torch.hub.get_dir(), "checkpoints", name)
+    return path if os.path.exists(path) else None
+
+
+class ContentLoss(nn.Module):
+    """VGG16 feature MSE at `features` indices 9 / 16 / 23, mean of the three (reference loss.py:7-84)."""
+
+    def __init__(self, pretrained_model="vgg16", content_layers=None):
+        super().__init__()
+        import torchvision.models as tvm
+        if pretrained_model not in ("vgg16",):
+            raise ValueError(f"Unsupported model: {pretrained_model}" if pretrained_model != "vgg19" else
+                             "vgg19 content loss is not built on the B200 path")
+        self.content_layers = content_layers or ["relu2_2", "relu3_3", "relu4_3"]
+        if self.content_layers != ["relu2_2", "relu3_3", "relu4_3"]:
+            raise NotImplementedError("ContentLoss on the B200 path taps the reference's default layers (indices 9/16/23)")
+        vgg = tvm.vgg16(weights=None)
+        ck = _hub_file("vgg16-397923af.pth")
+        if ck:
+            vgg.load_state_dict(torch.load(ck, map_location="cpu"))
+        else:
+            print("ContentLoss: pretrained VGG16 weights are not in the torch hub cache — using random-init features")
+        self.model = vgg.features.eval()
+        for p in self.model.parameters():
+            p.requires_grad = False
+        self.__dict__["_net"] = None
+
+    def forward(self, x, target):
+        _need_cuda(x, "ContentLoss")
+        if self.__dict__["_net"] is None:
+            self.__dict__["_net"] = _perc.vgg16_content_net(self.model)
+        return _perc.content_loss(self.__dict__["_net"], x, target)
+
+
+class _LPIPSAlex(nn.Module):
+    """Parameter container with lpips.LPIPS(net='alex')'s state_dict names (net.slice{1..5}.{0,3,6,8,10}.*,
+    lin{0..4}.model.1.weight, scaling_layer.{shift,scale})."""
+
+    def __init__(self):
+        super().__init__()
+        import torchvision.models as tvm
+        alex = tvm.alexnet(weights=None)
+        ck = _hub_file("alexnet-owt-7be5be79.pth")
+        if ck:
+            alex.load_state_dict(torch.load(ck, map_location="cpu"))
+        else:
+            print("PerceptualLoss: pretrained AlexNet / LPIPS weights are not available offline — using random-init weights")
+        f = alex.features
+        self.net = nn.Module()
+        for i, idx in enumerate((0, 3, 6, 8, 10)):
+            setattr(self.net, f"slice{i + 1}", nn.Sequential(OrderedDict([(str(idx), f[idx])])))
+        self.scaling_layer = nn.Module()
+        self.scaling_layer.register_buffer("shift", torch.tensor(_perc.LPIPS_SHIFT).view(1, 3, 1, 1))
+        self.scaling_layer.register_buffer("scale", torch.tensor(_perc.LPIPS_SCALE).view(1, 3, 1, 1))
+        for i, c in enumerate((64, 192, 384, 256, 256)):
+            lin = nn.Module()
+            conv = nn.Conv2d(c, 1, 1, bias=False)
+            with torch.no_grad():
+                conv.weight.copy_(torch.rand_like(conv.weight) / c)     # LPIPS' lin layers are non-negative
+            lin.model = nn.Sequential(OrderedDict([("0", nn.Dropout()), ("1", conv)]))
+            setattr(self, f"lin{i}", lin)
+        for p in self.parameters():
+            p.requires_grad = False
+        self.eval()
+
+    def convs(self):
+        return [getattr(self.net, f"slice{i + 1}")[0] for i in range(5)]
+
+    def lin_weights(self):
+        return [getattr(self, f"lin{i}").model[1].weight for i in range(5)]
+
+
+class PerceptualLoss(nn.Module):
+    """LPIPS(net='alex') on inputs mapped to [-1, 1]; returns [B,1,1,1] like lpips (reference loss.py:86-108)."""
+
+    def __init__(self, net="alex"):
+        super().__init__()
+        if net != "alex":
+            raise NotImplementedError("PerceptualLoss on the B200 path implements LPIPS(net='alex')")
+        self.loss_fn = _LPIPSAlex()
+        self.__dict__["_net"] = None
+
+    def forward(self, x, target):
+        _need_cuda(x, "PerceptualLoss")
+        if self.__dict__["_net"] is None:
+            self.__dict__["_net"] = _perc.alexnet_lpips_net(self.loss_fn.convs())
+        return _perc.lpips_distance(self.__dict__["_net"], self.loss_fn.lin_weights(), x, target)
+
+
 class DehazingLoss(nn.Module):
     def __init__(self, lambda_l1=1.0, lambda_content=0.1, lambda_perceptual=0.1):
         super().__init__()
         self.lambda_l1, self.lambda_content, self.lambda_perceptual = lambda_l1, lambda_content, lambda_perceptual
+        # the reference always builds both sub-losses (loss.py:121-123); a zero lambda skips building the trunk here
+        self.content_loss = ContentLoss() if lambda_content != 0 else None
+        self.perceptual_loss = PerceptualLoss() if lambda_perceptual != 0 else None
 
     def forward(self, pred, target):
         """Returns (total, {'l1','content','perceptual','total'}) like loss.py:125-162."""
         _need_cuda(pred, "DehazingLoss")
-        if self.lambda_content != 0 or self.lambda_perceptual != 0:
-            raise NotImplementedError(
-                "DehazingLoss: the VGG16 content term and the LPIPS term are not built on the B200 path yet "
-                "(they need the conv backward kernels); construct with lambda_content=0, lambda_perceptual=0")
         l1 = _L1Mean.apply(pred, target)
         zero = torch.zeros((), device=pred.device)
-        total = self.lambda_l1 * l1
-        return total, {"l1": l1, "content": zero, "perceptual": zero, "total": total}
+        content = self.content_loss(pred, target) if self.content_loss is not None else zero
+        perceptual = self.perceptual_loss(pred, target) if self.perceptual_loss is not None else zero
+        if perceptual.dim() > 0:
+            perceptual = perceptual.mean()
+        total = self.lambda_l1 * l1 + self.lambda_content * content + self.lambda_perceptual * perceptual
+        return total, {"l1": l1, "content": content, "perceptual": perceptual, "total": total}
 
 
 class JointLoss(nn.Module):

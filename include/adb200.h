@@ -276,6 +276,25 @@ ADB_API int adb_blend3_bwd(const float* dout, const float* y0, const float* y1, 
                            float temperature, int32_t b, int64_t chw, float* dy0, float* dy1, float* dy2, float* dweights,
                            float* dlogits, void* stream);
 
+/* Perceptual loss terms (training/loss.py:47-108: VGG16 content loss, LPIPS-alex), forward and d/d(pred).  The frozen
+ * feature networks run on adb_conv2d (forward: bias + ReLU fused; backward: the data-gradient form); these are the
+ * pieces around them.  Host pointers are marked _host. */
+ADB_API int adb_image_affine(const float* x, int32_t n, int32_t h, int32_t w, const float* scale3_host, const float* shift3_host,
+                             float* y, void* stream);           /* y = x*scale[c] + shift[c], NCHW fp32 (loss.py:63-67,104-105) */
+ADB_API int adb_maxpool_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
+                            void* y, void* stream);             /* nn.MaxPool2d(k, stride, pad), NHWC bf16, k in {2,3} */
+ADB_API int adb_maxpool_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k,
+                            int32_t stride, int32_t pad, void* dx, void* stream);
+/* out[0] += mean((a-b)^2) (F.mse_loss, loss.py:81); da (nullable, bf16) = grad_scale * 2(a-b)/numel */
+ADB_API int adb_mse_feat(const void* a, const void* b, int64_t numel, float grad_scale, float* out, void* da, void* stream);
+/* LPIPS tap: channel-unit-normalise both maps, lin-weighted squared difference, spatial mean: out[n] += value;
+ * dfa (nullable, bf16) = grad_scale * d value / d fa */
+ADB_API int adb_lpips_tap(const void* fa, const void* fb, int32_t n, int32_t h, int32_t w, int32_t c, const float* lin_w,
+                          float grad_scale, float* out, void* dfa, void* stream);
+/* Transpose of adb_stem_pack (gradient of a 3-channel stem w.r.t. the image): dx (NCHW fp32) (+)= scale[c] * col2im(dcols) */
+ADB_API int adb_stem_unpack(const void* dcols, int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t pad,
+                            int32_t stride, int32_t kp, const float* scale3_host, int32_t accumulate, float* dx, void* stream);
+
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

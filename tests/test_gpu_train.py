@@ -444,3 +444,89 @@ def test_soft_router_train_step():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Perceptual loss terms against the oracle (fp32, torch autograd) with the SAME random-init trunks.
+# Tolerances: values 1e-2 relative (north_star).  d/d(pred) flows through 10-13 bf16 conv layers with ReLU / max-pool
+# masks, so — as for the branch gradients above — it is bounded by the fp32 oracle's own error under bf16 storage:
+# ||g - g_ref|| <= 1.5 ||g_sim - g_ref|| + 0.05 ||g_ref||, and cos(g, g_ref) >= 0.9.
+def _smooth_pair(n, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    base = F.interpolate(torch.rand(n, 3, h // 8, w // 8, generator=g), size=(h, w), mode="bilinear", align_corners=False)
+    tgt = base.clamp(0, 1).cuda()
+    pred = (base * 0.8 + 0.15 + 0.05 * torch.rand(n, 3, h, w, generator=g)).clamp(0, 1).cuda()
+    return pred, tgt
+
+
+def _grad_vs_oracle(fn_ref, fn_ours, pred):
+    from helpers import oracle_bf16_storage
+    p1 = pred.clone().requires_grad_(True)
+    v_ref = fn_ref(p1)
+    (g_ref,) = torch.autograd.grad(v_ref.sum(), p1)
+    p2 = pred.clone().requires_grad_(True)
+    v_sim = oracle_bf16_storage(fn_ref, p2)
+    (g_sim,) = torch.autograd.grad(v_sim.sum(), p2)
+    p3 = pred.clone().requires_grad_(True)
+    v = fn_ours(p3)
+    v.sum().backward()
+    torch.cuda.synchronize()
+    return v.detach(), v_ref.detach(), p3.grad, g_ref, g_sim
+
+
+def test_content_loss_matches_oracle():
+    from helpers import make_branch  # noqa: F401  (sys.path)
+    import adam_oracle as oracle
+    from adam_dehaze_b200.training.loss import ContentLoss
+    torch.manual_seed(11)
+    crit = ContentLoss().cuda()
+    vsd = {k: v.detach().float() for k, v in crit.model.state_dict().items()}
+    pred, tgt = _smooth_pair(2, 64, 96, 70)
+    v, v_ref, g, g_ref, g_sim = _grad_vs_oracle(lambda p: oracle.content_loss(vsd, p, tgt), lambda p: crit(p, tgt), pred)
+    assert abs(v.item() - v_ref.item()) <= 1e-2 * abs(v_ref.item()), (v.item(), v_ref.item())
+    e, es, rn = (g - g_ref).norm().item(), (g_sim - g_ref).norm().item(), g_ref.norm().item()
+    cos = (g * g_ref).sum().item() / (g.norm().item() * rn)
+    assert e <= 1.5 * es + 0.05 * rn and cos >= 0.9, (e / rn, es / rn, cos)
+    with torch.no_grad():
+        assert abs(crit(pred, tgt).item() - v_ref.item()) <= 1e-2 * abs(v_ref.item())
+
+
+def test_lpips_matches_oracle():
+    from helpers import make_branch  # noqa: F401
+    import adam_oracle as oracle
+    from adam_dehaze_b200.training.loss import PerceptualLoss
+    torch.manual_seed(12)
+    crit = PerceptualLoss().cuda()
+    asd = {}
+    for i, idx in enumerate((0, 3, 6, 8, 10)):
+        conv = crit.loss_fn.convs()[i]
+        asd[f"{idx}.weight"], asd[f"{idx}.bias"] = conv.weight.detach().float(), conv.bias.detach().float()
+    lins = [w.detach().float() for w in crit.loss_fn.lin_weights()]
+    pred, tgt = _smooth_pair(2, 96, 128, 71)
+    v, v_ref, g, g_ref, g_sim = _grad_vs_oracle(lambda p: oracle.perceptual_lpips(asd, lins, p, tgt), lambda p: crit(p, tgt), pred)
+    assert v.shape == (2, 1, 1, 1)
+    assert (v - v_ref).abs().max().item() <= 1e-2 * v_ref.abs().max().item(), (v.flatten().tolist(), v_ref.flatten().tolist())
+    e, es, rn = (g - g_ref).norm().item(), (g_sim - g_ref).norm().item(), g_ref.norm().item()
+    cos = (g * g_ref).sum().item() / (g.norm().item() * rn)
+    assert e <= 1.5 * es + 0.05 * rn and cos >= 0.9, (e / rn, es / rn, cos)
+
+
+def test_dehazing_loss_full_and_joint_loss():
+    """DehazingLoss with the reference's lambdas (1.0, 0.1, 0.1) and JointLoss on top: components, total, gradient flow."""
+    from helpers import CONFIG
+    from adam_dehaze_b200.training.loss import get_dehazing_loss, get_joint_loss
+    torch.manual_seed(13)
+    crit = get_joint_loss(CONFIG).cuda()
+    pred, tgt = _smooth_pair(2, 64, 64, 72)
+    pred.requires_grad_(True)
+    logits = torch.tensor([[0.2, 0.1, -0.3], [1.0, -1.0, 0.0]], device="cuda", requires_grad=True)
+    labels = torch.tensor([0, 2], device="cuda")
+    total, parts = crit(pred, tgt, logits, labels)
+    dc = parts["dehazing_components"]
+    want = 1.0 * (1.0 * dc["l1"] + 0.1 * dc["content"] + 0.1 * dc["perceptual"]) + 0.2 * parts["classification"]
+    assert abs(total.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert abs(parts["classification"].item() - F.cross_entropy(logits.detach(), labels).item()) <= 1e-5
+    total.backward()
+    assert pred.grad is not None and pred.grad.abs().max().item() > 0 and logits.grad is not None
+    assert set(parts) == {"dehazing", "classification", "detection", "total", "dehazing_components"}
+    assert set(dc) == {"l1", "content", "perceptual", "total"}
