@@ -1,0 +1,112 @@
+"""Drop-in for training/train_dehazing.py (reference train_dehazing.py:16-223): `train_dehazing_model(model, level, config)`.
+
+Same loop — filter the batch by intensity level, zero_grad, forward in train() mode, DehazingLoss, backward, Adam
+(weight_decay 1e-4), validation PSNR, `best_model.pth` with the reference's checkpoint keys — but every tensor op is a
+libadb200 kernel: batch-statistics BatchNorm forward, dgrad/wgrad on tcgen05, one flat gradient all-reduce when
+torch.distributed is initialised, one fused Adam launch.  The reference's cv2 dataset, TensorBoard writer and skimage
+metrics are outside the hot path; loaders are injectable and default to the synthetic hazy recipe of
+SURVEY.md 8d, and validation PSNR is computed on the device.
+"""
+import os
+
+import torch
+
+from .loss import get_dehazing_loss
+from .optim import FlatAdam
+
+_LEVEL = {"low": 0, "medium": 1, "high": 2}
+
+
+def synthetic_loader(n_batches, batch, h, w, device, seed=42):
+    """Batches {'hazy','clear','intensity'} like data/dataset.py:97-124: I = clip(J t + 0.8 (1 - t)), t = exp(-beta d),
+    beta = {0.03, 0.06, 0.09}[intensity] (utils/helpers.py:241-258)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+    d = (0.3 + 0.7 * torch.sqrt((xx - 0.5) ** 2 + (yy - 0.2) ** 2)) * 100.0
+    betas = torch.tensor([0.03, 0.06, 0.09])
+    out = []
+    for _ in range(n_batches):
+        clear = torch.rand(batch, 3, h, w, generator=g)
+        labels = torch.arange(batch) % 3
+        t = torch.exp(-betas[labels].view(batch, 1, 1, 1) * d)
+        hazy = torch.clamp(clear * t + 0.8 * (1 - t), 0, 1)
+        out.append({"hazy": hazy.to(device), "clear": clear.to(device), "intensity": labels.to(device)})
+    return out
+
+
+def batch_psnr(pred, target):
+    """Mean over the batch of 10 log10(1 / mse_i), on the device (skimage peak_signal_noise_ratio, data_range=1)."""
+    mse = torch.mean((pred - target) ** 2, dim=(1, 2, 3)).clamp_min(1e-12)
+    return (10.0 * torch.log10(1.0 / mse)).mean()
+
+
+def train_step(model, criterion, optimizer, hazy, clear):
+    """train_dehazing.py:86-96: zero_grad, forward, loss, backward, step.  Returns (loss tensor, components)."""
+    optimizer.zero_grad()
+    out = model(hazy)
+    loss, parts = criterion(out, clear)
+    loss.backward()
+    optimizer.step()
+    return loss, parts
+
+
+def train_dehazing_model(model, intensity_level, config, train_loader=None, val_loader=None, epochs=30, criterion=None):
+    device = torch.device(config["device"])
+    if device.type != "cuda":
+        raise RuntimeError("train_dehazing_model: this build trains on B200 (sm_100a) only — config['device'] must be cuda")
+    model = model.to(device)
+    lr = config["dehazing"][intensity_level]["learning_rate"]
+    optimizer = FlatAdam(model.parameters(), lr=lr, weight_decay=0.0001)
+    criterion = (criterion if criterion is not None else get_dehazing_loss(config)).to(device)
+    if train_loader is None:
+        size = config.get("dataset", {}).get("image_size", [256, 256])
+        bs = config.get("dataset", {}).get("batch_size", 16)
+        train_loader = synthetic_loader(4, bs, size[0], size[1], device, seed=config.get("seed", 42))
+        val_loader = synthetic_loader(1, bs, size[0], size[1], device, seed=config.get("seed", 42) + 1)
+    ck_dir = os.path.join(config["dehazing"]["checkpoint_dir"], intensity_level)
+    os.makedirs(ck_dir, exist_ok=True)
+    k = _LEVEL[intensity_level]
+    best, bad_epochs, history = 0.0, 0, []
+    for epoch in range(epochs):
+        model.train()
+        tot, nb = 0.0, 0
+        for batch in train_loader:
+            sel = batch["intensity"] == k
+            if not bool(sel.any()):
+                continue
+            hazy, clear = batch["hazy"][sel].to(device), batch["clear"][sel].to(device)
+            loss, _ = train_step(model, criterion, optimizer, hazy, clear)
+            tot += loss.item()
+            nb += 1
+        model.eval()
+        vl, vp, vs = 0.0, 0.0, 0
+        with torch.no_grad():
+            for batch in (val_loader or []):
+                sel = batch["intensity"] == k
+                if not bool(sel.any()):
+                    continue
+                hazy, clear = batch["hazy"][sel].to(device), batch["clear"][sel].to(device)
+                out = model(hazy)
+                loss, _ = criterion(out, clear)
+                vl += loss.item() * hazy.size(0)
+                vp += batch_psnr(out, clear).item() * hazy.size(0)
+                vs += hazy.size(0)
+        vl, vp = (vl / vs, vp / vs) if vs else (0.0, 0.0)
+        # ReduceLROnPlateau(mode='min', factor=0.5, patience=5), train_dehazing.py:40-42
+        if history and vl >= min(history):
+            bad_epochs += 1
+            if bad_epochs > 5:
+                optimizer.lr *= 0.5
+                bad_epochs = 0
+        else:
+            bad_epochs = 0
+        history.append(vl)
+        print(f"Epoch {epoch + 1}/{epochs}:\n  Train Loss: {tot / max(1, nb):.4f}\n  Val Loss: {vl:.4f}, Val PSNR: {vp:.2f}")
+        if vp > best or epoch == 0:
+            best = vp
+            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
+                        "optimizer_state_dict": {"step": optimizer.step_count, "lr": optimizer.lr},
+                        "val_psnr": vp, "val_ssim": None, "val_loss": vl}, os.path.join(ck_dir, "best_model.pth"))
+    best_ck = torch.load(os.path.join(ck_dir, "best_model.pth"), map_location="cpu")
+    model.load_state_dict(best_ck["model_state_dict"])
+    return model

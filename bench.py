@@ -488,7 +488,7 @@ def run_train(args):
         dist.destroy_process_group()
 
 
-TRAIN_LAMBDAS = (0.0, 0.0)   # (content, perceptual) terms of DehazingLoss in the training bench
+TRAIN_LAMBDAS = (0.1, 0.1)   # (content, perceptual) terms of DehazingLoss in the training bench
 
 
 def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):

@@ -37,6 +37,7 @@ def parse_args():
     p.add_argument("--seed", type=int, default=None)
     p.add_argument("--synthetic", type=int, default=12, help="images to synthesise when no dataset directory exists")
     p.add_argument("--size", type=int, nargs=2, default=[256, 256], metavar=("H", "W"))
+    p.add_argument("--epochs", type=int, default=2, help="epochs per branch for --mode train_dehazing on synthetic data")
     return p.parse_args()
 
 
@@ -154,16 +155,15 @@ def main():
         torch.save({"hazy": hazy.cpu(), "dehazed": out.cpu()}, os.path.join(demo_dir, "demo.pt"))
         print(f"demo outputs written to {demo_dir}")
     elif args.mode == "train_dehazing":
-        branches = {"low": create_low_intensity_model(config), "medium": create_medium_intensity_model(config),
-                    "high": create_high_intensity_model(config)}
-        criterion = get_dehazing_loss(config)
-        hazy, clear, _ = synth_hazy(2, args.size[0], args.size[1], device, config["seed"])
-        model = branches["low"].to(device).train()
-        # The step of train_dehazing.py:71-96 (forward, criterion, backward, Adam).  The conv dgrad/wgrad and the
-        # batch-statistics BatchNorm kernels are not built yet, so this raises instead of silently using torch ops.
-        out = model(hazy)
-        loss, _ = criterion(out, clear)
-        loss.backward()
+        # training/train_dehazing.py:16-223 per intensity level, on synthetic batches when no dataset directory exists
+        from adam_dehaze_b200.training.train_dehazing import synthetic_loader, train_dehazing_model
+        makers = {"low": create_low_intensity_model, "medium": create_medium_intensity_model, "high": create_high_intensity_model}
+        bs = max(3, args.synthetic)
+        train = synthetic_loader(2, bs, args.size[0], args.size[1], device, seed=config["seed"])
+        val = synthetic_loader(1, bs, args.size[0], args.size[1], device, seed=config["seed"] + 1)
+        for level, mk in makers.items():
+            print(f"Training {level} intensity dehazing model...")
+            train_dehazing_model(mk(config), level, config, train_loader=train, val_loader=val, epochs=args.epochs)
     else:
         raise NotImplementedError(f"--mode {args.mode} is outside the B200 hot path (SURVEY.md §2: out of scope)")
 

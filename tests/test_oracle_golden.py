@@ -134,3 +134,34 @@ def test_synth_hazy_contract():
     assert 0 <= hazy.min() and hazy.max() <= 1
     # heavier beta -> closer to the airlight 0.8 everywhere
     assert (hazy[2] - 0.8).abs().mean() < (hazy[0] - 0.8).abs().mean()
+
+
+@pytest.mark.parametrize("name", ["low", "medium", "high"])
+def test_train_mode_oracle_matches_reference(name):
+    """oracle.train_mode() (batch-statistics BatchNorm) + torch autograd reproduces one training step of the unmodified
+    reference: output, L1 loss and every parameter gradient (fixtures: oracle/make_golden_train.py)."""
+    g = golden(f"train_{name}.pt")
+    m = make_branch(name)
+    assert fingerprint(m.state_dict()) == g["fingerprint"]
+    n, h, w = g["shape"]
+    x, tgt = rand_image(n, h, w, g["x_seed"]), rand_image(n, h, w, g["target_seed"])
+    fwd = {"low": oracle.light_forward, "medium": oracle.medium_forward, "high": oracle.complex_forward}[name]
+    with torch.enable_grad():
+        sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
+        with oracle.train_mode():
+            out = fwd(sd, x)
+        loss = (out - tgt).abs().mean()
+        names = [k for k, _ in m.named_parameters()]
+        grads = dict(zip(names, torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)))
+    assert torch.allclose(out, g["out"], rtol=0, atol=5e-6), (out - g["out"]).abs().max()
+    assert abs(loss.item() - g["loss"].item()) <= 1e-6
+    for k in names:
+        ref = g["grads"][k]
+        got = grads[k]
+        if isinstance(ref, dict):
+            assert tuple(got.shape) == ref["shape"]
+            scale = max(ref["norm"], 1e-9)
+            assert abs(got.norm().item() - ref["norm"]) <= 2e-3 * scale + 1e-9, k
+            assert (got.flatten()[:8] - ref["head"]).abs().max().item() <= 2e-3 * max(ref["head"].abs().max().item(), scale / got.numel() ** 0.5) + 1e-9, k
+        else:
+            assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-9, k
