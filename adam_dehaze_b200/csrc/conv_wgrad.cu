@@ -71,6 +71,22 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32
   return d;
 }
 
+// One pixel tile's MMAs as a straight-line run: 8 K steps of 16 pixels x NT taps (one accumulator per tap).
+template <int NT>
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_base, int N, uint64_t a_hi, uint32_t a_lo, uint64_t b_hi, uint32_t b_lo,
+                                            const uint32_t (&b_off)[8], const uint32_t (&t_off)[kWgMaxSetTaps], uint32_t idesc,
+                                            uint32_t accumulate) {
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const uint64_t a = a_hi | (uint64_t)(a_lo + (uint32_t)kk * 128u);          // + 16 pixel rows of 128 B
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint64_t b = b_hi | (uint64_t)(b_lo + b_off[kk] + t_off[j]);
+      umma_bf16(tmem_base + (uint32_t)(j * N), a, b, idesc, accumulate | (uint32_t)kk);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmL0,
                   const __grid_constant__ CUtensorMap tmL1, const __grid_constant__ WgK P) {
@@ -149,22 +165,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
     // ======================================================= MMA issuer
     int slot = 0; uint32_t phase = 0;
     uint32_t accumulate = 0;
+    // descriptor halves that never change, and the per-K-step start offsets (16-byte units) inside a stage
+    const uint64_t a_hi = make_mnmajor_desc(0, (uint32_t)P.s_group_bytes, 1024u);
+    const uint64_t b_hi = make_mnmajor_desc(0, (uint32_t)P.l_group_bytes, 1024u);
+    uint32_t b_off[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int px = kk * 16;
+      b_off[kk] = (uint32_t)(((px >> P.tw_shift) * P.halo_w + (px & (P.TW - 1))) * 8);
+    }
+    uint32_t t_off[kWgMaxSetTaps];
+#pragma unroll
+    for (int j = 0; j < kWgMaxSetTaps; ++j) t_off[j] = (uint32_t)S.ddw[j] * 8u;
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(full_bar(slot), phase, P.err_flag, 12);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sbase = base + (uint32_t)slot * (uint32_t)P.stage_bytes;
-        const uint32_t lbase = sbase + 2u * (uint32_t)P.s_group_bytes;
-#pragma unroll 1
-        for (int kk = 0; kk < 8; ++kk) {
-          const int px = kk * 16;
-          const int r = px >> P.tw_shift, c = px & (P.TW - 1);
-          const uint64_t a = make_mnmajor_desc(sbase + (uint32_t)px * 128u, (uint32_t)P.s_group_bytes, 1024u);
-          const uint32_t l_row = (uint32_t)(r * P.halo_w + c);
-          for (int j = 0; j < S.ntaps; ++j) {
-            const uint64_t b = make_mnmajor_desc(lbase + (l_row + S.ddw[j]) * 128u, (uint32_t)P.l_group_bytes, 1024u);
-            umma_bf16(tmem_base + (uint32_t)(j * N), a, b, P.idesc, accumulate | (uint32_t)kk);
-          }
+        const uint32_t a_lo = (sbase & 0x3FFFFu) >> 4;
+        const uint32_t b_lo = ((sbase + 2u * (uint32_t)P.s_group_bytes) & 0x3FFFFu) >> 4;
+        switch (S.ntaps) {
+          case 1: issue_wgrad<1>(tmem_base, N, a_hi, a_lo, b_hi, b_lo, b_off, t_off, P.idesc, accumulate); break;
+          case 2: issue_wgrad<2>(tmem_base, N, a_hi, a_lo, b_hi, b_lo, b_off, t_off, P.idesc, accumulate); break;
+          case 3: issue_wgrad<3>(tmem_base, N, a_hi, a_lo, b_hi, b_lo, b_off, t_off, P.idesc, accumulate); break;
+          case 4: issue_wgrad<4>(tmem_base, N, a_hi, a_lo, b_hi, b_lo, b_off, t_off, P.idesc, accumulate); break;
+          default: issue_wgrad<5>(tmem_base, N, a_hi, a_lo, b_hi, b_lo, b_off, t_off, P.idesc, accumulate); break;
         }
         umma_commit(empty_bar(slot));
         if (t == t_end - 1) umma_commit(done_bar);

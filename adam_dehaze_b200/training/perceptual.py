@@ -70,6 +70,10 @@ class FrozenNet:
         """images: NCHW fp32 [N,3,H,W] (pred rows first).  Returns (taps, saved)."""
         n, _, h, w = images.shape
         dev = images.device
+        for item in self.arch:
+            if item[0] in ("stem", "conv") and item[1].weight.device != dev:
+                raise RuntimeError(f"perceptual loss trunk lives on {item[1].weight.device} but the images are on {dev}: "
+                                   "move the criterion with .to(device) (train_dehazing.py:46) — there is no CPU path")
         st = _lib.current_stream()
         sc = (_lib.C.c_float * 3)(*self.in_scale)
         sh = (_lib.C.c_float * 3)(*self.in_shift)

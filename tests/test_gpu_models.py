@@ -175,8 +175,12 @@ def test_losses_forward_backward():
     assert torch.allclose(pred.grad, p2.grad, rtol=1e-2, atol=1e-9)
     assert torch.allclose(logits.grad, l2.grad, rtol=1e-2, atol=1e-7)
     assert set(parts) == {"dehazing", "classification", "detection", "total", "dehazing_components"}
-    with pytest.raises(NotImplementedError):
-        get_dehazing_loss(CONFIG)(pred, tgt)             # content / LPIPS terms are refused, never silently dropped
+    full = get_dehazing_loss(CONFIG)                     # reference lambdas (1.0, 0.1, 0.1): VGG16 + LPIPS trunks
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        full(pred, tgt)                                   # criterion still on the CPU: refused, never a silent fallback
+    t2, parts2 = full.cuda()(pred, tgt)
+    assert parts2["content"].item() > 0 and parts2["perceptual"].item() > 0
+    assert abs(t2.item() - (parts2["l1"] + 0.1 * parts2["content"] + 0.1 * parts2["perceptual"]).item()) <= 1e-5 * abs(t2.item())
 
 
 def test_blocks_standalone():

@@ -182,11 +182,51 @@ def test_no_cpu_fallback_and_train_mode_refused():
     clf = make_classifier()
     with pytest.raises(RuntimeError, match="no CPU path"):
         clf(torch.rand(1, 3, 32, 32))
-    assert m.train().training
-    # train mode is refused before any device work (checked with a meta "cuda-less" probe of the guard itself)
+    # train() mode has no CPU path either (the training kernels are CUDA only), and HDEN / the non-default variants
+    # refuse train() mode instead of silently running torch ops
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.train()(torch.rand(1, 3, 16, 16))
     from adam_dehaze_b200 import engine
     with pytest.raises(NotImplementedError, match="eval"):
-        engine.require_inference(m, "LightweightDehazeModel")
+        engine.require_inference(clf.train(), "FogIntensityClassifier")
+    v = make_branch("corun").train()
+    eng = v._branch_engine()
+    with pytest.raises(NotImplementedError, match="default branch models"):
+        eng._forward_train(torch.rand(1, 3, 64, 64), None, None)
+
+
+def test_wgrad_desc_struct_matches_header_field_order():
+    hdr = open(os.path.join(ROOT, "include", "adb200.h")).read()
+    body = hdr[hdr.index("typedef struct adb_wgrad_desc {"):hdr.index("} adb_wgrad_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"[\s\*](\w+)\s*[;,]", body)
+    assert names == [f[0] for f in _lib.WgradDesc._fields_]
+
+
+def test_dgrad_weight_transforms_match_autograd():
+    """The data-gradient launches are ordinary convs with transformed weights (training/autograd.py): check the
+    transforms against torch autograd on CPU in fp32 (3x3 stride 1; 4x4 stride 2 <-> ConvTranspose2d(4,2,1))."""
+    import torch.nn.functional as F
+    with torch.enable_grad():
+        _check_dgrad_transforms(F)
+
+
+def _check_dgrad_transforms(F):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 8, 10, generator=g, requires_grad=True)
+    w = torch.randn(6, 4, 3, 3, generator=g)
+    dz = torch.randn(1, 6, 8, 10, generator=g)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, padding=1), x, dz)
+    wd = w.flip(2, 3).permute(1, 0, 2, 3)                      # _dgrad_spec_s1's weight
+    assert torch.allclose(F.conv2d(dz, wd, padding=1), ref, atol=1e-5)
+    w4 = torch.randn(6, 4, 4, 4, generator=g)
+    dz2 = torch.randn(1, 6, 4, 5, generator=g)
+    (ref2,) = torch.autograd.grad(F.conv2d(x, w4, stride=2, padding=1), x, dz2)
+    assert torch.allclose(F.conv_transpose2d(dz2, w4, stride=2, padding=1), ref2, atol=1e-5)   # weight as is
+    wt = torch.randn(4, 6, 4, 4, generator=g)
+    dy = torch.randn(1, 6, 16, 20, generator=g)
+    (ref3,) = torch.autograd.grad(F.conv_transpose2d(x, wt, stride=2, padding=1), x, dy)
+    assert torch.allclose(F.conv2d(dy, wt, stride=2, padding=1), ref3, atol=1e-4)              # weight as is
 
 
 def test_product_never_imports_oracle():
