@@ -342,7 +342,7 @@ int wg_plan(const adb_wgrad_desc* d, WgPlan& pl, int sm_count, int max_smem) {
   // ---- K tiles: 128 S pixels = TH rows x TW columns, TW >= 16 so a K step of 16 pixels stays inside one row
   int TW = 128;
   while (TW > P.grid_w && TW > 16) TW >>= 1;
-  ADB_REQUIRE(P.grid_w >= 16, "adb_wgrad: maps narrower than 16 pixels are unsupported (got %d)", P.grid_w);
+  // (maps narrower than 16 pixels still use TW = 16: a K step is then one zero-padded tile row)
   P.TW = TW; P.TH = 128 / TW;
   P.tw_shift = 0;
   while ((1 << P.tw_shift) < TW) ++P.tw_shift;

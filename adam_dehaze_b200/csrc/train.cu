@@ -848,6 +848,56 @@ __global__ void stem_unpack_kernel(const __nv_bfloat16* __restrict__ dcols, int 
   }
 }
 
+// ------------------------------------------------------------------ classifier head / pooling backward (classifier.py:72-97)
+// dx[n,h,w,c] (bf16) = dfeat[n,c] * scale  — backward of the global average pool (scale = 1/hw)
+__global__ void broadcast_hw_kernel(const float* __restrict__ dfeat, int n, long long hw, int c, float scale,
+                                    __nv_bfloat16* __restrict__ dx) {
+  const int G = c / 8;
+  const long long total = (long long)n * hw * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    const long long p = t / G;
+    const int img = (int)(p / hw);
+    float f[8];
+    load8f(dfeat + (size_t)img * c + g * 8, f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] *= scale;
+    *reinterpret_cast<uint4*>(dx + (size_t)p * c + g * 8) = pack8(f);
+  }
+}
+// out = a * b, zeroed where gate <= 0 (dropout masks, ReLU backward of the head)
+__global__ void mul_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gate, long long n,
+                               float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = a[i] * (b ? b[i] : 1.f);
+    out[i] = (gate && gate[i] <= 0.f) ? 0.f : v;
+  }
+}
+// nn.Linear backward on small fp32 matrices: dx[n][fin] = dy W ; dw[fout][fin] = dy^T x ; db[fout] = sum_n dy
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, int n, int fin, int fout,
+                                     float* __restrict__ dx) {
+  const int i = blockIdx.y;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < fin; k += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int o = 0; o < fout; ++o) acc = fmaf(dy[(size_t)i * fout + o], w[(size_t)o * fin + k], acc);
+    dx[(size_t)i * fin + k] = acc;
+  }
+}
+__global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, int n, int fin, int fout,
+                                     float* __restrict__ dw, float* __restrict__ db) {
+  const int o = blockIdx.y;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < fin; k += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc = fmaf(dy[(size_t)i * fout + o], x[(size_t)i * fin + k], acc);
+    dw[(size_t)o * fin + k] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += dy[(size_t)i * fout + o];
+    db[o] = s;
+  }
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1128,6 +1178,34 @@ int adb_stem_unpack(const void* dcols, int32_t n, int32_t h, int32_t w, int32_t 
   const int ho = kh > 1 ? (h + 2 * pad - kh) / stride + 1 : h;
   stem_unpack_kernel<<<grid_for((long long)n * h * w, 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
       ADB_BF(dcols), n, h, w, ho, wo, kh > 1 ? kh : 1, kw, pad, stride, kp, scale3_host[0], scale3_host[1], scale3_host[2], accumulate, dx);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_broadcast_hw(const float* dfeat, int32_t n, int32_t h, int32_t w, int32_t c, float scale, void* dx, void* stream) {
+  ADB_REQUIRE(dfeat && dx && n > 0 && c % 8 == 0, "adb_broadcast_hw: bad arguments");
+  const long long hw = (long long)h * w;
+  broadcast_hw_kernel<<<grid_for((long long)n * hw * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(dfeat, n, hw, c, scale, ADB_BFM(dx));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_mul_f32(const float* a, const float* b, const float* gate, int64_t n, float* out, void* stream) {
+  ADB_REQUIRE(a && out && n > 0, "adb_mul_f32: bad arguments");
+  mul_f32_kernel<<<grid_for(n, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(a, b, gate, n, out);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_linear_bwd(const float* x, const float* w, const float* dy, int32_t n, int32_t fin, int32_t fout, float* dx /*nullable*/,
+                   float* dw, float* db, void* stream) {
+  ADB_REQUIRE(x && w && dy && dw && db && n > 0 && fin > 0 && fout > 0, "adb_linear_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    linear_bwd_dx_kernel<<<dim3((fin + 127) / 128, n), 128, 0, st>>>(dy, w, n, fin, fout, dx);
+    ADB_CUDA_OK(cudaGetLastError());
+  }
+  linear_bwd_dw_kernel<<<dim3((fin + 127) / 128, fout), 128, 0, st>>>(dy, x, n, fin, fout, dw, db);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

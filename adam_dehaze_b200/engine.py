@@ -510,6 +510,17 @@ class ResNetEngine:
         self.clf = classifier
         self._ver = _Versioned(classifier)
         self.S = None
+        self.train_cache = None
+
+    def _forward_train(self, x):
+        """train() mode (train_joint.py:117-121,141): batch-statistics BatchNorm, dropout in the head, kernel-built backward."""
+        from .training import autograd as _ag
+        b, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
+        if self.train_cache is None:
+            self.train_cache = _ag._WeightCache()
+        return _ag.train_forward_classifier(self, x.contiguous())
 
     def specs(self):
         stale = self._ver.stale()   # always evaluated: it records the signature the packed specs correspond to
@@ -537,7 +548,8 @@ class ResNetEngine:
 
     def forward(self, x, chunk=None):
         require_cuda(x, "FogIntensityClassifier")
-        require_inference(self.clf, "FogIntensityClassifier")
+        if self.clf.training:
+            return self._forward_train(x)
         x = x.contiguous()
         b, _, h, w = x.shape
         if h % 32 or w % 32:

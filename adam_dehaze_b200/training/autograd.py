@@ -72,6 +72,20 @@ def _pad_rows16(w):
     return out
 
 
+def _embed4x4(w, pad):
+    """A k x k stride-2 conv with padding `pad` reads x[2i + r - pad]; as a 4x4 pad-1 kernel the tap sits at r + 1 - pad
+    (4x4 p1 -> itself, 3x3 p1 -> rows/cols 0..2, 1x1 p0 -> the single tap at (1, 1))."""
+    co, ci, kh, kw = w.shape
+    if kh == 4 and kw == 4 and pad == 1:
+        return w
+    o = 1 - pad
+    if o < 0 or o + kh > 4 or o + kw > 4:
+        raise NotImplementedError(f"stride-2 {kh}x{kw} pad {pad} conv has no data-gradient form on the B200 path")
+    out = torch.zeros((co, ci, 4, 4), dtype=w.dtype, device=w.device)
+    out[:, :, o:o + kh, o:o + kw] = w
+    return out
+
+
 def _dgrad_spec_s1(w):
     """W [co][ci][k][k] -> spec of dX = conv(dZ, rot180(W)^T); dZ carries pad16(co) channels."""
     wd = _pad_rows16(w.detach().float()).flip(2, 3).permute(1, 0, 2, 3).contiguous()
@@ -166,8 +180,9 @@ class Tape:
             off = hi
             if stride == 1:
                 spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: _dgrad_spec_s1(w[:, lo:hi]))
-            else:   # 4x4 stride-2 conv: dX = ConvTranspose2d(dZ, W)
-                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_convT(_pad_rows16(w.detach()[:, lo:hi])))
+            else:   # stride-2 conv: dX = ConvTranspose2d(dZ, W) — the 4x4/pad-1 sub-pixel kernel, smaller filters embedded
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_convT(
+                    _embed4x4(_pad_rows16(w.detach()[:, lo:hi]), conv.padding[0])))
             s.accumulate_conv(spec, dz)
 
     def convT_bn_act(self, convT, bn, act, srcs):
@@ -200,6 +215,100 @@ class Tape:
                 self.pg[b] = torch.zeros_like(b, dtype=torch.float32)
         self.back.append(backward)
         return out
+
+    def stem_full_bn_act(self, conv, bn, act, x):
+        """7x7 stride-2 3->C stem (torchvision resnet conv1/bn1/relu) over the full-im2col operand (K = 147 -> 160)."""
+        w = conv.weight
+        co = w.shape[0]
+
+        def build():
+            wp = torch.zeros(ops.pad16(co), 160, dtype=torch.bfloat16, device=w.device)
+            wp[:co, :147] = w.detach().float().permute(0, 2, 3, 1).reshape(co, 147).to(torch.bfloat16)
+            scale, shift = ops.fold_bn(co, None, None, device=w.device)
+            return ConvSpec(CONV_S1, 1, 1, 0, co, wp.contiguous(), scale, shift, ACT_NONE)
+        fspec = self.wc.get(("f", id(conv)), (w,), build)
+        cols = ops.stem_pack(x, 7, 3, 160, stride=2, kh=7)
+        z = ops.conv2d(fspec, cols)
+        c = fspec.cout_pad
+        y, mean, rstd = self._bn_forward(z, c, bn, act)
+        out = Node(y, c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            _, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=False)
+            self.pg[w] = ops.wgrad(dz, cols, kh=1, kw=1, pad=0, cs=c, layout=WG_STEM, stem_kw=49).view_as(w)
+        self.back.append(backward)
+        return out
+
+    def maxpool(self, x, k, stride, pad):
+        n, h, w, c = x.t.shape
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.t.device)
+        _lib.call("adb_maxpool_fwd", _lib.ptr(x.t), n, h, w, c, k, stride, pad, _lib.ptr(y), _lib.current_stream())
+        out = Node(y, x.c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dx = torch.empty_like(x.t)
+            _lib.call("adb_maxpool_bwd", _lib.ptr(dy), _lib.ptr(x.t), _lib.ptr(y), n, h, w, c, k, stride, pad, _lib.ptr(dx),
+                      _lib.current_stream())
+            x.accumulate(dx)
+        self.back.append(backward)
+        return out
+
+    def global_avgpool(self, x):
+        """[n,h,w,c] bf16 -> fp32 [n,c]; its gradient arrives through `head_backward` (dfeat)."""
+        n, h, w, c = x.t.shape
+        feats = ops.global_avgpool(x.t)
+        out = Node(feats, c)
+
+        def backward():
+            df = out.grad
+            out.grad = None
+            dx = torch.empty_like(x.t)
+            _lib.call("adb_broadcast_hw", _lib.ptr(df), n, h, w, c, 1.0 / (h * w), _lib.ptr(dx), _lib.current_stream())
+            x.accumulate(dx)
+        self.back.append(backward)
+        return out
+
+    def head_mlp(self, head, feats):
+        """Dropout -> Linear -> ReLU -> Dropout -> Linear (classifier.py:72-78) in train() mode; masks from torch's RNG."""
+        f = feats.t
+        n, fin = f.shape
+        dev = f.device
+        st = _lib.current_stream()
+        p1, p2 = float(head[0].p), float(head[3].p)
+        l1, l2 = head[1], head[4]
+        m1 = (torch.rand((n, fin), device=dev) >= p1).float() / (1.0 - p1)
+        m2 = (torch.rand((n, l1.out_features), device=dev) >= p2).float() / (1.0 - p2)
+        x0 = torch.empty_like(f)
+        _lib.call("adb_mul_f32", _lib.ptr(f), _lib.ptr(m1), None, f.numel(), _lib.ptr(x0), st)
+        h = ops.linear(x0, l1.weight, l1.bias, relu=True)
+        h2 = torch.empty_like(h)
+        _lib.call("adb_mul_f32", _lib.ptr(h), _lib.ptr(m2), None, h.numel(), _lib.ptr(h2), st)
+        logits = ops.linear(h2, l2.weight, l2.bias, relu=False)
+
+        def backward(dlogits, dfeat_extra):
+            dh2 = torch.empty_like(h2)
+            dw2, db2 = torch.empty_like(l2.weight), torch.empty_like(l2.bias)
+            _lib.call("adb_linear_bwd", _lib.ptr(h2), _lib.ptr(l2.weight.detach()), _lib.ptr(dlogits), n, l1.out_features, l2.out_features,
+                      _lib.ptr(dh2), _lib.ptr(dw2), _lib.ptr(db2), st)
+            dh = torch.empty_like(h)
+            _lib.call("adb_mul_f32", _lib.ptr(dh2), _lib.ptr(m2), _lib.ptr(h), h.numel(), _lib.ptr(dh), st)     # dropout + ReLU gate
+            dx0 = torch.empty_like(x0)
+            dw1, db1 = torch.empty_like(l1.weight), torch.empty_like(l1.bias)
+            _lib.call("adb_linear_bwd", _lib.ptr(x0), _lib.ptr(l1.weight.detach()), _lib.ptr(dh), n, fin, l1.out_features,
+                      _lib.ptr(dx0), _lib.ptr(dw1), _lib.ptr(db1), st)
+            df = torch.empty_like(f)
+            _lib.call("adb_mul_f32", _lib.ptr(dx0), _lib.ptr(m1), None, f.numel(), _lib.ptr(df), st)
+            if dfeat_extra is not None:
+                df = df + dfeat_extra          # gradient through the returned features (GatedRouter)
+            self.pg[l1.weight], self.pg[l1.bias], self.pg[l2.weight], self.pg[l2.bias] = dw1, db1, dw2, db2
+            feats.grad = df
+        self.head_backward = backward
+        return logits
 
     def res_block(self, rb, x):
         t = self.conv_bn_act(rb.conv1.block[0], rb.conv1.block[1], ACT_RELU, [x])
@@ -290,6 +399,13 @@ class Tape:
         return out
 
     # ------------------------------------------------------------------ reverse sweep
+    def backward_classifier(self, dlogits, dfeats):
+        self.head_backward(dlogits, dfeats)
+        for fn in reversed(self.back):
+            fn()
+        self.back = []
+        return self.pg
+
     def backward(self, dout):
         self.head_backward(dout)
         for fn in reversed(self.back):
@@ -339,6 +455,50 @@ def forward_unet(t, m, x, attn):
     r = t.conv_block(m.output_conv[0], [x2, f0])
     r = t.conv_block(m.output_conv[1], [r])
     return t.image_head(m.output_conv[2], r, x, IMG_GUIDED if attn else IMG_RESIDUAL, ACT_TANH, guidance=guidance)
+
+
+def forward_resnet(t, clf, x):
+    """FogIntensityClassifier.forward (classifier.py:80-97) with a torchvision resnet18/34 backbone in train() mode."""
+    bb = clf.backbone
+    f = t.stem_full_bn_act(bb.conv1, bb.bn1, ACT_RELU, x)
+    f = t.maxpool(f, 3, 2, 1)
+    for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
+        for blk in layer:
+            u = t.conv_bn_act(blk.conv1, blk.bn1, ACT_RELU, [f])
+            idn = f if blk.downsample is None else t.conv_bn_act(blk.downsample[0], blk.downsample[1], ACT_NONE, [f])
+            f = t.conv_bn_act(blk.conv2, blk.bn2, ACT_RELU, [u], residual=idn)
+    feats = t.global_avgpool(f)
+    logits = t.head_mlp(clf.classifier, feats)
+    return logits, feats.t
+
+
+class ClassifierTrainFn(torch.autograd.Function):
+    """autograd node of the HDEN forward in train() mode; returns (logits, features)."""
+
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        tape = Tape(engine.train_cache)
+        logits, feats = forward_resnet(tape, engine.clf, x)
+        ctx.tape, ctx.params = tape, params
+        return logits, feats
+
+    @staticmethod
+    def backward(ctx, dlogits, dfeats):
+        tape = ctx.tape
+        ctx.tape = None
+        if dlogits is None:
+            dlogits = torch.zeros((dfeats.shape[0], tape_classes(ctx)), device=dfeats.device)
+        pg = tape.backward_classifier(dlogits.contiguous().float(), None if dfeats is None else dfeats.contiguous().float())
+        return (None, None) + tuple(pg.get(p) for p in ctx.params)
+
+
+def tape_classes(ctx):
+    return ctx.params[-1].shape[0]
+
+
+def train_forward_classifier(engine, x):
+    params = tuple(engine.clf.parameters())
+    return ClassifierTrainFn.apply(engine, x, *params)
 
 
 class BranchTrainFn(torch.autograd.Function):

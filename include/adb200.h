@@ -295,6 +295,14 @@ ADB_API int adb_lpips_tap(const void* fa, const void* fb, int32_t n, int32_t h, 
 ADB_API int adb_stem_unpack(const void* dcols, int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t pad,
                             int32_t stride, int32_t kp, const float* scale3_host, int32_t accumulate, float* dx, void* stream);
 
+/* HDEN in train() mode (train_joint.py:129-150 trains the classifier through the router): backward of the global
+ * average pool, element-wise products for the head's dropout masks / ReLU gate, and nn.Linear backward (classifier.py:72-78). */
+ADB_API int adb_broadcast_hw(const float* dfeat, int32_t n, int32_t h, int32_t w, int32_t c, float scale, void* dx, void* stream);
+ADB_API int adb_mul_f32(const float* a, const float* b /*nullable*/, const float* gate /*nullable: 0 where gate <= 0*/, int64_t n,
+                        float* out, void* stream);
+ADB_API int adb_linear_bwd(const float* x, const float* w, const float* dy, int32_t n, int32_t fin, int32_t fout, float* dx,
+                           float* dw, float* db, void* stream);
+
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

@@ -530,3 +530,80 @@ def test_dehazing_loss_full_and_joint_loss():
     assert pred.grad is not None and pred.grad.abs().max().item() > 0 and logits.grad is not None
     assert set(parts) == {"dehazing", "classification", "detection", "total", "dehazing_components"}
     assert set(dc) == {"l1", "content", "perceptual", "total"}
+
+
+def test_classifier_train_step_matches_oracle():
+    """HDEN (resnet18) in train() mode — train_joint.py:117-150 trains it through the router: batch-statistics BN through the
+    BasicBlocks (3x3 stride-2 and 1x1 stride-2 downsample convs, max-pool, global average pool) and the head MLP, forward
+    and backward vs the fp32 oracle under autograd.  Dropout is disabled (p = 0) for the comparison; same end-to-end
+    gradient criterion as the branch models (bf16-storage floor)."""
+    from helpers import make_classifier, oracle_bf16_storage, rand_image
+    import adam_oracle as oracle
+    clf = make_classifier("resnet18").cuda().train()
+    clf.classifier[0].p = 0.0
+    clf.classifier[3].p = 0.0
+    x = rand_image(4, 128, 160, 21).cuda()
+    labels = torch.tensor([0, 2, 1, 1], device="cuda")
+    sd = {k: v.detach().clone().float().requires_grad_(v.dtype.is_floating_point) for k, v in clf.state_dict().items()}
+    names = [k for k, _ in clf.named_parameters()]
+
+    def run(fn):
+        with oracle.train_mode():
+            lg, ft = fn()
+        loss = F.cross_entropy(lg, labels)
+        return lg.detach(), ft.detach(), loss.detach(), dict(zip(names, torch.autograd.grad(loss, [sd[k] for k in names])))
+    ref_lg, ref_ft, ref_loss, ref_g = run(lambda: oracle.classifier_forward(sd, x, "resnet18"))
+    sim_lg, sim_ft, _, sim_g = run(lambda: oracle_bf16_storage(oracle.classifier_forward, sd, x, "resnet18"))
+    floor_ft = (sim_ft - ref_ft).abs().max().item()       # batch statistics over 4x5x4 samples at layer4 amplify bf16 rounding
+    floor_lg = (sim_lg - ref_lg).abs().max().item()
+    from adam_dehaze_b200.training.loss import _CrossEntropy
+    logits, feats = clf(x)
+    loss = _CrossEntropy.apply(logits, labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert (logits - ref_lg).abs().max().item() <= max(3e-2 * max(1.0, ref_lg.abs().max().item()), 1.5 * floor_lg)
+    assert (feats - ref_ft).abs().max().item() <= max(3e-2 * ref_ft.abs().max().item(), 1.5 * floor_ft)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * abs(ref_loss.item())
+    tot_e = tot_s = tot_r = 0.0
+    for k, p in clf.named_parameters():
+        assert p.grad is not None and p.grad.shape == ref_g[k].shape, k
+        e, es, rn = (p.grad - ref_g[k]).norm().item(), (sim_g[k] - ref_g[k]).norm().item(), ref_g[k].norm().item()
+        tot_e += e * e; tot_s += es * es; tot_r += rn * rn
+        assert (p.grad * ref_g[k]).sum().item() > 0 or rn < 1e-7, k
+    assert tot_e ** 0.5 <= 1.25 * tot_s ** 0.5 + 0.02 * tot_r ** 0.5, (tot_e ** 0.5 / tot_r ** 0.5, tot_s ** 0.5 / tot_r ** 0.5)
+    # dropout active: a second forward differs, and the head still back-propagates
+    clf.classifier[0].p, clf.classifier[3].p = 0.3, 0.2
+    a, _ = clf(x)
+    b, _ = clf(x)
+    assert (a - b).abs().max().item() > 0
+
+
+def test_joint_training_step_with_classifier():
+    """train_joint.py:129-150: classifier(x) -> SoftRouter(x, logits) -> JointLoss -> backward -> optimizer over
+    router.parameters() (which include the classifier and the three branches)."""
+    from helpers import CONFIG, make_branch, make_classifier, rand_image
+    from adam_dehaze_b200.models.routing import create_router
+    from adam_dehaze_b200.training.loss import JointLoss, DehazingLoss
+    from adam_dehaze_b200.training.optim import FlatAdam
+    branches = {k: make_branch(k) for k in ("low", "medium", "high")}
+    clf = make_classifier("resnet18")
+    router = create_router(branches, clf, dict(CONFIG, routing={"type": "soft", "temperature": 0.5})).cuda().train()
+    crit = JointLoss(1.0, 0.2, 0.5, dehazing_loss=DehazingLoss(1.0, 0.0, 0.0)).cuda()
+    params = list(router.parameters())
+    assert any(p is q for p in params for q in clf.parameters())        # the classifier trains with the router
+    opt = FlatAdam(params, lr=5e-5, weight_decay=1e-4)
+    x, tgt = rand_image(3, 64, 64, 31).cuda(), rand_image(3, 64, 64, 32).cuda()
+    labels = torch.tensor([0, 1, 2], device="cuda")
+    losses = []
+    for it in range(3):
+        opt.zero_grad()
+        logits, _ = clf(x)
+        out, info = router(x, logits)
+        loss, parts = crit(out, tgt, logits, labels)
+        loss.backward()
+        if it == 0:
+            missing = [k for k, p in router.named_parameters() if p.grad is None]
+            assert not missing, missing[:5]
+        opt.step()
+        losses.append(loss.item())
+    assert all(l == l for l in losses) and losses[-1] < losses[0] + 0.05, losses
