@@ -58,7 +58,7 @@ inline int sm_count() {
 constexpr int kRedThreads = 256;
 inline int red_blocks(long long pixels, int c, int sms) {
   const int G = c / 8, PY = std::max(1, kRedThreads / G);
-  return (int)std::max<long long>(1, std::min<long long>((pixels + PY * 8 - 1) / (PY * 8), (long long)sms * 4));
+  return (int)std::max<long long>(1, std::min<long long>((pixels + PY * 8 - 1) / (PY * 8), (long long)sms * 8));
 }
 
 // ------------------------------------------------------------------ per-channel reductions over a map
@@ -80,25 +80,43 @@ chan_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, const __nv_
   for (int q = 0; q < 8; ++q) { a[q] = 0.f; b[q] = 0.f; mu[q] = 0.f; rs[q] = 0.f; }
   if (py < PY) {
     if (MODE == 1 && z) { load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); }
-    for (long long p = (long long)blockIdx.x * PY + py; p < pixels; p += (long long)gridDim.x * PY) {
+    const long long step = (long long)gridDim.x * PY;
+    for (long long p0 = (long long)blockIdx.x * PY + py; p0 < pixels; p0 += 2 * step) {
+      const long long p1 = p0 + step;
+      const bool two = p1 < pixels;
       if (MODE == 0) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), f);
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(z + (size_t)p0 * pitch_z + g * 8));
+        const uint4 r1 = two ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p1 * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
+        float f[8], h[8];
+        unpack8(r0, f); unpack8(r1, h);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { a[q] += f[q]; b[q] = fmaf(f[q], f[q], b[q]); }
+        for (int q = 0; q < 8; ++q) { a[q] += f[q] + h[q]; b[q] = fmaf(f[q], f[q], fmaf(h[q], h[q], b[q])); }
       } else {
-        float d[8], yy[8], zz[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)), d);
-        if (y) unpack8(__ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch_y + g * 8)), yy);
-        if (z) unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), zz);
+        // both pixels' loads are issued before either is consumed
+        uint4 rd[2], ry[2], rz[2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float gg = y ? d[q] * act_grad(yy[q], act) : d[q];
-          d[q] = gg;
-          a[q] += gg;
-          if (z) b[q] = fmaf(gg, (zz[q] - mu[q]) * rs[q], b[q]);
+        for (int u = 0; u < 2; ++u) {
+          const long long p = u ? p1 : p0;
+          const bool live = u == 0 || two;
+          rd[u] = live ? __ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)) : make_uint4(0, 0, 0, 0);
+          ry[u] = (live && y) ? __ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch_y + g * 8)) : make_uint4(0, 0, 0, 0);
+          rz[u] = (live && z) ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
         }
-        if (g_out) *reinterpret_cast<uint4*>(g_out + (size_t)p * pitch_g + g * 8) = pack8(d);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) break;
+          const long long p = u ? p1 : p0;
+          float d[8], yy[8], zz[8];
+          unpack8(rd[u], d); unpack8(ry[u], yy); unpack8(rz[u], zz);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float gg = y ? d[q] * act_grad(yy[q], act) : d[q];
+            d[q] = gg;
+            a[q] += gg;
+            if (z) b[q] = fmaf(gg, (zz[q] - mu[q]) * rs[q], b[q]);
+          }
+          if (g_out) *reinterpret_cast<uint4*>(g_out + (size_t)p * pitch_g + g * 8) = pack8(d);
+        }
       }
     }
 #pragma unroll
@@ -117,17 +135,48 @@ chan_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, const __nv_
   }
 }
 
+// Fold the per-block partials [nblocks][2][c] of 8 channels per CTA: 32 lanes per channel each sum every 32nd block in
+// fp64, then one thread per (channel, which) adds the 32 lane sums in lane order — a fixed tree, so results are
+// deterministic.  Returns (through shared memory) sums[which][8].  blockDim = 256 = 32 lanes x 8 channels.
+constexpr int kFoldLanes = 32;
+__device__ __forceinline__ void fold_partials8(const float* __restrict__ partials, int nblocks, int c, int ch0, double (*s_out)[8]) {
+  __shared__ double s_lane[2][kFoldLanes][8];
+  const int chl = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int ch = ch0 + chl;
+  double a = 0.0, b = 0.0;
+  if (ch < c) {
+#pragma unroll 4
+    for (int k = lane; k < nblocks; k += kFoldLanes) {
+      a += (double)partials[(size_t)k * 2 * c + ch];
+      b += (double)partials[(size_t)k * 2 * c + c + ch];
+    }
+  }
+  s_lane[0][lane][chl] = a;
+  s_lane[1][lane][chl] = b;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, cc = threadIdx.x & 7;
+    double t = 0.0;
+    for (int l = 0; l < kFoldLanes; ++l) t += s_lane[which][l][cc];
+    s_out[which][cc] = t;
+  }
+  __syncthreads();
+}
+
 // BatchNorm2d(train) statistics -> the epilogue affine, plus the running-statistics update (momentum, unbiased variance).
+// grid = c/8 CTAs of 256 threads.
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int c, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                    float* running_mean, float* running_var, long long* num_batches_tracked,
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                    float* __restrict__ shift) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  __shared__ double s_sum[2][8];
+  fold_partials8(partials, nblocks, c, blockIdx.x * 8, s_sum);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (threadIdx.x >= 8) return;
+  const int ch = blockIdx.x * 8 + threadIdx.x;
   if (ch >= c) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < nblocks; ++k) { s += partials[(size_t)k * 2 * c + ch]; ss += partials[(size_t)k * 2 * c + c + ch]; }
+  const double s = s_sum[0][threadIdx.x], ss = s_sum[1][threadIdx.x];
   const double m = s / count;
   double var = ss / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -170,10 +219,12 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, int accumulate, float* dgamma, float* dbeta,
                                        float* __restrict__ coef) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_sum[2][8];
+  fold_partials8(partials, nblocks, c, blockIdx.x * 8, s_sum);
+  if (threadIdx.x >= 8) return;
+  const int ch = blockIdx.x * 8 + threadIdx.x;
   if (ch >= c) return;
-  double sg = 0.0, sgx = 0.0;
-  for (int k = 0; k < nblocks; ++k) { sg += partials[(size_t)k * 2 * c + ch]; sgx += partials[(size_t)k * 2 * c + c + ch]; }
+  const double sg = s_sum[0][threadIdx.x], sgx = s_sum[1][threadIdx.x];
   if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.f) + (float)sg;
   if (!gamma) return;
   if (dgamma) dgamma[ch] = (accumulate ? dgamma[ch] : 0.f) + (float)sgx;
@@ -940,7 +991,7 @@ int adb_bn_train_stats(const void* z, int64_t pixels, int32_t c, int32_t pitch, 
   chan_reduce_kernel<0><<<nb, kRedThreads, (size_t)PY * 2 * c * sizeof(float), st>>>(ADB_BF(z), pitch, nullptr, 0, nullptr, 0, pixels, c, 0,
                                                                                    nullptr, nullptr, nullptr, 0, scratch);
   ADB_CUDA_OK(cudaGetLastError());
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, nb, c, (double)pixels, gamma, beta, eps, momentum, running_mean, running_var,
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, beta, eps, momentum, running_mean, running_var,
                                                       reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
@@ -971,7 +1022,7 @@ int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t pitch_y,
   chan_reduce_kernel<1><<<nb, kRedThreads, (size_t)PY * 2 * c * sizeof(float), st>>>(ADB_BF(z), pitch_z, ADB_BF(dy), pitch_dy, ADB_BF(y), pitch_y,
                                                                                    pixels, c, act, mean, rstd, ADB_BFM(g_out), pitch_g, scratch);
   ADB_CUDA_OK(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
   ADB_CUDA_OK(cudaGetLastError());
   if (gamma) {
     bn_bwd_apply_kernel<<<grid_for(pixels * G, 256, sms, 16), 256, 0, st>>>(ADB_BF(g_out), pitch_g, ADB_BF(z), pitch_z, pixels, c, coef,

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 import os
+import sys
 from collections import OrderedDict
 
 from .. import ops
@@ -81,7 +82,7 @@ class ContentLoss(nn.Module):
         if ck:
             vgg.load_state_dict(torch.load(ck, map_location="cpu"))
         else:
-            print("ContentLoss: pretrained VGG16 weights are not in the torch hub cache — using random-init features")
+            print("ContentLoss: pretrained VGG16 weights are not in the torch hub cache — using random-init features", file=sys.stderr)
         self.model = vgg.features.eval()
         for p in self.model.parameters():
             p.requires_grad = False
@@ -106,7 +107,7 @@ class _LPIPSAlex(nn.Module):
         if ck:
             alex.load_state_dict(torch.load(ck, map_location="cpu"))
         else:
-            print("PerceptualLoss: pretrained AlexNet / LPIPS weights are not available offline — using random-init weights")
+            print("PerceptualLoss: pretrained AlexNet / LPIPS weights are not available offline — using random-init weights", file=sys.stderr)
         f = alex.features
         self.net = nn.Module()
         for i, idx in enumerate((0, 3, 6, 8, 10)):
@@ -185,8 +186,8 @@ class JointLoss(nn.Module):
         if pred_intensity is not None and target_intensity is not None:
             ce = _CrossEntropy.apply(pred_intensity, target_intensity)
         else:
-            ce = torch.tensor(0.0, device=pred.device)
-        det = detection_loss if detection_loss is not None else torch.tensor(0.0, device=pred.device)
+            ce = torch.zeros((), device=pred.device)      # (torch.tensor(0.0, device=...) is a synchronising H2D copy)
+        det = detection_loss if detection_loss is not None else torch.zeros((), device=pred.device)
         total = self.lambda_dehazing * dehazing + self.lambda_classification * ce + self.lambda_detection * det
         return total, {"dehazing": dehazing, "classification": ce, "detection": det, "total": total,
                        "dehazing_components": parts}

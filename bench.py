@@ -314,7 +314,7 @@ def main():
 
 
 # --------------------------------------------------------------------------- training step (BASELINE configs[4])
-TRAIN_METRIC = "training samples/sec, joint step (SoftRouter over Light/Medium/Complex, DehazingLoss, Adam) @512x512"
+TRAIN_METRIC = "training samples/sec, joint step (HDEN + SoftRouter over Light/Medium/Complex, JointLoss, Adam) @512x512"
 
 
 def run_train(args):
@@ -342,11 +342,16 @@ def run_train(args):
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     B = 16 if args.batch == 256 else args.batch
     Hh, Ww = (512, 512) if (args.height, args.width) == (H, W) else (args.height, args.width)
-    cfg = dict(CFG, classifier=dict(CFG["classifier"], model=args.hden), routing={"type": "soft", "temperature": 0.5})
+    # the joint step trains HDEN through the router (train_joint.py:80-88,117-121); the trainable HDEN arm on the B200 path
+    # is the reference's own default, resnet18 (densenet121 has inference kernels only)
+    hden = "resnet18" if args.hden == "densenet121" else args.hden
+    cfg = dict(CFG, classifier=dict(CFG["classifier"], model=hden), routing={"type": "soft", "temperature": 0.5})
     branches, clf = build_models(cfg, device=dev)
-    router = SoftRouter(branches, classifier=None, temperature=0.5).to(dev).train()
-    crit = DehazingLoss(lambda_l1=1.0, lambda_content=TRAIN_LAMBDAS[0], lambda_perceptual=TRAIN_LAMBDAS[1]).to(dev)
-    opt = FlatAdam(router.parameters(), lr=1e-4, weight_decay=1e-4)
+    router = SoftRouter(branches, classifier=clf, temperature=0.5).to(dev).train()
+    from adam_dehaze_b200.training.loss import JointLoss
+    crit = JointLoss(1.0, 0.2, 0.5, dehazing_loss=DehazingLoss(lambda_l1=1.0, lambda_content=TRAIN_LAMBDAS[0],
+                                                                 lambda_perceptual=TRAIN_LAMBDAS[1])).to(dev)
+    opt = FlatAdam(router.parameters(), lr=5e-5, weight_decay=1e-4)
     nparams = sum(p.numel() for p in router.parameters())
     hazy, labels = synth_batch_on_device(B, Hh, Ww, dev, seed=42 + rank)
     clear = torch.rand((B, 3, Hh, Ww), generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev)
@@ -365,10 +370,9 @@ def run_train(args):
 
     def step():
         opt.zero_grad()
-        with torch.no_grad():
-            logits, _ = clf(hazy)                      # HDEN (eval): its logits weight the blend
+        logits, _ = clf(hazy)                          # HDEN in train() mode: its logits weight the blend and feed the CE term
         out, info = router(hazy, logits)
-        loss, parts = crit(out, clear)
+        loss, parts = crit(out, clear, logits, labels)
         loss.backward()
         opt.step()
         return loss
@@ -380,6 +384,22 @@ def run_train(args):
 
     for _ in range(max(3, args.warmup)):
         step()
+    if os.environ.get("ADB_PROFILE_HOST") and world == 1:    # developer aid: where the host time of a step goes
+        import cProfile
+        import pstats
+        torch.cuda.synchronize()
+        pr = cProfile.Profile()
+        t0 = time.perf_counter()
+        pr.enable()
+        for _ in range(3):
+            step()
+        pr.disable()
+        host_s = (time.perf_counter() - t0) / 3
+        torch.cuda.synchronize()
+        sys.stderr.write(f"host time per step (launch only, no sync): {host_s * 1e3:.1f} ms\n")
+        st_ = pstats.Stats(pr, stream=sys.stderr).sort_stats("tottime")
+        st_.print_stats(28)
+        st_.print_callers("masked_select|built-in method torch.tensor|run_backward")
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -423,9 +443,10 @@ def run_train(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = t2.item() / args.steps
 
-    # ---- instrumented step (rank 0): CUDA events around every C-ABI call -> tensor-pipe kernels' achieved TFLOP/s
+    # ---- instrumented step: CUDA events around every C-ABI call -> tensor-pipe kernels' achieved TFLOP/s.
+    #      Every rank runs it (the step holds the gradient all-reduce, so the ranks must stay in lock-step); rank 0 reports.
     detail = None
-    if rank == 0:
+    if True:
         calls = []
 
         def timed(name, *a):
@@ -466,13 +487,14 @@ def run_train(args):
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                 "how": f"launch FLOPs (padded-channel 2*MAC of every conv fwd/dgrad/wgrad launch) / CUDA-event time over the {n_mma} tensor-pipe launches of one step",
                 "flops_per_launch_avg": mma_fl / max(1, n_mma), "ms_per_launch_avg": mma_ms / max(1, n_mma)}
+    if rank == 0:
         line = {
             "metric": TRAIN_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: joint training step, {B} samples/GPU at {Hh}x{Ww}, SoftRouter(T=0.5) over "
-                                   f"Light+Medium+Complex in train() mode, HDEN({args.hden}) logits (eval), DehazingLoss "
-                                   f"lambdas (1.0, {TRAIN_LAMBDAS[0]}, {TRAIN_LAMBDAS[1]}), FlatAdam(lr 1e-4, wd 1e-4), one flat "
+                                   f"Light+Medium+Complex + HDEN({hden}), all in train() mode, JointLoss(1.0, 0.2, 0.5) over DehazingLoss "
+                                   f"lambdas (1.0, {TRAIN_LAMBDAS[0]}, {TRAIN_LAMBDAS[1]}) + CE, FlatAdam(lr 5e-5, wd 1e-4), one flat "
                                    f"{nparams * 4 / 2**20:.0f} MiB gradient all-reduce per step",
                        "samples_per_gpu_per_step": B, "height": Hh, "width": Ww, "trainable_params": nparams,
                        "l2": f"activations {B}x{Hh}x{Ww} per layer (> 126 MB L2 for every full-resolution map)"},

@@ -308,6 +308,12 @@ ADB_API int adb_linear_bwd(const float* x, const float* w, const float* dy, int3
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* Image-quality metrics on the device (evaluation/metrics.py:13-36): per image PSNR
+ * (data_range 1) and SSIM with skimage's defaults on the channel-mean grayscale (7x7 uniform window, sample
+ * covariance, K1 = 0.01, K2 = 0.03, mean over the interior).  pred/target: NCHW fp32 [n,3,h,w]; scratch: 2n doubles. */
+ADB_API int adb_image_metrics(const float* pred, const float* target, int32_t n, int32_t h, int32_t w, double* scratch,
+                              float* psnr, float* ssim, void* stream);
+
 /* Developer aid: copy the clock64() timeline CTA 0 recorded during the last adb_conv2d launched with tune_flags bit 2
  * ([6 roles][256 events]: A producer, B producer, MMA ready, MMA issued, epilogue start, epilogue end). Synchronises. */
 ADB_API int adb_debug_timeline(int64_t* host_out, int32_t count);

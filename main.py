@@ -94,8 +94,14 @@ def build(config, device):
 
 
 def psnr(a, b):
-    mse = torch.mean((a - b) ** 2, dim=(1, 2, 3)).clamp_min(1e-12)
-    return (10.0 * torch.log10(1.0 / mse)).mean().item()
+    """Batch-mean PSNR from the on-device metrics kernel (evaluation/metrics.py:13-36 without the per-image host copy)."""
+    from adam_dehaze_b200.evaluation.metrics import image_metrics
+    return image_metrics(a, b)[0].mean().item()
+
+
+def ssim(a, b):
+    from adam_dehaze_b200.evaluation.metrics import image_metrics
+    return image_metrics(a, b)[1].mean().item()
 
 
 def evaluate(config, args, device, root):
@@ -117,6 +123,7 @@ def evaluate(config, args, device, root):
         else:
             out, _ = router(hazy)
         results["joint_psnr"] = psnr(out, clear)
+        results["joint_ssim"] = ssim(out, clear)
         results["classifier_accuracy"] = (logits.argmax(1) == labels).float().mean().item()
     path = os.path.join(config["evaluation"]["results_dir"], "evaluation.json")
     with open(path, "w") as fh:

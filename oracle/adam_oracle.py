@@ -376,3 +376,29 @@ def synth_hazy(n, h, w, betas=(0.03, 0.06, 0.09), seed=42, device="cpu"):
     t = torch.exp(-beta * d.view(1, 1, h, w))
     hazy = torch.clamp(clear * t + 0.8 * (1 - t), 0, 1)
     return hazy.to(device), clear.to(device), labels.to(device)
+
+
+# --------------------------------------------------------------------------- image-quality metrics (evaluation/metrics.py)
+def image_metrics(pred, target):
+    """calculate_image_metrics, evaluation/metrics.py:13-36, for ONE image pair ([3,H,W] tensors in [0,1]).
+
+    scikit-image is not installed offline, so PSNR/SSIM follow its published algorithms (skimage 0.19+
+    `peak_signal_noise_ratio(data_range=1)`; `structural_similarity(gray_t, gray_p, data_range=1)` with the defaults:
+    7x7 uniform_filter, use_sample_covariance=True, K1=0.01, K2=0.03, mean over the map cropped by 3 pixels) restated
+    with scipy.ndimage.uniform_filter in float64.  PARITY UNPINNED against skimage itself."""
+    import numpy as np
+    from scipy.ndimage import uniform_filter
+    p = pred.detach().cpu().double().numpy().transpose(1, 2, 0)
+    t = target.detach().cpu().double().numpy().transpose(1, 2, 0)
+    mse = np.mean((t - p) ** 2)
+    psnr = 10.0 * np.log10(1.0 / mse)
+    x, y = t.mean(axis=2), p.mean(axis=2)
+    win, npix = 7, 49
+    cov_norm = npix / (npix - 1.0)
+    ux, uy = uniform_filter(x, size=win), uniform_filter(y, size=win)
+    uxx, uyy, uxy = uniform_filter(x * x, size=win), uniform_filter(y * y, size=win), uniform_filter(x * y, size=win)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    pad = (win - 1) // 2
+    return {"psnr": float(psnr), "ssim": float(s[pad:-pad, pad:-pad].mean())}

@@ -177,3 +177,31 @@ def test_upsample_bilinear_align_corners(scale):
     got = ops.nhwc_to_nchw(out)[:, 8:24]
     assert (got - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -8
     assert (out[..., :8].float() == 3.0).all() and (out[..., 24:].float() == 3.0).all()
+
+
+def test_image_metrics_on_device():
+    """PSNR / SSIM on the device vs the oracle's restatement of skimage's algorithms.
+    Tolerance: fp32 window sums vs float64 — |dPSNR| <= 1e-3 dB, |dSSIM| <= 1e-4."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import adam_oracle as oracle
+    from adam_dehaze_b200.evaluation.metrics import ImageQualityMetrics, calculate_image_metrics, image_metrics
+    g = torch.Generator().manual_seed(3)
+    base = torch.nn.functional.interpolate(torch.rand(3, 3, 12, 20, generator=g), size=(45, 77), mode="bilinear")
+    tgt = base.clamp(0, 1).cuda()
+    pred = (base + 0.05 * torch.randn(3, 3, 45, 77, generator=g)).clamp(0, 1).cuda()
+    psnr, ssim = image_metrics(pred, tgt)
+    for i in range(3):
+        ref = oracle.image_metrics(pred[i], tgt[i])
+        assert abs(psnr[i].item() - ref["psnr"]) <= 1e-3, (psnr[i].item(), ref["psnr"])
+        assert abs(ssim[i].item() - ref["ssim"]) <= 1e-4, (ssim[i].item(), ref["ssim"])
+    one = calculate_image_metrics(pred[0], tgt[0])
+    assert abs(one["psnr"] - psnr[0].item()) < 1e-6 and set(one) == {"psnr", "ssim"}
+    m = ImageQualityMetrics(with_lpips=False)
+    m.add_sample(pred[0], tgt[0], category="low")
+    m.add_sample(pred[1:], tgt[1:])
+    avg = m.compute_averages()
+    assert avg["low"]["samples"] == 1 and avg["all"]["samples"] == 2
+    assert abs(avg["all"]["psnr"] - psnr[1:].mean().item()) < 1e-4
+    p_same, s_same = image_metrics(tgt, tgt)
+    assert torch.isinf(p_same).all() and (s_same - 1).abs().max().item() < 1e-5
