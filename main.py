@@ -148,7 +148,8 @@ def main():
     device = torch.device(config["device"])
     if device.type != "cuda":
         raise RuntimeError("this build runs on B200 (sm_100a) only: pass --device cuda[:i]")
-    torch.cuda.set_device(device)
+    if device.index is not None:
+        torch.cuda.set_device(device)
 
     if args.mode == "evaluate":
         evaluate(config, args, device, root)
