@@ -39,6 +39,7 @@ class ConvDesc(C.Structure):
         ("n_dev", C.c_void_p), ("n_start", C.c_int32),
         ("tune_mt", C.c_int32), ("tune_stages", C.c_int32), ("tune_acc_stages", C.c_int32),
         ("tune_flags", C.c_int32),
+        ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p),
     ]
 
 

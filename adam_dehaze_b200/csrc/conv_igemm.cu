@@ -31,7 +31,10 @@ namespace {
 using namespace adb;
 
 constexpr int kThreads = 384;         // 4 role warps + 8 epilogue warps
+constexpr int kThreadsPre = 512;      // + 4 operand-transform warps (pre-activation fused into the A operand, DenseNet)
 constexpr int kEpiWarp0 = 4;          // first epilogue warp
+constexpr int kEpiWarps = 8;
+constexpr int kPreWarp0 = kEpiWarp0 + kEpiWarps;   // first transform warp (kPre kernels only)
 constexpr int kMaxTaps = 25;        // up to 5x5 (AlexNet conv2 inside LPIPS, loss.py:91)
 constexpr int kMaxGroups = 4;
 constexpr int kMaxStages = 12;
@@ -109,6 +112,9 @@ struct ConvK {
   const float* dot_w; float dot_b; float* dot_out;
   int img_mode;
   const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
+  int c0;                             // channels of src0 (weight K offset of src1's first chunk)
+  const float* pre_scale;             // optional pre-activation relu(x*pre_scale[c] + pre_shift[c]) applied to the A operand
+  const float* pre_shift;
   int* err_flag;
   long long* dbg;   // optional timeline buffer (tune_flags bit 2): [6 roles][256 events] of clock64() from CTA 0
   int dbg_detail;   // tune_flags bit 6: the buffer instead holds a flat sequence of epilogue sub-step stamps (warp 4, lane 0)
@@ -116,11 +122,11 @@ struct ConvK {
 
 struct SmemLayout {
   // byte offsets from the 1024-aligned base
-  uint32_t a_off, b_off, slab_off, scale_off, bar_off, total;
+  uint32_t a_off, b_off, slab_off, scale_off, pre_off, bar_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes, int b_slots, int b_slot_bytes,
-                                                  int slab_bytes, int n_slab_bufs, int cout_pad) {
+                                                  int slab_bytes, int n_slab_bufs, int cout_pad, int pre_channels = 0) {
   SmemLayout L;
   uint32_t off = 0;
   L.a_off = off; off += (uint32_t)a_slots * a_slot_bytes;
@@ -128,7 +134,9 @@ __host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes,
   L.slab_off = off; off += (uint32_t)n_slab_bufs * slab_bytes;
   L.scale_off = off; off += (uint32_t)cout_pad * 8;      // scale then shift, fp32
   off = (off + 15u) & ~15u;
-  L.bar_off = off; off += 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16;  // fullA, emptyA, fullB, emptyB, tmem full/empty, tmem ptr
+  L.pre_off = off; off += (uint32_t)pre_channels * 8;    // pre-activation scale then shift, fp32 (kPre kernels)
+  off = (off + 15u) & ~15u;
+  L.bar_off = off; off += 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16 + 8u * kMaxASlots;  // fullA, emptyA, fullB, emptyB, tmem full/empty, tmem ptr, readyA
   L.total = off;
   return L;
 }
@@ -306,8 +314,8 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
   }
 }
 
-template <int kAct, bool kPair, int kEpi>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kAct, bool kPair, int kEpi, bool kPre = false>
+__global__ void __launch_bounds__(kPre ? kThreadsPre : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                   const __grid_constant__ ConvK P) {
@@ -316,7 +324,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
 
-  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
+  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad,
+                                   kPre ? P.ctot : 0);
   const uint32_t a_base = base + L.a_off;
   const uint32_t b_base = base + L.b_off;
   const uint32_t slab_base = base + L.slab_off;
@@ -329,6 +338,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   auto emptyB = [&](int s) { return bar_base + 8u * (2 * kMaxASlots + kMaxBSlots + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 2 + a); };
+  auto readyA = [&](int s) { return bar_base + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 6 + s); };   // (after the tmem pointer word)
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4));
 
@@ -362,6 +372,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int s = 0; s < P.a_slots; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < P.b_slots; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPair ? 16 : 8); }   // 8 epilogue warps per CTA
+    if (kPre) for (int s = 0; s < P.a_slots; ++s) mbar_init(readyA(s), 4);                                 // 4 transform warps
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -373,10 +384,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       tmem_relinquish();
     }
   }
-  if (warp >= kEpiWarp0) {
+  if (warp >= kEpiWarp0 && warp < kPreWarp0) {
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.cout_pad; i += 256) {
       s_scale[i] = P.scale[i];
       s_shift[i] = P.shift[i];
+    }
+  }
+  float* s_pre = reinterpret_cast<float*>(base_ptr + L.pre_off);   // [ctot] scale then [ctot] shift
+  if (kPre && warp >= kPreWarp0) {
+    for (int i = threadIdx.x - kPreWarp0 * 32; i < P.ctot; i += 128) {
+      s_pre[i] = P.pre_scale[i];
+      s_pre[P.ctot + i] = P.pre_shift[i];
     }
   }
   tc_fence_before();
@@ -424,7 +442,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int brow = tc.g * P.cout_pad + tc.nt * P.BN + rank * (P.BN / P.ncta);   // pair: each CTA holds half of the N rows
       const int nal = P.n_aloads[tc.g];
       for (int c = 0; c < nchunks; ++c) {
-        const int kc = (c >= P.chunks0 ? P.chunks0 * P.Ck + (c - P.chunks0) * P.Ck : c * P.Ck);   // channel offset in the concat
+        const int kc = (c >= P.chunks0 ? P.c0 + (c - P.chunks0) * P.Ck : c * P.Ck);   // channel offset in the concat
         for (int a = 0; a < nal; ++a) {
           const ALoad al = P.aloads[tc.g][a];
           for (int j0 = 0; j0 < al.tap_count; j0 += P.taps_per_slot) {
@@ -464,7 +482,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       for (int c = 0; c < nchunks; ++c) {
         for (int a = 0; a < nal; ++a) {
           const ALoad al = P.aloads[tc.g][a];
-          mbar_wait(fullA(sa), pa, P.err_flag, 3);
+          mbar_wait(kPre ? readyA(sa) : fullA(sa), pa, P.err_flag, 3);
           const uint32_t a_slot = a_base + (uint32_t)sa * P.a_slot_bytes;
           for (int j0 = 0; j0 < al.tap_count; j0 += P.taps_per_slot) {
             const int nt = min(P.taps_per_slot, (int)al.tap_count - j0);
@@ -513,7 +531,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (kPre && warp >= kPreWarp0) {
+    // ======================================================= operand transform (4 warps): the consumer's pre-activation
+    // relu(x*scale[c] + shift[c]) (DenseNet norm1/relu1 ahead of conv1 — a different affine of the same concat for every
+    // layer) is applied to each A box in shared memory between the TMA fill and the MMAs, so the normalised copy of the
+    // concat never goes through HBM.  16-byte chunks; the channel of a chunk follows from the TMA swizzle.
+    int slot = 0; uint32_t phase = 0;
+    const int tid = threadIdx.x - kPreWarp0 * 32;
+    const uint32_t swz_mask = ((uint32_t)P.row_bytes >> 4) - 1u;
+    const float* pre_sc = s_pre;
+    const float* pre_sh = s_pre + P.ctot;
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = decode_tile(P, t, rank);
+      const int nal = P.n_aloads[tc.g];
+      for (int c = 0; c < nchunks; ++c) {
+        const int kc = (c >= P.chunks0 ? P.c0 + (c - P.chunks0) * P.Ck : c * P.Ck);
+        for (int a = 0; a < nal; ++a) {
+          mbar_wait(fullA(slot), phase, P.err_flag, 7);
+          const uint32_t sbase = a_base + (uint32_t)slot * P.a_slot_bytes;
+          // a thread's chunks are 2048 B apart (16 or 32 whole rows), so their swizzle phase — hence their channel group —
+          // is the same for every chunk it touches: the affine is loaded once per box
+          const uint32_t o0 = (uint32_t)tid * 16u;
+          const uint32_t lo = o0 ^ (((o0 >> 7) & swz_mask) << 4);
+          const int ch = kc + (int)((lo & ((uint32_t)P.row_bytes - 1u)) >> 1);
+          const float4 s0 = *reinterpret_cast<const float4*>(pre_sc + ch), s1 = *reinterpret_cast<const float4*>(pre_sc + ch + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(pre_sh + ch), h1 = *reinterpret_cast<const float4*>(pre_sh + ch + 4);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const uint32_t nbytes = (uint32_t)P.a_tx_bytes;
+          for (uint32_t o = o0; o < nbytes; o += 4u * 2048u) {        // four independent chunks in flight per thread
+            uint32_t v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t a = o + (uint32_t)u * 2048u;
+              if (a < nbytes)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]) : "r"(sbase + a) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t a = o + (uint32_t)u * 2048u;
+              if (a < nbytes) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&v[u][i]);
+                  v[u][i] = pack_bf16x2_relu(fmaf(__low2float(b2), sc[2 * i], sh[2 * i]), fmaf(__high2float(b2), sc[2 * i + 1], sh[2 * i + 1]));
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sbase + a), "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
+              }
+            }
+          }
+          fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core's async-proxy operand reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(readyA(slot));
+          if (++slot == P.a_slots) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kPreWarp0) {
     // ======================================================= epilogue (8 warps; thread = pixel row of the tile)
     // Warps 4-7 and 8-11 both cover the four TMEM lane quarters (a warp may only read lanes 32*(warp%4)..+31); the two
     // warps of a quarter split the tile's work items, which doubles the instruction throughput of an otherwise
@@ -535,7 +609,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       ADB_DBGE(12);
       const uint32_t tmem_tile = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * P.MT * P.bn_cols);
       if (kEpi == ADB_EPI_FEATURE) {
-        if (P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
+        // (kPre kernels run 512 threads = 128 registers each: their epilogue uses the 32-channel slab at most)
+        if (!kPre && P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
         else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
         else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
         if (ewi == 0) { ADB_DBG(4, dbg_i); }
@@ -639,6 +714,16 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   P.chunks0 = d->c0 / Ck; P.chunks1 = d->c1 / Ck;
   P.pitch0 = d->c0_pitch; P.pitch1 = d->src1 ? d->c1_pitch : d->c0_pitch;
   P.ctot = d->c0 + d->c1;
+  P.c0 = d->c0;
+  const bool pre = d->pre_scale != nullptr;
+  if (pre) {
+    ADB_REQUIRE(d->pre_shift != nullptr, "adb_conv2d: pre_scale and pre_shift go together");
+    ADB_REQUIRE(d->kind == ADB_CONV_S1 && d->kh == 1 && d->kw == 1 && d->epi == ADB_EPI_FEATURE,
+                "adb_conv2d: the fused pre-activation is built for 1x1 stride-1 FEATURE convs (zero padding of a k x k conv applies "
+                "to the ACTIVATED input, which an in-operand transform cannot reproduce)");
+    ADB_REQUIRE(P.ctot <= 4096, "adb_conv2d: pre-activation tables hold at most 4096 channels");
+  }
+  P.pre_scale = d->pre_scale; P.pre_shift = d->pre_shift;
 
   // ---- raw taps per group: (space-to-depth phases, pixel offsets, position in the packed K order)
   RawTap raw[kMaxGroups][kMaxTaps];
@@ -703,6 +788,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   int ncta = ((P.BN >= 48 || (P.BN >= 32 && P.ctot >= 128)) && P.ntaps > 1 && sub_tiles >= 8LL * 148) ? 2 : 1;
   if (d->tune_flags & 16) ncta = 2;
   if (d->tune_flags & 32) ncta = 1;
+  if (pre) ncta = 1;
   P.ncta = ncta;
   // sub-tiles per CTA: two share every weight box when their accumulators fit TMEM; measured (profiles/r1_pair_sweep.txt):
   // pairs prefer MT = 2 even single-buffered (N = 192), except at N = 256 where double buffering wins.
@@ -793,6 +879,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   P.b_slot_bytes = P.taps_per_slot * P.b_tap_stride;
   if (d->epi == ADB_EPI_FEATURE) {
     P.Cs = pick_chunk(P.BN);
+    if (pre) P.Cs = std::min(P.Cs, 32);
     P.n_slabs = P.BN / P.Cs;
     P.slab_bytes = 128 * P.Cs * 2;
   } else {
@@ -810,7 +897,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   P.n_slab_bufs = 2;
   int a_slots = 2, b_slots = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    const SmemLayout fixed = smem_layout(0, 0, 0, 0, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
+    const SmemLayout fixed = smem_layout(0, 0, 0, 0, P.slab_bytes, P.n_slab_bufs, P.cout_pad, pre ? P.ctot : 0);
     const int avail = budget - (int)fixed.total;
     a_slots = 2;
     b_slots = (avail - a_slots * P.a_slot_bytes) / P.b_slot_bytes;
@@ -928,7 +1015,9 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
     tmOut = tmA0;
   }
 
-  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad);
+  const bool pre = d->pre_scale != nullptr;
+  const SmemLayout L = smem_layout(P.a_slots, P.a_slot_bytes, P.b_slots, P.b_slot_bytes, P.slab_bytes, P.n_slab_bufs, P.cout_pad,
+                                   pre ? P.ctot : 0);
   int smem = (int)L.total + 1024;
   smem = std::max(smem, 120 * 1024);  // one CTA per SM: the CTA owns the SM's TMEM
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, ConvK);
@@ -938,7 +1027,11 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   if (d->epi == ADB_EPI_FEATURE) {
     const int a = d->act == ADB_ACT_RELU ? 0 : (d->act == ADB_ACT_NONE ? 1 : 2);
     which = a * 2 + (pair ? 1 : 0);
+    if (pre) which = 8 + a;
     switch (which) {
+      case 8: fn = conv_igemm_kernel<ADB_ACT_RELU, false, ADB_EPI_FEATURE, true>; break;
+      case 9: fn = conv_igemm_kernel<ADB_ACT_NONE, false, ADB_EPI_FEATURE, true>; break;
+      case 10: fn = conv_igemm_kernel<-1, false, ADB_EPI_FEATURE, true>; break;
       case 0: fn = conv_igemm_kernel<ADB_ACT_RELU, false, ADB_EPI_FEATURE>; break;
       case 1: fn = conv_igemm_kernel<ADB_ACT_RELU, true, ADB_EPI_FEATURE>; break;
       case 2: fn = conv_igemm_kernel<ADB_ACT_NONE, false, ADB_EPI_FEATURE>; break;
@@ -951,8 +1044,8 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
     if (d->epi == ADB_EPI_DOT) { fn = conv_igemm_kernel<-1, false, ADB_EPI_DOT>; which = 6; }
     else { fn = conv_igemm_kernel<-1, false, ADB_EPI_IMAGE>; which = 7; }
   }
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
-  static int max_pairs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  static bool configured[11] = {false, false, false, false, false, false, false, false, false, false, false};
+  static int max_pairs[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (!configured[which]) {
     ADB_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
     configured[which] = true;
@@ -960,7 +1053,7 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   const long long max_tiles = (long long)d->n * P.tiles_w * P.tiles_h * P.ngroups * P.n_tiles_n;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(pre ? kThreadsPre : kThreads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];

@@ -591,7 +591,8 @@ class DenseNetEngine:
 
     Dense blocks are concat-free: every layer's 3x3 conv stores its 32 new channels straight into the block's
     [n,h,w,C_total] buffer at its channel offset.  norm2/relu2 ride in conv1's epilogue; norm1/relu1 (a different affine
-    of the same concat per layer) is one adb_affine_relu pass ahead of conv1."""
+    of the same concat per layer) is applied to conv1's input operand in shared memory (adb_conv_desc.pre_scale/shift),
+    so no normalised copy of the concat is ever written."""
 
     def __init__(self, classifier):
         self.clf = classifier
@@ -656,14 +657,13 @@ class DenseNetEngine:
                 pending = None
                 c = c_in
                 for (pre, c1, c2) in layers:
-                    a = ops.affine_relu(buf, c, pre[0], pre[1])
-                    t = ops.conv2d(c1, a)
+                    # norm1/relu1 ride inside conv1's operand path (adb_conv_desc.pre_*): the block buffer is read once
+                    t = ops.conv2d(c1, buf, c0=c, pre=pre)
                     ops.conv2d(c2, t, dst=buf, dst_c_off=c)
                     c += 32
                 if bi < 3:
                     pre, conv = S["trans"][bi]
-                    a = ops.affine_relu(buf, c, pre[0], pre[1])
-                    pending = ("avg", ops.conv2d(conv, a))
+                    pending = ("avg", ops.conv2d(conv, buf, c0=c, pre=pre))
                     c_in = conv.cout
                     hh, ww = hh // 2, ww // 2
                 else:

@@ -126,7 +126,7 @@ def _out_hw(spec, h, w):
 
 
 def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, residual=None, n=None, n_dev=None,
-           n_start=0, epi=EPI_FEATURE, dot=None, image=None, tune=None):
+           n_start=0, epi=EPI_FEATURE, dot=None, image=None, tune=None, pre=None):
     """Launch one fused conv.  src*/dst/residual: NHWC bf16.  Returns dst (FEATURE), dot_out (DOT) or None (IMAGE).
 
     dot   = (dot_w fp32[16], dot_b float, dot_out fp32[n,h,w])
@@ -171,6 +171,8 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     if n_dev is not None:
         d.n_dev = n_dev.data_ptr()
     d.n_start = n_start
+    if pre is not None:        # (scale, shift) fp32 over the input channels: relu(x*scale + shift) fused into the operand
+        d.pre_scale, d.pre_shift = pre[0].data_ptr(), pre[1].data_ptr()
     if tune:
         d.tune_mt, d.tune_stages, d.tune_acc_stages = tune.get("mt", 0), tune.get("stages", 0), tune.get("acc", 0)
         d.tune_flags = tune.get("flags", 0)

@@ -92,6 +92,11 @@ typedef struct adb_conv_desc {
   /* --- tuning (0 = choose automatically) */
   int32_t tune_mt, tune_stages, tune_acc_stages;
   int32_t tune_flags;   /* bit 0: one TMA box per tap (no halo re-use); bit 1: descriptor base-offset experiment */
+  /* --- optional pre-activation fused into the input operand (1x1 stride-1 FEATURE convs): the conv sees
+         relu(x[..., c]*pre_scale[c] + pre_shift[c]) over the c0+c1 input channels.  DenseNet's norm1/relu1 ahead of conv1
+         and the transition norm/relu (torchvision densenet121 called as the north_star's HDEN) — every dense layer applies
+         a different affine to the same concatenated map, so it cannot ride in the producer's epilogue. */
+  const float* pre_scale; const float* pre_shift;
 } adb_conv_desc;
 
 /* Weight packing order expected in w_packed (done on the host side by adam_dehaze_b200/engine.py):

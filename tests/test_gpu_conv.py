@@ -268,3 +268,23 @@ def test_dynamic_bucket_count(tune):
     ref = F.conv2d(x, wt, padding=1)
     _close(ops.nhwc_to_nchw(dst)[:2], ref[:2])
     assert (dst[2:].float() == 7.0).all()
+
+
+@pytest.mark.parametrize("cin,pitch,cout,h,w,n", [(64, 64, 128, 16, 32, 2), (96, 256, 128, 24, 40, 2), (224, 256, 128, 16, 16, 3),
+                                                   (512, 1024, 256, 8, 16, 2)])
+def test_conv1x1_fused_pre_activation(cin, pitch, cout, h, w, n):
+    """relu(x*s + b) fused into the A operand of a 1x1 conv (DenseNet norm1/relu1 -> conv1), reading a channel prefix of a
+    wider buffer.  Reference: torch fp32 on the bf16-rounded operands; the fused path rounds the activated input to bf16
+    exactly like the unfused adb_affine_relu pass did."""
+    ops = _ops()
+    x = _rand_fm(n, pitch, h, w, 31)
+    wt = _rand_w((cout, cin, 1, 1), 32, cin)
+    g = torch.Generator().manual_seed(33)
+    s = (torch.rand(cin, generator=g) + 0.5).cuda()
+    b = (torch.randn(cin, generator=g) * 0.3).cuda()
+    bn = _bn(cout, 34)
+    act_in = F.relu(x[:, :cin] * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)).to(torch.bfloat16).float()
+    ref = F.relu(_bn_ref(F.conv2d(act_in, wt), bn))
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU, pad=0)
+    got = ops.conv2d(spec, ops.nchw_to_nhwc(x, pitch), c0=cin, pre=(s.contiguous(), b.contiguous()))
+    _close(ops.nhwc_to_nchw(got, cout), ref)
