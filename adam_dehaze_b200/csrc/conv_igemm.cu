@@ -113,6 +113,7 @@ struct ConvK {
   int img_mode;
   const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
   int c0;                             // channels of src0 (weight K offset of src1's first chunk)
+  int ks_last0, ks_last1;             // K steps (of 16 channels) in the last chunk of src0 / src1 (ragged 64-channel chunking)
   const float* pre_scale;             // optional pre-activation relu(x*pre_scale[c] + pre_shift[c]) applied to the A operand
   const float* pre_shift;
   int* err_flag;
@@ -470,7 +471,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int sa = 0; uint32_t pa = 0;
     int sb = 0; uint32_t pb = 0;
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
-    const int ksteps = P.Ck / 16;
+    const int ksteps_full = P.Ck / 16;
     const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, 0);
@@ -480,6 +481,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t d_base = tmem_base + (uint32_t)(acc * P.MT * P.bn_cols);
       uint32_t accumulate = 0;
       for (int c = 0; c < nchunks; ++c) {
+        const int ksteps = c == P.chunks0 - 1 ? P.ks_last0 : (c == nchunks - 1 ? P.ks_last1 : ksteps_full);
         for (int a = 0; a < nal; ++a) {
           const ALoad al = P.aloads[tc.g][a];
           mbar_wait(kPre ? readyA(sa) : fullA(sa), pa, P.err_flag, 3);
@@ -502,10 +504,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
                 if (P.MT == 2) {
                   if (ksteps == 4) issue_mmas<kPair, 2, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 3) issue_mmas<kPair, 2, 3>(d_base, d1, a0, a1, b0, P.idesc, first);
                   else if (ksteps == 2) issue_mmas<kPair, 2, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
                   else issue_mmas<kPair, 2, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
                 } else {
                   if (ksteps == 4) issue_mmas<kPair, 1, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
+                  else if (ksteps == 3) issue_mmas<kPair, 1, 3>(d_base, d1, a0, a1, b0, P.idesc, first);
                   else if (ksteps == 2) issue_mmas<kPair, 1, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
                   else issue_mmas<kPair, 1, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
                 }
@@ -553,7 +557,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           // is the same for every chunk it touches: the affine is loaded once per box
           const uint32_t o0 = (uint32_t)tid * 16u;
           const uint32_t lo = o0 ^ (((o0 >> 7) & swz_mask) << 4);
-          const int ch = kc + (int)((lo & ((uint32_t)P.row_bytes - 1u)) >> 1);
+          const int ch = min(kc + (int)((lo & ((uint32_t)P.row_bytes - 1u)) >> 1), P.ctot - 8);   // (ragged tail: never read by an MMA)
           const float4 s0 = *reinterpret_cast<const float4*>(pre_sc + ch), s1 = *reinterpret_cast<const float4*>(pre_sc + ch + 4);
           const float4 h0 = *reinterpret_cast<const float4*>(pre_sh + ch), h1 = *reinterpret_cast<const float4*>(pre_sh + ch + 4);
           const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -710,8 +714,17 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   int Ck = pick_chunk(d->c0);
   if (d->src1) Ck = std::min(Ck, pick_chunk(d->c1));
   ADB_REQUIRE(Ck > 0 && d->c0 % Ck == 0 && (d->c1 % Ck) == 0, "adb_conv2d: channel counts %d/%d must be multiples of 16", d->c0, d->c1);
+  // Ragged chunking: channel counts such as 48 / 96 / 160 would force 16- or 32-channel boxes (32/64-byte TMA rows and twice
+  // to four times the barrier round trips per MMA).  Use 64-channel boxes anyway and issue only the K steps that hold real
+  // channels in each source's last chunk; whatever the box fetches beyond them (zero fill, or a neighbour's channels) is
+  // never read by an MMA.  Not for the space-to-depth view, whose channel axis interleaves the two column phases.
+  const bool ragged = Ck < 64 && d->kind != ADB_CONV_S2 && !(d->tune_flags & 128) &&
+                      (d->c0 >= 48 || d->c1 >= 48);
+  if (ragged) Ck = 64;
   P.Ck = Ck; P.row_bytes = Ck * 2;
-  P.chunks0 = d->c0 / Ck; P.chunks1 = d->c1 / Ck;
+  P.chunks0 = (d->c0 + Ck - 1) / Ck; P.chunks1 = (d->c1 + Ck - 1) / Ck;
+  P.ks_last0 = (d->c0 - (P.chunks0 - 1) * Ck) / 16;
+  P.ks_last1 = d->c1 ? (d->c1 - (P.chunks1 - 1) * Ck) / 16 : 0;
   P.pitch0 = d->c0_pitch; P.pitch1 = d->src1 ? d->c1_pitch : d->c0_pitch;
   P.ctot = d->c0 + d->c1;
   P.c0 = d->c0;

@@ -80,6 +80,53 @@ def _blend(y0, y1, y2, logits, temperature):
     return ops.blend3(y0, y1, y2, logits, temperature)
 
 
+class _GateMLPFn(torch.autograd.Function):
+    """GatedRouter.gate_network up to the softmax (routing.py:155-163): Linear-ReLU-Dropout-Linear-ReLU-Linear, forward
+    and backward on adb_linear / adb_linear_bwd / adb_mul_f32; the dropout mask comes from torch's RNG in train() mode."""
+
+    @staticmethod
+    def forward(ctx, feats, w0, b0, w3, b3, w5, b5, p_drop, training):
+        from .. import _lib
+        feats = feats.contiguous().float()
+        st = _lib.current_stream()
+        h0 = ops.linear(feats, w0, b0, relu=True)
+        if training and p_drop > 0:
+            mask = (torch.rand_like(h0) >= p_drop).float() / (1.0 - p_drop)
+            h0d = torch.empty_like(h0)
+            _lib.call("adb_mul_f32", _lib.ptr(h0), _lib.ptr(mask), None, h0.numel(), _lib.ptr(h0d), st)
+        else:
+            mask, h0d = None, h0
+        h1 = ops.linear(h0d, w3, b3, relu=True)
+        logits = ops.linear(h1, w5, b5, relu=False)
+        ctx.save_for_backward(feats, h0, h0d, h1, w0, w3, w5)
+        ctx.mask = mask
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        from .. import _lib
+        feats, h0, h0d, h1, w0, w3, w5 = ctx.saved_tensors
+        st = _lib.current_stream()
+        n = feats.shape[0]
+        dlogits = dlogits.contiguous().float()
+
+        def lin_bwd(x, w, dy):
+            dx = torch.empty_like(x)
+            dw, db = torch.empty_like(w), torch.empty(w.shape[0], dtype=torch.float32, device=w.device)
+            _lib.call("adb_linear_bwd", _lib.ptr(x), _lib.ptr(w.detach()), _lib.ptr(dy), n, w.shape[1], w.shape[0], _lib.ptr(dx),
+                      _lib.ptr(dw), _lib.ptr(db), st)
+            return dx, dw, db
+
+        def gate(d, m, act):      # d * m, zeroed where the ReLU output `act` is not positive
+            out = torch.empty_like(d)
+            _lib.call("adb_mul_f32", _lib.ptr(d), _lib.ptr(m), _lib.ptr(act), d.numel(), _lib.ptr(out), st)
+            return out
+        dh1, dw5, db5 = lin_bwd(h1, w5, dlogits)
+        dh0d, dw3, db3 = lin_bwd(h0d, w3, gate(dh1, None, h1))
+        dfeat, dw0, db0 = lin_bwd(feats, w0, gate(dh0d, ctx.mask, h0))
+        return dfeat, dw0, db0, dw3, db3, dw5, db5, None, None
+
+
 class SoftRouter(nn.Module):
     def __init__(self, models, classifier=None, temperature=1.0, device="cuda"):
         super().__init__()
@@ -120,17 +167,20 @@ class GatedRouter(nn.Module):
     def forward(self, x):
         """Returns (blend, {'gate_weights', 'individual_outputs'}) like routing.py:173-226 (eval mode)."""
         _engine.require_cuda(x, "GatedRouter")
-        _engine.require_inference(self, "GatedRouter")
         if self.classifier is None:
             raise NotImplementedError("GatedRouter without a classifier (uniform weights) is not built on the B200 path")
         _, feats = self.classifier(x)
         g = self.gate_network
-        hid = ops.linear(feats, g[0].weight, g[0].bias, relu=True)
-        gate_logits = ops.head_mlp(hid, g[3].weight.detach(), g[3].bias.detach(), g[5].weight.detach(), g[5].bias.detach())
+        if torch.is_grad_enabled() and (self.training or feats.requires_grad):
+            gate_logits = _GateMLPFn.apply(feats, g[0].weight, g[0].bias, g[3].weight, g[3].bias, g[5].weight, g[5].bias,
+                                           float(g[2].p), self.training)
+        else:
+            hid = ops.linear(feats, g[0].weight, g[0].bias, relu=True)
+            gate_logits = ops.head_mlp(hid, g[3].weight.detach(), g[3].bias.detach(), g[5].weight.detach(), g[5].bias.detach())
         outs = {name: self.models[name](x) for name in _NAMES if name in self.models}
         if len(outs) != 3:
             raise NotImplementedError("GatedRouter on the B200 path blends exactly the three branches low/medium/high")
-        blend, weights = ops.blend3(outs["low"], outs["medium"], outs["high"], gate_logits, 1.0)
+        blend, weights = _blend(outs["low"], outs["medium"], outs["high"], gate_logits, 1.0)
         return blend, {"gate_weights": weights, "individual_outputs": outs}
 
 

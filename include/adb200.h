@@ -104,7 +104,7 @@ typedef struct adb_conv_desc {
  *   ADB_CONVT_4X4S2:            phase g = a*2 + b (a = oh&1, b = ow&1); tap (i,j), i,j in {0,1};
  *                               r = a ? 2*i : 1 + 2*i   (input row  q + (a ? 1-i : -i));  s likewise from b, j
  *                               w_packed[g][co][(i*2 + j)*cin + ci] = Wt[ci][co][r][s]
- *   ktot must be a multiple of the K chunk (the largest of 64/32/16 dividing c0 and c1).
+ *   c0 and c1 are multiples of 16; the kernel walks K in 64-channel chunks (ragged last chunk per source).
  */
 
 /* Library / device */

@@ -19,6 +19,7 @@ H, W = 1024, 2048
 def _fp32_reference():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(True)      # (tests/test_oracle_golden.py switches autograd off at import time)
     yield
     torch.cuda.synchronize()
     from adam_dehaze_b200 import _lib

@@ -30,6 +30,7 @@ def _close(out, ref, rel, abs_):
 def _no_tf32():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(True)      # (tests/test_oracle_golden.py switches autograd off at import time)
     yield
     from adam_dehaze_b200 import _lib
     torch.cuda.synchronize()
@@ -607,3 +608,34 @@ def test_joint_training_step_with_classifier():
         opt.step()
         losses.append(loss.item())
     assert all(l == l for l in losses) and losses[-1] < losses[0] + 0.05, losses
+
+
+def test_gated_router_train_step():
+    """GatedRouter (routing.py:134-226) in train() mode: the gate MLP on the classifier features is trained through the
+    blend; gate-MLP gradients (dropout off) against torch autograd on the same features / branch outputs."""
+    from helpers import CONFIG, make_branch, make_classifier, rand_image
+    from adam_dehaze_b200.models.routing import create_router
+    branches = {k: make_branch(k) for k in ("low", "medium", "high")}
+    clf = make_classifier("resnet18")
+    torch.manual_seed(3)
+    router = create_router(branches, clf, dict(CONFIG, routing={"type": "gated", "temperature": 0.5})).cuda().train()
+    router.gate_network[2].p = 0.0
+    clf.classifier[0].p = clf.classifier[3].p = 0.0
+    x, tgt = rand_image(2, 64, 64, 41).cuda(), rand_image(2, 64, 64, 42).cuda()
+    out, info = router(x)
+    loss = (out - tgt).abs().mean()
+    loss.backward()
+    g = router.gate_network
+    assert all(p.grad is not None for p in router.parameters())
+    # reference: same features and branch outputs, gate MLP + softmax + blend in torch
+    with torch.no_grad():
+        _, feats = clf(x)       # train-mode forward again: identical batch statistics, dropout disabled
+    ys = [info["individual_outputs"][k].detach() for k in ("low", "medium", "high")]
+    ws = [p.detach().clone().requires_grad_(True) for p in (g[0].weight, g[0].bias, g[3].weight, g[3].bias, g[5].weight, g[5].bias)]
+    h = F.relu(F.linear(F.relu(F.linear(feats, ws[0], ws[1])), ws[2], ws[3]))
+    wts = torch.softmax(F.linear(h, ws[4], ws[5]), 1)
+    ref = sum(wts[:, k].view(-1, 1, 1, 1) * ys[k] for k in range(3))
+    (ref - tgt).abs().mean().backward()
+    assert torch.allclose(info["gate_weights"], wts.detach(), atol=2e-3)
+    for p, r in zip((g[0].weight, g[0].bias, g[3].weight, g[3].bias, g[5].weight, g[5].bias), ws):
+        _close(p.grad, r.grad, 5e-2, 1e-7)
