@@ -407,8 +407,10 @@ def run_train(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     torch.cuda.nvtx.range_push("adb_timed")
-    for _ in range(args.steps):
+    torch.cuda.profiler.start()       # ncu --profile-from-start off: loss.backward() runs in autograd's worker thread,
+    for _ in range(args.steps):       # which a per-thread NVTX range would miss
         loss = step()
+    torch.cuda.profiler.stop()
     torch.cuda.nvtx.range_pop()
     e1.record()
     barrier()

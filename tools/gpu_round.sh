@@ -9,8 +9,12 @@ python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_${TAG}_
 python bench.py --mode train --steps 3 --warmup 3 > gpurun_out/bench_${TAG}_train.json 2> gpurun_out/bench_${TAG}_train.err
 SMALL="--mode train --steps 1 --warmup 3 --batch 4"
 python bench.py $SMALL > gpurun_out/plain_train_small_${TAG}.json 2> gpurun_out/plain_train_small_${TAG}.err &&
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "adb_timed/" --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_train_${TAG}.csv python bench.py $SMALL > gpurun_out/ncu_launches_train_${TAG}.log 2>&1
+ISMALL="--steps 1 --warmup 3 --batch 12 --no-e2e --no-cpu-baseline"
+python bench.py $ISMALL > gpurun_out/plain_small_${TAG}.json 2> gpurun_out/plain_small_${TAG}.err &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "adb_timed/" --csv \
+    --log-file gpurun_out/launches_${TAG}.csv python bench.py $ISMALL > gpurun_out/ncu_launches_${TAG}.log 2>&1
 python tools/prof_wgrad.py > gpurun_out/prof_wgrad_${TAG}.txt 2>&1
 for shape in med_64_3x3 cpx_192_3x3; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_wgrad_${shape} \
