@@ -114,6 +114,7 @@ struct ConvK {
   const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
   int c0;                             // channels of src0 (weight K offset of src1's first chunk)
   int ks_last0, ks_last1;             // K steps (of 16 channels) in the last chunk of src0 / src1 (ragged 64-channel chunking)
+  int a_sbo_bytes;                    // byte distance between the 8-row groups of an A view (8*row_bytes, or one halo row for 8-wide 2-D tiles)
   const float* pre_scale;             // optional pre-activation relu(x*pre_scale[c] + pre_shift[c]) applied to the A operand
   const float* pre_shift;
   int* err_flag;
@@ -472,7 +473,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int sb = 0; uint32_t pb = 0;
     int acc = 0; uint32_t acc_phase = 0; int dbg_i = 0;
     const int ksteps_full = P.Ck / 16;
-    const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // everything but the start address
+    const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // (weights) everything but the start address
+    // A views: same, except that the 8-row groups of an 8-pixel-wide 2-D tile are one halo row apart
+    const uint64_t desc_hi_a = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((uint32_t)P.a_sbo_bytes >> 4) & 0x3FFF) << 32);
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, 0);
       const int nal = P.n_aloads[tc.g];
@@ -498,7 +501,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 const uint32_t shift = P.taps[tc.g][al.tap_begin + j0 + jj].shift_px;
                 const uint64_t b0 = desc_hi | (uint64_t)(((b_slot + (uint32_t)jj * P.b_tap_stride) & 0x3FFFFu) >> 4);
                 const uint32_t a_addr0 = a_slot + shift * (uint32_t)P.row_bytes;
-                const uint64_t a0 = desc_hi | (uint64_t)((a_addr0 & 0x3FFFFu) >> 4);
+                const uint64_t a0 = desc_hi_a | (uint64_t)((a_addr0 & 0x3FFFFu) >> 4);
                 const uint64_t a1 = a0 + (uint64_t)(((uint32_t)P.sub_px * (uint32_t)P.row_bytes) >> 4);
                 const uint32_t first = accumulate | (uint32_t)jj;
                 const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
@@ -792,6 +795,14 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   // ---- pixel tile
   int TW = 128;
   while (TW > P.grid_w && TW > 8) TW >>= 1;
+  // 2-D tiles (16 rows x 8 pixels; tune_flags bit 8): all taps share one halo box that over-fetches 1.4x (1.33x at MT = 2)
+  // instead of the one-row tile's 2x; each 8-row group of the UMMA operand is one image row of the tile, one halo row
+  // (TW + 2 pixels) from the next, which the descriptor's stride-byte-offset expresses directly.  Measured (tools/ab_conv.py,
+  // same process, interleaved): no gain on the operand-light shapes it was meant for (Light 32->32, Medium 64->64, DenseNet
+  // 128->32 are epilogue-latency bound, not fetch bound) and 6-8 % slower with a residual (less coalesced residual rows),
+  // so it is opt-in only.
+  bool tile2d = (d->tune_flags & 256) && d->kind == ADB_CONV_S1 && d->kw > 1 && P.grid_w >= 8;
+  if (tile2d) TW = 8;
   P.TW = TW; P.TH = 128 / TW;
   const long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
   // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA (operand reads and TMA fill), which is what
@@ -847,7 +858,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
         dw_min = std::min(dw_min, q.dw); dw_max = std::max(dw_max, q.dw);
         dh_min = std::min(dh_min, q.dh); dh_max = std::max(dh_max, q.dh);
       }
-      const bool can_share = !(d->tune_flags & 1) && (P.TH == 1 || dw_max == dw_min);
+      const bool can_share = !(d->tune_flags & 1) && (P.TH == 1 || dw_max == dw_min || tile2d);
       if (!can_share) { nm = 1; members[0] = t0; dw_min = dw_max = f.dw; dh_min = dh_max = f.dh; }
       ADB_REQUIRE(nal < kMaxALoads, "adb_conv2d: too many A loads");
       ALoad& al = P.aloads[g][nal++];
@@ -866,6 +877,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   }
   P.halo_w = P.TW + ew;
   P.sub_px = P.TH * P.halo_w;
+  P.a_sbo_bytes = (tile2d && ew > 0) ? P.halo_w * P.row_bytes : 8 * P.row_bytes;
   for (int g = 0; g < P.ngroups; ++g)
     for (int t = 0; t < P.ntaps; ++t) {
       const int ddh = P.taps[g][t].shift_px >> 8, ddw = P.taps[g][t].shift_px & 0xFF;

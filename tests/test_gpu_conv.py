@@ -97,6 +97,13 @@ CONV_CASES = [
     (64, 48, 3, 1, 32, 32, {"flags": 16}),            # N = 48: 24 weight rows per CTA
     (64, 64, 3, 1, 6, 128, {"flags": 16, "mt": 1}),   # 3 pair-rows: odd row count
     (512, 128, 1, 2, 16, 32, {"flags": 16}),          # 1x1 (DenseNet bottleneck shape)
+    # 2-D tiles (16 rows x 8 pixels, all nine taps share one halo box; descriptor SBO = one halo row) forced on: flags bit 8
+    (32, 32, 3, 2, 32, 64, {"flags": 256}),
+    (64, 64, 3, 2, 64, 128, {"flags": 256, "mt": 1}),
+    (64, 64, 3, 2, 64, 128, {"flags": 256, "mt": 2}),
+    (128, 32, 3, 2, 40, 72, {"flags": 256}),           # DenseNet 3x3 shape, ragged both ways
+    (96, 96, 3, 1, 48, 24, {"flags": 256}),            # ragged K chunks + 2-D tiles
+    (64, 64, 3, 4, 128, 256, {"flags": 256 | 16}),     # 2-D tiles in CTA-pair mode
 ]
 
 
@@ -115,7 +122,7 @@ def test_conv_s1(cin, cout, k, n, h, w, tune):
         assert y[..., cout:].float().abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("tune", [None, {"flags": 16}], ids=["auto", "pair"])
+@pytest.mark.parametrize("tune", [None, {"flags": 16}, {"flags": 256}], ids=["auto", "pair", "tile2d"])
 def test_conv_bias_residual(tune):
     ops = _ops()
     x = _rand_fm(2, 64, 32, 48, 4)
