@@ -949,6 +949,31 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* 
   }
 }
 
+// backward of the 2x2/2 average pool (DenseNet transition): dx[2y+a, 2x+b] = dy[y, x] / 4
+__global__ void avgpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int pitch_dy, int n, int h, int w, int c,
+                                      __nv_bfloat16* __restrict__ dx, int pitch_dx) {
+  const int G = c / 8, ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * h * w * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xi = (int)(p % w); p /= w;
+    const int yi = (int)(p % h);
+    const int img = (int)(p / h);
+    float f[8];
+    const int yo = yi >> 1, xo = xi >> 1;
+    if (yo < ho && xo < wo) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (((size_t)img * ho + yo) * wo + xo) * pitch_dy + g * 8)), f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] *= 0.25f;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(dx + (((size_t)img * h + yi) * w + xi) * pitch_dx + g * 8) = pack8(f);
+  }
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1257,6 +1282,15 @@ int adb_linear_bwd(const float* x, const float* w, const float* dy, int32_t n, i
     ADB_CUDA_OK(cudaGetLastError());
   }
   linear_bwd_dw_kernel<<<dim3((fin + 127) / 128, fout), 128, 0, st>>>(dy, x, n, fin, fout, dw, db);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx, int32_t pitch_dx,
+                       void* stream) {
+  ADB_REQUIRE(dy && dx && n > 0 && c % 8 == 0 && pitch_dy % 8 == 0 && pitch_dx % 8 == 0, "adb_avgpool2x2_bwd: bad arguments");
+  avgpool2x2_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(dy), pitch_dy, n, h, w, c, ADB_BFM(dx), pitch_dx);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

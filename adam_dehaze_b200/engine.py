@@ -598,6 +598,9 @@ class DenseNetEngine:
         self.clf = classifier
         self._ver = _Versioned(classifier)
         self.S = None
+        self.train_cache = None
+
+    _forward_train = ResNetEngine._forward_train
 
     @staticmethod
     def _affine(bn):
@@ -629,7 +632,8 @@ class DenseNetEngine:
 
     def forward(self, x, chunk=None):
         require_cuda(x, "FogIntensityClassifier")
-        require_inference(self.clf, "FogIntensityClassifier")
+        if self.clf.training:
+            return self._forward_train(x)
         x = x.contiguous()
         b, _, h, w = x.shape
         if h % 32 or w % 32:

@@ -125,6 +125,15 @@ def _out_hw(spec, h, w):
     return h, w
 
 
+def _pitch(t):
+    """Channel pitch of an NHWC map that is dense in n/h/w: a contiguous tensor or a last-dim slice of one."""
+    n, h, w, c = t.shape
+    p = t.stride(2) if w > 1 else (t.stride(1) // max(1, w) if h > 1 else (t.stride(0) // max(1, h * w) if n > 1 else c))
+    assert t.stride(3) == 1 and p >= c and p % 8 == 0 and (t.storage_offset() * 2) % 16 == 0, "not an NHWC map / channel slice"
+    assert (w == 1 or t.stride(2) == p) and (h == 1 or t.stride(1) == w * p) and (n == 1 or t.stride(0) == h * w * p)
+    return p
+
+
 def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, residual=None, n=None, n_dev=None,
            n_start=0, epi=EPI_FEATURE, dot=None, image=None, tune=None, pre=None):
     """Launch one fused conv.  src*/dst/residual: NHWC bf16.  Returns dst (FEATURE), dot_out (DOT) or None (IMAGE).
@@ -132,11 +141,12 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     dot   = (dot_w fp32[16], dot_b float, dot_out fp32[n,h,w])
     image = dict(mode=IMG_*, x=NCHW fp32, out=NCHW fp32, index=int32|None, guidance=fp32|None, alpha=fp32 scalar|None)
     """
-    assert src0.dtype == torch.bfloat16 and src0.is_cuda and src0.is_contiguous()
-    nb, h, w, p0 = src0.shape
+    assert src0.dtype == torch.bfloat16 and src0.is_cuda
+    nb, h, w, _ = src0.shape
+    p0 = _pitch(src0)        # contiguous map, or a channel slice [..., a:b] of a wider one (DenseNet block buffer)
     n = nb if n is None else n
     d = ConvDesc()
-    d.src0, d.c0, d.c0_pitch = src0.data_ptr(), (c0 or p0), p0
+    d.src0, d.c0, d.c0_pitch = src0.data_ptr(), (c0 or src0.shape[3]), p0
     if src1 is not None:
         assert src1.shape[:3] == src0.shape[:3] and src1.is_contiguous()
         d.src1, d.c1, d.c1_pitch = src1.data_ptr(), (c1 or src1.shape[3]), src1.shape[3]
@@ -152,8 +162,8 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
         assert dst.dtype == torch.bfloat16 and dst.is_contiguous() and tuple(dst.shape[:3]) == (nb, ho, wo)
         d.dst, d.dst_pitch, d.dst_c_off = dst.data_ptr(), dst.shape[3], dst_c_off
         if residual is not None:
-            assert residual.is_contiguous() and tuple(residual.shape[:3]) == (nb, ho, wo)
-            d.residual, d.res_pitch = residual.data_ptr(), residual.shape[3]
+            assert tuple(residual.shape[:3]) == (nb, ho, wo)
+            d.residual, d.res_pitch = residual.data_ptr(), _pitch(residual)
         ret = dst
     elif epi == EPI_DOT:
         dot_w, dot_b, dot_out = dot
@@ -198,10 +208,10 @@ def wgrad(small, large0, large1=None, *, kind=CONV_S1, kh=3, kw=3, pad=1, cs=Non
 
     small: NHWC bf16 [n, hs, ws, pitch]; large0/large1: NHWC bf16 [n, h, w, pitch] (concat sources).
     Returns the fp32 gradient in the parameter layout ([cs_true][c0+c1][kh][kw], or [cs_true][3][kh][stem_kw] for STEM)."""
-    assert small.dtype == torch.bfloat16 and large0.dtype == torch.bfloat16 and small.is_contiguous() and large0.is_contiguous()
+    assert small.dtype == torch.bfloat16 and large0.dtype == torch.bfloat16 and large0.is_contiguous()
     nb, h, w, p0 = large0.shape
     d = WgradDesc()
-    d.grad, d.cg, d.cg_pitch = small.data_ptr(), (cs or small.shape[3]), small.shape[3]
+    d.grad, d.cg, d.cg_pitch = small.data_ptr(), (cs or small.shape[3]), _pitch(small)
     d.cg_true = cs_true or 0
     d.act0, d.c0, d.c0_pitch = large0.data_ptr(), (c0 or p0), p0
     if large1 is not None:

@@ -38,13 +38,39 @@ class Node:
             _lib.call("adb_add_bf16", _lib.ptr(self.grad), p, _lib.ptr(g), g.shape[3], n * h * w, self.c, _lib.current_stream())
 
     def accumulate_conv(self, spec, src):
-        """grad += conv(src) with the accumulation fused into the conv epilogue where the kernel allows it."""
+        """grad += conv(src) with the accumulation fused into the conv epilogue where the kernel allows it.
+        `spec` may be a list of (channel offset, spec) pieces when the gradient has more channels than one launch's N range
+        (DenseNet 1x1 convs over up to 1024 concatenated channels)."""
+        if isinstance(spec, list):
+            if self.grad is None:
+                nb, h, w, _ = src.shape
+                self.grad = torch.empty((nb, h, w, self.c), dtype=torch.bfloat16, device=src.device)
+                for off, sp in spec:
+                    ops.conv2d(sp, src, dst=self.grad, dst_c_off=off)
+            else:
+                for off, sp in spec:
+                    ops.conv2d(sp, src, dst=self.grad, dst_c_off=off, residual=self.grad[..., off:off + sp.cout_pad])
+            return
         if self.grad is None:
             self.grad = ops.conv2d(spec, src)
         elif spec.kind == CONVT_4X4S2:       # the sub-pixel store path has no residual input
             self.accumulate(ops.conv2d(spec, src))
         else:
             ops.conv2d(spec, src, dst=self.grad, residual=self.grad)
+
+
+class BlockBuffer:
+    """DenseNet block buffer: the raw (pre-norm) features of a dense block, [n,h,w,C_total] bf16, written in place by the
+    layers' 3x3 convs at their channel offsets (the concat is never materialised), plus its lazily zeroed gradient."""
+    __slots__ = ("t", "c", "grad")
+
+    def __init__(self, t):
+        self.t, self.c, self.grad = t, t.shape[3], None
+
+    def g(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.t)
+        return self.grad
 
 
 class _WeightCache:
@@ -178,7 +204,10 @@ class Tape:
         for i, s in enumerate(srcs):
             lo, hi = off, off + s.c
             off = hi
-            if stride == 1:
+            if stride == 1 and hi - lo > 512:      # more gradient channels than one launch's N range: 256-channel pieces
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: [
+                    (o - lo, _dgrad_spec_s1(w[:, o:min(o + 256, hi)])) for o in range(lo, hi, 256)])
+            elif stride == 1:
                 spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: _dgrad_spec_s1(w[:, lo:hi]))
             else:   # stride-2 conv: dX = ConvTranspose2d(dZ, W) — the 4x4/pad-1 sub-pixel kernel, smaller filters embedded
                 spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_convT(
@@ -309,6 +338,81 @@ class Tape:
             feats.grad = df
         self.head_backward = backward
         return logits
+
+    # ------------------------------------------------------------------ DenseNet pieces (torchvision densenet121 as HDEN)
+    def bn_act_prefix(self, B, c, bn, act):
+        """norm/relu over the first c channels of a block buffer -> a dense [n,h,w,c] map (norm1/relu1 of a dense layer,
+        the transition norm, norm5).  Backward adds dz into the buffer gradient's channel prefix."""
+        n, h, w, pitch = B.t.shape
+        px = n * h * w
+        dev = B.t.device
+        st = _lib.current_stream()
+        scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
+        stats = _f32(4 * c, dev)
+        mean, rstd, scale, shift = stats[:c], stats[c:2 * c], stats[2 * c:3 * c], stats[3 * c:]
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        _lib.call("adb_bn_train_stats", _lib.ptr(B.t), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
+                  _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
+                  _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+        _lib.call("adb_affine_act", _lib.ptr(B.t), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift), None, 0, act, _lib.ptr(y), c, st)
+        out = Node(y, c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            sc2 = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
+            dgamma, dbeta = _f32(c, dev), _f32(c, dev)
+            _lib.call("adb_bn_bwd", _lib.ptr(dy), c, _lib.ptr(y), c, _lib.ptr(B.t), pitch, px, c, act, _lib.ptr(bn.weight), _lib.ptr(mean),
+                      _lib.ptr(rstd), _lib.ptr(sc2), _lib.ptr(dy), c, _lib.ptr(dy), c, _lib.ptr(dgamma), _lib.ptr(dbeta), 0, st)
+            self.pg[bn.weight], self.pg[bn.bias] = dgamma, dbeta
+            _lib.call("adb_add_bf16", _lib.ptr(B.g()), pitch, _lib.ptr(dy), c, px, c, st)
+        self.back.append(backward)
+        return out
+
+    def conv_plain(self, conv, src, into=None, c_off=0):
+        """A bias-free conv with no norm / activation after it (DenseNet conv2 / transition conv).  `into`: write the output
+        at channel offset c_off of a BlockBuffer (its gradient is read from the buffer gradient's slice)."""
+        w = conv.weight
+        co = w.shape[0]
+        fspec = self.wc.get(("f", id(conv)), (w,), lambda: ConvSpec.from_conv(w, stride=conv.stride[0], pad=conv.padding[0]))
+        if into is None:
+            out = Node(ops.conv2d(fspec, src.t, c0=src.c), co)
+        else:
+            ops.conv2d(fspec, src.t, c0=src.c, dst=into.t, dst_c_off=c_off)
+            out = None
+
+        def backward():
+            if into is None:
+                dz = out.grad
+                out.grad = None
+            else:
+                dz = into.g()[..., c_off:c_off + co]
+            self._conv_backward(conv, dz, co, [src])
+        self.back.append(backward)
+        return out
+
+    def avgpool_into(self, x, B, c):
+        n, h, w, _ = x.t.shape
+        ops.avgpool2x2(x.t, c=c, out=B.t)
+
+        def backward():
+            dx = torch.empty_like(x.t)
+            _lib.call("adb_avgpool2x2_bwd", _lib.ptr(B.g()), B.t.shape[3], n, h, w, c, _lib.ptr(dx), x.t.shape[3], _lib.current_stream())
+            x.accumulate(dx)
+        self.back.append(backward)
+
+    def maxpool3x3s2_into(self, x, B, c):
+        n, h, w, _ = x.t.shape
+        ops.maxpool3x3s2(x.t, out=B.t)
+
+        def backward():
+            dy = B.g()[..., :c].contiguous()
+            y = B.t[..., :c].contiguous()
+            dx = torch.empty_like(x.t)
+            _lib.call("adb_maxpool_bwd", _lib.ptr(dy), _lib.ptr(x.t), _lib.ptr(y), n, h, w, c, 3, 2, 1, _lib.ptr(dx), _lib.current_stream())
+            x.accumulate(dx)
+        self.back.append(backward)
 
     def res_block(self, rb, x):
         t = self.conv_bn_act(rb.conv1.block[0], rb.conv1.block[1], ACT_RELU, [x])
@@ -472,13 +576,52 @@ def forward_resnet(t, clf, x):
     return logits, feats.t
 
 
+def forward_densenet(t, clf, x):
+    """FogIntensityClassifier.forward with the torchvision densenet121 backbone (the north_star's HDEN) in train() mode:
+    stem conv0/norm0/relu0/pool0, four dense blocks (norm1-relu1-conv1-norm2-relu2-conv2 per layer, concat by writing into
+    the block buffer), three transitions (norm-relu-conv-avgpool), norm5-relu, global average pool, the reference head."""
+    ft = clf.backbone.features
+    f = t.stem_full_bn_act(ft.conv0, ft.norm0, ACT_RELU, x)
+    n, h, w, c_in = f.t.shape
+    hh, ww = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    dev = f.t.device
+    pending = ("max", f)
+    for bi in range(4):
+        layers = list(getattr(ft, f"denseblock{bi + 1}").children())
+        c_total = c_in + 32 * len(layers)
+        B = BlockBuffer(torch.empty((n, hh, ww, c_total), dtype=torch.bfloat16, device=dev))
+        if pending[0] == "max":
+            t.maxpool3x3s2_into(pending[1], B, c_in)
+        else:
+            t.avgpool_into(pending[1], B, c_in)
+        c = c_in
+        for layer in layers:
+            y1 = t.bn_act_prefix(B, c, layer.norm1, ACT_RELU)
+            u = t.conv_bn_act(layer.conv1, layer.norm2, ACT_RELU, [y1])
+            t.conv_plain(layer.conv2, u, into=B, c_off=c)
+            c += 32
+        if bi < 3:
+            tr = getattr(ft, f"transition{bi + 1}")
+            y = t.bn_act_prefix(B, c, tr.norm, ACT_RELU)
+            z = t.conv_plain(tr.conv, y)
+            pending = ("avg", z)
+            c_in = tr.conv.weight.shape[0]
+            hh, ww = hh // 2, ww // 2
+        else:
+            y = t.bn_act_prefix(B, c, ft.norm5, ACT_RELU)
+    feats = t.global_avgpool(y)
+    logits = t.head_mlp(clf.classifier, feats)
+    return logits, feats.t
+
+
 class ClassifierTrainFn(torch.autograd.Function):
     """autograd node of the HDEN forward in train() mode; returns (logits, features)."""
 
     @staticmethod
     def forward(ctx, engine, x, *params):
         tape = Tape(engine.train_cache)
-        logits, feats = forward_resnet(tape, engine.clf, x)
+        fwd = forward_densenet if engine.clf.model_name == "densenet121" else forward_resnet
+        logits, feats = fwd(tape, engine.clf, x)
         ctx.tape, ctx.params = tape, params
         return logits, feats
 

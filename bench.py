@@ -342,9 +342,8 @@ def run_train(args):
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     B = 16 if args.batch == 256 else args.batch
     Hh, Ww = (512, 512) if (args.height, args.width) == (H, W) else (args.height, args.width)
-    # the joint step trains HDEN through the router (train_joint.py:80-88,117-121); the trainable HDEN arm on the B200 path
-    # is the reference's own default, resnet18 (densenet121 has inference kernels only)
-    hden = "resnet18" if args.hden == "densenet121" else args.hden
+    # the joint step trains HDEN through the router (train_joint.py:80-88,117-121)
+    hden = args.hden
     cfg = dict(CFG, classifier=dict(CFG["classifier"], model=hden), routing={"type": "soft", "temperature": 0.5})
     branches, clf = build_models(cfg, device=dev)
     router = SoftRouter(branches, classifier=clf, temperature=0.5).to(dev).train()

@@ -308,6 +308,10 @@ ADB_API int adb_mul_f32(const float* a, const float* b /*nullable*/, const float
 ADB_API int adb_linear_bwd(const float* x, const float* w, const float* dy, int32_t n, int32_t fin, int32_t fout, float* dx,
                            float* dw, float* db, void* stream);
 
+/* backward of adb_avgpool2x2 (DenseNet transition pool): dx[n, h, w, :c] = dy[n, h/2, w/2, :c] / 4; h, w of dx */
+ADB_API int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
+                               int32_t pitch_dx, void* stream);
+
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

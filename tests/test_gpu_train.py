@@ -533,18 +533,19 @@ def test_dehazing_loss_full_and_joint_loss():
     assert set(dc) == {"l1", "content", "perceptual", "total"}
 
 
-def test_classifier_train_step_matches_oracle():
-    """HDEN (resnet18) in train() mode — train_joint.py:117-150 trains it through the router: batch-statistics BN through the
+@pytest.mark.parametrize("arch,shape", [("resnet18", (4, 128, 160)), ("densenet121", (3, 128, 128))])
+def test_classifier_train_step_matches_oracle(arch, shape):
+    """HDEN (resnet18, and the north_star's densenet121) in train() mode — train_joint.py:117-150 trains it through the router: batch-statistics BN through the
     BasicBlocks (3x3 stride-2 and 1x1 stride-2 downsample convs, max-pool, global average pool) and the head MLP, forward
     and backward vs the fp32 oracle under autograd.  Dropout is disabled (p = 0) for the comparison; same end-to-end
     gradient criterion as the branch models (bf16-storage floor)."""
     from helpers import make_classifier, oracle_bf16_storage, rand_image
     import adam_oracle as oracle
-    clf = make_classifier("resnet18").cuda().train()
+    clf = make_classifier(arch).cuda().train()
     clf.classifier[0].p = 0.0
     clf.classifier[3].p = 0.0
-    x = rand_image(4, 128, 160, 21).cuda()
-    labels = torch.tensor([0, 2, 1, 1], device="cuda")
+    x = rand_image(*shape, 21).cuda()
+    labels = torch.tensor([0, 2, 1, 1], device="cuda")[:shape[0]]
     sd = {k: v.detach().clone().float().requires_grad_(v.dtype.is_floating_point) for k, v in clf.state_dict().items()}
     names = [k for k, _ in clf.named_parameters()]
 
@@ -553,8 +554,8 @@ def test_classifier_train_step_matches_oracle():
             lg, ft = fn()
         loss = F.cross_entropy(lg, labels)
         return lg.detach(), ft.detach(), loss.detach(), dict(zip(names, torch.autograd.grad(loss, [sd[k] for k in names])))
-    ref_lg, ref_ft, ref_loss, ref_g = run(lambda: oracle.classifier_forward(sd, x, "resnet18"))
-    sim_lg, sim_ft, _, sim_g = run(lambda: oracle_bf16_storage(oracle.classifier_forward, sd, x, "resnet18"))
+    ref_lg, ref_ft, ref_loss, ref_g = run(lambda: oracle.classifier_forward(sd, x, arch))
+    sim_lg, sim_ft, _, sim_g = run(lambda: oracle_bf16_storage(oracle.classifier_forward, sd, x, arch))
     floor_ft = (sim_ft - ref_ft).abs().max().item()       # batch statistics over 4x5x4 samples at layer4 amplify bf16 rounding
     floor_lg = (sim_lg - ref_lg).abs().max().item()
     from adam_dehaze_b200.training.loss import _CrossEntropy

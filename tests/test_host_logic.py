@@ -182,13 +182,13 @@ def test_no_cpu_fallback_and_train_mode_refused():
     clf = make_classifier()
     with pytest.raises(RuntimeError, match="no CPU path"):
         clf(torch.rand(1, 3, 32, 32))
-    # train() mode has no CPU path either (the training kernels are CUDA only), and HDEN / the non-default variants
-    # refuse train() mode instead of silently running torch ops
+    # train() mode has no CPU path either (the training kernels are CUDA only), and the non-default variants refuse
+    # train() mode instead of silently running torch ops
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.train()(torch.rand(1, 3, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        clf.train()(torch.rand(1, 3, 32, 32))
     from adam_dehaze_b200 import engine
-    with pytest.raises(NotImplementedError, match="eval"):
-        engine.require_inference(clf.train(), "FogIntensityClassifier")
     v = make_branch("corun").train()
     eng = v._branch_engine()
     with pytest.raises(NotImplementedError, match="default branch models"):
