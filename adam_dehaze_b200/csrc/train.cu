@@ -974,6 +974,17 @@ __global__ void avgpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
   }
 }
 
+// Re-pack a parameter for the kernels after an optimizer step: out[i] = bf16(src[idx[i]]) (0 where idx[i] < 0).  The
+// index map is derived once per packing (training/autograd.py), so a step re-packs every weight with one launch each
+// instead of a dozen torch ops.
+__global__ void gather_cast_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n,
+                                   __nv_bfloat16* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = __ldg(idx + i);
+    out[i] = __float2bfloat16(k >= 0 ? __ldg(src + k) : 0.f);
+  }
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1291,6 +1302,13 @@ int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, i
   ADB_REQUIRE(dy && dx && n > 0 && c % 8 == 0 && pitch_dy % 8 == 0 && pitch_dx % 8 == 0, "adb_avgpool2x2_bwd: bad arguments");
   avgpool2x2_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
       ADB_BF(dy), pitch_dy, n, h, w, c, ADB_BFM(dx), pitch_dx);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream) {
+  ADB_REQUIRE(src && idx && out && n > 0, "adb_gather_cast: bad arguments");
+  gather_cast_kernel<<<grid_for(n, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n, ADB_BFM(out));
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

@@ -23,6 +23,27 @@ def pad16(c):
     return max(16, (c + 15) // 16 * 16)
 
 
+_PACK_DTYPE = [torch.bfloat16]
+
+
+class pack_as:
+    """`with pack_as(torch.float32):` — the pack_* functions keep fp32 instead of rounding to bf16.  Used once per packing
+    to derive its index map (pack an arange): every pack function is a pure permutation + zero padding."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        _PACK_DTYPE.append(self.dtype)
+
+    def __exit__(self, *a):
+        _PACK_DTYPE.pop()
+
+
+def pack_dtype():
+    return _PACK_DTYPE[-1]
+
+
 # --------------------------------------------------------------------------- packing (host logic, CPU-testable)
 def fold_bn(cout, bias=None, bn=None, cout_pad=None, device=None):
     """Epilogue affine of Conv(+bias) -> BatchNorm(eval): y = acc*scale + shift  (base_model.py:11-16).
@@ -54,8 +75,8 @@ def pack_conv_weight(w, cout_pad=None):
     co, ci, kh, kw = w.shape
     cout_pad = cout_pad or pad16(co)
     p = w.detach().float().permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
-    out = torch.zeros(cout_pad, kh * kw * ci, dtype=torch.bfloat16, device=w.device)
-    out[:co] = p.to(torch.bfloat16)
+    out = torch.zeros(cout_pad, kh * kw * ci, dtype=pack_dtype(), device=w.device)
+    out[:co] = p.to(pack_dtype())
     return out.contiguous()
 
 
@@ -64,7 +85,7 @@ def pack_convT_weight(wt, cout_pad=None):
     ci, co, kh, kw = wt.shape
     assert kh == 4 and kw == 4
     cout_pad = cout_pad or pad16(co)
-    out = torch.zeros(4, cout_pad, 4 * ci, dtype=torch.bfloat16, device=wt.device)
+    out = torch.zeros(4, cout_pad, 4 * ci, dtype=pack_dtype(), device=wt.device)
     w = wt.detach().float()
     for a in range(2):
         for b in range(2):
@@ -73,7 +94,7 @@ def pack_convT_weight(wt, cout_pad=None):
                     r = 2 * i if a else 1 + 2 * i
                     s = 2 * j if b else 1 + 2 * j
                     t = i * 2 + j
-                    out[a * 2 + b, :co, t * ci:(t + 1) * ci] = w[:, :, r, s].t().to(torch.bfloat16)
+                    out[a * 2 + b, :co, t * ci:(t + 1) * ci] = w[:, :, r, s].t().to(pack_dtype())
     return out.contiguous()
 
 
@@ -84,7 +105,7 @@ def pack_stem_weight(w, kp, cout_pad=None):
     cout_pad = cout_pad or pad16(co)
     out = torch.zeros(cout_pad, kh, kp, dtype=torch.float32, device=w.device)
     out[:co, :, :3 * kw] = w.detach().float().permute(0, 2, 3, 1).reshape(co, kh, kw * 3)
-    return out.reshape(cout_pad, kh * kp).to(torch.bfloat16).contiguous()
+    return out.reshape(cout_pad, kh * kp).to(pack_dtype()).contiguous()
 
 
 class ConvSpec:

@@ -73,18 +73,59 @@ class BlockBuffer:
         return self.grad
 
 
+def _flat_specs(obj):
+    if isinstance(obj, ConvSpec):
+        return [obj]
+    if isinstance(obj, (list, tuple)):
+        out = []
+        for o in obj:
+            out += _flat_specs(o)
+        return out
+    return []
+
+
+def derive_index_maps(build, weight):
+    """Build a packing and, for each of its bf16 tensors, the int32 map `packed.flat[i] = weight.flat[idx[i]]` (-1 = zero
+    padding): the same builder applied to an arange under ops.pack_as(float32) (pack functions only permute and pad)."""
+    val = build(weight)
+    with torch.no_grad(), ops.pack_as(torch.float32):
+        ramp = torch.arange(1, weight.numel() + 1, dtype=torch.float32, device=weight.device).view(weight.shape)
+        ival = build(ramp)
+    maps = [(sp.w_packed, (isp.w_packed.reshape(-1).to(torch.int32) - 1).contiguous())
+            for sp, isp in zip(_flat_specs(val), _flat_specs(ival))]
+    return val, maps
+
+
 class _WeightCache:
-    """bf16 packings of a parameter for the forward and the data-gradient launches, rebuilt when the parameter changes."""
+    """bf16 packings of a parameter for the forward and the data-gradient launches.  When the parameter changes (optimizer
+    step) a packing built with `weight=` is refreshed by ONE adb_gather_cast launch through an index map derived once
+    (the same builder applied to an arange under ops.pack_as(float32)); other entries are rebuilt."""
 
     def __init__(self):
         self._c = {}
 
-    def get(self, key, params, build):
+    def get(self, key, params, build, weight=None, bias=None):
+        """build(): returns the packing (a ConvSpec, or nested lists/tuples of them).  With `weight` given, build takes
+        the weight tensor as its only argument."""
         sig = tuple((p.data_ptr(), p._version) for p in params if p is not None)
         hit = self._c.get(key)
-        if hit is None or hit[0] != sig:
-            hit = (sig, build())
-            self._c[key] = hit
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        if weight is None:
+            hit = (sig, build(), None)
+        elif hit is None or hit[2] is None or hit[3] != weight.data_ptr():
+            val, maps = derive_index_maps(build, weight)
+            hit = (sig, val, maps, weight.data_ptr())
+        else:
+            wf = weight.detach()
+            st = _lib.current_stream()
+            for packed, idx in hit[2]:
+                _lib.call("adb_gather_cast", _lib.ptr(wf), _lib.ptr(idx), idx.numel(), _lib.ptr(packed), st)
+            if bias is not None:
+                for sp in _flat_specs(hit[1]):
+                    sp.shift[:bias.numel()].copy_(bias.detach())
+            hit = (sig, hit[1], hit[2], hit[3])
+        self._c[key] = hit
         return hit[1]
 
 
@@ -166,9 +207,10 @@ class Tape:
         w, b = conv.weight, conv.bias
         stride = conv.stride[0]
         if stem_kp:
-            fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_stem(w, stem_kp, bias=b))
+            fspec = self.wc.get(("f", id(conv)), (w, b), lambda wt: ConvSpec.from_stem(wt, stem_kp, bias=b), weight=w, bias=b)
         else:
-            fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_conv(w, bias=b, stride=stride, pad=conv.padding[0]))
+            fspec = self.wc.get(("f", id(conv)), (w, b), lambda wt: ConvSpec.from_conv(wt, bias=b, stride=stride, pad=conv.padding[0]),
+                                weight=w, bias=b)
         a = srcs[0]
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
@@ -205,19 +247,19 @@ class Tape:
             lo, hi = off, off + s.c
             off = hi
             if stride == 1 and hi - lo > 512:      # more gradient channels than one launch's N range: 256-channel pieces
-                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: [
-                    (o - lo, _dgrad_spec_s1(w[:, o:min(o + 256, hi)])) for o in range(lo, hi, 256)])
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda wt, lo=lo, hi=hi: [
+                    (o - lo, _dgrad_spec_s1(wt[:, o:min(o + 256, hi)])) for o in range(lo, hi, 256)], weight=w)
             elif stride == 1:
-                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: _dgrad_spec_s1(w[:, lo:hi]))
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda wt, lo=lo, hi=hi: _dgrad_spec_s1(wt[:, lo:hi]), weight=w)
             else:   # stride-2 conv: dX = ConvTranspose2d(dZ, W) — the 4x4/pad-1 sub-pixel kernel, smaller filters embedded
-                spec = self.wc.get(("d", id(conv), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_convT(
-                    _embed4x4(_pad_rows16(w.detach()[:, lo:hi]), conv.padding[0])))
+                spec = self.wc.get(("d", id(conv), i), (w,), lambda wt, lo=lo, hi=hi: ConvSpec.from_convT(
+                    _embed4x4(_pad_rows16(wt.detach()[:, lo:hi]), conv.padding[0])), weight=w)
             s.accumulate_conv(spec, dz)
 
     def convT_bn_act(self, convT, bn, act, srcs):
         """nn.ConvTranspose2d(4,2,1) + bias -> BatchNorm2d(train) -> act (decoder `up`, medium:53-55,63-65; high:57-59,68-70)."""
         w, b = convT.weight, convT.bias
-        fspec = self.wc.get(("f", id(convT)), (w, b), lambda: ConvSpec.from_convT(w, bias=b))
+        fspec = self.wc.get(("f", id(convT)), (w, b), lambda wt: ConvSpec.from_convT(wt, bias=b), weight=w, bias=b)
         a = srcs[0]
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
@@ -236,7 +278,8 @@ class Tape:
                 off = hi
                 # dWt[ci][co][r][s]: the stride-2 form with the maps swapped (small = layer input, large = dz)
                 ops.wgrad(s.t, dz, kind=CONV_S2, kh=4, kw=4, pad=1, cs=s.c, c0=c, out=gw[lo:hi])
-                spec = self.wc.get(("d", id(convT), i), (w,), lambda lo=lo, hi=hi: ConvSpec.from_conv(w.detach()[lo:hi], stride=2, pad=1))
+                spec = self.wc.get(("d", id(convT), i), (w,), lambda wt, lo=lo, hi=hi: ConvSpec.from_conv(wt.detach()[lo:hi], stride=2, pad=1),
+                                   weight=w)
                 s.accumulate_conv(spec, dz)
             self.pg[w] = gw
             if b is not None:
@@ -250,12 +293,12 @@ class Tape:
         w = conv.weight
         co = w.shape[0]
 
-        def build():
-            wp = torch.zeros(ops.pad16(co), 160, dtype=torch.bfloat16, device=w.device)
-            wp[:co, :147] = w.detach().float().permute(0, 2, 3, 1).reshape(co, 147).to(torch.bfloat16)
-            scale, shift = ops.fold_bn(co, None, None, device=w.device)
+        def build(wt):
+            wp = torch.zeros(ops.pad16(co), 160, dtype=ops.pack_dtype(), device=wt.device)
+            wp[:co, :147] = wt.detach().float().permute(0, 2, 3, 1).reshape(co, 147).to(ops.pack_dtype())
+            scale, shift = ops.fold_bn(co, None, None, device=wt.device)
             return ConvSpec(CONV_S1, 1, 1, 0, co, wp.contiguous(), scale, shift, ACT_NONE)
-        fspec = self.wc.get(("f", id(conv)), (w,), build)
+        fspec = self.wc.get(("f", id(conv)), (w,), build, weight=w)
         cols = ops.stem_pack(x, 7, 3, 160, stride=2, kh=7)
         z = ops.conv2d(fspec, cols)
         c = fspec.cout_pad
@@ -375,7 +418,7 @@ class Tape:
         at channel offset c_off of a BlockBuffer (its gradient is read from the buffer gradient's slice)."""
         w = conv.weight
         co = w.shape[0]
-        fspec = self.wc.get(("f", id(conv)), (w,), lambda: ConvSpec.from_conv(w, stride=conv.stride[0], pad=conv.padding[0]))
+        fspec = self.wc.get(("f", id(conv)), (w,), lambda wt: ConvSpec.from_conv(wt, stride=conv.stride[0], pad=conv.padding[0]), weight=w)
         if into is None:
             out = Node(ops.conv2d(fspec, src.t, c0=src.c), co)
         else:
@@ -478,7 +521,7 @@ class Tape:
     def image_head(self, conv, src, x, mode, act, guidance=None, alpha=None):
         """Final nn.Conv2d(c, 3, 3, padding=1) + act + the output arithmetic -> NCHW fp32 (low:45, medium:117, high:135-138)."""
         w, b = conv.weight, conv.bias
-        fspec = self.wc.get(("f", id(conv)), (w, b), lambda: ConvSpec.from_conv(w, bias=b, pad=conv.padding[0]))
+        fspec = self.wc.get(("f", id(conv)), (w, b), lambda wt: ConvSpec.from_conv(wt, bias=b, pad=conv.padding[0]), weight=w, bias=b)
         z = ops.conv2d(fspec, src.t, c0=src.c)
         n, h, wd, pitch = z.shape
         out = torch.empty_like(x)

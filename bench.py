@@ -468,9 +468,18 @@ def run_train(args):
         torch.cuda.synchronize()
         set_call(inner)
         by, fl = {}, {}
+        slow = []
         for nm, ea, eb, f in calls:
-            by[nm] = by.get(nm, 0.0) + ea.elapsed_time(eb)
+            ms_ = ea.elapsed_time(eb)
+            by[nm] = by.get(nm, 0.0) + ms_
             fl[nm] = fl.get(nm, 0.0) + f
+            slow.append((ms_, nm))
+        if os.environ.get("ADB_PROFILE_HOST") and rank == 0:
+            slow.sort(reverse=True)
+            sys.stderr.write("slowest calls: " + ", ".join(f"{n}:{m:.2f}" for m, n in slow[:25]) + "\n")
+            ms_ = torch.cuda.memory_stats()
+            sys.stderr.write(f"allocator: reserved {ms_['reserved_bytes.all.peak'] / 2**30:.1f} GiB, alloc retries {ms_['num_alloc_retries']}, "
+                             f"cudaMalloc segments {ms_['segment.all.allocated']}, freed {ms_['segment.all.freed']}\n")
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak = peaks.get("bf16_tflops_sustained") or 1400.0
         mma_ms = by.get("adb_conv2d", 0.0) + by.get("adb_wgrad", 0.0)

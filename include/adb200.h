@@ -312,6 +312,10 @@ ADB_API int adb_linear_bwd(const float* x, const float* w, const float* dy, int3
 ADB_API int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
                                int32_t pitch_dx, void* stream);
 
+/* Weight re-packing after an optimizer step: out[i] = bf16(src[idx[i]]), 0 where idx[i] < 0 (idx = the packing's
+ * permutation of the fp32 parameter, derived once on the host side). */
+ADB_API int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream);
+
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

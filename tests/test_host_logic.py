@@ -347,3 +347,32 @@ def test_gradient_bucket_allreduce_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_weight_repack_index_maps():
+    """After an optimizer step every packing is refreshed by one gather through an index map derived once
+    (training/autograd.derive_index_maps).  The map must reproduce the direct packing for every layout in use:
+    conv, stride-1 dgrad (rotated / transposed / row-padded / channel-sliced), ConvTranspose phases, embedded 3x3 stride-2
+    dgrad, horizontally packed stems."""
+    from adam_dehaze_b200.training import autograd as ag
+    from adam_dehaze_b200.ops import ConvSpec
+    g = torch.Generator().manual_seed(4)
+    cases = [
+        (torch.randn(48, 32, 3, 3, generator=g), lambda wt: ConvSpec.from_conv(wt, pad=1)),
+        (torch.randn(3, 32, 3, 3, generator=g), lambda wt: ag._dgrad_spec_s1(wt)),
+        (torch.randn(64, 96, 3, 3, generator=g), lambda wt: [(o, ag._dgrad_spec_s1(wt[:, o:o + 32])) for o in (0, 32, 64)]),
+        (torch.randn(64, 32, 4, 4, generator=g), lambda wt: ConvSpec.from_convT(wt)),
+        (torch.randn(32, 16, 3, 3, generator=g), lambda wt: ConvSpec.from_convT(ag._embed4x4(ag._pad_rows16(wt), 1))),
+        (torch.randn(32, 16, 1, 1, generator=g), lambda wt: ConvSpec.from_convT(ag._embed4x4(ag._pad_rows16(wt), 0))),
+        (torch.randn(32, 3, 7, 7, generator=g), lambda wt: ConvSpec.from_stem(wt, 32)),
+        (torch.randn(128, 64, 4, 4, generator=g), lambda wt: ConvSpec.from_conv(wt[32:96], stride=2, pad=1)),
+    ]
+    for w, build in cases:
+        val, maps = ag.derive_index_maps(build, w)
+        w2 = torch.randn(w.shape, generator=g)
+        fresh = ag._flat_specs(build(w2))
+        assert len(maps) == len(fresh) >= 1
+        src = torch.cat([torch.zeros(1), w2.reshape(-1)])
+        for (packed, idx), sp in zip(maps, fresh):
+            got = src[(idx.long() + 1)].to(torch.bfloat16).view(sp.w_packed.shape)
+            assert packed.shape == sp.w_packed.shape and torch.equal(got, sp.w_packed)
