@@ -36,12 +36,14 @@ __device__ __forceinline__ float act_grad(float y, int act) {
   if (act == ADB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (act == ADB_ACT_TANH) return 1.f - y * y;
   if (act == ADB_ACT_SIGMOID) return y * (1.f - y);
+  if (act == ADB_ACT_SIGMOID2) return 0.5f * (1.f - y * y);
   return 1.f;
 }
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == ADB_ACT_RELU) return fmaxf(v, 0.f);
   if (act == ADB_ACT_TANH) return tanhf(v);
   if (act == ADB_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (act == ADB_ACT_SIGMOID2) return 2.f / (1.f + __expf(-v)) - 1.f;
   return v;
 }
 

@@ -571,6 +571,20 @@ def forward_light(t, m, x):
     return t.image_head(m.output_conv[1], f, x, IMG_BLEND, ACT_SIGMOID, alpha=m.skip_alpha)
 
 
+def forward_low_unet(t, m, x):
+    """LowIntensityDehazeModel.forward (non-default Light variant), low_intensity.py:96-115."""
+    f0 = t.conv_block(m.init_conv, [t.stem(x, 3, 1, 16)], stem_kp=16)
+    f = t.conv_block(m.down1[0], [f0])
+    f = t.res_block(m.down1[1], f)
+    for rb in m.bottleneck:
+        f = t.res_block(rb, f)
+    up = t.convT_bn_act(m.up1[0], m.up1[1], ACT_RELU, [f])
+    r = t.conv_block(m.output_conv[0], [up, f0])
+    r = t.conv_block(m.output_conv[1], [r])
+    # clamp(x + (sigmoid(z) - 0.5) * 2): the head's activation is 2*sigmoid(z) - 1
+    return t.image_head(m.output_conv[2], r, x, IMG_RESIDUAL, _lib.ACT_SIGMOID2)
+
+
 def forward_unet(t, m, x, attn):
     """MediumIntensityDehazeModel.forward (medium_intensity.py:78-117) / HighIntensityDehazeModel.forward (high:92-138)."""
     guidance = None
@@ -695,6 +709,8 @@ class BranchTrainFn(torch.autograd.Function):
         tape = Tape(engine.train_cache)
         if engine.kind == "light":
             out = forward_light(tape, engine.model, x)
+        elif engine.kind == "low_unet":
+            out = forward_low_unet(tape, engine.model, x)
         elif engine.kind in ("unet", "unet_attn"):
             out = forward_unet(tape, engine.model, x, engine.kind == "unet_attn")
         else:

@@ -40,7 +40,8 @@ typedef enum {
 } adb_status;
 
 /* activation applied by the conv epilogue */
-enum { ADB_ACT_NONE = 0, ADB_ACT_RELU = 1, ADB_ACT_TANH = 2, ADB_ACT_SIGMOID = 3 };
+enum { ADB_ACT_NONE = 0, ADB_ACT_RELU = 1, ADB_ACT_TANH = 2, ADB_ACT_SIGMOID = 3,
+       ADB_ACT_SIGMOID2 = 4 /* 2*sigmoid(v) - 1 (LowIntensityDehazeModel's (out - 0.5)*2, low_intensity.py:113); adb_img_head_* only */ };
 
 /* convolution kinds (the geometry the implicit-GEMM producer walks) */
 enum {

@@ -138,7 +138,8 @@ def _train_case(name, n, h, w, seed=5):
     x = rand_image(n, h, w, seed).cuda()
     tgt = rand_image(n, h, w, seed + 1).cuda()
     sd = {k: v.detach().clone().float().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
-    fwd = {"low": oracle.light_forward, "medium": oracle.medium_forward, "high": oracle.complex_forward}[name]
+    fwd = {"low": oracle.light_forward, "medium": oracle.medium_forward, "high": oracle.complex_forward,
+           "low_unet": oracle.low_unet_forward}[name]
     names = [k for k, _ in m.named_parameters()]
 
     def grads_of(out):
@@ -159,7 +160,7 @@ def _train_case(name, n, h, w, seed=5):
     return m, out, loss, ref_out.detach(), sim_out.detach(), ref_loss, ref_grads, sim_grads, rm_before
 
 
-@pytest.mark.parametrize("name,n,h,w", [("low", 2, 32, 48), ("medium", 2, 64, 64), ("high", 2, 64, 64)])
+@pytest.mark.parametrize("name,n,h,w", [("low", 2, 32, 48), ("medium", 2, 64, 64), ("high", 2, 64, 64), ("low_unet", 2, 48, 64)])
 def test_branch_train_step_matches_oracle(name, n, h, w):
     from helpers import psnr
     m, out, loss, ref_out, sim_out, ref_loss, ref_grads, sim_grads, rm_before = _train_case(name, n, h, w)

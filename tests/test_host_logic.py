@@ -191,7 +191,7 @@ def test_no_cpu_fallback_and_train_mode_refused():
     from adam_dehaze_b200 import engine
     v = make_branch("corun").train()
     eng = v._branch_engine()
-    with pytest.raises(NotImplementedError, match="default branch models"):
+    with pytest.raises(NotImplementedError, match="default branch models"):   # corun / dual_branch: inference kernels only
         eng._forward_train(torch.rand(1, 3, 64, 64), None, None)
 
 
