@@ -89,6 +89,7 @@ SIGNATURES = {
     "adb_image_metrics": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "adb_avgpool2x2_bwd": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "adb_gather_cast": [_P, _P, _L, _P, _P],
+    "adb_upsample_bilinear_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],

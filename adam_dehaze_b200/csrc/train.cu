@@ -987,6 +987,54 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int* __r
   }
 }
 
+// backward of nn.UpsamplingBilinear2d(scale) (align_corners=True; medium_intensity.py:146,151, high_intensity.py:171,173)
+// as a gather: a source pixel collects from every destination pixel whose two-tap footprint touches it, with the weights
+// recomputed exactly as the forward computes them.  dy may be a channel slice of a wider map (pitch_dy, c_off).
+__global__ void upsample_bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int pitch_dy, int c_off, int n, int h, int w,
+                                             int c, int scale, __nv_bfloat16* __restrict__ dx) {
+  const int G = c / 8, ho = h * scale, wo = w * scale;
+  const float rh = ho > 1 ? (float)(h - 1) / (float)(ho - 1) : 0.f;
+  const float rw = wo > 1 ? (float)(w - 1) / (float)(wo - 1) : 0.f;
+  const long long total = (long long)n * h * w * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % G);
+    long long p = t / G;
+    const int xi = (int)(p % w); p /= w;
+    const int yi = (int)(p % h);
+    const int img = (int)(p / h);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    // destination rows whose source coordinate lies in (yi - 1, yi + 1)
+    const int yo_lo = rh > 0.f ? max(0, (int)floorf((float)(yi - 1) / rh)) : 0;
+    const int yo_hi = rh > 0.f ? min(ho - 1, (int)ceilf((float)(yi + 1) / rh)) : ho - 1;
+    const int xo_lo = rw > 0.f ? max(0, (int)floorf((float)(xi - 1) / rw)) : 0;
+    const int xo_hi = rw > 0.f ? min(wo - 1, (int)ceilf((float)(xi + 1) / rw)) : wo - 1;
+    for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+      const float sy = rh * (float)yo;
+      const int y0 = (int)sy;
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+      const float ly = sy - (float)y0;
+      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+        const float sx = rw * (float)xo;
+        const int x0 = (int)sx;
+        const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+        const float lx = sx - (float)x0;
+        const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (((size_t)img * ho + yo) * wo + xo) * pitch_dy + c_off + g * 8)), f);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(wgt, f[q], acc[q]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + (((size_t)img * h + yi) * w + xi) * c + g * 8) = pack8(acc);
+  }
+}
+
 __global__ void fill_int_kernel(int* p, long long n, int v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -1223,7 +1271,7 @@ int adb_image_affine(const float* x, int32_t n, int32_t h, int32_t w, const floa
 }
 
 int adb_maxpool_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad, void* y, void* stream) {
-  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && k >= 2 && k <= 3 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_fwd: bad arguments");
+  ADB_REQUIRE(x && y && n > 0 && c % 8 == 0 && k >= 2 && k <= 4 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_fwd: bad arguments");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   ADB_REQUIRE(ho > 0 && wo > 0, "adb_maxpool_fwd: empty output");
   maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
@@ -1234,7 +1282,7 @@ int adb_maxpool_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, i
 
 int adb_maxpool_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride,
                     int32_t pad, void* dx, void* stream) {
-  ADB_REQUIRE(dy && x && y && dx && n > 0 && c % 8 == 0 && k >= 2 && k <= 3 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_bwd: bad arguments");
+  ADB_REQUIRE(dy && x && y && dx && n > 0 && c % 8 == 0 && k >= 2 && k <= 4 && stride >= 1 && pad >= 0 && pad < k, "adb_maxpool_bwd: bad arguments");
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
       ADB_BF(dy), ADB_BF(x), ADB_BF(y), n, h, w, c, k, stride, pad, ho, wo, ADB_BFM(dx));
@@ -1311,6 +1359,15 @@ int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, i
 int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream) {
   ADB_REQUIRE(src && idx && out && n > 0, "adb_gather_cast: bad arguments");
   gather_cast_kernel<<<grid_for(n, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n, ADB_BFM(out));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_upsample_bilinear_bwd(const void* dy, int32_t pitch_dy, int32_t c_off, int32_t n, int32_t h, int32_t w, int32_t c, int32_t scale,
+                              void* dx, void* stream) {
+  ADB_REQUIRE(dy && dx && n > 0 && c % 8 == 0 && pitch_dy % 8 == 0 && c_off % 8 == 0 && scale >= 1 && scale <= 8, "adb_upsample_bilinear_bwd: bad arguments");
+  upsample_bilinear_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+      ADB_BF(dy), pitch_dy, c_off, n, h, w, c, scale, ADB_BFM(dx));
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

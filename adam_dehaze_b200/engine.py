@@ -253,9 +253,6 @@ class BranchEngine:
         name = type(self.model).__name__
         if index is not None or out is not None:
             raise NotImplementedError(f"{name}: routed buckets are an inference path; train() mode takes a plain batch")
-        if self.kind not in ("light", "unet", "unet_attn", "low_unet"):
-            raise NotImplementedError(f"{name}: training on the B200 path covers the default branch models (and the "
-                                      "LowIntensityDehazeModel variant); call .eval() for inference — there is no torch fallback")
         b, _, h, w = x.shape
         need, wmin = (1, 16) if self.kind == "light" else ((2, 32) if self.kind == "low_unet" else (4, 64))
         if h % need or w % need or w < wmin:

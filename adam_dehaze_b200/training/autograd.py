@@ -159,6 +159,30 @@ def _dgrad_spec_s1(w):
     return ConvSpec.from_conv(wd, stride=1, pad=w.shape[2] // 2)
 
 
+class _PaddedBN:
+    """A BatchNorm2d whose width is not a multiple of 16, seen through buffers padded to the conv's N (gamma = beta = 0 and
+    unit running variance in the padding, so padded channels normalise to exactly 0)."""
+
+    def __init__(self, bn, c):
+        self.bn, self.eps, self.momentum = bn, bn.eps, bn.momentum
+        co = bn.num_features
+        dev = bn.weight.device
+
+        def pad(t, fill):
+            out = torch.full((c,), fill, dtype=torch.float32, device=dev)
+            out[:co] = t.detach().float()
+            return out
+        self.weight, self.bias = pad(bn.weight, 0.0), pad(bn.bias, 0.0)
+        self.running_mean, self.running_var = pad(bn.running_mean, 0.0), pad(bn.running_var, 1.0)
+        self.num_batches_tracked = bn.num_batches_tracked
+
+    def write_back(self):
+        co = self.bn.num_features
+        with torch.no_grad():
+            self.bn.running_mean.copy_(self.running_mean[:co])
+            self.bn.running_var.copy_(self.running_var[:co])
+
+
 class Tape:
     def __init__(self, model_cache):
         self.back = []
@@ -215,17 +239,22 @@ class Tape:
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
         c = fspec.cout_pad
-        assert c == fspec.cout, "BatchNorm layers have channel counts that are multiples of 16"
-        y, mean, rstd = self._bn_forward(z, c, bn, act, None if residual is None else residual.t)
+        bnp = bn if c == fspec.cout else _PaddedBN(bn, c)     # e.g. 24 channels inside a 32-channel map: padded affine
+        y, mean, rstd = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t)
+        if bnp is not bn:
+            bnp.write_back()
         out = Node(y, c)
 
         def backward():
             dy = out.grad
             out.grad = None
-            g, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=residual is not None)
+            g, dz = self._bn_backward(dy, y, z, c, act, bnp, mean, rstd, keep_g=residual is not None)
+            if bnp is not bn:
+                co = fspec.cout
+                self.pg[bn.weight], self.pg[bn.bias] = self.pg.pop(bnp.weight)[:co].contiguous(), self.pg.pop(bnp.bias)[:co].contiguous()
             if residual is not None:
                 residual.accumulate(g)
-            self._conv_backward(conv, dz, c, srcs, stem_kp)
+            self._conv_backward(conv, dz, c, srcs, stem_kp, cz_true=None if c == fspec.cout else fspec.cout)
         self.back.append(backward)
         return out
 
@@ -457,6 +486,36 @@ class Tape:
             x.accumulate(dx)
         self.back.append(backward)
 
+    def upsample(self, x, scale):
+        """nn.UpsamplingBilinear2d(scale_factor=scale) (align_corners=True)."""
+        n, h, w, c = x.t.shape
+        y = ops.upsample_bilinear(x.t, scale)
+        out = Node(y, x.c)
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            dx = torch.empty_like(x.t)
+            _lib.call("adb_upsample_bilinear_bwd", _lib.ptr(dy), dy.shape[3], 0, n, h, w, c, scale, _lib.ptr(dx), _lib.current_stream())
+            x.accumulate(dx)
+        self.back.append(backward)
+        return out
+
+    def concat(self, nodes):
+        """torch.cat(..., dim=1) of more than two maps (COrunInspiredModel's three scales, medium_intensity.py:184)."""
+        y = torch.cat([nd.t[..., :nd.c] for nd in nodes], dim=3).contiguous()
+        out = Node(y, y.shape[3])
+
+        def backward():
+            dy = out.grad
+            out.grad = None
+            off = 0
+            for nd in nodes:
+                nd.accumulate(dy[..., off:off + nd.c].contiguous())
+                off += nd.c
+        self.back.append(backward)
+        return out
+
     def res_block(self, rb, x):
         t = self.conv_bn_act(rb.conv1.block[0], rb.conv1.block[1], ACT_RELU, [x])
         return self.conv_bn_act(rb.conv2.block[0], rb.conv2.block[1], ACT_RELU, [t], residual=x)
@@ -495,12 +554,16 @@ class Tape:
         self.back.append(backward)
         return out
 
-    def dot_head(self, conv1x1, src):
-        """nn.Conv2d(c, 1, 1) + Sigmoid -> fp32 [n,h,w] guidance map (detail_branch tail, high:87-89)."""
+    def dot_head(self, conv1x1, src, complement=False):
+        """nn.Conv2d(c, 1, 1) + Sigmoid -> fp32 [n,h,w] guidance map (detail_branch tail, high:87-89).
+        complement: returns 1 - sigmoid(.) = sigmoid(-.) (DualBranchAttentionModel's (1 - transmission), high:217-221)."""
         n, h, w, pitch = src.t.shape
         c = src.c
-        wv = conv1x1.weight.detach().float().reshape(-1).contiguous()
-        bv = conv1x1.bias.detach().float().reshape(-1).contiguous()
+        sign = -1.0 if complement else 1.0
+        cw = conv1x1.weight.numel()
+        wv = torch.zeros(c, dtype=torch.float32, device=src.t.device)
+        wv[:cw] = sign * conv1x1.weight.detach().float().reshape(-1)
+        bv = (sign * conv1x1.bias.detach().float()).reshape(-1).contiguous()
         g = torch.empty((n, h, w), dtype=torch.float32, device=src.t.device)
         _lib.call("adb_dot_head_fwd", _lib.ptr(src.t), pitch, c, _lib.ptr(wv), _lib.ptr(bv), n * h * w, _lib.ptr(g), _lib.current_stream())
         out = Node(g, 1)
@@ -512,8 +575,8 @@ class Tape:
             red = _f32(c + 1, g.device)
             _lib.call("adb_dot_head_bwd", _lib.ptr(dg), _lib.ptr(g), _lib.ptr(src.t), pitch, c, _lib.ptr(wv), n * h * w, _lib.ptr(dy),
                       pitch, _lib.ptr(red), _lib.current_stream())
-            self.pg[conv1x1.weight] = red[:c].view_as(conv1x1.weight)
-            self.pg[conv1x1.bias] = red[c:c + 1].view_as(conv1x1.bias)
+            self.pg[conv1x1.weight] = (sign * red[:cw]).view_as(conv1x1.weight)
+            self.pg[conv1x1.bias] = (sign * red[c:c + 1]).view_as(conv1x1.bias)
             src.accumulate(dy)
         self.back.append(backward)
         return out
@@ -583,6 +646,37 @@ def forward_low_unet(t, m, x):
     r = t.conv_block(m.output_conv[1], [r])
     # clamp(x + (sigmoid(z) - 0.5) * 2): the head's activation is 2*sigmoid(z) - 1
     return t.image_head(m.output_conv[2], r, x, IMG_RESIDUAL, _lib.ACT_SIGMOID2)
+
+
+def forward_corun(t, m, x):
+    """COrunInspiredModel.forward (non-default Medium variant), medium_intensity.py:170-190."""
+    f0 = t.conv_block(m.init_conv, [t.stem(x, 7, 3, 32)], stem_kp=32)
+    s1 = t.conv_block(m.scale1_conv, [f0])
+    s2 = t.upsample(t.conv_block(m.scale2_conv[1], [t.maxpool(f0, 2, 2, 0)]), 2)
+    s3 = t.upsample(t.conv_block(m.scale3_conv[1], [t.maxpool(f0, 4, 4, 0)]), 4)
+    g = t.conv_block(m.fusion_conv, [t.concat([s1, s2, s3])])
+    for rb in m.residual_blocks:
+        g = t.res_block(rb, g)
+    r = t.conv_block(m.output_conv[0], [g])
+    return t.image_head(m.output_conv[1], r, x, IMG_RESIDUAL, ACT_TANH)
+
+
+def forward_dual(t, m, x):
+    """DualBranchAttentionModel.forward (non-default Complex variant), high_intensity.py:203-223."""
+    gb, lb, tb, fc = m.global_branch, m.local_branch, m.transmission_branch, m.fusion_conv
+    g = t.conv_block(gb[0], [t.stem(x, 7, 3, 32)], stem_kp=32)
+    g = t.attention(gb[3], t.res_block(gb[2], t.maxpool(g, 2, 2, 0)))
+    g = t.attention(gb[6], t.res_block(gb[5], t.maxpool(g, 2, 2, 0)))
+    g = t.upsample(t.res_block(gb[7], g), 2)
+    g = t.upsample(t.res_block(gb[9], g), 2)
+    G = t.conv_block(gb[11], [g])
+    lf = t.conv_block(lb[0], [t.stem(x, 3, 1, 16)], stem_kp=16)
+    lf = t.res_block(lb[2], t.res_block(lb[1], lf))
+    L = t.conv_block(lb[3], [lf])
+    tr = t.conv_block(tb[1], [t.conv_block(tb[0], [G, L])])
+    one_minus_t = t.dot_head(tb[2], tr, complement=True)
+    r = t.conv_block(fc[0], [G, L])
+    return t.image_head(fc[1], r, x, IMG_GUIDED, ACT_TANH, guidance=one_minus_t)
 
 
 def forward_unet(t, m, x, attn):
@@ -711,6 +805,10 @@ class BranchTrainFn(torch.autograd.Function):
             out = forward_light(tape, engine.model, x)
         elif engine.kind == "low_unet":
             out = forward_low_unet(tape, engine.model, x)
+        elif engine.kind == "corun":
+            out = forward_corun(tape, engine.model, x)
+        elif engine.kind == "dual":
+            out = forward_dual(tape, engine.model, x)
         elif engine.kind in ("unet", "unet_attn"):
             out = forward_unet(tape, engine.model, x, engine.kind == "unet_attn")
         else:

@@ -630,7 +630,7 @@ def run_e2e(torch, dist, world, dev, step, hazy, args, B):
     """Public-API step from pinned host memory.  The batch streams through in chunks on three CUDA streams (H2D, compute,
     D2H) with two device buffers each way, so copies overlap the kernels; every byte of the batch crosses PCIe in both
     directions inside the timed region."""
-    chunk = min(B, 32)
+    chunk = min(B, 48)      # 16 images per branch per chunk = one full micro-batch each
     shape = (B,) + tuple(hazy.shape[1:])
     try:
         host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True)

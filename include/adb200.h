@@ -288,7 +288,7 @@ ADB_API int adb_blend3_bwd(const float* dout, const float* y0, const float* y1, 
 ADB_API int adb_image_affine(const float* x, int32_t n, int32_t h, int32_t w, const float* scale3_host, const float* shift3_host,
                              float* y, void* stream);           /* y = x*scale[c] + shift[c], NCHW fp32 (loss.py:63-67,104-105) */
 ADB_API int adb_maxpool_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride, int32_t pad,
-                            void* y, void* stream);             /* nn.MaxPool2d(k, stride, pad), NHWC bf16, k in {2,3} */
+                            void* y, void* stream);             /* nn.MaxPool2d(k, stride, pad), NHWC bf16, k in {2,3,4} */
 ADB_API int adb_maxpool_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k,
                             int32_t stride, int32_t pad, void* dx, void* stream);
 /* out[0] += mean((a-b)^2) (F.mse_loss, loss.py:81); da (nullable, bf16) = grad_scale * 2(a-b)/numel */
@@ -316,6 +316,10 @@ ADB_API int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int3
 /* Weight re-packing after an optimizer step: out[i] = bf16(src[idx[i]]), 0 where idx[i] < 0 (idx = the packing's
  * permutation of the fp32 parameter, derived once on the host side). */
 ADB_API int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream);
+
+/* backward of adb_upsample_bilinear (align_corners=True): dx[n,h,w,c] from dy[n, h*scale, w*scale, c_off : c_off+c] */
+ADB_API int adb_upsample_bilinear_bwd(const void* dy, int32_t pitch_dy, int32_t c_off, int32_t n, int32_t h, int32_t w,
+                                      int32_t c, int32_t scale, void* dx, void* stream);
 
 /* One Adam step on a flat fp32 tensor with torch.optim.Adam semantics (train_dehazing.py:33-37: weight_decay is L2
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */

@@ -182,17 +182,15 @@ def test_no_cpu_fallback_and_train_mode_refused():
     clf = make_classifier()
     with pytest.raises(RuntimeError, match="no CPU path"):
         clf(torch.rand(1, 3, 32, 32))
-    # train() mode has no CPU path either (the training kernels are CUDA only), and the non-default variants refuse
-    # train() mode instead of silently running torch ops
+    # train() mode has no CPU path either (the training kernels are CUDA only)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.train()(torch.rand(1, 3, 16, 16))
     with pytest.raises(RuntimeError, match="no CPU path"):
         clf.train()(torch.rand(1, 3, 32, 32))
     from adam_dehaze_b200 import engine
     v = make_branch("corun").train()
-    eng = v._branch_engine()
-    with pytest.raises(NotImplementedError, match="default branch models"):   # corun / dual_branch: inference kernels only
-        eng._forward_train(torch.rand(1, 3, 64, 64), None, None)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        v(torch.rand(1, 3, 64, 64))
 
 
 def test_wgrad_desc_struct_matches_header_field_order():
