@@ -41,6 +41,18 @@ class HardRouter(nn.Module):
             inten, masks, bidx, bcnt = ops.route(intensity=intensity.to(x.device))
         else:
             raise ValueError("HardRouter needs a classifier or an explicit intensity tensor")
+        if any(m.training for m in self.models.values()):
+            # train() mode (routing.py:55-61 under model.train()): each branch sees its own sub-batch (its BatchNorm statistics
+            # are the sub-batch's, as in the reference) and autograd must reach it, so the buckets are gathered / scattered
+            # with differentiable index ops; the bucket sizes are read on the host (one sync per batch, training only).
+            counts = bcnt.tolist()
+            for name, model in self.models.items():
+                k = _NAMES.index(name)
+                if counts[k] == 0:
+                    continue
+                idx = bidx[k, :counts[k]].long()
+                outputs = outputs.index_copy(0, idx, model(x.index_select(0, idx)))
+            return outputs, {"intensity": inten, "low_mask": masks[0], "medium_mask": masks[1], "high_mask": masks[2]}
         for name, model in self.models.items():
             k = _NAMES.index(name)
             model.forward_bucket(x, outputs, bidx[k], bcnt[k:k + 1], count=x.shape[0])

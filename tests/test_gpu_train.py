@@ -670,3 +670,23 @@ def test_gated_router_train_step():
     assert torch.allclose(info["gate_weights"], wts.detach(), atol=2e-3)
     for p, r in zip((g[0].weight, g[0].bias, g[3].weight, g[3].bias, g[5].weight, g[5].bias), ws):
         _close(p.grad, r.grad, 5e-2, 1e-7)
+
+
+def test_hard_router_train_mode():
+    """HardRouter under model.train(): every image goes through its own branch's sub-batch (batch-statistics BN over the
+    bucket), gradients reach exactly the branches that received images."""
+    from helpers import CONFIG, make_branch, rand_image
+    from adam_dehaze_b200.models.routing import create_router
+    branches = {k: make_branch(k) for k in ("low", "medium", "high")}
+    router = create_router(branches, None, CONFIG).cuda().train()
+    x, tgt = rand_image(5, 64, 64, 51).cuda(), rand_image(5, 64, 64, 52).cuda()
+    labels = torch.tensor([1, 0, 1, 1, 0], device="cuda")
+    out, info = router(x, intensity=labels)
+    assert torch.equal(info["intensity"], labels)
+    (out - tgt).abs().mean().backward()
+    assert all(p.grad is not None for p in branches["low"].parameters())
+    assert all(p.grad is not None for p in branches["medium"].parameters())
+    assert all(p.grad is None for p in branches["high"].parameters())          # no sample routed there
+    with torch.no_grad():
+        alone = branches["medium"](x[[0, 2, 3]].contiguous())                   # same sub-batch -> same batch statistics
+    assert (out[[0, 2, 3]] - alone).abs().max().item() <= 1e-6
