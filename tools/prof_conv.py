@@ -42,6 +42,10 @@ SHAPES = [
     ("cpx_192_3x3_resdst", "resdst", (192,), 192, 3, 4, 512, 1024),
     ("dense_1x1_512_128", "s1", (512,), 128, 1, 8, 128, 256),
     ("dense_3x3_128_32", "s1", (128,), 32, 3, 8, 128, 256),
+    # DenseNet conv1 with the consumer pre-activation fused into the operand: (c_in, buffer pitch)
+    ("dense_pre_224_128", "pre", (224, 256), 128, 1, 8, 256, 512),
+    ("dense_pre_480_128", "pre", (480, 512), 128, 1, 8, 128, 256),
+    ("dense_pre_992_128", "pre", (992, 1024), 128, 1, 8, 64, 128),
 ]
 
 
@@ -49,6 +53,24 @@ def run(shape, tune, reps):
     name, kind, cins, cout, k, n, h, w = shape
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
+    if kind == "pre":
+        cin, pitch = cins
+        buf = torch.randn((n, h, w, pitch), generator=g, device=dev).to(torch.bfloat16)
+        wt = torch.randn((cout, cin, 1, 1), generator=g, device=dev) / cin ** 0.5
+        spec = ops.ConvSpec.from_conv(wt, act=ops.ACT_RELU, pad=0)
+        pre = (torch.rand(cin, generator=g, device=dev) + 0.5, torch.randn(cin, generator=g, device=dev) * 0.1)
+        dst = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=dev)
+        kw = dict(c0=cin, pre=pre, dst=dst, tune=tune)
+        ops.conv2d(spec, buf, **kw)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ops.conv2d(spec, buf, **kw)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        return ms, 2.0 * n * h * w * cin * cout / (ms * 1e-3) / 1e12
     srcs = [torch.randn((n, h, w, c), generator=g, device=dev).to(torch.bfloat16) for c in cins]
     cin = sum(cins)
     kwargs = {}
