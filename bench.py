@@ -602,6 +602,8 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
     launches = sum(v["conv_launches"] for v in per_branch.values())
     roof = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None, "peak_source": src,
+            "traffic_ref": "per-launch dram bytes of representative conv shapes from ncu --set full: profiles/r1_conv_ncu_full.md, "
+                           "profiles/r1_dense_pre_ncu.md (DRAM traffic ~= algorithmic bytes: no re-reads)",
             "how": f"sum of true conv FLOPs / sum of CUDA-event durations over the {launches} conv launches of one pass of "
                    f"Light+Medium+Complex+HDEN on {nimg} images at {hazy.shape[2]}x{hazy.shape[3]} (equal-thirds mix weighting)",
             "flops_per_launch_avg": tot_fl * 1e12 * nimg / max(1, launches) / 2,
