@@ -52,6 +52,7 @@ class WgradDesc(C.Structure):
         ("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
         ("dw", C.c_void_p), ("layout", C.c_int32), ("stem_kw", C.c_int32), ("accumulate", C.c_int32),
+        ("mode", C.c_int32),
     ]
 
 

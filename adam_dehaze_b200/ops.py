@@ -224,7 +224,7 @@ def _wgrad_workspace(nbytes, device):
 
 
 def wgrad(small, large0, large1=None, *, kind=CONV_S1, kh=3, kw=3, pad=1, cs=None, cs_true=None, c0=None, c1=None, n=None,
-          out=None, layout=WG_OIHW, stem_kw=0, accumulate=False):
+          out=None, layout=WG_OIHW, stem_kw=0, accumulate=False, mode=0):
     """Weight gradient of one conv: out[m][c][r][s] (+)= sum small[.., m] * large[.. + tap, c]  (see adb_wgrad in adb200.h).
 
     small: NHWC bf16 [n, hs, ws, pitch]; large0/large1: NHWC bf16 [n, h, w, pitch] (concat sources).
@@ -240,7 +240,7 @@ def wgrad(small, large0, large1=None, *, kind=CONV_S1, kh=3, kw=3, pad=1, cs=Non
         d.act1, d.c1, d.c1_pitch = large1.data_ptr(), (c1 or large1.shape[3]), large1.shape[3]
     d.n, d.h_in, d.w_in = (nb if n is None else n), h, w
     d.kind, d.kh, d.kw, d.pad = kind, kh, kw, pad
-    d.layout, d.stem_kw, d.accumulate = layout, stem_kw, int(bool(accumulate))
+    d.layout, d.stem_kw, d.accumulate, d.mode = layout, stem_kw, int(bool(accumulate)), mode
     rows = d.cg_true or d.cg
     if out is None:
         shape = (rows, 3, kh, stem_kw) if layout == WG_STEM else (rows, d.c0 + d.c1, kh, kw)

@@ -224,6 +224,7 @@ typedef struct adb_wgrad_desc {
   int32_t kind, kh, kw, pad;                                         /* ADB_CONV_S1 ('same') or ADB_CONV_S2 (halving) */
   float* workspace; int64_t workspace_bytes;
   float* dw; int32_t layout; int32_t stem_kw; int32_t accumulate;    /* accumulate != 0: dw += result */
+  int32_t mode;   /* 0 = choose (tap-packed kernel when cg <= 64), 1 = channel-major kernel, 2 = tap-packed kernel */
 } adb_wgrad_desc;
 ADB_API int64_t adb_wgrad_workspace_bytes(const adb_wgrad_desc* desc);
 ADB_API int adb_wgrad(const adb_wgrad_desc* desc, void* stream);

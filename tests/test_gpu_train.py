@@ -61,6 +61,25 @@ def test_wgrad_s1(cin, cout, k, h, w, n):
     _close(got, ref, 2e-3, 1e-4)
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["channel_major", "tap_packed"])
+@pytest.mark.parametrize("cin,cout,k,h,w,n,kind", [
+    (64, 64, 3, 32, 64, 2, 0), (32, 32, 3, 20, 48, 2, 0), (128, 64, 3, 16, 40, 1, 0), (96, 48, 3, 24, 32, 2, 0),
+    (64, 16, 1, 16, 32, 2, 0), (64, 64, 4, 32, 64, 2, 1), (160, 32, 3, 8, 16, 3, 0), (64, 64, 3, 4, 16, 2, 0),
+    (96, 96, 3, 16, 48, 2, 0), (64, 128, 4, 32, 64, 1, 1), (96, 192, 4, 16, 32, 2, 1), (128, 256, 1, 16, 32, 1, 0), (48, 80, 3, 16, 32, 1, 0),
+])
+def test_wgrad_both_kernels(cin, cout, k, h, w, n, kind, mode):
+    """The channel-major kernel (M = dZ channels) and the tap-packed kernel (M = (tap, X channel) pairs, chosen when the
+    gradient has <= 64 channels) give the same weight gradient."""
+    ops = _ops()
+    stride = 2 if kind == 1 else 1
+    pad = 1 if k > 1 else 0
+    x, dz = _fm(n, cin, h, w, 14), _fm(n, cout, h // stride, w // stride, 15)
+    ref = _wgrad_ref(x, dz, k, stride, pad)
+    got = ops.wgrad(ops.nchw_to_nhwc(dz, cout), ops.nchw_to_nhwc(x, cin), kind=ops.CONV_S2 if kind == 1 else ops.CONV_S1,
+                    kh=k, kw=k, pad=pad, mode=mode)
+    _close(got, ref, 2e-3, 1e-4)
+
+
 def test_wgrad_concat_sources_and_true_rows():
     ops = _ops()
     n, h, w = 2, 16, 64

@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 channel-major kernel, 2 tap-packed kernel")
     args = ap.parse_args()
     print(f"{'shape':18s} {'ms':>8s} {'TFLOP/s':>9s}")
     for name, (n, h, w, ci, co, k, kind) in SHAPES.items():
@@ -34,7 +35,7 @@ def main():
         hs, ws = (h // 2, w // 2) if kind == ops.CONV_S2 else (h, w)
         dz = torch.randn((n, hs, ws, co), generator=g, device="cuda").to(torch.bfloat16)
         out = torch.empty((co, ci, k, k), dtype=torch.float32, device="cuda")
-        kw = dict(kind=kind, kh=k, kw=k, pad=1 if k > 1 else 0, out=out)
+        kw = dict(kind=kind, kh=k, kw=k, pad=1 if k > 1 else 0, out=out, mode=args.mode)
         ops.wgrad(dz, x, **kw)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
