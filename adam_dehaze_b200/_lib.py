@@ -71,6 +71,7 @@ SIGNATURES = {
     "adb_bn_train_stats": [_P, _L, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "adb_affine_act": [_P, _I, _L, _I, _P, _P, _P, _I, _I, _P, _I, _P],
     "adb_bn_bwd": [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P],
+    "adb_bn_relu_bwd": [_P, _I, _P, _I, _L, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P],
     "adb_add_bf16": [_P, _I, _P, _I, _L, _I, _P],
     "adb_img_head_fwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "adb_img_head_bwd": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -429,6 +429,7 @@ struct WgtK {
   int chunks0, chunks1, c0, c1, pitch0, pitch1;
   int halo_w, halo_h;
   int N, s_groups;                 // dZ channels per MMA (multiple of 16, <= 256) and the 64-channel boxes that hold them
+  int nparts;                      // dZ channel ranges of N each (> 1 when all taps x all dZ channels do not fit TMEM, e.g. 192)
   int s_bytes, l_bytes, stage_bytes, stages;
   int tmem_cols;
   uint32_t idesc;
@@ -452,9 +453,11 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
       reinterpret_cast<volatile uint32_t*>(base_ptr + (size_t)P.stages * P.stage_bytes + 8u * (2 * kWgMaxStages + 1));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // blockIdx.x = unit * splits + split ; unit = set * nchunks + chunk
+  // blockIdx.x = unit * splits + split ; unit = (set * nchunks + chunk) * nparts + part
   const int split = (int)(blockIdx.x % (unsigned)P.splits);
-  const int unit = (int)(blockIdx.x / (unsigned)P.splits);
+  int unit = (int)(blockIdx.x / (unsigned)P.splits);
+  const int n_base = (unit % P.nparts) * P.N;     // first dZ channel of this unit
+  unit /= P.nparts;
   const int nchunks = P.chunks0 + P.chunks1;
   const int chunk = unit % nchunks;
   const WgtSet S = P.sets[unit / nchunks];
@@ -498,7 +501,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         const uint32_t sbase = base + (uint32_t)slot * (uint32_t)P.stage_bytes;
         mbar_expect_tx(full_bar(slot), tx);
         for (int g = 0; g < P.s_groups; ++g)
-          tma_load_5d(sbase + (uint32_t)g * (128u * 128u), &tmS, full_bar(slot), g * 64, w0, 0, h0, img);
+          tma_load_5d(sbase + (uint32_t)g * (128u * 128u), &tmS, full_bar(slot), n_base + g * 64, w0, 0, h0, img);
         tma_load_5d(sbase + (uint32_t)P.s_bytes, tmL, full_bar(slot), S.c_mul * pitch + ch_base, w0 + S.dw0, S.p, h0 + S.dh0, img);
       }
       __syncwarp();
@@ -568,7 +571,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
       const bool row_ok = j < S.ntaps && ch_base + ci < c_src;
       const size_t kcol = row_ok ? (size_t)S.kidx[j] * ctot + k_src + ch_base + ci : 0;
       for (int c16 = 0; c16 < P.N / 16; ++c16) {
-        if (c16 * 16 >= P.cs) break;
+        if (n_base + c16 * 16 >= P.cs) break;
         float v[16];
         if (have) {
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * P.N + c16 * 16), v);
@@ -580,7 +583,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_consta
         if (row_ok) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const int co = c16 * 16 + k;
+            const int co = n_base + c16 * 16 + k;
             if (co < P.cs) slab[(size_t)co * P.ktot + kcol] = v[k];     // consecutive lanes = consecutive ci: coalesced
           }
         }
@@ -661,12 +664,20 @@ int wgt_plan(const adb_wgrad_desc* d, WgtPlan& pl, int sm_count, int max_smem) {
   P.chunks0 = (d->c0 + 63) / 64; P.chunks1 = (d->c1 + 63) / 64;
   int max_tiles = 1;
   for (int i = 0; i < P.nsets; ++i) max_tiles = std::max(max_tiles, (P.sets[i].ntaps + 1) / 2);
+  // one accumulator per tap pair must fit TMEM (512 columns): gradients with an odd multiple of 64 channels that do not
+  // fit (192 x 5 tap pairs) are cut into equal dZ channel ranges, one unit each (X is then read once per range)
+  P.nparts = 1;
   P.N = (d->cg + 15) / 16 * 16;
+  if (d->cg % 128 != 0)
+    while (P.nparts < 4 && (P.N > 256 || max_tiles * P.N > 512)) {
+      ++P.nparts;
+      P.N = ((d->cg + P.nparts - 1) / P.nparts + 15) / 16 * 16;
+    }
   if (P.N > 256) return 1;
   P.s_groups = (P.N + 63) / 64;
   int cols = 32;
   while (cols < max_tiles * P.N) cols <<= 1;
-  if (cols > 512) return 1;                      // one accumulator per tap pair must fit TMEM
+  if (cols > 512) return 1;
   P.tmem_cols = cols;
   P.idesc = make_idesc_bf16(128u, (uint32_t)P.N) | (1u << 15) | (1u << 16);
   P.cs = d->cg;
@@ -681,7 +692,7 @@ int wgt_plan(const adb_wgrad_desc* d, WgtPlan& pl, int sm_count, int max_smem) {
   if (stages < 2) return 1;
   P.stages = stages;
   pl.smem = stages * P.stage_bytes + bar_bytes + 1024;
-  pl.units = P.nsets * (P.chunks0 + P.chunks1);
+  pl.units = P.nsets * (P.chunks0 + P.chunks1) * P.nparts;
   int splits = std::max(1, (2 * sm_count + pl.units - 1) / pl.units);
   splits = std::min(splits, std::max(1, P.total_tiles / 4));
   splits = std::min(splits, P.total_tiles);

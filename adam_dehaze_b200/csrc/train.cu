@@ -256,6 +256,90 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, int pit
   }
 }
 
+// ---- BatchNorm + ReLU backward without the activation output: the ReLU mask is recomputed from z with the forward's own
+// (scale, shift) — fmaf(z, scale, shift) > 0 is exactly the sign test affine_act_kernel's output passed — so neither y is
+// read nor g = dy*mask written and re-read: 2 + 3 streamed passes instead of 4 + 3 (no residual input: y = relu(BN(z))).
+__global__ void __launch_bounds__(kRedThreads)
+bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, const __nv_bfloat16* __restrict__ dy, int pitch_dy,
+                          long long pixels, int c, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ partials) {
+  const int G = c / 8;
+  const int PY = blockDim.x / G;
+  const int g = threadIdx.x % G, py = threadIdx.x / G;
+  extern __shared__ float sm[];   // [PY][2][c]
+  float a[8], b[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a[q] = 0.f; b[q] = 0.f; }
+  if (py < PY) {
+    float mu[8], rs[8], sc[8], sh[8];
+    load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); load8f(scale + g * 8, sc); load8f(shift + g * 8, sh);
+    const long long step = (long long)gridDim.x * PY;
+    for (long long p0 = (long long)blockIdx.x * PY + py; p0 < pixels; p0 += 4 * step) {
+      uint4 rd[4], rz[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * step;
+        const bool live = p < pixels;
+        rd[u] = live ? __ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)) : make_uint4(0, 0, 0, 0);
+        rz[u] = live ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float d[8], zz[8];
+        unpack8(rd[u], d); unpack8(rz[u], zz);     // dead pixels carry dy = 0: no contribution
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float gg = fmaf(zz[q], sc[q], sh[q]) > 0.f ? d[q] : 0.f;
+          a[q] += gg;
+          b[q] = fmaf(gg, (zz[q] - mu[q]) * rs[q], b[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sm[(py * 2 + 0) * c + g * 8 + q] = a[q];
+      sm[(py * 2 + 1) * c + g * 8 + q] = b[q];
+    }
+  }
+  __syncthreads();
+  float* mine = partials + (size_t)blockIdx.x * 2 * c;
+  for (int ch = threadIdx.x; ch < 2 * c; ch += blockDim.x) {
+    const int which = ch / c, cc = ch - which * c;
+    float s = 0.f;
+    for (int r = 0; r < PY; ++r) s += sm[(r * 2 + which) * c + cc];
+    mine[ch] = s;
+  }
+}
+
+// dz (+)= A*g + B*z + C with g = dy * [fmaf(z, scale, shift) > 0]; dz may alias dy.  ACC: dz is a gradient buffer that
+// already holds other consumers' contributions (DenseNet block buffer prefix) and is read-modified-written.
+template <bool ACC>
+__global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int pitch_dy, const __nv_bfloat16* __restrict__ z,
+                                         int pitch_z, long long pixels, int c, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, const float* __restrict__ coef,
+                                         __nv_bfloat16* dz, int pitch_dz) {
+  const int G = c / 8;
+  const long long total = pixels * G;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(t % G);
+    const long long p = t / G;
+    float gg[8], zz[8], A[8], B[8], Cc[8], sc[8], sh[8], prev[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + gi * 8)), gg);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + gi * 8)), zz);
+    if (ACC) unpack8(*reinterpret_cast<const uint4*>(dz + (size_t)p * pitch_dz + gi * 8), prev);
+    load8f(coef + gi * 8, A); load8f(coef + c + gi * 8, B); load8f(coef + 2 * c + gi * 8, Cc);
+    load8f(scale + gi * 8, sc); load8f(shift + gi * 8, sh);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float g = fmaf(zz[q], sc[q], sh[q]) > 0.f ? gg[q] : 0.f;
+      float v = fmaf(A[q], g, fmaf(B[q], zz[q], Cc[q]));
+      if (ACC) v = prev[q] + __bfloat162float(__float2bfloat16(v));     // same rounding as a separate dz map + adb_add_bf16
+      gg[q] = v;
+    }
+    *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + gi * 8) = pack8(gg);
+  }
+}
+
 __global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ a, int pitch_a, const __nv_bfloat16* __restrict__ b, int pitch_b,
                                 long long pixels, int c) {
   const int G = c / 8;
@@ -1115,6 +1199,32 @@ int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t pitch_y,
                                                                             ADB_BFM(dz), pitch_dz);
     ADB_CUDA_OK(cudaGetLastError());
   }
+  return ADB_OK;
+}
+
+int adb_bn_relu_bwd(const void* dy, int32_t pitch_dy, const void* z, int32_t pitch_z, int64_t pixels, int32_t c, const float* scale,
+                    const float* shift, const float* gamma, const float* mean, const float* rstd, float* scratch, void* dz,
+                    int32_t pitch_dz, int32_t dz_accumulate, float* dgamma, float* dbeta, int32_t accumulate, void* stream) {
+  ADB_REQUIRE(dy && z && scale && shift && gamma && mean && rstd && scratch && dz, "adb_bn_relu_bwd: null pointer");
+  ADB_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0 && c <= 2048 && pitch_dy % 8 == 0 && pitch_z % 8 == 0 && pitch_dz % 8 == 0,
+              "adb_bn_relu_bwd: bad shape (pixels=%lld c=%d)", (long long)pixels, c);
+  ADB_REQUIRE(!dz_accumulate || dz != dy, "adb_bn_relu_bwd: an accumulated dz cannot alias dy");
+  const int sms = sm_count();
+  const int nb = red_blocks(pixels, c, sms);
+  const int G = c / 8, PY = std::max(1, kRedThreads / G);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* coef = scratch + (size_t)nb * 2 * c;
+  bn_relu_bwd_reduce_kernel<<<nb, kRedThreads, (size_t)PY * 2 * c * sizeof(float), st>>>(ADB_BF(z), pitch_z, ADB_BF(dy), pitch_dy, pixels, c,
+                                                                                       scale, shift, mean, rstd, scratch);
+  ADB_CUDA_OK(cudaGetLastError());
+  bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
+  ADB_CUDA_OK(cudaGetLastError());
+  const int grid = grid_for(pixels * G, 256, sms, 16);
+  if (dz_accumulate)
+    bn_relu_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
+  else
+    bn_relu_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
+  ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }
 

@@ -205,16 +205,25 @@ class Tape:
         y = torch.empty_like(z)
         _lib.call("adb_affine_act", _lib.ptr(z), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift),
                   _lib.ptr(residual), 0 if residual is None else residual.shape[3], act, _lib.ptr(y), pitch, st)
-        return y, mean, rstd
+        return y, stats
 
-    def _bn_backward(self, dy, y, z, c, act, bn, mean, rstd, keep_g):
-        """Returns (g, dz).  g = dy*act'(y) (written over dy); dz aliases g unless keep_g."""
+    def _bn_backward(self, dy, y, z, c, act, bn, stats, keep_g):
+        """Returns (g, dz).  g = dy*act'(y) (written over dy); dz aliases g unless keep_g.  `stats` = the forward's
+        [mean | rstd | scale | shift].  ReLU layers whose g nobody else needs take adb_bn_relu_bwd (mask recomputed from z:
+        neither y is read nor g written) and return (None, dz)."""
         n, h, w, pitch = dy.shape
         px = n * h * w
         dev = dy.device
+        mean, rstd, scale, shift = stats[:c], stats[c:2 * c], stats[2 * c:3 * c], stats[3 * c:]
         scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
-        dz = torch.empty_like(dy) if keep_g else dy
         dgamma, dbeta = _f32(c, dev), _f32(c, dev)
+        if act == ACT_RELU and not keep_g:
+            _lib.call("adb_bn_relu_bwd", _lib.ptr(dy), pitch, _lib.ptr(z), z.shape[3], px, c, _lib.ptr(scale), _lib.ptr(shift),
+                      _lib.ptr(bn.weight), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scratch), _lib.ptr(dy), pitch, 0,
+                      _lib.ptr(dgamma), _lib.ptr(dbeta), 0, _lib.current_stream())
+            self.pg[bn.weight], self.pg[bn.bias] = dgamma, dbeta
+            return None, dy
+        dz = torch.empty_like(dy) if keep_g else dy
         _lib.call("adb_bn_bwd", _lib.ptr(dy), pitch, _lib.ptr(y), 0 if y is None else y.shape[3], _lib.ptr(z), z.shape[3], px, c, act,
                   _lib.ptr(bn.weight), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scratch), _lib.ptr(dy), pitch, _lib.ptr(dz), pitch,
                   _lib.ptr(dgamma), _lib.ptr(dbeta), 0, _lib.current_stream())
@@ -240,7 +249,7 @@ class Tape:
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
         c = fspec.cout_pad
         bnp = bn if c == fspec.cout else _PaddedBN(bn, c)     # e.g. 24 channels inside a 32-channel map: padded affine
-        y, mean, rstd = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t)
+        y, stats = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t)
         if bnp is not bn:
             bnp.write_back()
         out = Node(y, c)
@@ -248,7 +257,7 @@ class Tape:
         def backward():
             dy = out.grad
             out.grad = None
-            g, dz = self._bn_backward(dy, y, z, c, act, bnp, mean, rstd, keep_g=residual is not None)
+            g, dz = self._bn_backward(dy, y, z, c, act, bnp, stats, keep_g=residual is not None)
             if bnp is not bn:
                 co = fspec.cout
                 self.pg[bn.weight], self.pg[bn.bias] = self.pg.pop(bnp.weight)[:co].contiguous(), self.pg.pop(bnp.bias)[:co].contiguous()
@@ -293,13 +302,13 @@ class Tape:
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
         c = fspec.cout_pad
-        y, mean, rstd = self._bn_forward(z, c, bn, act)
+        y, stats = self._bn_forward(z, c, bn, act)
         out = Node(y, c)
 
         def backward():
             dy = out.grad
             out.grad = None
-            _, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=False)
+            _, dz = self._bn_backward(dy, y, z, c, act, bn, stats, keep_g=False)
             gw = torch.empty_like(w, dtype=torch.float32)
             off = 0
             for i, s in enumerate(srcs):
@@ -331,13 +340,13 @@ class Tape:
         cols = ops.stem_pack(x, 7, 3, 160, stride=2, kh=7)
         z = ops.conv2d(fspec, cols)
         c = fspec.cout_pad
-        y, mean, rstd = self._bn_forward(z, c, bn, act)
+        y, stats = self._bn_forward(z, c, bn, act)
         out = Node(y, c)
 
         def backward():
             dy = out.grad
             out.grad = None
-            _, dz = self._bn_backward(dy, y, z, c, act, bn, mean, rstd, keep_g=False)
+            _, dz = self._bn_backward(dy, y, z, c, act, bn, stats, keep_g=False)
             self.pg[w] = ops.wgrad(dz, cols, kh=1, kw=1, pad=0, cs=c, layout=WG_STEM, stem_kw=49).view_as(w)
         self.back.append(backward)
         return out
@@ -435,6 +444,12 @@ class Tape:
             out.grad = None
             sc2 = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
             dgamma, dbeta = _f32(c, dev), _f32(c, dev)
+            if act == ACT_RELU:     # mask from z, dz added straight into the buffer gradient's prefix
+                _lib.call("adb_bn_relu_bwd", _lib.ptr(dy), c, _lib.ptr(B.t), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift),
+                          _lib.ptr(bn.weight), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(sc2), _lib.ptr(B.g()), pitch, 1,
+                          _lib.ptr(dgamma), _lib.ptr(dbeta), 0, st)
+                self.pg[bn.weight], self.pg[bn.bias] = dgamma, dbeta
+                return
             _lib.call("adb_bn_bwd", _lib.ptr(dy), c, _lib.ptr(y), c, _lib.ptr(B.t), pitch, px, c, act, _lib.ptr(bn.weight), _lib.ptr(mean),
                       _lib.ptr(rstd), _lib.ptr(sc2), _lib.ptr(dy), c, _lib.ptr(dy), c, _lib.ptr(dgamma), _lib.ptr(dbeta), 0, st)
             self.pg[bn.weight], self.pg[bn.bias] = dgamma, dbeta

@@ -250,6 +250,15 @@ ADB_API int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t 
                        int64_t pixels, int32_t c, int32_t act, const float* gamma, const float* mean, const float* rstd,
                        float* scratch, void* g_out, int32_t pitch_g, void* dz, int32_t pitch_dz, float* dgamma, float* dbeta,
                        int32_t accumulate, void* stream);
+/* The same backward for y = relu(BN(z)) with no residual input, without touching y or materialising g: the ReLU mask is
+ * recomputed as fmaf(z, scale, shift) > 0 from the (scale, shift) adb_bn_train_stats returned for the forward (the exact
+ * expression adb_affine_act evaluated), so the pass structure is read(dy, z) + read(dy, z)/write(dz) instead of
+ * read(dy, y, z)/write(g) + read(g, z)/write(dz).  dz may alias dy; dz_accumulate != 0: dz += result (the gradient prefix
+ * of a DenseNet block buffer, replacing a separate adb_add_bf16 pass).  base_model.py:15-24, torchvision densenet norm/relu. */
+ADB_API int adb_bn_relu_bwd(const void* dy, int32_t pitch_dy, const void* z, int32_t pitch_z, int64_t pixels, int32_t c,
+                            const float* scale, const float* shift, const float* gamma, const float* mean, const float* rstd,
+                            float* scratch, void* dz, int32_t pitch_dz, int32_t dz_accumulate, float* dgamma, float* dbeta,
+                            int32_t accumulate, void* stream);
 /* a[..., :c] += b[..., :c] (gradient accumulation at a fan-out: skip connections, concat sources). */
 ADB_API int adb_add_bf16(void* a, int32_t pitch_a, const void* b, int32_t pitch_b, int64_t pixels, int32_t c, void* stream);
 

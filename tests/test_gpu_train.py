@@ -66,6 +66,7 @@ def test_wgrad_s1(cin, cout, k, h, w, n):
     (64, 64, 3, 32, 64, 2, 0), (32, 32, 3, 20, 48, 2, 0), (128, 64, 3, 16, 40, 1, 0), (96, 48, 3, 24, 32, 2, 0),
     (64, 16, 1, 16, 32, 2, 0), (64, 64, 4, 32, 64, 2, 1), (160, 32, 3, 8, 16, 3, 0), (64, 64, 3, 4, 16, 2, 0),
     (96, 96, 3, 16, 48, 2, 0), (64, 128, 4, 32, 64, 1, 1), (96, 192, 4, 16, 32, 2, 1), (128, 256, 1, 16, 32, 1, 0), (48, 80, 3, 16, 32, 1, 0),
+    (64, 192, 3, 16, 32, 2, 0), (96, 160, 3, 16, 32, 1, 0), (32, 224, 3, 8, 16, 1, 0), (192, 192, 3, 8, 32, 2, 0),
 ])
 def test_wgrad_both_kernels(cin, cout, k, h, w, n, kind, mode):
     """The channel-major kernel (M = dZ channels) and the tap-packed kernel (M = (tap, X channel) pairs, chosen when the
@@ -77,6 +78,23 @@ def test_wgrad_both_kernels(cin, cout, k, h, w, n, kind, mode):
     ref = _wgrad_ref(x, dz, k, stride, pad)
     got = ops.wgrad(ops.nchw_to_nhwc(dz, cout), ops.nchw_to_nhwc(x, cin), kind=ops.CONV_S2 if kind == 1 else ops.CONV_S1,
                     kh=k, kw=k, pad=pad, mode=mode)
+    _close(got, ref, 2e-3, 1e-4)
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["channel_major", "tap_packed"])
+def test_wgrad_gradient_is_trailing_slice_of_block_buffer(mode):
+    """DenseNet conv2: dZ is the LAST 32 channels of the block-buffer gradient (autograd.conv_plain).  The 64-channel TMA
+    box must stop at the slice (zero fill), neither reading the neighbour's values into the result nor running past the
+    end of the allocation; the buffer sits at the very end of its own cudaMalloc block here."""
+    ops = _ops()
+    n, h, w, pitch, co, ci = 2, 8, 16, 256, 32, 128
+    raw = torch.empty(n * h * w * pitch, dtype=torch.bfloat16, device="cuda")
+    buf = raw.view(n, h, w, pitch)
+    buf.copy_(torch.randn(n, h, w, pitch, generator=torch.Generator().manual_seed(31)).to(torch.bfloat16))
+    x = _fm(n, ci, h, w, 32)
+    dz = buf[..., pitch - co:]
+    ref = _wgrad_ref(x, dz.permute(0, 3, 1, 2).float(), 3, 1, 1)
+    got = ops.wgrad(dz, ops.nchw_to_nhwc(x, ci), kh=3, kw=3, pad=1, cs=co, mode=mode)
     _close(got, ref, 2e-3, 1e-4)
 
 
@@ -282,6 +300,25 @@ def test_bn_train_forward_backward(c, act, with_res):
     _close(dbeta, grads[2], 5e-3, 1e-3)
     if with_res:
         _close(_nchw(gt, c), grads[3], 1e-2, 1e-3)
+    if act == 1 and not with_res:
+        # the y-free path: ReLU mask recomputed from z with the forward's (scale, shift); in place over dy, then accumulated
+        # into a wider gradient buffer's prefix (DenseNet block buffer)
+        dg2, db2 = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        dy2 = dyt.clone()
+        _call("adb_bn_relu_bwd", _ptr(dy2), c, _ptr(zt), c, px, c, _ptr(scale), _ptr(shift), _ptr(gamma.detach()), _ptr(mean), _ptr(rstd),
+              _ptr(scratch), _ptr(dy2), c, 0, _ptr(dg2), _ptr(db2), 0)
+        _close(_nchw(dy2, c), grads[0], 1e-2, 1e-3)
+        _close(dg2, grads[1], 5e-3, 1e-3)
+        _close(db2, grads[2], 5e-3, 1e-3)
+        _close(dg2, dgamma, 1e-5, 1e-5)        # same sums as the y-based kernel up to fp32 summation order
+        _close(db2, dbeta, 1e-5, 1e-5)
+        pitch = c + 16
+        base = torch.randn(n, h, w, pitch, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16).cuda()
+        acc = base.clone()
+        _call("adb_bn_relu_bwd", _ptr(dyt), c, _ptr(zt), c, px, c, _ptr(scale), _ptr(shift), _ptr(gamma.detach()), _ptr(mean), _ptr(rstd),
+              _ptr(scratch), _ptr(acc), pitch, 1, _ptr(dg2), _ptr(db2), 0)
+        assert torch.equal(acc[..., :c], (base[..., :c].float() + dy2.float()).to(torch.bfloat16))
+        assert torch.equal(acc[..., c:], base[..., c:])
 
 
 @pytest.mark.parametrize("mode,act", [(0, 3), (1, 2), (2, 2)])

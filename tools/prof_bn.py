@@ -1,4 +1,4 @@
-"""Time adb_bn_train_stats / adb_affine_act / adb_bn_bwd on the shapes of the training step (CUDA events)."""
+"""Time adb_bn_train_stats / adb_affine_act / adb_bn_bwd / adb_bn_relu_bwd on the shapes of the training step (CUDA events)."""
 import os
 import sys
 
@@ -28,8 +28,12 @@ for (px, c, pitch) in [(4194304, 64, 64), (4194304, 96, 96), (1048576, 192, 192)
     def bwd():
         _lib.call("adb_bn_bwd", P(dy), c, P(y), c, P(z), pitch, px, c, 1, P(g), P(st4[0]), P(st4[1]), P(scratch), P(dy), c, P(dy), c, P(dg), P(db), 0,
                   _lib.current_stream())
+
+    def bwd_relu():
+        _lib.call("adb_bn_relu_bwd", P(dy), c, P(z), pitch, px, c, P(st4[2]), P(st4[3]), P(g), P(st4[0]), P(st4[1]), P(scratch), P(dy), c, 0,
+                  P(dg), P(db), 0, _lib.current_stream())
     out = []
-    for fn, passes in ((stats, 1), (act, 2), (bwd, 7)):
+    for fn, passes in ((stats, 1), (act, 2), (bwd, 7), (bwd_relu, 5)):
         fn()
         torch.cuda.synchronize()
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
