@@ -31,6 +31,19 @@ __device__ __forceinline__ void load8f(const float* p, float* f) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+// Streaming 16-byte loads as volatile asm: the front end otherwise sinks each load of an unrolled batch next to its first
+// use (seen in SASS: loads issued pair by pair between the compute of the previous pair), which leaves too few bytes in
+// flight per SM to cover HBM latency.  Volatile asm keeps the batch together in program order.
+__device__ __forceinline__ uint4 ld_stream_nc(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld_stream(const void* p) {      // coherent: the buffer may be written by this kernel (in place)
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 // derivative of the activation expressed through its OUTPUT y
 __device__ __forceinline__ float act_grad(float y, int act) {
   if (act == ADB_ACT_RELU) return y > 0.f ? 1.f : 0.f;
@@ -55,6 +68,31 @@ inline int grid_for(long long work_items, int threads, int sm_count, int waves =
 inline int sm_count() {
   adbh::DeviceInfo di;
   return adbh::device_info(&di) == ADB_OK ? di.sm_count : 148;
+}
+
+// ---- streaming elementwise kernels over [pixels][c] maps (16-byte items, G = c/8 items per pixel).
+// The grid's thread count S is a multiple of G, so a thread's items t, t+S, t+2S, ... all sit in the SAME channel group:
+// the per-channel parameters are loaded once, no division runs inside the loop, and kEwU items per stream are in flight
+// per thread before the first is consumed (2048 threads x 16 B per SM alone cannot cover HBM latency).
+constexpr int kEwU = 4;
+constexpr int kEwThreads = 256;
+inline int ew_grid(long long pixels, int G, int sms, int waves = 8) {
+  int a = G, b = kEwThreads;
+  while (b) { const int t = a % b; a = b; b = t; }          // a = gcd(G, 256)
+  const int m = G / a;                                       // grid must be a multiple of m
+  const long long items = pixels * G;
+  long long blocks = (items + (long long)kEwThreads * kEwU - 1) / ((long long)kEwThreads * kEwU);
+  blocks = std::min<long long>(blocks, (long long)sms * waves);
+  blocks = std::max<long long>(m, blocks / m * m);
+  return (int)blocks;
+}
+struct EwIt { long long p, dp; int g; };
+__device__ __forceinline__ EwIt ew_begin(int G) {
+  const long long S = (long long)gridDim.x * blockDim.x;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  EwIt it;
+  it.p = t / G; it.g = (int)(t - it.p * G); it.dp = S / G;
+  return it;
 }
 
 constexpr int kRedThreads = 256;
@@ -87,22 +125,24 @@ chan_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, const __nv_
       const long long p1 = p0 + step;
       const bool two = p1 < pixels;
       if (MODE == 0) {
-        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(z + (size_t)p0 * pitch_z + g * 8));
-        const uint4 r1 = two ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p1 * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
+        const uint4 r0 = ld_stream_nc(z + (size_t)p0 * pitch_z + g * 8);
+        const uint4 r1 = ld_stream_nc(z + (size_t)(two ? p1 : p0) * pitch_z + g * 8);
         float f[8], h[8];
         unpack8(r0, f); unpack8(r1, h);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { a[q] += f[q] + h[q]; b[q] = fmaf(f[q], f[q], fmaf(h[q], h[q], b[q])); }
+        for (int q = 0; q < 8; ++q) {
+          if (!two) h[q] = 0.f;
+          a[q] += f[q] + h[q]; b[q] = fmaf(f[q], f[q], fmaf(h[q], h[q], b[q]));
+        }
       } else {
         // both pixels' loads are issued before either is consumed
         uint4 rd[2], ry[2], rz[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const long long p = u ? p1 : p0;
-          const bool live = u == 0 || two;
-          rd[u] = live ? __ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)) : make_uint4(0, 0, 0, 0);
-          ry[u] = (live && y) ? __ldg(reinterpret_cast<const uint4*>(y + (size_t)p * pitch_y + g * 8)) : make_uint4(0, 0, 0, 0);
-          rz[u] = (live && z) ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
+          const long long p = (u && two) ? p1 : p0;      // a dead second slot re-reads p0 (never consumed): unconditional loads
+          rd[u] = ld_stream_nc(dy + (size_t)p * pitch_dy + g * 8);
+          ry[u] = y ? ld_stream_nc(y + (size_t)p * pitch_y + g * 8) : make_uint4(0, 0, 0, 0);
+          rz[u] = z ? ld_stream_nc(z + (size_t)p * pitch_z + g * 8) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -196,22 +236,39 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nbloc
 }
 
 // y = act(z*scale + shift (+ residual))
-__global__ void affine_act_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, long long pixels, int c,
-                                  const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const __nv_bfloat16* __restrict__ res, int pitch_r, int act, __nv_bfloat16* __restrict__ y,
-                                  int pitch_y) {
-  const int G = c / 8;
-  const long long total = pixels * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const long long p = t / G;
-    float f[8], sc[8], sh[8], r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)), f);
-    load8f(scale + g * 8, sc); load8f(shift + g * 8, sh);
-    if (res) unpack8(__ldg(reinterpret_cast<const uint4*>(res + (size_t)p * pitch_r + g * 8)), r);
+__global__ void __launch_bounds__(kEwThreads)
+affine_act_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, long long pixels, int c,
+                  const float* __restrict__ scale, const float* __restrict__ shift,
+                  const __nv_bfloat16* __restrict__ res, int pitch_r, int act, __nv_bfloat16* __restrict__ y,
+                  int pitch_y) {
+  const EwIt it = ew_begin(c / 8);
+  const int co = it.g * 8;
+  float sc[8], sh[8];
+  load8f(scale + co, sc); load8f(shift + co, sh);
+  for (long long p0 = it.p; p0 < pixels; p0 += kEwU * it.dp) {
+    uint4 rz[kEwU], rr[kEwU];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) f[q] = act_fwd(fmaf(f[q], sc[q], sh[q]) + (res ? r[q] : 0.f), act);
-    *reinterpret_cast<uint4*>(y + (size_t)p * pitch_y + g * 8) = pack8(f);
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp < pixels ? p0 + u * it.dp : p0;     // dead slots re-read p0: loads stay unconditional
+      rz[u] = ld_stream_nc(z + (size_t)p * pitch_z + co);
+      if (res) rr[u] = ld_stream_nc(res + (size_t)p * pitch_r + co);
+    }
+    // channel-outer / pixel-inner: the first output already needs every load of the batch, so none can be sunk below it
+    float f[kEwU][8], r[kEwU][8];
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      unpack8(rz[u], f[u]);
+      if (res) unpack8(rr[u], r[u]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int u = 0; u < kEwU; ++u) f[u][q] = act_fwd(fmaf(f[u][q], sc[q], sh[q]) + (res ? r[u][q] : 0.f), act);
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp;
+      if (p < pixels) *reinterpret_cast<uint4*>(y + (size_t)p * pitch_y + co) = pack8(f[u]);
+    }
   }
 }
 
@@ -238,21 +295,34 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
   coef[2 * c + ch] = (float)(-k * mg - B * (double)mean[ch]);
 }
 
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, int pitch_g, const __nv_bfloat16* __restrict__ z,
-                                    int pitch_z, long long pixels, int c, const float* __restrict__ coef,
-                                    __nv_bfloat16* __restrict__ dz, int pitch_dz) {
-  const int G = c / 8;
-  const long long total = pixels * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int gi = (int)(t % G);
-    const long long p = t / G;
-    float gg[8], zz[8], A[8], B[8], Cc[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(g + (size_t)p * pitch_g + gi * 8)), gg);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + gi * 8)), zz);
-    load8f(coef + gi * 8, A); load8f(coef + c + gi * 8, B); load8f(coef + 2 * c + gi * 8, Cc);
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* g, int pitch_g, const __nv_bfloat16* __restrict__ z,
+                    int pitch_z, long long pixels, int c, const float* __restrict__ coef,
+                    __nv_bfloat16* dz, int pitch_dz) {
+  const EwIt it = ew_begin(c / 8);
+  const int co = it.g * 8;
+  float A[8], B[8], Cc[8];
+  load8f(coef + co, A); load8f(coef + c + co, B); load8f(coef + 2 * c + co, Cc);
+  for (long long p0 = it.p; p0 < pixels; p0 += kEwU * it.dp) {
+    uint4 rg[kEwU], rz[kEwU];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) gg[q] = fmaf(A[q], gg[q], fmaf(B[q], zz[q], Cc[q]));
-    *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + gi * 8) = pack8(gg);
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp < pixels ? p0 + u * it.dp : p0;
+      rg[u] = ld_stream(g + (size_t)p * pitch_g + co);        // dz may alias g: plain loads
+      rz[u] = ld_stream_nc(z + (size_t)p * pitch_z + co);
+    }
+    float gg[kEwU][8], zz[kEwU][8];
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) { unpack8(rg[u], gg[u]); unpack8(rz[u], zz[u]); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int u = 0; u < kEwU; ++u) gg[u][q] = fmaf(A[q], gg[u][q], fmaf(B[q], zz[u][q], Cc[q]));
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp;
+      if (p < pixels) *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + co) = pack8(gg[u]);
+    }
   }
 }
 
@@ -278,21 +348,27 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, cons
       uint4 rd[4], rz[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long p = p0 + u * step;
-        const bool live = p < pixels;
-        rd[u] = live ? __ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + g * 8)) : make_uint4(0, 0, 0, 0);
-        rz[u] = live ? __ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + g * 8)) : make_uint4(0, 0, 0, 0);
+        // unconditional loads (a dead slot re-reads p0) so that all eight are issued before the first is consumed
+        const long long p = p0 + u * step < pixels ? p0 + u * step : p0;
+        rd[u] = ld_stream_nc(dy + (size_t)p * pitch_dy + g * 8);
+        rz[u] = ld_stream_nc(z + (size_t)p * pitch_z + g * 8);
       }
+      float d[4][8], zz[4][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float d[8], zz[8];
-        unpack8(rd[u], d); unpack8(rz[u], zz);     // dead pixels carry dy = 0: no contribution
+      for (int u = 0; u < 4; ++u) { unpack8(rd[u], d[u]); unpack8(rz[u], zz[u]); }
+      // channel-outer / pixel-inner: the first channel's sums need all eight loads, so none can be sunk below its use
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float gg = fmaf(zz[q], sc[q], sh[q]) > 0.f ? d[q] : 0.f;
-          a[q] += gg;
-          b[q] = fmaf(gg, (zz[q] - mu[q]) * rs[q], b[q]);
+      for (int q = 0; q < 8; ++q) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool live = p0 + u * step < pixels;
+          const float gg = (live && fmaf(zz[u][q], sc[q], sh[q]) > 0.f) ? d[u][q] : 0.f;
+          sa += gg;
+          sb = fmaf(gg, (zz[u][q] - mu[q]) * rs[q], sb);
         }
+        a[q] += sa;
+        b[q] += sb;
       }
     }
 #pragma unroll
@@ -314,45 +390,73 @@ bn_relu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, cons
 // dz (+)= A*g + B*z + C with g = dy * [fmaf(z, scale, shift) > 0]; dz may alias dy.  ACC: dz is a gradient buffer that
 // already holds other consumers' contributions (DenseNet block buffer prefix) and is read-modified-written.
 template <bool ACC>
-__global__ void bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int pitch_dy, const __nv_bfloat16* __restrict__ z,
-                                         int pitch_z, long long pixels, int c, const float* __restrict__ scale,
-                                         const float* __restrict__ shift, const float* __restrict__ coef,
-                                         __nv_bfloat16* dz, int pitch_dz) {
-  const int G = c / 8;
-  const long long total = pixels * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int gi = (int)(t % G);
-    const long long p = t / G;
-    float gg[8], zz[8], A[8], B[8], Cc[8], sc[8], sh[8], prev[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (size_t)p * pitch_dy + gi * 8)), gg);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(z + (size_t)p * pitch_z + gi * 8)), zz);
-    if (ACC) unpack8(*reinterpret_cast<const uint4*>(dz + (size_t)p * pitch_dz + gi * 8), prev);
-    load8f(coef + gi * 8, A); load8f(coef + c + gi * 8, B); load8f(coef + 2 * c + gi * 8, Cc);
-    load8f(scale + gi * 8, sc); load8f(shift + gi * 8, sh);
+__global__ void __launch_bounds__(kEwThreads)
+bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int pitch_dy, const __nv_bfloat16* __restrict__ z,
+                         int pitch_z, long long pixels, int c, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ coef,
+                         __nv_bfloat16* dz, int pitch_dz) {
+  const EwIt it = ew_begin(c / 8);
+  const int co = it.g * 8;
+  float A[8], B[8], Cc[8], sc[8], sh[8];
+  load8f(coef + co, A); load8f(coef + c + co, B); load8f(coef + 2 * c + co, Cc);
+  load8f(scale + co, sc); load8f(shift + co, sh);
+  for (long long p0 = it.p; p0 < pixels; p0 += kEwU * it.dp) {
+    uint4 rd[kEwU], rz[kEwU], rp[kEwU];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float g = fmaf(zz[q], sc[q], sh[q]) > 0.f ? gg[q] : 0.f;
-      float v = fmaf(A[q], g, fmaf(B[q], zz[q], Cc[q]));
-      if (ACC) v = prev[q] + __bfloat162float(__float2bfloat16(v));     // same rounding as a separate dz map + adb_add_bf16
-      gg[q] = v;
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp < pixels ? p0 + u * it.dp : p0;
+      rd[u] = ld_stream(dy + (size_t)p * pitch_dy + co);     // dz may alias dy: plain loads
+      rz[u] = ld_stream_nc(z + (size_t)p * pitch_z + co);
+      if (ACC) rp[u] = ld_stream(dz + (size_t)p * pitch_dz + co);
     }
-    *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + gi * 8) = pack8(gg);
+    float gg[kEwU][8], zz[kEwU][8], prev[kEwU][8];
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      unpack8(rd[u], gg[u]); unpack8(rz[u], zz[u]);
+      if (ACC) unpack8(rp[u], prev[u]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int u = 0; u < kEwU; ++u) {
+        const float g = fmaf(zz[u][q], sc[q], sh[q]) > 0.f ? gg[u][q] : 0.f;
+        float v = fmaf(A[q], g, fmaf(B[q], zz[u][q], Cc[q]));
+        if (ACC) v = prev[u][q] + __bfloat162float(__float2bfloat16(v));     // same rounding as a separate dz map + adb_add_bf16
+        gg[u][q] = v;
+      }
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp;
+      if (p < pixels) *reinterpret_cast<uint4*>(dz + (size_t)p * pitch_dz + co) = pack8(gg[u]);
+    }
   }
 }
 
-__global__ void add_bf16_kernel(__nv_bfloat16* __restrict__ a, int pitch_a, const __nv_bfloat16* __restrict__ b, int pitch_b,
-                                long long pixels, int c) {
-  const int G = c / 8;
-  const long long total = pixels * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const long long p = t / G;
-    float x[8], y[8];
-    unpack8(*reinterpret_cast<const uint4*>(a + (size_t)p * pitch_a + g * 8), x);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(b + (size_t)p * pitch_b + g * 8)), y);
+__global__ void __launch_bounds__(kEwThreads)
+add_bf16_kernel(__nv_bfloat16* __restrict__ a, int pitch_a, const __nv_bfloat16* __restrict__ b, int pitch_b,
+                long long pixels, int c) {
+  const EwIt it = ew_begin(c / 8);
+  const int co = it.g * 8;
+  for (long long p0 = it.p; p0 < pixels; p0 += kEwU * it.dp) {
+    uint4 ra[kEwU], rb[kEwU];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) x[q] += y[q];
-    *reinterpret_cast<uint4*>(a + (size_t)p * pitch_a + g * 8) = pack8(x);
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp < pixels ? p0 + u * it.dp : p0;
+      ra[u] = ld_stream(a + (size_t)p * pitch_a + co);
+      rb[u] = ld_stream_nc(b + (size_t)p * pitch_b + co);
+    }
+    float x[kEwU][8], y[kEwU][8];
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) { unpack8(ra[u], x[u]); unpack8(rb[u], y[u]); }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int u = 0; u < kEwU; ++u) x[u][q] += y[u][q];
+#pragma unroll
+    for (int u = 0; u < kEwU; ++u) {
+      const long long p = p0 + u * it.dp;
+      if (p < pixels) *reinterpret_cast<uint4*>(a + (size_t)p * pitch_a + co) = pack8(x[u]);
+    }
   }
 }
 
@@ -1171,7 +1275,7 @@ int adb_affine_act(const void* z, int32_t pitch_z, int64_t pixels, int32_t c, co
                    const void* residual, int32_t pitch_r, int32_t act, void* y, int32_t pitch_y, void* stream) {
   ADB_REQUIRE(z && scale && shift && y, "adb_affine_act: null pointer");
   ADB_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0 && pitch_z % 8 == 0 && pitch_y % 8 == 0 && (!residual || pitch_r % 8 == 0), "adb_affine_act: bad shape");
-  affine_act_kernel<<<grid_for(pixels * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(
+  affine_act_kernel<<<ew_grid(pixels, c / 8, sm_count()), kEwThreads, 0, (cudaStream_t)stream>>>(
       ADB_BF(z), pitch_z, pixels, c, scale, shift, ADB_BF(residual), pitch_r, act, ADB_BFM(y), pitch_y);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
@@ -1195,7 +1299,7 @@ int adb_bn_bwd(const void* dy, int32_t pitch_dy, const void* y, int32_t pitch_y,
   bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
   ADB_CUDA_OK(cudaGetLastError());
   if (gamma) {
-    bn_bwd_apply_kernel<<<grid_for(pixels * G, 256, sms, 16), 256, 0, st>>>(ADB_BF(g_out), pitch_g, ADB_BF(z), pitch_z, pixels, c, coef,
+    bn_bwd_apply_kernel<<<ew_grid(pixels, G, sms), kEwThreads, 0, st>>>(ADB_BF(g_out), pitch_g, ADB_BF(z), pitch_z, pixels, c, coef,
                                                                             ADB_BFM(dz), pitch_dz);
     ADB_CUDA_OK(cudaGetLastError());
   }
@@ -1219,18 +1323,18 @@ int adb_bn_relu_bwd(const void* dy, int32_t pitch_dy, const void* z, int32_t pit
   ADB_CUDA_OK(cudaGetLastError());
   bn_bwd_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, mean, rstd, accumulate, dgamma, dbeta, coef);
   ADB_CUDA_OK(cudaGetLastError());
-  const int grid = grid_for(pixels * G, 256, sms, 16);
+  const int grid = ew_grid(pixels, G, sms);
   if (dz_accumulate)
-    bn_relu_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
+    bn_relu_bwd_apply_kernel<true><<<grid, kEwThreads, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
   else
-    bn_relu_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
+    bn_relu_bwd_apply_kernel<false><<<grid, kEwThreads, 0, st>>>(ADB_BF(dy), pitch_dy, ADB_BF(z), pitch_z, pixels, c, scale, shift, coef, ADB_BFM(dz), pitch_dz);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }
 
 int adb_add_bf16(void* a, int32_t pitch_a, const void* b, int32_t pitch_b, int64_t pixels, int32_t c, void* stream) {
   ADB_REQUIRE(a && b && pixels > 0 && c % 8 == 0 && pitch_a % 8 == 0 && pitch_b % 8 == 0, "adb_add_bf16: bad arguments");
-  add_bf16_kernel<<<grid_for(pixels * (c / 8), 256, sm_count(), 16), 256, 0, (cudaStream_t)stream>>>(ADB_BFM(a), pitch_a, ADB_BF(b), pitch_b, pixels, c);
+  add_bf16_kernel<<<ew_grid(pixels, c / 8, sm_count()), kEwThreads, 0, (cudaStream_t)stream>>>(ADB_BFM(a), pitch_a, ADB_BF(b), pitch_b, pixels, c);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

@@ -40,6 +40,44 @@ def batch_psnr(pred, target):
     return (10.0 * torch.log10(1.0 / mse)).mean()
 
 
+class LossMeter:
+    """Every step's loss value on the host without draining the launch queue.
+
+    The reference reads `loss.item()` right after each step (train_dehazing.py:95), which makes the host wait for the whole
+    step before it can queue the next one.  Here step i's scalar is copied to pinned host memory on the stream (4 bytes
+    D2H per step) and read once step i+1 has been queued; `flush()` reads the last one.  `total` / `count` / `last` hold
+    the same numbers the reference accumulates, one step later."""
+
+    def __init__(self):
+        self._slots = [torch.empty(1, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self._events = [torch.cuda.Event() for _ in range(2)]
+        self._pending, self._next = None, 0
+        self.total, self.count, self.last = 0.0, 0, None
+
+    def _read(self, i):
+        self._events[i].synchronize()
+        self.last = float(self._slots[i][0])
+        self.total += self.last
+        self.count += 1
+
+    def push(self, loss):
+        """Queue the D2H copy of this step's loss; returns the previous step's value (None on the first call)."""
+        i = self._next
+        self._next ^= 1
+        self._slots[i].copy_(loss.detach().reshape(1), non_blocking=True)
+        self._events[i].record()
+        prev, self._pending = self._pending, i
+        if prev is not None:
+            self._read(prev)
+        return self.last
+
+    def flush(self):
+        if self._pending is not None:
+            self._read(self._pending)
+            self._pending = None
+        return self.last
+
+
 def train_step(model, criterion, optimizer, hazy, clear):
     """train_dehazing.py:86-96: zero_grad, forward, loss, backward, step.  Returns (loss tensor, components)."""
     optimizer.zero_grad()
@@ -69,15 +107,16 @@ def train_dehazing_model(model, intensity_level, config, train_loader=None, val_
     best, bad_epochs, history = 0.0, 0, []
     for epoch in range(epochs):
         model.train()
-        tot, nb = 0.0, 0
+        meter = LossMeter()
         for batch in train_loader:
             sel = batch["intensity"] == k
             if not bool(sel.any()):
                 continue
             hazy, clear = batch["hazy"][sel].to(device), batch["clear"][sel].to(device)
             loss, _ = train_step(model, criterion, optimizer, hazy, clear)
-            tot += loss.item()
-            nb += 1
+            meter.push(loss)
+        meter.flush()
+        tot, nb = meter.total, meter.count
         model.eval()
         vl, vp, vs = 0.0, 0.0, 0
         with torch.no_grad():
