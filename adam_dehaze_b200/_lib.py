@@ -177,5 +177,7 @@ def ptr(t):
 
 
 def current_stream():
+    """The calling thread's current CUDA stream as a raw handle.  Read through torch's C accessor: `torch.cuda.current_stream()`
+    builds a Stream object through several Python layers (~15 us, x ~1.4 k calls per training step)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))

@@ -253,21 +253,17 @@ affine_act_kernel(const __nv_bfloat16* __restrict__ z, int pitch_z, long long pi
       rz[u] = ld_stream_nc(z + (size_t)p * pitch_z + co);
       if (res) rr[u] = ld_stream_nc(res + (size_t)p * pitch_r + co);
     }
-    // channel-outer / pixel-inner: the first output already needs every load of the batch, so none can be sunk below it
-    float f[kEwU][8], r[kEwU][8];
-#pragma unroll
-    for (int u = 0; u < kEwU; ++u) {
-      unpack8(rz[u], f[u]);
-      if (res) unpack8(rr[u], r[u]);
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-      for (int u = 0; u < kEwU; ++u) f[u][q] = act_fwd(fmaf(f[u][q], sc[q], sh[q]) + (res ? r[u][q] : 0.f), act);
+    // (pixel-outer compute here: the channel-outer form costs 128 registers with the activation switch and measured slower)
 #pragma unroll
     for (int u = 0; u < kEwU; ++u) {
       const long long p = p0 + u * it.dp;
-      if (p < pixels) *reinterpret_cast<uint4*>(y + (size_t)p * pitch_y + co) = pack8(f[u]);
+      if (p >= pixels) break;
+      float f[8], r[8];
+      unpack8(rz[u], f);
+      if (res) unpack8(rr[u], r);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = act_fwd(fmaf(f[q], sc[q], sh[q]) + (res ? r[q] : 0.f), act);
+      *reinterpret_cast<uint4*>(y + (size_t)p * pitch_y + co) = pack8(f);
     }
   }
 }

@@ -383,6 +383,12 @@ def run_train(args):
 
     for _ in range(max(3, args.warmup)):
         step()
+    import gc
+    torch.cuda.synchronize()
+    m0 = torch.cuda.memory_allocated()
+    found = gc.collect()           # untimed: anything only the cycle collector can free would otherwise be released at a random later step
+    if rank == 0:
+        sys.stderr.write(f"gc.collect() after warm-up: {found} unreachable objects, {(m0 - torch.cuda.memory_allocated()) / 2**20:.0f} MiB of device memory released\n")
     if os.environ.get("ADB_PROFILE_HOST") and world == 1:    # developer aid: where the host time of a step goes
         import cProfile
         import pstats
@@ -407,8 +413,10 @@ def run_train(args):
     e0.record()
     torch.cuda.nvtx.range_push("adb_timed")
     torch.cuda.profiler.start()       # ncu --profile-from-start off: loss.backward() runs in autograd's worker thread,
+    host_t = [time.perf_counter()]
     for _ in range(args.steps):       # which a per-thread NVTX range would miss
         loss = step()
+        host_t.append(time.perf_counter())
     torch.cuda.profiler.stop()
     torch.cuda.nvtx.range_pop()
     e1.record()
@@ -440,10 +448,15 @@ def run_train(args):
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
+    host_e = [time.perf_counter()]
     for _ in range(args.steps):
         e2e_step()
+        host_e.append(time.perf_counter())
     e2e_loss = meter.flush()       # the last step's loss is on the host before the clock stops
     b.record()
+    if rank == 0:                  # host queueing time per step (stderr): a host-bound phase shows up here, not in the kernels
+        sys.stderr.write("host ms per step, resident loop: " + " ".join(f"{(y - x) * 1e3:.0f}" for x, y in zip(host_t, host_t[1:])) +
+                         " | e2e loop: " + " ".join(f"{(y - x) * 1e3:.0f}" for x, y in zip(host_e, host_e[1:])) + "\n")
     barrier()
     t2 = torch.tensor([a.elapsed_time(b)], device=dev)
     if world > 1:
