@@ -584,8 +584,10 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
             torch.cuda.synchronize()
             rec.clear()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.nvtx.range_push(f"adb_roofline_{name}")     # the launches tools/conv_traffic.py reads dram bytes for
             s.record(); m(x); e.record()
             torch.cuda.synchronize()
+            torch.cuda.nvtx.range_pop()
             conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
             flops = sum(f for _, _, f in rec)
             per_branch[name] = {"ms": s.elapsed_time(e) / nimg, "conv_ms": conv_ms / nimg, "conv_launches": len(rec),
@@ -619,9 +621,21 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
     if not peak:
         peak, src = 1400.0, "fallback sustained figure, B200_PROFILING.md (of fallback)"
     launches = sum(v["conv_launches"] for v in per_branch.values())
+    # dram bytes per conv launch of this same pass, from the committed ncu capture (tools/conv_traffic.py); same weighting
+    # and same 8-image pass as flops_per_launch_avg, so bytes/launch and FLOPs/launch describe the same average launch
+    traffic, traffic_src = None, "profiles/r1_conv_traffic.json missing"
+    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj.get("images") == nimg and tj.get("hden") == hden and (tj.get("height"), tj.get("width")) == (hazy.shape[2], hazy.shape[3]):
+            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+        else:
+            traffic_src = "profiles/r1_conv_traffic.json was captured on a different pass shape"
     roof = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": src,
-            "traffic_ref": "per-launch dram bytes of representative conv shapes from ncu --set full: profiles/r1_conv_ncu_full.md, "
+            "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+            "peak_source": src,
+            "traffic_ref": "ncu --set full captures of representative conv shapes: profiles/r1_conv_ncu_full.md, "
                            "profiles/r1_dense_pre_ncu.md (DRAM traffic ~= algorithmic bytes: no re-reads)",
             "how": f"sum of true conv FLOPs / sum of CUDA-event durations over the {launches} conv launches of one pass of "
                    f"Light+Medium+Complex+HDEN on {nimg} images at {hazy.shape[2]}x{hazy.shape[3]} (equal-thirds mix weighting)",
