@@ -98,7 +98,9 @@ __device__ __forceinline__ EwIt ew_begin(int G) {
 constexpr int kRedThreads = 256;
 inline int red_blocks(long long pixels, int c, int sms) {
   const int G = c / 8, PY = std::max(1, kRedThreads / G);
-  return (int)std::max<long long>(1, std::min<long long>((pixels + PY * 8 - 1) / (PY * 8), (long long)sms * 8));
+  // <= 4 blocks per SM: the streaming kernels hold 2-4 blocks of 256 threads per SM anyway, and the finalize kernels'
+  // fold (a handful of CTAs walking every block's partials) costs time proportional to the block count
+  return (int)std::max<long long>(1, std::min<long long>((pixels + PY * 8 - 1) / (PY * 8), (long long)sms * 4));
 }
 
 // ------------------------------------------------------------------ per-channel reductions over a map
@@ -187,8 +189,19 @@ __device__ __forceinline__ void fold_partials8(const float* __restrict__ partial
   const int ch = ch0 + chl;
   double a = 0.0, b = 0.0;
   if (ch < c) {
-#pragma unroll 4
-    for (int k = lane; k < nblocks; k += kFoldLanes) {
+    // eight blocks' partials are loaded before any is added (the loads are independent; the fp64 adds stay in block order)
+    int k = lane;
+    for (; k + 7 * kFoldLanes < nblocks; k += 8 * kFoldLanes) {
+      float va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        va[u] = __ldg(partials + (size_t)(k + u * kFoldLanes) * 2 * c + ch);
+        vb[u] = __ldg(partials + (size_t)(k + u * kFoldLanes) * 2 * c + c + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+    }
+    for (; k < nblocks; k += kFoldLanes) {
       a += (double)partials[(size_t)k * 2 * c + ch];
       b += (double)partials[(size_t)k * 2 * c + c + ch];
     }
