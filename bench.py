@@ -214,8 +214,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line (NCCL prints its version there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs (its version line at any level >= VERSION) off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     torch.set_grad_enabled(False)
@@ -336,8 +335,7 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs (its version line at any level >= VERSION) off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     B = 16 if args.batch == 256 else args.batch
