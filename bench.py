@@ -42,6 +42,15 @@ CFG = {
 TFLOP_PER_IMAGE = {"low": 0.278, "medium": 3.591, "high": 8.059, "densenet121": 0.237, "resnet18": 0.152}
 
 
+
+def quiet_nccl_stdout():
+    """Keep stdout to the ONE JSON line under torchrun: NCCL writes its log (the "NCCL version ..." line at NCCL_DEBUG=VERSION
+    or above) to stdout unless NCCL_DEBUG_FILE names a file — and it honours NCCL_DEBUG_FILE only above the VERSION level."""
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,7 +223,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs (its version line at any level >= VERSION) off stdout: ONE JSON line
+        quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     torch.set_grad_enabled(False)
@@ -335,7 +344,7 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL logs (its version line at any level >= VERSION) off stdout: ONE JSON line
+        quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
     B = 16 if args.batch == 256 else args.batch

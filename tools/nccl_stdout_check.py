@@ -1,7 +1,10 @@
 """stdout must stay clean when NCCL initialises at NCCL_DEBUG=VERSION (bench.py prints ONE JSON line): world-size-1 NCCL group."""
 import os
+import sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 os.environ["NCCL_DEBUG"] = "VERSION"
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+from bench import quiet_nccl_stdout
+quiet_nccl_stdout()
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 os.environ.setdefault("MASTER_PORT", "29533")
 import torch
