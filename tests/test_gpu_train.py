@@ -746,3 +746,17 @@ def test_hard_router_train_mode():
     with torch.no_grad():
         alone = branches["medium"](x[[0, 2, 3]].contiguous())                   # same sub-batch -> same batch statistics
     assert (out[[0, 2, 3]] - alone).abs().max().item() <= 1e-6
+
+
+def test_loss_meter_reads_every_step_one_step_late():
+    """training.train_dehazing.LossMeter: step i's loss reaches the host when step i+1 is pushed (or at flush), through
+    pinned memory — the numbers the reference accumulates with loss.item() (train_dehazing.py:95), without a per-step sync."""
+    from adam_dehaze_b200.training.train_dehazing import LossMeter
+    m = LossMeter()
+    vals = [0.5, 1.25, 2.0, 4.0]
+    seen = []
+    for v in vals:
+        seen.append(m.push(torch.tensor(v, device="cuda") * 1.0))
+    assert seen == [None, 0.5, 1.25, 2.0]
+    assert m.flush() == 4.0 and m.count == 4 and abs(m.total - sum(vals)) < 1e-6
+    assert m.flush() == 4.0 and m.count == 4        # idempotent

@@ -374,3 +374,56 @@ def test_weight_repack_index_maps():
         for (packed, idx), sp in zip(maps, fresh):
             got = src[(idx.long() + 1)].to(torch.bfloat16).view(sp.w_packed.shape)
             assert packed.shape == sp.w_packed.shape and torch.equal(got, sp.w_packed)
+
+
+def test_roofline_traffic_json_follows_from_the_committed_ncu_capture():
+    """bench.py's roofline.traffic is read from profiles/r1_conv_traffic.json; that file must be exactly what
+    tools/conv_traffic.py computes from the committed ncu csv of the roofline pass (no hand-edited number)."""
+    import json
+    import subprocess
+    csv_path = os.path.join(ROOT, "profiles", "r1m", "ncu_conv_traffic.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "conv_traffic.py"), csv_path], capture_output=True, text=True, check=True)
+    got = json.loads(out.stdout)
+    want = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")))
+    assert got["launches"] == want["launches"] == 179
+    assert abs(got["dram_bytes_per_launch_avg"] - want["dram_bytes_per_launch_avg"]) <= 1e-6 * want["dram_bytes_per_launch_avg"]
+    assert set(got["per_model"]) == {"low", "medium", "high", "densenet121"}
+    assert got["per_model"]["densenet121"]["launches"] == 120 and got["per_model"]["high"]["launches"] == 26
+
+
+def test_tape_sweep_leaves_no_reference_cycle():
+    """After the reverse sweep the tape holds neither closures nor gradients: everything a step allocated is released by
+    reference count, in a fixed order (a leftover tape<->closure cycle made the caching allocator's state differ from step
+    to step and stalled steps in cudaMalloc — profiles/r1_train_summary.md)."""
+    import gc
+    import weakref
+    from adam_dehaze_b200.training.autograd import Tape
+
+    class Probe:
+        pass
+    order = []
+    t = Tape(None)
+    probes = [Probe() for _ in range(3)]
+    refs = [weakref.ref(p) for p in probes]
+    alive_at_run = []
+    for i, p in enumerate(probes):
+        def fn(i=i, p=p, t=t):
+            order.append(i)
+            alive_at_run.append([r() is not None for r in refs])
+            t.pg[i] = i
+        t.back.append(fn)
+    t.head_backward = lambda dout, t=t: order.append("head")
+    del probes, p, fn
+    gc.disable()
+    try:
+        pg = t.backward(None)
+        assert order == ["head", 2, 1, 0] and pg == {0: 0, 1: 1, 2: 2}
+        # a closure (and what it captured) is gone as soon as it has run: when closure 0 runs, probes 2 and 1 are already dead
+        assert alive_at_run[-1] == [True, False, False]
+        assert all(r() is None for r in refs)
+        assert t.back == [] and t.head_backward is None and t.pg == {}
+        wt = weakref.ref(t)
+        del t
+        assert wt() is None          # freed by reference count alone (the cycle collector is off)
+    finally:
+        gc.enable()
