@@ -193,3 +193,38 @@ def test_blocks_standalone():
     out_r, out_a = rb(xr).cpu(), ab(xa).cpu()
     assert (out_r - g["res_out"]).abs().max().item() <= 2e-2 * g["res_out"].abs().max().item()
     assert (out_a - g["attn_out"]).abs().max().item() <= 2e-2 * g["attn_out"].abs().max().item()
+
+
+def test_detection_handoff_normalises_the_dehazed_batch_in_one_launch():
+    """IntegratedDetectionSystem (reference detection.py:95-127): the detector receives, per image, (dehazed - mean) / std
+    with the ImageNet constants; (detections, dehazed) come back.  fp32 tolerance 1e-6 (x*(1/s) - m/s vs (x - m)/s)."""
+    import torch.nn as nn
+    from adam_dehaze_b200.models import detection as det
+
+    class Dehazer(nn.Module):
+        def forward(self, x):
+            return x * 0.5 + 0.25, {"intensity": None}
+
+    class Detector(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.zeros(1))
+            self.seen = None
+
+        def forward(self, images, targets=None):
+            self.seen = images
+            return [{"boxes": torch.zeros(0, 4), "n": i} for i in range(len(images))]
+
+    x = torch.rand(3, 3, 40, 72, generator=torch.Generator().manual_seed(3)).cuda()
+    system = det.create_integrated_system(Dehazer(), Detector()).cuda()
+    results, dehazed = system(x)
+    torch.cuda.synchronize()
+    mean = torch.tensor(det.IMAGENET_MEAN, device="cuda").view(3, 1, 1)
+    std = torch.tensor(det.IMAGENET_STD, device="cuda").view(3, 1, 1)
+    assert torch.equal(dehazed, x * 0.5 + 0.25) and len(results) == 3
+    seen = system.detection_model.seen
+    assert isinstance(seen, list) and len(seen) == 3 and all(t.shape == (3, 40, 72) for t in seen)
+    for i in range(3):
+        assert (seen[i] - (dehazed[i] - mean) / std).abs().max().item() <= 1e-6
+    results2, _ = system(list(x.unbind(0)))          # the detection loader hands over a list of images
+    assert len(results2) == 3

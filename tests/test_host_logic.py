@@ -427,3 +427,20 @@ def test_tape_sweep_leaves_no_reference_cycle():
         assert wt() is None          # freed by reference count alone (the cycle collector is off)
     finally:
         gc.enable()
+
+
+def test_detection_handoff_factories_and_errors():
+    """models/detection.py drop-in surface (reference detection.py:7-139): unknown detector names raise ValueError, the
+    integrated system freezes the detector's parameters, and the hand-off has no CPU path."""
+    import torch.nn as nn
+    from adam_dehaze_b200.models import detection as det
+    with pytest.raises(ValueError, match="Unsupported detection model"):
+        det.DetectionModel(model_name="yolo")
+    with pytest.raises(ValueError):
+        det.create_detection_model({"detection": {"model": "nope", "pretrained": False}})
+    detector = nn.Linear(2, 2)
+    system = det.create_integrated_system(nn.Identity(), detector)
+    assert isinstance(system, det.IntegratedDetectionSystem)
+    assert all(not p.requires_grad for p in system.detection_model.parameters())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        det.normalize_for_detection(torch.rand(1, 3, 8, 8))
