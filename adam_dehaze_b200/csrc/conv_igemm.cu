@@ -721,6 +721,9 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   // to four times the barrier round trips per MMA).  Use 64-channel boxes anyway and issue only the K steps that hold real
   // channels in each source's last chunk; whatever the box fetches beyond them (zero fill, or a neighbour's channels) is
   // never read by an MMA.  Not for the space-to-depth view, whose channel axis interleaves the two column phases.
+  // 32-channel sources keep their 32-channel boxes: a half-empty 64-channel box was tried (to give the Light branch's A
+  // operand 128-byte rows) and measured slower — 0.319 vs 0.279 ms on light_32_3x3, the doubled halo slot also no longer
+  // fits shared memory at 1024x2048 (profiles/r1m/prof_conv_ragged32.txt).
   const bool ragged = Ck < 64 && d->kind != ADB_CONV_S2 && !(d->tune_flags & 128) &&
                       (d->c0 >= 48 || d->c1 >= 48);
   if (ragged) Ck = 64;
@@ -972,13 +975,16 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
 }
 
 // 5-D view {C, W, P, H, N} of an NHWC bf16 buffer; s2d = space-to-depth (stride-2 read / sub-pixel write) view.
-int make_act_tmap(CUtensorMap* m, const void* base, int pitch, int n, int h, int w, bool s2d, int box_c, int box_w,
+// c_dim = the channel extent a box may touch (plain view only): an input map's own channel count, so that a ragged
+// 64-channel box over a narrower source — a channel slice of a wider buffer included — is zero-filled past it instead of
+// reading a neighbour's channels or running past the end of the allocation; the pitch for an output map.
+int make_act_tmap(CUtensorMap* m, const void* base, int c_dim, int pitch, int n, int h, int w, bool s2d, int box_c, int box_w,
                   int box_h, int span) {
   uint64_t dims[5], strides[4];
   uint32_t box[5] = {(uint32_t)box_c, (uint32_t)box_w, 1u, (uint32_t)box_h, 1u};
   const uint64_t px = (uint64_t)pitch * 2;
   if (!s2d) {
-    dims[0] = pitch; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
+    dims[0] = c_dim; dims[1] = w; dims[2] = 1; dims[3] = h; dims[4] = n;
     strides[0] = px; strides[1] = px * w; strides[2] = px * w; strides[3] = px * w * h;
   } else {
     dims[0] = 2 * (uint64_t)pitch; dims[1] = w / 2; dims[2] = 2; dims[3] = h / 2; dims[4] = n;
@@ -1016,10 +1022,10 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
 
   alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
   const bool s2d_in = d->kind == ADB_CONV_S2;
-  st = make_act_tmap(&tmA0, d->src0, d->c0_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
+  st = make_act_tmap(&tmA0, d->src0, d->c0, d->c0_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
   if (st != ADB_OK) return st;
   if (d->src1) {
-    st = make_act_tmap(&tmA1, d->src1, d->c1_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
+    st = make_act_tmap(&tmA1, d->src1, d->c1, d->c1_pitch, d->n, d->h_in, d->w_in, s2d_in, P.Ck, box_w, box_h, P.row_bytes);
     if (st != ADB_OK) return st;
   } else {
     tmA1 = tmA0;
@@ -1034,7 +1040,7 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   if (d->epi == ADB_EPI_FEATURE) {
     // one store box per epilogue warp: its 32 tile rows = 32 pixels of one image row, or 32/TW whole rows of a narrow tile
     const int qw = std::min(P.TW, 32), qh = 32 / qw;
-    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->n, out_h, out_w, d->kind == ADB_CONVT_4X4S2, P.Cs, qw, qh, P.Cs * 2);
+    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->dst_pitch, d->n, out_h, out_w, d->kind == ADB_CONVT_4X4S2, P.Cs, qw, qh, P.Cs * 2);
     if (st != ADB_OK) return st;
   } else {
     tmOut = tmA0;

@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--ab-flags", type=int, default=None, help="time each shape with default tuning and with these tune flags (e.g. 128 = no ragged 64-channel boxes)")
     args = ap.parse_args()
     peak = 1414.7
     try:
@@ -131,6 +132,8 @@ def main():
     except Exception:
         pass
     tunes = [None]
+    if args.ab_flags is not None:
+        tunes = [None, {"flags": args.ab_flags}]
     if args.sweep:
         tunes = [{"flags": 32}, {"flags": 16}, {"flags": 16, "mt": 1}, {"flags": 16, "mt": 2}, {"flags": 32, "mt": 1}, {"flags": 32, "mt": 2}]
     for shape in SHAPES:
