@@ -57,6 +57,45 @@ class FlatAdam:
     def param_groups(self):
         return [{"params": self.params, "lr": self.lr}]
 
+    def state_dict(self):
+        """torch.optim.Adam's layout ({'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}), so the
+        'optimizer_state_dict' entry of a checkpoint (train_dehazing.py:196-203) is interchangeable with the reference's."""
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FlatAdam.load_state_dict: expected one parameter group over the same parameters")
+        g = groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        steps = set()
+        with torch.no_grad():
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                st = sd["state"].get(i, sd["state"].get(str(i)))
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"FlatAdam.load_state_dict: state {i} has shape {tuple(st['exp_avg'].shape)}, parameter {tuple(p.shape)}")
+                n = p.numel()
+                self.exp_avg[o:o + n].view(p.shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + n].view(p.shape).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("FlatAdam.load_state_dict: per-parameter step counts differ (one fused step per iteration is assumed)")
+        self.step_count = steps.pop() if steps else 0
+
     def zero_grad(self, set_to_none=True):
         for p in self.params:
             p.grad = None

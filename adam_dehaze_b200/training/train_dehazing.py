@@ -88,7 +88,8 @@ def train_step(model, criterion, optimizer, hazy, clear):
     return loss, parts
 
 
-def train_dehazing_model(model, intensity_level, config, train_loader=None, val_loader=None, epochs=30, criterion=None):
+def train_dehazing_model(model, intensity_level, config, train_loader=None, val_loader=None, epochs=30, criterion=None,
+                         resume=False):
     device = torch.device(config["device"])
     if device.type != "cuda":
         raise RuntimeError("train_dehazing_model: this build trains on B200 (sm_100a) only — config['device'] must be cuda")
@@ -105,7 +106,18 @@ def train_dehazing_model(model, intensity_level, config, train_loader=None, val_
     os.makedirs(ck_dir, exist_ok=True)
     k = _LEVEL[intensity_level]
     best, bad_epochs, history = 0.0, 0, []
-    for epoch in range(epochs):
+    first_epoch = 0
+    last_path = os.path.join(ck_dir, "last_checkpoint.pth")
+    if resume and os.path.exists(last_path):
+        # main.py:50 parses --resume but the reference never acts on it; here the last epoch's model,
+        # Adam moments / step count / learning rate and the plateau scheduler's history are restored and training continues
+        ck = torch.load(last_path, map_location=device)
+        model.load_state_dict(ck["model_state_dict"])
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+        best, bad_epochs, history = ck["best_val_psnr"], ck["bad_epochs"], list(ck["val_loss_history"])
+        first_epoch = ck["epoch"] + 1
+        print(f"Resumed {intensity_level} from {last_path} at epoch {first_epoch + 1}")
+    for epoch in range(first_epoch, epochs):
         model.train()
         meter = LossMeter()
         for batch in train_loader:
@@ -143,9 +155,11 @@ def train_dehazing_model(model, intensity_level, config, train_loader=None, val_
         print(f"Epoch {epoch + 1}/{epochs}:\n  Train Loss: {tot / max(1, nb):.4f}\n  Val Loss: {vl:.4f}, Val PSNR: {vp:.2f}")
         if vp > best or epoch == 0:
             best = vp
-            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
-                        "optimizer_state_dict": {"step": optimizer.step_count, "lr": optimizer.lr},
+            torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
                         "val_psnr": vp, "val_ssim": None, "val_loss": vl}, os.path.join(ck_dir, "best_model.pth"))
+        torch.save({"epoch": epoch, "model_state_dict": model.state_dict(), "optimizer_state_dict": optimizer.state_dict(),
+                    "val_psnr": vp, "val_ssim": None, "val_loss": vl, "best_val_psnr": best, "bad_epochs": bad_epochs,
+                    "val_loss_history": history}, last_path)
     best_ck = torch.load(os.path.join(ck_dir, "best_model.pth"), map_location="cpu")
     model.load_state_dict(best_ck["model_state_dict"])
     return model

@@ -171,7 +171,7 @@ def main():
         val = synthetic_loader(1, bs, args.size[0], args.size[1], device, seed=config["seed"] + 1)
         for level, mk in makers.items():
             print(f"Training {level} intensity dehazing model...")
-            train_dehazing_model(mk(config), level, config, train_loader=train, val_loader=val, epochs=args.epochs)
+            train_dehazing_model(mk(config), level, config, train_loader=train, val_loader=val, epochs=args.epochs, resume=args.resume)
     else:
         raise NotImplementedError(f"--mode {args.mode} is outside the B200 hot path (SURVEY.md §2: out of scope)")
 

@@ -760,3 +760,39 @@ def test_loss_meter_reads_every_step_one_step_late():
     assert seen == [None, 0.5, 1.25, 2.0]
     assert m.flush() == 4.0 and m.count == 4 and abs(m.total - sum(vals)) < 1e-6
     assert m.flush() == 4.0 and m.count == 4        # idempotent
+
+
+def test_train_driver_resume_continues_the_same_run(tmp_path):
+    """train_dehazing_model(..., resume=True) (main.py --resume, which the reference parses and ignores): two epochs run in one go
+    and one epoch + a resumed second epoch end with the same parameters, Adam step count and checkpoint keys
+    (train_dehazing.py:196-203)."""
+    import copy
+    import os
+    from helpers import CONFIG, make_branch
+    from adam_dehaze_b200.training.loss import DehazingLoss
+    from adam_dehaze_b200.training.train_dehazing import synthetic_loader, train_dehazing_model
+
+    def run(ck_dir, schedule):
+        cfg = copy.deepcopy(CONFIG)
+        cfg["device"] = "cuda:0"
+        cfg["dehazing"]["low"]["learning_rate"] = 1e-3
+        cfg["dehazing"]["checkpoint_dir"] = str(ck_dir)
+        train = synthetic_loader(2, 6, 32, 32, "cuda:0", seed=5)
+        val = synthetic_loader(1, 6, 32, 32, "cuda:0", seed=6)
+        model = None
+        for epochs, resume in schedule:
+            model = make_branch("low", seed=11)          # a fresh process would start from fresh weights too
+            model = train_dehazing_model(model, "low", cfg, train_loader=train, val_loader=val, epochs=epochs,
+                                         criterion=DehazingLoss(1.0, 0.0, 0.0), resume=resume)
+        return torch.load(os.path.join(str(ck_dir), "low", "last_checkpoint.pth"), map_location="cpu")
+
+    a = run(tmp_path / "straight", [(2, False)])
+    b = run(tmp_path / "resumed", [(1, False), (2, True)])
+    assert a["epoch"] == b["epoch"] == 1
+    assert set(a) >= {"epoch", "model_state_dict", "optimizer_state_dict", "val_psnr", "val_ssim", "val_loss"}
+    for k in a["model_state_dict"]:
+        # (a resume that lost the Adam moments or the step count would move every weight by ~lr = 1e-3 on its first step)
+        assert torch.allclose(a["model_state_dict"][k].float(), b["model_state_dict"][k].float(), rtol=1e-3, atol=2e-5), k
+    sa, sb = a["optimizer_state_dict"]["state"], b["optimizer_state_dict"]["state"]
+    assert float(sa[0]["step"]) == float(sb[0]["step"]) > 0
+    assert torch.allclose(sa[0]["exp_avg"], sb[0]["exp_avg"], rtol=1e-3, atol=1e-7)

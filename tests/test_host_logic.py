@@ -444,3 +444,35 @@ def test_detection_handoff_factories_and_errors():
     assert all(not p.requires_grad for p in system.detection_model.parameters())
     with pytest.raises(RuntimeError, match="no CPU path"):
         det.normalize_for_detection(torch.rand(1, 3, 8, 8))
+
+
+def test_flat_adam_state_dict_is_interchangeable_with_torch_adam():
+    """FlatAdam.state_dict()/load_state_dict() use torch.optim.Adam's layout, so 'optimizer_state_dict' in a checkpoint
+    written by either side loads into the other (train_dehazing.py:196-203)."""
+    from adam_dehaze_b200.training.optim import FlatAdam
+    g = torch.Generator().manual_seed(9)
+    shapes = [(4, 3, 3, 3), (4,), (7, 5)]
+    ref_params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    ours_params = [torch.nn.Parameter(p.detach().clone()) for p in ref_params]
+    adam = torch.optim.Adam(ref_params, lr=3e-4, weight_decay=1e-4)
+    for _ in range(2):
+        for p in ref_params:
+            p.grad = torch.randn(p.shape, generator=g)
+        adam.step()
+    sd = adam.state_dict()
+    flat = FlatAdam(ours_params, lr=1.0)
+    assert flat.state_dict()["state"] == {}
+    flat.load_state_dict(sd)
+    assert flat.step_count == 2 and flat.lr == 3e-4 and flat.weight_decay == 1e-4 and tuple(flat.betas) == (0.9, 0.999)
+    for i, (p, o) in enumerate(zip(ours_params, flat.offsets)):
+        assert torch.equal(flat.exp_avg[o:o + p.numel()].view(p.shape), sd["state"][i]["exp_avg"])
+        assert torch.equal(flat.exp_avg_sq[o:o + p.numel()].view(p.shape), sd["state"][i]["exp_avg_sq"])
+    back = flat.state_dict()
+    adam2 = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ref_params], lr=1.0)
+    adam2.load_state_dict(back)
+    st2 = adam2.state_dict()
+    assert st2["param_groups"][0]["lr"] == 3e-4
+    for i in range(len(shapes)):
+        assert torch.equal(st2["state"][i]["exp_avg"], sd["state"][i]["exp_avg"]) and float(st2["state"][i]["step"]) == 2.0
+    with pytest.raises(ValueError):
+        FlatAdam([torch.nn.Parameter(torch.zeros(3))]).load_state_dict(sd)
