@@ -476,3 +476,14 @@ def test_flat_adam_state_dict_is_interchangeable_with_torch_adam():
         assert torch.equal(st2["state"][i]["exp_avg"], sd["state"][i]["exp_avg"]) and float(st2["state"][i]["step"]) == 2.0
     with pytest.raises(ValueError):
         FlatAdam([torch.nn.Parameter(torch.zeros(3))]).load_state_dict(sd)
+
+
+def test_integration_doc_names_every_exported_entry_point():
+    """INTEGRATION.md's entry-point table must account for every ADB_API symbol of include/adb200.h (names may be grouped as
+    `adb_x_fwd/bwd`)."""
+    hdr = open(os.path.join(ROOT, "include", "adb200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = sorted(set(re.findall(r"ADB_API[^;]*?\b(adb_\w+)\s*\(", hdr)))
+    missing = [s for s in declared
+               if s not in doc and s.replace("_fwd", "_fwd/bwd") not in doc and not (s.endswith("_bwd") and s[:-4] + "_fwd/bwd" in doc)]
+    assert not missing, missing
