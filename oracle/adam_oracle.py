@@ -378,6 +378,16 @@ def synth_hazy(n, h, w, betas=(0.03, 0.06, 0.09), seed=42, device="cpu"):
     return hazy.to(device), clear.to(device), labels.to(device)
 
 
+# --------------------------------------------------------------------------- detection hand-off (models/detection.py)
+def detection_normalize(dehazed):
+    """IntegratedDetectionSystem.forward, models/detection.py:109-121: per image, (img - mean[c]) / std[c] with the ImageNet
+    constants; returns the list of [3,H,W] tensors the detector receives.  Pinned by tests/golden/detection_handoff.pt
+    (oracle/make_golden_detection.py runs the unmodified reference class)."""
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dehazed.device).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=dehazed.device).view(3, 1, 1)
+    return [img.clone().sub(mean).div(std) for img in dehazed]
+
+
 # --------------------------------------------------------------------------- image-quality metrics (evaluation/metrics.py)
 def image_metrics(pred, target):
     """calculate_image_metrics, evaluation/metrics.py:13-36, for ONE image pair ([3,H,W] tensors in [0,1]).

@@ -228,3 +228,7 @@ def test_detection_handoff_normalises_the_dehazed_batch_in_one_launch():
         assert (seen[i] - (dehazed[i] - mean) / std).abs().max().item() <= 1e-6
     results2, _ = system(list(x.unbind(0)))          # the detection loader hands over a list of images
     assert len(results2) == 3
+    # the same batch through the UNMODIFIED reference class on CPU (tests/golden/detection_handoff.pt)
+    g = golden("detection_handoff.pt")
+    assert tuple(g["shape"]) == (3, 40, 72) and g["seed"] == 3
+    assert (torch.stack(seen).cpu() - g["normalized"]).abs().max().item() <= 1e-6

@@ -165,3 +165,15 @@ def test_train_mode_oracle_matches_reference(name):
             assert (got.flatten()[:8] - ref["head"]).abs().max().item() <= 2e-3 * max(ref["head"].abs().max().item(), scale / got.numel() ** 0.5) + 1e-9, k
         else:
             assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-9, k
+
+
+def test_detection_handoff_oracle_matches_reference():
+    """oracle.detection_normalize == what the unmodified IntegratedDetectionSystem hands its detector (detection.py:109-121)."""
+    g = golden("detection_handoff.pt")
+    n, h, w = g["shape"]
+    x = rand_image(n, h, w, g["seed"])
+    dehazed = x * 0.5 + 0.25
+    assert torch.equal(dehazed, g["dehazed"])
+    got = torch.stack(oracle.detection_normalize(dehazed))
+    assert torch.equal(got, g["normalized"])
+
