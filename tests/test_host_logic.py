@@ -487,3 +487,44 @@ def test_integration_doc_names_every_exported_entry_point():
     missing = [s for s in declared
                if s not in doc and s.replace("_fwd", "_fwd/bwd") not in doc and not (s.endswith("_bwd") and s[:-4] + "_fwd/bwd" in doc)]
     assert not missing, missing
+
+
+def test_bench_keeps_stdout_to_one_json_line_under_nccl(monkeypatch):
+    """bench.quiet_nccl_stdout: NCCL honours NCCL_DEBUG_FILE only above the VERSION level, and prints its version line to
+    stdout at VERSION — so VERSION is raised to WARN and the log file defaults to stderr; explicit settings are kept."""
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setenv("NCCL_DEBUG", "VERSION")
+    monkeypatch.delenv("NCCL_DEBUG_FILE", raising=False)
+    bench.quiet_nccl_stdout()
+    assert os.environ["NCCL_DEBUG"] == "WARN" and os.environ["NCCL_DEBUG_FILE"] == "/dev/stderr"
+    monkeypatch.setenv("NCCL_DEBUG", "INFO")
+    monkeypatch.setenv("NCCL_DEBUG_FILE", "/tmp/nccl.%h.%p.log")
+    bench.quiet_nccl_stdout()
+    assert os.environ["NCCL_DEBUG"] == "INFO" and os.environ["NCCL_DEBUG_FILE"] == "/tmp/nccl.%h.%p.log"
+    monkeypatch.delenv("NCCL_DEBUG", raising=False)
+    monkeypatch.delenv("NCCL_DEBUG_FILE", raising=False)
+    bench.quiet_nccl_stdout()
+    assert "NCCL_DEBUG" not in os.environ and os.environ["NCCL_DEBUG_FILE"] == "/dev/stderr"
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_lines():
+    """The `clocks` object of the bench line: median SM clock under load, max clock, throttle reasons, peak power."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+    s = bench.ClockSampler(0)
+    s.proc = Proc()
+    s.lines = ["1650, 1965, 980.5, Not Active, Not Active, Not Active, Active",
+               "1665, 1965, 990.1, Not Active, Not Active, Not Active, Active",
+               "1950, 1965, 400.0, Not Active, Not Active, Not Active, Not Active",
+               "garbage line", "N/A, 1965, 1.0, x, x, x, x"]
+    out = s.stop()
+    assert out["sm_mhz"] == 1665.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert out["power_w_max"] == 990.1 and out["samples"] == 3
