@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("tune_mt", C.c_int32), ("tune_stages", C.c_int32), ("tune_acc_stages", C.c_int32),
         ("tune_flags", C.c_int32),
         ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p),
+        ("w_fold", C.c_void_p),
     ]
 
 

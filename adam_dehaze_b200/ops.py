@@ -13,7 +13,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, 
                    EPI_IMAGE, IMG_BLEND, IMG_GUIDED, IMG_RESIDUAL, WG_OIHW, WG_STEM, ConvDesc, WgradDesc)
 
 __all__ = [
-    "pad16", "fold_bn", "pack_conv_weight", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
+    "pad16", "fold_bn", "pack_conv_weight", "pack_conv_weight_fold", "fold_eligible", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
     "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "maxpool_kxk", "upsample_bilinear", "head_mlp",
     "linear", "route", "blend3", "l1_mse", "cross_entropy", "wgrad",
 ]
@@ -80,6 +80,24 @@ def pack_conv_weight(w, cout_pad=None):
     return out.contiguous()
 
 
+def fold_eligible(co, kh, kw, stride, pad, cout_pad=None):
+    """3x3 stride-1 'same' convs whose three filter rows fit one MMA's N (3*cout_pad <= 256): the rolling-row kernel."""
+    cp = cout_pad or pad16(co)
+    return kh == 3 and kw == 3 and stride == 1 and pad == 1 and cp % 32 == 0 and 3 * cp <= 256
+
+
+def pack_conv_weight_fold(w, cout_pad=None):
+    """nn.Conv2d 3x3 weight [co, ci, 3, 3] -> bf16 [3 (s), 3*cout_pad, ci]: row (2 - r)*cout_pad + co of column tap s
+    (adb_conv_desc.w_fold, include/adb200.h) — filter row r lands in the N block of the output row it contributes to."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    cout_pad = cout_pad or pad16(co)
+    out = torch.zeros(3, 3, cout_pad, ci, dtype=pack_dtype(), device=w.device)      # [s][blk][co][ci]
+    p = w.detach().float().permute(3, 2, 0, 1)                                       # [s][r][co][ci]
+    out[:, :, :co] = p.flip(1).to(pack_dtype())
+    return out.reshape(3, 3 * cout_pad, ci).contiguous()
+
+
 def pack_convT_weight(wt, cout_pad=None):
     """nn.ConvTranspose2d(4, 2, 1) weight [ci, co, 4, 4] -> bf16 [4 phases, cout_pad, 4*ci] (include/adb200.h)."""
     ci, co, kh, kw = wt.shape
@@ -111,18 +129,20 @@ def pack_stem_weight(w, kp, cout_pad=None):
 class ConvSpec:
     """Packed parameters + geometry of one fused conv launch."""
 
-    def __init__(self, kind, kh, kw, pad, cout, w_packed, scale, shift, act):
+    def __init__(self, kind, kh, kw, pad, cout, w_packed, scale, shift, act, w_fold=None):
         self.kind, self.kh, self.kw, self.pad = kind, kh, kw, pad
         self.cout = cout
         self.cout_pad = scale.numel()
         self.w_packed, self.scale, self.shift, self.act = w_packed, scale, shift, act
+        self.w_fold = w_fold      # row-folded packing for the rolling-row kernel (eligible 3x3 convs only)
 
     @staticmethod
     def from_conv(weight, bias=None, bn=None, act=ACT_NONE, stride=1, pad=None):
         co, ci, kh, kw = weight.shape
         pad = kh // 2 if pad is None else pad
         scale, shift = fold_bn(co, bias, bn, device=weight.device)
-        return ConvSpec(CONV_S1 if stride == 1 else CONV_S2, kh, kw, pad, co, pack_conv_weight(weight), scale, shift, act)
+        fold = pack_conv_weight_fold(weight) if fold_eligible(co, kh, kw, stride, pad) else None
+        return ConvSpec(CONV_S1 if stride == 1 else CONV_S2, kh, kw, pad, co, pack_conv_weight(weight), scale, shift, act, fold)
 
     @staticmethod
     def from_convT(weight, bias=None, bn=None, act=ACT_NONE):
@@ -174,6 +194,8 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     d.n, d.h_in, d.w_in = n, h, w
     d.kind, d.kh, d.kw, d.pad = spec.kind, spec.kh, spec.kw, spec.pad
     d.w_packed, d.scale, d.shift = spec.w_packed.data_ptr(), spec.scale.data_ptr(), spec.shift.data_ptr()
+    if spec.w_fold is not None:
+        d.w_fold = spec.w_fold.data_ptr()
     d.cout, d.cout_pad, d.act, d.epi = spec.cout, spec.cout_pad, spec.act, epi
     ho, wo = _out_hw(spec, h, w)
     ret = None

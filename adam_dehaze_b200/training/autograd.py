@@ -93,6 +93,8 @@ def derive_index_maps(build, weight):
         ival = build(ramp)
     maps = [(sp.w_packed, (isp.w_packed.reshape(-1).to(torch.int32) - 1).contiguous())
             for sp, isp in zip(_flat_specs(val), _flat_specs(ival))]
+    maps += [(sp.w_fold, (isp.w_fold.reshape(-1).to(torch.int32) - 1).contiguous())
+             for sp, isp in zip(_flat_specs(val), _flat_specs(ival)) if sp.w_fold is not None]
     return val, maps
 
 

@@ -92,12 +92,19 @@ typedef struct adb_conv_desc {
   const int32_t* n_dev; int32_t n_start;
   /* --- tuning (0 = choose automatically) */
   int32_t tune_mt, tune_stages, tune_acc_stages;
-  int32_t tune_flags;   /* bit 0: one TMA box per tap (no halo re-use); bit 1: descriptor base-offset experiment */
+  int32_t tune_flags;   /* bit 0: one TMA box per tap (no halo re-use); bit 1: descriptor base-offset experiment;
+                           bit 9 (512): never take the rolling-row kernel (w_fold ignored) */
   /* --- optional pre-activation fused into the input operand (1x1 stride-1 FEATURE convs): the conv sees
          relu(x[..., c]*pre_scale[c] + pre_shift[c]) over the c0+c1 input channels.  DenseNet's norm1/relu1 ahead of conv1
          and the transition norm/relu (torchvision densenet121 called as the north_star's HDEN) — every dense layer applies
          a different affine to the same concatenated map, so it cannot ride in the producer's epilogue. */
   const float* pre_scale; const float* pre_shift;
+  /* --- optional row-folded packing of a 3x3 stride-1 filter (NULL = not provided).  When it is given and the launch is
+         eligible (FEATURE epilogue, cout_pad a multiple of 32 with 3*cout_pad <= 256, w_in >= 128, filter fits shared
+         memory) adb_conv2d runs the rolling-row kernel (csrc/conv_roll.cu): the three filter rows ride in the MMA's N
+         dimension and accumulate into adjacent output rows held in TMEM.
+         w_fold[s][(2 - r)*cout_pad + co][c] = W[co][c][r][s], bf16 [3][3*cout_pad][c0+c1]. */
+  const void* w_fold;
 } adb_conv_desc;
 
 /* Weight packing order expected in w_packed (done on the host side by adam_dehaze_b200/engine.py):

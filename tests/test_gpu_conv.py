@@ -295,3 +295,63 @@ def test_conv1x1_fused_pre_activation(cin, pitch, cout, h, w, n):
     spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU, pad=0)
     got = ops.conv2d(spec, ops.nchw_to_nhwc(x, pitch), c0=cin, pre=(s.contiguous(), b.contiguous()))
     _close(ops.nhwc_to_nchw(got, cout), ref)
+
+
+# ---------------------------------------------------------------- rolling-row kernel (csrc/conv_roll.cu)
+ROLL_CASES = [
+    # (c0, c1, cout, n, h, w, residual, tune)
+    (32, 0, 32, 2, 40, 128, False, None),             # Light 32->32: 64-byte operand rows, ring of 16 wraps twice
+    (32, 0, 32, 1, 70, 256, True, None),              # + residual, two strips, two segments (SH = 64 then 6 rows)
+    (64, 0, 64, 2, 33, 128, True, None),              # Medium 64->64: ring of 8, odd height
+    (128, 0, 32, 2, 24, 128, False, None),            # DenseNet conv2: two 64-channel chunks
+    (64, 64, 64, 1, 20, 256, False, None),            # channel concat of two sources
+    (96, 0, 32, 1, 18, 192, False, None),             # ragged K chunk (96 = 64 + 32) and a ragged last strip (192 = 128 + 64)
+    (32, 0, 32, 3, 130, 136, True, {"mt": 2}),        # 16-row segments: many segment boundaries, 8-pixel last strip
+    (16, 0, 32, 1, 9, 128, False, None),              # 32-byte operand rows
+    (32, 0, 32, 1, 1, 128, False, None),              # a single image row
+    (64, 0, 64, 1, 2, 512, True, {"stages": 2}),
+    (32, 0, 32, 24, 64, 128, True, None),             # several segments per CTA: slot phases carry across segments
+]
+
+
+@pytest.mark.parametrize("c0,c1,cout,n,h,w,residual,tune", ROLL_CASES)
+def test_conv_roll(c0, c1, cout, n, h, w, residual, tune):
+    """3x3 convs with 3*cout <= 256 and W >= 128 take the rolling-row kernel; same tolerance as the tap-by-tap kernel, and
+    the two kernels agree with each other to bf16 output rounding."""
+    ops = _ops()
+    a = _rand_fm(n, c0, h, w, 40)
+    b = _rand_fm(n, c1, h, w, 41) if c1 else None
+    wt = _rand_w((cout, c0 + c1, 3, 3), 42, (c0 + c1) * 9)
+    bn = _bn(cout, 43)
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU)
+    assert spec.w_fold is not None
+    res = _rand_fm(n, cout, h, w, 44) if residual else None
+    kw = dict(residual=ops.nchw_to_nhwc(res) if residual else None)
+    an, bn_ = ops.nchw_to_nhwc(a), (ops.nchw_to_nhwc(b) if c1 else None)
+    y = ops.conv2d(spec, an, bn_, tune=tune, **kw)
+    x = torch.cat([a, b], 1) if c1 else a
+    ref = _bn_ref(F.conv2d(x, wt, padding=1), bn)
+    ref = F.relu(ref + res if residual else ref)
+    _close(ops.nhwc_to_nchw(y, cout), ref)
+    y_old = ops.conv2d(spec, an, bn_, tune={"flags": 512}, **kw)
+    _close(ops.nhwc_to_nchw(y, cout), ops.nhwc_to_nchw(y_old, cout), rel=8e-3, abs_=1e-3)
+
+
+def test_conv_roll_channel_slice_in_place_and_bucket_count():
+    """DenseNet use: the 3x3 conv stores its 32 channels into a slice of the block buffer; ResidualBlock use: dst == residual
+    (in place); routed buckets: images beyond the live count stay untouched."""
+    ops = _ops()
+    x = _rand_fm(3, 128, 16, 128, 45)
+    wt = _rand_w((32, 128, 3, 3), 46, 128 * 9)
+    dst = torch.zeros((3, 16, 128, 96), dtype=torch.bfloat16, device="cuda")
+    n_dev = torch.tensor([6], dtype=torch.int32, device="cuda")     # bucket of 6, this launch covers [4, 7): 2 live images
+    ops.conv2d(ops.ConvSpec.from_conv(wt), ops.nchw_to_nhwc(x), dst=dst, dst_c_off=32, n_dev=n_dev, n_start=4)
+    ref = F.conv2d(x, wt, padding=1)
+    _close(ops.nhwc_to_nchw(dst)[:2, 32:64], ref[:2])
+    assert dst[..., :32].float().abs().max().item() == 0.0 and dst[..., 64:].float().abs().max().item() == 0.0
+    assert dst[2].float().abs().max().item() == 0.0
+    f = _rand_fm(2, 32, 48, 256, 47)
+    w2 = _rand_w((32, 32, 3, 3), 48, 288)
+    fn = ops.nchw_to_nhwc(f)
+    ops.conv2d(ops.ConvSpec.from_conv(w2, act=ops.ACT_RELU), fn.clone(), dst=fn, residual=fn)
+    _close(ops.nhwc_to_nchw(fn), F.relu(F.conv2d(f, w2, padding=1) + f))

@@ -94,6 +94,34 @@ def test_pack_conv_s1_and_concat():
     assert y[..., 20:].abs().max() == 0
 
 
+def test_pack_conv_fold_rows_accumulate_into_adjacent_output_rows():
+    """The rolling-row kernel's algebra (csrc/conv_roll.cu): E_j[w,(blk,co)] = sum_{s,ci} X[j,w+s-1,ci] Wf[s][blk*cp+co][ci],
+    out[h] = E_{h-1}[blk 2] + E_h[blk 1] + E_{h+1}[blk 0], must reproduce F.conv2d(padding=1) with the packing of
+    ops.pack_conv_weight_fold."""
+    import torch.nn.functional as F
+    from adam_dehaze_b200 import ops
+    torch.manual_seed(0)
+    co, ci, h, w = 24, 16, 7, 10
+    wt = torch.randn(co, ci, 3, 3)
+    x = torch.randn(1, ci, h, w)
+    with ops.pack_as(torch.float32):
+        wf = ops.pack_conv_weight_fold(wt)            # [3][3*cp][ci]
+    cp = ops.pad16(co)
+    assert wf.shape == (3, 3 * cp, ci) and cp == 32
+    assert ops.fold_eligible(co, 3, 3, 1, 1) and not ops.fold_eligible(96, 3, 3, 1, 1) and not ops.fold_eligible(16, 3, 3, 1, 1)
+    xp = F.pad(x, (1, 1, 0, 0))[0].permute(1, 2, 0)    # [h][w+2][ci]
+    out = torch.zeros(h, w, cp)
+    for j in range(h):
+        e = sum(xp[j, s:s + w] @ wf[s].t() for s in range(3))       # [w][3*cp]
+        for blk in range(3):
+            hh = j - 1 + blk
+            if 0 <= hh < h:
+                out[hh] += e[:, blk * cp:(blk + 1) * cp]
+    ref = F.conv2d(x, wt, padding=1)[0].permute(1, 2, 0)
+    assert torch.allclose(out[..., :co], ref, atol=1e-4)
+    assert out[..., co:].abs().max() == 0
+
+
 @pytest.mark.parametrize("k,pad", [(4, 1), (3, 1), (1, 0)])
 def test_pack_conv_s2(k, pad):
     g = torch.Generator().manual_seed(1)
@@ -357,6 +385,7 @@ def test_weight_repack_index_maps():
     g = torch.Generator().manual_seed(4)
     cases = [
         (torch.randn(48, 32, 3, 3, generator=g), lambda wt: ConvSpec.from_conv(wt, pad=1)),
+        (torch.randn(32, 32, 3, 3, generator=g), lambda wt: ConvSpec.from_conv(wt, pad=1)),        # carries a w_fold packing too
         (torch.randn(3, 32, 3, 3, generator=g), lambda wt: ag._dgrad_spec_s1(wt)),
         (torch.randn(64, 96, 3, 3, generator=g), lambda wt: [(o, ag._dgrad_spec_s1(wt[:, o:o + 32])) for o in (0, 32, 64)]),
         (torch.randn(64, 32, 4, 4, generator=g), lambda wt: ConvSpec.from_convT(wt)),
@@ -369,11 +398,13 @@ def test_weight_repack_index_maps():
         val, maps = ag.derive_index_maps(build, w)
         w2 = torch.randn(w.shape, generator=g)
         fresh = ag._flat_specs(build(w2))
-        assert len(maps) == len(fresh) >= 1
+        # one map per w_packed, then one per row-folded packing (rolling-row kernel) of the specs that carry one
+        targets = [sp.w_packed for sp in fresh] + [sp.w_fold for sp in fresh if sp.w_fold is not None]
+        assert len(maps) == len(targets) >= 1
         src = torch.cat([torch.zeros(1), w2.reshape(-1)])
-        for (packed, idx), sp in zip(maps, fresh):
-            got = src[(idx.long() + 1)].to(torch.bfloat16).view(sp.w_packed.shape)
-            assert packed.shape == sp.w_packed.shape and torch.equal(got, sp.w_packed)
+        for (packed, idx), tgt in zip(maps, targets):
+            got = src[(idx.long() + 1)].to(torch.bfloat16).view(tgt.shape)
+            assert packed.shape == tgt.shape and torch.equal(got, tgt)
 
 
 def test_roofline_traffic_json_follows_from_the_committed_ncu_capture():
