@@ -94,6 +94,7 @@ SIGNATURES = {
     "adb_gather_cast": [_P, _P, _L, _P, _P],
     "adb_upsample_bilinear_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "adb_adam_step_segments": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _I, _P, _P, _P, _P, _P],
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
@@ -109,6 +110,7 @@ SIGNATURES = {
     "adb_head_mlp": [_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
     "adb_linear": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "adb_route": [_P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "adb_zero_unrouted": [_P, _P, _I, _L, _P],
     "adb_blend3": [_P, _P, _P, _P, _F, _I, _L, _P, _P, _P],
     "adb_l1_mse_fwd": [_P, _P, _L, _P, _P],
     "adb_l1_bwd": [_P, _P, _L, _F, _P, _P],

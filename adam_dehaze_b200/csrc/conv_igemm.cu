@@ -894,6 +894,16 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream);
 
 static long long* g_dbg = nullptr;
 
+namespace adbc {
+// the (lazily allocated, zeroed on `stream`) debug buffer adb_debug_timeline() reads back
+int debug_buffer(long long** out, void* stream) {
+  if (!g_dbg) ADB_CUDA_OK(cudaMalloc(&g_dbg, 6 * 256 * sizeof(long long)));
+  ADB_CUDA_OK(cudaMemsetAsync(g_dbg, 0, 6 * 256 * sizeof(long long), (cudaStream_t)stream));
+  *out = g_dbg;
+  return ADB_OK;
+}
+}
+
 extern "C" int adb_debug_timeline(int64_t* host_out, int32_t count) {
   if (!g_dbg || !host_out || count > 6 * 256) return adbh::fail(ADB_ERR_INVALID, "adb_debug_timeline: no timeline recorded");
   ADB_CUDA_OK(cudaMemcpy(host_out, g_dbg, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost));

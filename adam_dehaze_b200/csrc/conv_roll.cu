@@ -29,11 +29,14 @@ namespace {
 using namespace adb;
 using namespace adbc;
 
-constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiSets = 3;                         // epilogue warp sets (4 lane-quarter warps each) taking every third output row
+constexpr int kEpiWarps = 4 * kEpiSets;
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 512
 constexpr int kMaxASlots = 8;
 constexpr int kMaxRing = 16;
 constexpr int kStripW = 128;
+constexpr int kMaxG = 4;
 
 struct RollK {
   int n, n_start;
@@ -43,8 +46,9 @@ struct RollK {
   FastDiv fd_strips, fd_segs;
   int Ck, row_bytes;
   int chunks0, chunks1, pitch0, pitch1, c0, ks_last0, ks_last1;
-  int CP, R;                       // cout_pad (columns of one ring slot), ring slots
+  int CP, R, logR;                 // cout_pad (columns of one ring slot), ring slots (a power of two)
   int a_slots, a_slot_bytes, a_tx_bytes;
+  int G, a_row_bytes;              // input rows per operand box (one barrier round trip per G rows), bytes of one row in it
   int b_box_bytes, b_bytes_total;
   uint32_t idesc[3];               // N = CP, 2*CP, 3*CP
   int act;
@@ -55,7 +59,13 @@ struct RollK {
   int Cs, n_slabs, stage_bytes;    // epilogue slab channels, slabs per row, staging bytes per epilogue warp
   int out_c_off;
   int* err_flag;
+  long long* dbg;                  // tune_flags bit 2: wait-cycle statistics of CTA `dbg_cta` (see tools/roll_stats.py)
+  int dbg_cta;
 };
+
+// stall accounting: `acc += cycles spent in the statement` for the debug CTA only
+#define ROLL_T0() const long long _t0 = dbg_on ? clock64() : 0
+#define ROLL_ACC(slot) do { if (dbg_on) dbg_acc[slot] += clock64() - _t0; } while (0)
 
 struct RollSmem { uint32_t a_off, b_off, stage_off, scale_off, bar_off, total; };
 
@@ -64,7 +74,7 @@ __host__ __device__ inline RollSmem roll_smem(int a_slots, int a_slot_bytes, int
   uint32_t off = 0;
   L.a_off = off; off += (uint32_t)a_slots * a_slot_bytes;
   L.b_off = off; off += (uint32_t)b_bytes;
-  L.stage_off = off; off += 8u * (uint32_t)stage_bytes;
+  L.stage_off = off; off += (uint32_t)kEpiWarps * (uint32_t)stage_bytes;
   L.scale_off = off; off += (uint32_t)cp * 8;
   off = (off + 15u) & ~15u;
   L.bar_off = off; off += 8u * (2 * kMaxASlots + 1 + 2 * kMaxRing) + 16;
@@ -80,6 +90,56 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// D[tmem] += A[smem] * B[smem] with the descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc)
+      : "memory");
+}
+
+struct RollIssue {
+  uint32_t hi;          // descriptor high word (SBO, version, swizzle mode)
+  uint32_t tap;         // A start-address step per column tap (one pixel row), 16-byte units
+  uint32_t sstep;       // B start-address step per column tap (nchunks weight boxes)
+};
+struct RollRow {        // one input row's window of output rows
+  uint32_t d0, id0;     // first piece: TMEM column base, instruction descriptor
+  uint32_t id1;         // second piece (across the ring wrap, at TMEM column 0); 0 = none
+  uint32_t b0, b1;      // weight descriptor low words of the two pieces (chunk 0, tap 0)
+};
+
+// all MMAs of one (input row, channel chunk): 3 column taps x kKs K steps (x 2 pieces across the ring wrap)
+template <int kKs, bool kTwo>
+__device__ __forceinline__ void roll_issue(const RollIssue& I, const RollRow& r, uint32_t a_lo, uint32_t cb, uint32_t d1) {
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+#pragma unroll
+    for (int kk = 0; kk < kKs; ++kk) {
+      const uint32_t a = a_lo + (uint32_t)s * I.tap + (uint32_t)(kk * 2);
+      umma_acc(r.d0, a, r.b0 + cb + (uint32_t)s * I.sstep + (uint32_t)(kk * 2), I.hi, r.id0);
+      if (kTwo) umma_acc(d1, a, r.b1 + cb + (uint32_t)s * I.sstep + (uint32_t)(kk * 2), I.hi, r.id1);
+    }
+  }
+}
+
+// the rows of one operand box (row g lives a_row_step further on), one straight-line MMA stream per row
+template <int kKs>
+__device__ __forceinline__ void roll_issue_group(const RollIssue& I, const RollRow (&rr)[kMaxG], int ng, uint32_t a_lo,
+                                                 uint32_t a_row_step, uint32_t cb, uint32_t d1) {
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) {
+    if (g < ng) {
+      if (rr[g].id1 == 0u) roll_issue<kKs, false>(I, rr[g], a_lo + (uint32_t)g * a_row_step, cb, d1);
+      else roll_issue<kKs, true>(I, rr[g], a_lo + (uint32_t)g * a_row_step, cb, d1);
+    }
+  }
+}
+
 struct Seg { int img, w0, h0, rows; };
 
 __device__ __forceinline__ Seg decode_seg(const RollK& P, int t) {
@@ -92,70 +152,149 @@ __device__ __forceinline__ Seg decode_seg(const RollK& P, int t) {
   return s;
 }
 
-// residual pixels of one output row quarter (32 px x Cs channels), lane-transposed for coalesced 16-byte reads
-template <int CS16>
-__device__ __forceinline__ void roll_load_residual(const RollK& P, int img, int h, int w0, int sl, int ew, int lane,
-                                                   uint4 (&q)[CS16 * 2]) {
-  constexpr int CPR = CS16 * 2;
-  const int ch = sl * (CS16 * 16) + (lane % CPR) * 8;
-#pragma unroll
-  for (int i = 0; i < CPR; ++i) {
-    const int w = w0 + ew * 32 + i * (32 / CPR) + lane / CPR;
-    q[i] = (w < P.W) ? __ldg(reinterpret_cast<const uint4*>(P.residual + (((size_t)img * P.H + h) * P.W + w) * P.res_pitch + ch))
-                     : make_uint4(0, 0, 0, 0);
-  }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(z) : "memory");
 }
 
-template <int kAct, int CS16>
+// Epilogue of the rolling-row kernel.  Output rows are numbered g = 0, 1, 2, ... in the order this CTA produces them
+// (continuing across its segments); row g lives in ring slot g & (R-1) and its barriers are in phase (g >> logR) & 1, so
+// neither side keeps per-slot state.  Set `set` of kEpiSets takes the rows with g % kEpiSets == set; a warp handles the
+// 32 pixels of its TMEM lane quarter, 32 channels at a time: TMEM -> registers, slot zeroed and returned at once (every
+// MMA accumulates), then affine (+ residual) / activation -> bf16 -> swizzled staging -> one TMA store.
+template <int kAct, bool kRes>
 __device__ __forceinline__ void roll_epilogue(const RollK& P, const CUtensorMap* tmOut, uint32_t tmem_base, uint32_t bar_full0,
                                               uint32_t bar_empty0, uint32_t sbuf, const float* s_scale, const float* s_shift,
-                                              int ew, int half, int lane, int unit, int nunits, int total) {
-  constexpr int Cs = CS16 * 16;
-  const bool has_res = P.residual != nullptr;
+                                              int ew, int set, int lane, int unit, int nunits, int total) {
+  const bool dbg_on = P.dbg && (int)blockIdx.x == P.dbg_cta && ew == 0 && set == 0;
+  long long dbg_acc[5] = {0, 0, 0, 0, 0};     // full wait, staging wait, slab, zero+return, rows
+  const long long dbg_start = dbg_on ? clock64() : 0;
   const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-  uint32_t full_phase = 0;                                  // one phase bit per ring slot
+  const uint32_t rmask = (uint32_t)P.R - 1u;
   // every slot starts zeroed and free
-  for (int s = half; s < P.R; s += 2) {
-    for (int c = 0; c < P.CP; c += 16) tmem_st16_zero(lane_base + (uint32_t)(s * P.CP + c));
+  for (int s = set; s < P.R; s += kEpiSets) {
+    for (int c = 0; c < P.CP; c += 32) tmem_st32_zero(lane_base + (uint32_t)(s * P.CP + c));
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty0 + 8u * s);
   }
-  uint4 q[CS16 * 2];
+  // staging addresses (64-byte rows, SWIZZLE_64B): this lane's own row (4 chunks), and — for the residual bounce — the
+  // chunk this lane fetches in load i (row i*8 + lane/4, chunk lane%4: coalesced 16-byte global reads)
+  uint32_t sw_row[4], sw_ld[4];
 #pragma unroll
-  for (int i = 0; i < CS16 * 2; ++i) q[i] = make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < 4; ++i) {
+    sw_row[i] = sbuf + swizzle_addr((uint32_t)lane * 64u + (uint32_t)i * 16u, 64u);
+    sw_ld[i] = sbuf + swizzle_addr((uint32_t)(i * 8 + lane / 4) * 64u + (uint32_t)(lane % 4) * 16u, 64u);
+  }
+  const int px = ew * 32 + (lane >> 2);                    // + i*8: tile pixel of residual load i
+  const int res_ch = (lane & 3) * 8;
+  uint32_t g_base = 0;                                       // g of the current segment's first row
+  uint32_t rem = 0;                                          // g_base % kEpiSets
   for (int t = unit; t < total; t += nunits) {
     const Seg sg = decode_seg(P, t);
-    for (int i = half; i < sg.rows; i += 2) {
+    const int first = (set + kEpiSets - (int)rem) % kEpiSets;
+    for (int i = first; i < sg.rows; i += kEpiSets) {
       const int h = sg.h0 + i;
-      const int slot = i % P.R;
-      if (has_res) roll_load_residual<CS16>(P, sg.img, h, sg.w0, 0, ew, lane, q);   // independent of the accumulator
-      mbar_wait(bar_full0 + 8u * slot, (full_phase >> slot) & 1u, P.err_flag, 4);
-      full_phase ^= 1u << slot;
+      const uint32_t g = g_base + (uint32_t)i;
+      const uint32_t slot = g & rmask, par = (g >> P.logR) & 1u;
+      const __nv_bfloat16* res_row = kRes ? P.residual + (((size_t)sg.img * P.H + h) * P.W + sg.w0) * P.res_pitch + res_ch : nullptr;
+      uint4 q[4];
+      if (kRes) {                                             // first slab's residual: independent of the accumulator
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          q[k] = (sg.w0 + px + k * 8 < P.W) ? __ldg(reinterpret_cast<const uint4*>(res_row + (size_t)(px + k * 8) * P.res_pitch))
+                                            : make_uint4(0, 0, 0, 0);
+      }
+      { ROLL_T0(); mbar_wait(bar_full0 + 8u * slot, par, P.err_flag, 4); ROLL_ACC(0); }
+      if (dbg_on) dbg_acc[4] += 1;
       tc_fence_after();
       for (int sl = 0; sl < P.n_slabs; ++sl) {
-        if (sl > 0 && has_res) roll_load_residual<CS16>(P, sg.img, h, sg.w0, sl, ew, lane, q);
-        if (lane == 0) tma_store_wait_read<0>();             // the previous store has finished reading the staging buffer
-        __syncwarp();
-        compute_slab<kAct, CS16>(lane_base + (uint32_t)(slot * P.CP + sl * Cs), q, has_res, s_scale + sl * Cs, s_shift + sl * Cs,
-                                 sbuf, lane, P.act);
+        const long long _ts = dbg_on ? clock64() : 0;
+        float v[32];
+        tmem_ld32(lane_base + slot * (uint32_t)P.CP + (uint32_t)(sl * 32), v);
+        if (sl > 0 && kRes) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            q[k] = (sg.w0 + px + k * 8 < P.W) ? __ldg(reinterpret_cast<const uint4*>(res_row + (size_t)(px + k * 8) * P.res_pitch + sl * 32))
+                                              : make_uint4(0, 0, 0, 0);
+        }
+        { ROLL_T0();
+          if (lane == 0) tma_store_wait_read<0>();           // the previous store has finished reading the staging buffer
+          __syncwarp();
+          ROLL_ACC(1); }
+        if (kRes) {                                           // bounce the residual through the staging buffer: lane <- its own row
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sw_ld[k]), "r"(q[k].x), "r"(q[k].y), "r"(q[k].z), "r"(q[k].w) : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[k].x), "=r"(q[k].y), "=r"(q[k].z), "=r"(q[k].w) : "r"(sw_row[k]) : "memory");
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        if (sl == P.n_slabs - 1) {                            // accumulator row is in registers: zero the slot and hand it back
+          ROLL_T0();
+          for (int c = 0; c < P.CP; c += 32) tmem_st32_zero(lane_base + slot * (uint32_t)P.CP + (uint32_t)c);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_relaxed(bar_empty0 + 8u * slot);
+          ROLL_ACC(3);
+        }
+        const float* sc_ptr = s_scale + sl * 32;
+        const float* sh_ptr = s_shift + sl * 32;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                         // 8 channels = one 16-byte chunk of the staging row
+          const float4 sa = *reinterpret_cast<const float4*>(sc_ptr + k * 8), sb = *reinterpret_cast<const float4*>(sc_ptr + k * 8 + 4);
+          const float4 ha = *reinterpret_cast<const float4*>(sh_ptr + k * 8), hb = *reinterpret_cast<const float4*>(sh_ptr + k * 8 + 4);
+          const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+          const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+          const uint32_t qs[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float y0 = fmaf(v[k * 8 + 2 * e], sc[2 * e], sh[2 * e]);
+            float y1 = fmaf(v[k * 8 + 2 * e + 1], sc[2 * e + 1], sh[2 * e + 1]);
+            if (kRes) {
+              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[e]);
+              y0 += __low2float(b2); y1 += __high2float(b2);
+            }
+            pk[e] = (kAct == ADB_ACT_RELU) ? pack_bf16x2_relu(y0, y1) : pack_bf16x2(act_t<kAct>(y0, P.act), act_t<kAct>(y1, P.act));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sw_row[k]), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_5d(tmOut, sbuf, P.out_c_off + sl * Cs, sg.w0 + ew * 32, 0, h, sg.img);
+          tma_store_5d(tmOut, sbuf, P.out_c_off + sl * 32, sg.w0 + ew * 32, 0, h, sg.img);
           tma_store_commit();
         }
+        if (dbg_on) dbg_acc[2] += clock64() - _ts;
       }
-      // hand the slot back zeroed: every MMA accumulates
-      for (int c = 0; c < P.CP; c += 16) tmem_st16_zero(lane_base + (uint32_t)(slot * P.CP + c));
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(bar_empty0 + 8u * slot);
     }
+    g_base += (uint32_t)sg.rows;
+    rem = (rem + (uint32_t)sg.rows) % kEpiSets;
   }
   if (lane == 0) tma_store_wait_all<0>();
+  if (dbg_on && lane == 0) {
+    for (int i = 0; i < 5; ++i) P.dbg[32 + i] = dbg_acc[i];
+    P.dbg[37] = clock64() - dbg_start;
+  }
 }
 
 template <int kAct>
@@ -203,7 +342,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tmem_relinquish();
   }
   if (warp >= kEpiWarp0) {
-    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.CP; i += 256) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < P.CP; i += 32 * kEpiWarps) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -213,14 +352,18 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   if (warp == 0) {
     // ======================================================= A producer: one 130-pixel row box per (input row, channel chunk)
     int slot = 0; uint32_t phase = 0;
+    const bool dbg_on = P.dbg && (int)blockIdx.x == P.dbg_cta;
+    long long dbg_acc[2] = {0, 0};
+    const long long dbg_start = dbg_on ? clock64() : 0;
     for (int t = unit; t < total; t += nunits) {
       const Seg sg = decode_seg(P, t);
       const int jb = max(sg.h0 - 1, 0), je = min(sg.h0 + sg.rows, P.H - 1);
-      for (int j = jb; j <= je; ++j) {
+      for (int j = jb; j <= je; j += P.G) {               // rows past je in the last group are loaded (or zero-filled) and ignored
         for (int c = 0; c < nchunks; ++c) {
           const bool s1 = c >= P.chunks0;
           const int coff = (s1 ? c - P.chunks0 : c) * P.Ck;
-          mbar_wait(emptyA(slot), phase ^ 1u, P.err_flag, 1);
+          { ROLL_T0(); mbar_wait(emptyA(slot), phase ^ 1u, P.err_flag, 1); ROLL_ACC(0); }
+          dbg_acc[1] += 1;
           if (elect_one()) {
             mbar_expect_tx(fullA(slot), (uint32_t)P.a_tx_bytes);
             tma_load_5d(a_base + (uint32_t)slot * P.a_slot_bytes, s1 ? &tmA1 : &tmA0, fullA(slot), coff, sg.w0 - 1, 0, j, sg.img);
@@ -230,6 +373,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         }
       }
     }
+    if (dbg_on && lane == 0) { P.dbg[0] = dbg_acc[0]; P.dbg[1] = dbg_acc[1]; P.dbg[2] = clock64() - dbg_start; }
   } else if (warp == 3) {
     // ======================================================= weights: the whole filter, once
     if (total > 0 && elect_one()) {
@@ -243,70 +387,92 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ======================================================= MMA issuer
+    // One thread feeds MMAs that take ~N/2 cycles each (48 at N = 96), so the issue path has to be a few instructions per
+    // MMA: every descriptor is a 32-bit low word (start address | LBO flag, advanced by register adds) paired with a
+    // constant high word; ring slots advance by counters and masks; the taps and K steps are unrolled at compile time.
     int sa = 0; uint32_t pa = 0;
-    uint32_t empty_phase = 0;                                // one phase bit per ring slot
+    uint32_t g_base = 0;                                     // running output-row number of the segment's first row (see roll_epilogue)
     const int ksteps_full = P.Ck / 16;
-    const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);
+    const uint64_t desc_t = make_kmajor_desc(0, P.row_bytes);
+    RollIssue I;
+    I.hi = (uint32_t)(desc_t >> 32);
+    I.tap = (uint32_t)P.row_bytes >> 4;
+    I.sstep = (uint32_t)(nchunks * P.b_box_bytes) >> 4;
+    const uint32_t lo_flags = (uint32_t)desc_t;              // LBO field
+    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | lo_flags, a_step = (uint32_t)P.a_slot_bytes >> 4;
+    const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | lo_flags, box_step = (uint32_t)P.b_box_bytes >> 4;
+    const uint32_t blk_step = (uint32_t)(P.CP * P.row_bytes) >> 4;
+    const uint32_t rmask = (uint32_t)P.R - 1u;
+    const uint32_t a_row_step = (uint32_t)P.a_row_bytes >> 4;
+    uint32_t a_lo = a_lo0;
+    const bool dbg_on = P.dbg && (int)blockIdx.x == P.dbg_cta;
+    long long dbg_acc[4] = {0, 0, 0, 0};          // ring wait, fullA wait, issue, input rows
+    const long long dbg_start = dbg_on ? clock64() : 0;
     if (total > 0) mbar_wait(fullB, 0, P.err_flag, 6);
     for (int t = unit; t < total; t += nunits) {
       const Seg sg = decode_seg(P, t);
       const int jb = max(sg.h0 - 1, 0), je = min(sg.h0 + sg.rows, P.H - 1);
       const int h_last = sg.h0 + sg.rows - 1;
       int next_new = sg.h0, next_commit = sg.h0;
-      for (int j = jb; j <= je; ++j) {
-        const int hi = min(j + 1, h_last), lo = max(j - 1, sg.h0);
-        // output rows entering the window need their (zeroed) ring slot back from the epilogue
-        for (; next_new <= hi; ++next_new) {
-          const int slot = (next_new - sg.h0) % P.R;
-          mbar_wait(empty0 + 8u * slot, (empty_phase >> slot) & 1u, P.err_flag, 2);
-          empty_phase ^= 1u << slot;
+      const uint32_t g_off = g_base - (uint32_t)sg.h0;       // g of image row h = g_off + h
+      for (int j0 = jb; j0 <= je; j0 += P.G) {
+        const int ng = min(P.G, je - j0 + 1);                // input rows of this group
+        const int j_last = j0 + ng - 1;
+        // output rows entering the group's windows need their (zeroed) ring slot back from the epilogue
+        const int hi_g = min(j_last + 1, h_last);
+        for (; next_new <= hi_g; ++next_new) {
+          const uint32_t g = g_off + (uint32_t)next_new;
+          ROLL_T0(); mbar_wait(empty0 + 8u * (g & rmask), (g >> P.logR) & 1u, P.err_flag, 2); ROLL_ACC(0);
         }
-        tc_fence_after();
-        // the window's slots are adjacent except across the ring wrap: one or two MMA pieces
-        const int slot_lo = (lo - sg.h0) % P.R;
-        const int nrows = hi - lo + 1;
-        const int n0 = min(nrows, P.R - slot_lo), n1 = nrows - n0;
-        const int blk0 = lo - (j - 1);                       // weight column block of the first window row
-        const int done_to = (j == je) ? h_last : j - 1;      // output rows complete after this input row
+        if (dbg_on) dbg_acc[3] += ng;
+        // per input row: its window of output rows = ring slots, adjacent except across the ring wrap (one or two MMA pieces)
+        RollRow rr[kMaxG];
+#pragma unroll
+        for (int g = 0; g < kMaxG; ++g) {
+          const int j = j0 + g;
+          const int hi = min(j + 1, h_last), lo = max(j - 1, sg.h0);
+          const uint32_t slot_lo = (g_off + (uint32_t)lo) & rmask;
+          const int nrows = hi - lo + 1;
+          const int n0 = min(nrows, P.R - (int)slot_lo), n1 = nrows - n0;
+          const uint32_t blk0 = (uint32_t)(lo - (j - 1));    // weight column block of the first window row
+          rr[g].d0 = tmem_base + slot_lo * (uint32_t)P.CP;
+          rr[g].id0 = P.idesc[max(n0, 1) - 1];
+          rr[g].id1 = n1 > 0 ? P.idesc[n1 - 1] : 0u;
+          rr[g].b0 = b_lo0 + blk0 * blk_step;
+          rr[g].b1 = rr[g].b0 + (uint32_t)n0 * blk_step;
+        }
+        const int done_to = (j_last == je) ? h_last : j_last - 1;   // output rows complete after this group
         for (int c = 0; c < nchunks; ++c) {
           const int ksteps = c == P.chunks0 - 1 ? P.ks_last0 : (c == nchunks - 1 ? P.ks_last1 : ksteps_full);
-          mbar_wait(fullA(sa), pa, P.err_flag, 3);
+          { ROLL_T0(); mbar_wait(fullA(sa), pa, P.err_flag, 3); ROLL_ACC(1); }
           tc_fence_after();
+          const long long _ti = dbg_on ? clock64() : 0;
           if (elect_one()) {
-            const uint32_t a_slot = a_base + (uint32_t)sa * P.a_slot_bytes;
-#pragma unroll 1
-            for (int s = 0; s < 3; ++s) {
-              const uint32_t b_box = b_base + (uint32_t)(s * nchunks + c) * P.b_box_bytes;
-              const uint64_t a0 = desc_hi | (uint64_t)(((a_slot + (uint32_t)(s * P.row_bytes)) & 0x3FFFFu) >> 4);
-              {
-                const uint64_t b0 = desc_hi | (uint64_t)(((b_box + (uint32_t)(blk0 * P.CP * P.row_bytes)) & 0x3FFFFu) >> 4);
-                const uint32_t d = tmem_base + (uint32_t)(slot_lo * P.CP);
-                const uint32_t id = P.idesc[n0 - 1];
-                for (int kk = 0; kk < ksteps; ++kk) umma_bf16(d, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), id, 1u);
-              }
-              if (n1 > 0) {
-                const uint64_t b1 = desc_hi | (uint64_t)(((b_box + (uint32_t)((blk0 + n0) * P.CP * P.row_bytes)) & 0x3FFFFu) >> 4);
-                const uint32_t id = P.idesc[n1 - 1];
-                for (int kk = 0; kk < ksteps; ++kk) umma_bf16(tmem_base, a0 + (uint64_t)(kk * 2), b1 + (uint64_t)(kk * 2), id, 1u);
-              }
-            }
+            const uint32_t cb = (uint32_t)c * box_step;
+            if (ksteps == 4) roll_issue_group<4>(I, rr, ng, a_lo, a_row_step, cb, tmem_base);
+            else if (ksteps == 2) roll_issue_group<2>(I, rr, ng, a_lo, a_row_step, cb, tmem_base);
+            else if (ksteps == 3) roll_issue_group<3>(I, rr, ng, a_lo, a_row_step, cb, tmem_base);
+            else roll_issue_group<1>(I, rr, ng, a_lo, a_row_step, cb, tmem_base);
             umma_commit(emptyA(sa));
             if (c == nchunks - 1)
-              for (int h = next_commit; h <= done_to; ++h) umma_commit(full0 + 8u * ((h - sg.h0) % P.R));
+              for (int h = next_commit; h <= done_to; ++h) umma_commit(full0 + 8u * ((g_off + (uint32_t)h) & rmask));
           }
           __syncwarp();
-          if (++sa == P.a_slots) { sa = 0; pa ^= 1u; }
+          if (dbg_on) dbg_acc[2] += clock64() - _ti;
+          a_lo += a_step;
+          if (++sa == P.a_slots) { sa = 0; pa ^= 1u; a_lo = a_lo0; }
         }
         next_commit = max(next_commit, done_to + 1);
       }
+      g_base += (uint32_t)sg.rows;
     }
+    if (dbg_on && lane == 0) { for (int i = 0; i < 4; ++i) P.dbg[16 + i] = dbg_acc[i]; P.dbg[20] = clock64() - dbg_start; }
   } else if (warp >= kEpiWarp0) {
     const int ewi = warp - kEpiWarp0;
-    const int ew = ewi & 3, half = ewi >> 2;
+    const int ew = ewi & 3, set = ewi >> 2;
     const uint32_t sbuf = base + L.stage_off + (uint32_t)ewi * (uint32_t)P.stage_bytes;
-    if (P.Cs == 64) roll_epilogue<kAct, 4>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, half, lane, unit, nunits, total);
-    else if (P.Cs == 32) roll_epilogue<kAct, 2>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, half, lane, unit, nunits, total);
-    else roll_epilogue<kAct, 1>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, half, lane, unit, nunits, total);
+    if (P.residual) roll_epilogue<kAct, true>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, set, lane, unit, nunits, total);
+    else roll_epilogue<kAct, false>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, set, lane, unit, nunits, total);
   }
 
   tc_fence_before();
@@ -317,6 +483,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
 }  // namespace
 
 namespace adbc {
+
+int debug_buffer(long long** out, void* stream);   // conv_igemm.cu
 
 // Whether adb_conv2d should take the rolling-row kernel for this descriptor (w_fold given by the caller).
 bool roll_eligible(const adb_conv_desc* d) {
@@ -332,8 +500,7 @@ bool roll_eligible(const adb_conv_desc* d) {
   const int chunks = (d->c0 + Ck - 1) / Ck + (d->c1 + Ck - 1) / Ck;
   const int b_bytes = 9 * d->cout_pad * Ck * 2 * chunks;
   const int a_slot = round_up(130 * Ck * 2, 1024);
-  const int cs = pick_chunk(d->cout_pad);
-  return b_bytes + 3 * a_slot + 8 * 32 * cs * 2 + 4096 <= 226 * 1024;
+  return b_bytes + 3 * a_slot + 12 * 32 * 32 * 2 + 4096 <= 226 * 1024;
 }
 
 int conv_roll_launch(const adb_conv_desc* d, void* stream) {
@@ -362,7 +529,9 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   const int nchunks = P.chunks0 + P.chunks1;
   const int ctot = d->c0 + d->c1;
   P.CP = d->cout_pad; P.R = 512 / P.CP;
-  ADB_REQUIRE(P.R >= 6 && P.R <= kMaxRing && P.R % 2 == 0, "adb_conv2d(roll): ring of %d rows unsupported", P.R);
+  P.logR = 0;
+  while ((1 << P.logR) < P.R) ++P.logR;
+  ADB_REQUIRE(P.R >= 8 && P.R <= kMaxRing && (P.R & (P.R - 1)) == 0, "adb_conv2d(roll): ring of %d rows unsupported (power of two)", P.R);
   for (int i = 0; i < 3; ++i) P.idesc[i] = make_idesc_bf16(128u, (uint32_t)((i + 1) * P.CP));
   P.n = d->n; P.n_start = d->n_start; P.n_dev = d->n_dev;
   P.H = d->h_in; P.W = d->w_in;
@@ -377,14 +546,22 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   const long long total = (long long)d->n * P.strips * P.segs_h;
   ADB_REQUIRE((unsigned long long)total * (unsigned long long)std::max(P.strips, P.segs_h) < (1ULL << 32),
               "adb_conv2d(roll): %lld segments exceed the decode range; split the batch", total);
-  P.a_tx_bytes = 130 * P.row_bytes;
-  P.a_slot_bytes = round_up(P.a_tx_bytes, 1024);
+  P.a_row_bytes = 130 * P.row_bytes;
   P.b_box_bytes = 3 * P.CP * P.row_bytes;
   P.b_bytes_total = 3 * nchunks * P.b_box_bytes;
-  P.Cs = pick_chunk(P.CP); P.n_slabs = P.CP / P.Cs; P.stage_bytes = 32 * P.Cs * 2;
+  P.Cs = 32; P.n_slabs = P.CP / P.Cs; P.stage_bytes = 32 * P.Cs * 2;      // 32-channel slabs: 12 epilogue warps at <= 128 registers
   const int budget = di.max_smem_optin - 1024;
   const RollSmem fixed = roll_smem(0, 0, P.b_bytes_total, P.stage_bytes, P.CP);
-  int a_slots = std::min(kMaxASlots, (budget - (int)fixed.total) / P.a_slot_bytes);
+  const int avail = budget - (int)fixed.total;
+  // input rows per operand box: the MMA issuer pays one barrier round trip (and the tensor pipe one bubble) per box, so
+  // boxes carry as many rows as leave >= 3 boxes (and >= 2 row groups) in flight and half the TMEM ring to the epilogue
+  int G = std::min(kMaxG, P.R / 4);
+  if (d->tune_acc_stages > 0 && !(d->tune_flags & 4)) G = std::min(G, d->tune_acc_stages);
+  while (G > 1 && round_up(G * P.a_row_bytes, 1024) * std::max(3, 2 * nchunks) > avail) G >>= 1;
+  P.G = G;
+  P.a_tx_bytes = G * P.a_row_bytes;
+  P.a_slot_bytes = round_up(P.a_tx_bytes, 1024);
+  int a_slots = std::min(kMaxASlots, avail / P.a_slot_bytes);
   ADB_REQUIRE(a_slots >= 3, "adb_conv2d(roll): pipeline does not fit shared memory");
   if (d->tune_stages > 0) a_slots = std::min(a_slots, std::max(2, d->tune_stages));
   P.a_slots = a_slots;
@@ -392,12 +569,17 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   P.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); P.res_pitch = d->res_pitch;
   P.out_c_off = d->dst_c_off;
   P.err_flag = adbh::kernel_err_flag();
+  if (d->tune_flags & 4) {
+    st = debug_buffer(&P.dbg, stream);
+    if (st != ADB_OK) return st;
+    P.dbg_cta = d->tune_acc_stages > 0 ? d->tune_acc_stages : 0;     // which CTA reports (tune "acc" doubles as the selector)
+  }
 
   alignas(64) CUtensorMap tmA0, tmA1, tmB, tmOut;
-  st = make_act_tmap(&tmA0, d->src0, d->c0, d->c0_pitch, d->n, P.H, P.W, false, Ck, 130, 1, P.row_bytes);
+  st = make_act_tmap(&tmA0, d->src0, d->c0, d->c0_pitch, d->n, P.H, P.W, false, Ck, 130, P.G, P.row_bytes);
   if (st != ADB_OK) return st;
   if (d->src1) {
-    st = make_act_tmap(&tmA1, d->src1, d->c1, d->c1_pitch, d->n, P.H, P.W, false, Ck, 130, 1, P.row_bytes);
+    st = make_act_tmap(&tmA1, d->src1, d->c1, d->c1_pitch, d->n, P.H, P.W, false, Ck, 130, P.G, P.row_bytes);
     if (st != ADB_OK) return st;
   } else {
     tmA1 = tmA0;

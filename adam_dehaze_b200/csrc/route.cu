@@ -70,7 +70,27 @@ route_kernel(const float* __restrict__ logits, const long long* __restrict__ int
   if (threadIdx.x < 3) bucket_count[threadIdx.x] = base[threadIdx.x];
 }
 
+// rows whose class id is outside {0,1,2} are written by no branch: the reference leaves them at zeros_like(x)
+// (routing.py:31,55-61).  Every other row is overwritten in full by its branch's image epilogue, so only these are cleared.
+__global__ void zero_unrouted_kernel(float* __restrict__ out, const long long* __restrict__ intensity, long long row_elems) {
+  const long long cls = intensity[blockIdx.y];
+  if (cls >= 0 && cls < 3) return;
+  float4* row = reinterpret_cast<float4*>(out + (size_t)blockIdx.y * row_elems);
+  const long long n4 = row_elems >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x < (row_elems & 3)) out[(size_t)blockIdx.y * row_elems + (n4 << 2) + threadIdx.x] = 0.f;
+}
+
 }  // namespace
+
+extern "C" int adb_zero_unrouted(float* out, const int64_t* intensity, int32_t b, int64_t row_elems, void* stream) {
+  ADB_REQUIRE(out && intensity && b > 0 && b <= 65535 && row_elems > 0, "adb_zero_unrouted: bad arguments");
+  ADB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (row_elems % 4 == 0 || b == 1), "adb_zero_unrouted: rows must be 16-byte aligned");
+  zero_unrouted_kernel<<<dim3(64, (unsigned)b), 256, 0, (cudaStream_t)stream>>>(out, reinterpret_cast<const long long*>(intensity), row_elems);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
 
 extern "C" int adb_route(const float* logits, const int64_t* intensity_in, int32_t b, int32_t classes,
                          int64_t* intensity, uint8_t* masks, int32_t* bucket_index, int32_t* bucket_count, void* stream) {

@@ -1251,6 +1251,51 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Per-parameter ("segment") Adam: torch.optim.Adam skips a parameter whose .grad is None — no moment decay, no weight decay,
+// no step count — so a branch that received no sample (HardRouter joint training) does not drift.  `live[s]` > 0 when
+// any rank produced a gradient for segment s this step (the flags ride at the tail of the all-reduced bucket).
+__global__ void adam_seg_prep_kernel(const float* __restrict__ live, int* __restrict__ step, float* __restrict__ bc1,
+                                     float* __restrict__ bc2s, int n_seg, float b1, float b2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg || !(live[s] > 0.f)) return;
+  const int st = step[s] + 1;
+  step[s] = st;
+  bc1[s] = 1.f - powf(b1, (float)st);
+  bc2s[s] = sqrtf(1.f - powf(b2, (float)st));
+}
+
+__global__ void adam_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n4, float lr, float b1, float b2, float eps, float wd, float grad_scale,
+                                const long long* __restrict__ seg_off, int n_seg, const float* __restrict__ live,
+                                const float* __restrict__ bc1, const float* __restrict__ bc2s) {
+  // segments start on multiples of 4 elements, so one lookup serves a float4
+  for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i4 * 4;
+    int lo = 0, hi = n_seg;                     // last segment whose offset is <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(seg_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    if (!(__ldg(live + lo) > 0.f)) continue;
+    const float c1 = __ldg(bc1 + lo), c2 = __ldg(bc2s + lo);
+    const float4 w4 = *reinterpret_cast<const float4*>(p + i), g4 = *reinterpret_cast<const float4*>(g + i);
+    float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+    float w[4] = {w4.x, w4.y, w4.z, w4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = fmaf(wd, w[k], gg[k] * grad_scale);
+      mm[k] = fmaf(b1, mm[k], (1.f - b1) * gr);
+      vv[k] = fmaf(b2, vv[k], (1.f - b2) * gr * gr);
+      const float denom = sqrtf(vv[k]) / c2 + eps;
+      w[k] = w[k] - (lr / c1) * (mm[k] / denom);
+    }
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(p + i) = make_float4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 }  // namespace
 
 #define ADB_BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
@@ -1602,6 +1647,19 @@ int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   const float bc2 = 1.f - powf(beta2, (float)step);
   adam_kernel<<<grid_for(numel, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
                                                                                      weight_decay, bc1, sqrtf(bc2), grad_scale);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, float grad_scale, const int64_t* seg_offsets, int32_t n_seg,
+                           const float* seg_live, int32_t* seg_step, float* seg_bc1, float* seg_bc2s, void* stream) {
+  ADB_REQUIRE(param && grad && exp_avg && exp_avg_sq && numel > 0 && numel % 4 == 0, "adb_adam_step_segments: bad arguments (numel %% 4 == 0)");
+  ADB_REQUIRE(seg_offsets && n_seg > 0 && seg_live && seg_step && seg_bc1 && seg_bc2s, "adb_adam_step_segments: null segment tables");
+  adam_seg_prep_kernel<<<(n_seg + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seg_live, seg_step, seg_bc1, seg_bc2s, n_seg, beta1, beta2);
+  adam_seg_kernel<<<grid_for(numel / 4, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, numel / 4, lr, beta1, beta2, eps, weight_decay, grad_scale,
+      reinterpret_cast<const long long*>(seg_offsets), n_seg, seg_live, seg_bc1, seg_bc2s);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

@@ -5,8 +5,9 @@ One engine per module instance.  It (re)packs weights whenever a parameter or BN
 counters), owns the activation buffers of a micro-batch, and walks a routed bucket micro-batch by micro-batch with the
 bucket's live count kept on the device (`n_dev`) — no host synchronisation anywhere on the path.
 
-Inference only for now: BatchNorm uses running statistics (module.eval()).  Calling a module in train() mode raises —
-there is no silent fallback to torch ops.
+eval(): BatchNorm uses running statistics folded into the conv epilogues (the launches below).  train(): the same engines
+hand the forward to training/autograd.py (batch-statistics BatchNorm on a tape, kernel-built backward).  There is no
+fallback to torch ops in either mode; CPU tensors raise.
 """
 import torch
 
@@ -24,10 +25,13 @@ def bn_args(bn):
 
 
 def require_inference(module, what):
+    """Stand-alone ConvBlock / ResidualBlock calls (BlockEngine) exist for eval-mode parity checks only; training goes through
+    the branch / classifier engines' train() path (training/autograd.py)."""
     if module.training:
         raise NotImplementedError(
-            f"{what}: the B200 path implements inference (BatchNorm with running statistics); call .eval() first. "
-            "Training kernels (dgrad/wgrad, batch-statistics BN) are not part of this build and there is no torch fallback.")
+            f"{what}: a stand-alone block call runs in eval mode only (BatchNorm with running statistics); call .eval() first, "
+            "or train the block as part of a branch model (LightweightDehazeModel etc.), whose train() mode is kernel-built. "
+            "There is no torch fallback.")
 
 
 def require_cuda(x, what):

@@ -28,7 +28,10 @@ class HardRouter(nn.Module):
         `intensity`; like the reference we take `intensity` literally (int64 class ids)."""
         _engine.require_cuda(x, "HardRouter")
         x = x.contiguous()
-        outputs = torch.zeros_like(x)
+        training = any(m.training for m in self.models.values())
+        # routing.py:31 starts from zeros_like(x); in eval mode every routed row is overwritten in full by its branch's image
+        # epilogue, so only the rows no branch owns (class id outside {0,1,2}) are cleared — on the device, after routing
+        outputs = torch.zeros_like(x) if training else torch.empty_like(x)
         if intensity is None and self.classifier is not None:
             with torch.no_grad():
                 logits, _ = self.classifier(x)
@@ -41,7 +44,10 @@ class HardRouter(nn.Module):
             inten, masks, bidx, bcnt = ops.route(intensity=intensity.to(x.device))
         else:
             raise ValueError("HardRouter needs a classifier or an explicit intensity tensor")
-        if any(m.training for m in self.models.values()):
+        if not training:
+            from .. import _lib
+            _lib.call("adb_zero_unrouted", _lib.ptr(outputs), _lib.ptr(inten), x.shape[0], x[0].numel(), _lib.current_stream())
+        if training:
             # train() mode (routing.py:55-61 under model.train()): each branch sees its own sub-batch (its BatchNorm statistics
             # are the sub-batch's, as in the reference) and autograd must reach it, so the buckets are gathered / scattered
             # with differentiable index ops; the bucket sizes are read on the host (one sync per batch, training only).

@@ -59,6 +59,14 @@ class Node:
             ops.conv2d(spec, src, dst=self.grad, residual=self.grad)
 
 
+def _touch_bn_buffers(bn):
+    """adb_bn_train_stats updates running_mean / running_var / num_batches_tracked through raw pointers; bump their torch
+    version counters so the eval-path packings keyed on `_version` (engine._Versioned) re-fold the new statistics even when
+    no optimizer step follows (train()-mode forward under no_grad, frozen modules, calibration passes)."""
+    from .optim import _bump_versions
+    _bump_versions([t for t in (bn.running_mean, bn.running_var, bn.num_batches_tracked) if t is not None])
+
+
 class BlockBuffer:
     """DenseNet block buffer: the raw (pre-norm) features of a dense block, [n,h,w,C_total] bf16, written in place by the
     layers' 3x3 convs at their channel offsets (the concat is never materialised), plus its lazily zeroed gradient."""
@@ -204,6 +212,7 @@ class Tape:
         _lib.call("adb_bn_train_stats", _lib.ptr(z), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
                   _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
                   _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        _touch_bn_buffers(bn)
         y = torch.empty_like(z)
         _lib.call("adb_affine_act", _lib.ptr(z), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift),
                   _lib.ptr(residual), 0 if residual is None else residual.shape[3], act, _lib.ptr(y), pitch, st)
@@ -437,6 +446,7 @@ class Tape:
         _lib.call("adb_bn_train_stats", _lib.ptr(B.t), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
                   _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
                   _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        _touch_bn_buffers(bn)
         y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
         _lib.call("adb_affine_act", _lib.ptr(B.t), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift), None, 0, act, _lib.ptr(y), c, st)
         out = Node(y, c)

@@ -2,8 +2,15 @@
 
 `FlatAdam` keeps every parameter as a view of ONE fp32 buffer, so a step is: gather the .grad tensors into the flat
 gradient buffer, one NCCL all-reduce over NVLink when torch.distributed is initialised (replicas + one
-gradient all-reduce per step, mean), and ONE adb_adam_step launch with torch.optim.Adam's arithmetic
+gradient all-reduce per step, mean), and ONE adb_adam_step_segments launch with torch.optim.Adam's arithmetic
 (weight_decay = L2 added to the gradient).  There is no torch fallback: the step runs on the CUDA device only.
+
+DistributedDataParallel / torch.optim.Adam behaviours kept:
+  * replicas start equal: the flat parameter buffer is broadcast from rank 0 at construction;
+  * every rank joins every all-reduce, whatever it computed: a parameter without a gradient on this rank contributes
+    zeros, and a per-parameter "has a gradient" flag rides at the tail of the same bucket;
+  * a parameter whose .grad is None on EVERY rank is skipped entirely (no moment decay, no weight decay, no step count),
+    as torch.optim.Adam does — a branch that saw no sample under HardRouter joint training does not drift.
 """
 import torch
 
@@ -22,7 +29,8 @@ def _bump_versions(params):
         except (TypeError, RuntimeError):
             pass
     with torch.no_grad():
-        torch._foreach_mul_(list(params), 1.0)
+        for p in params:
+            p.add_(0)          # in-place no-op: bumps the version for floating-point and integer tensors alike
 
 
 class FlatAdam:
@@ -39,8 +47,17 @@ class FlatAdam:
         for s in sizes:
             self.offsets.append(self.offsets[-1] + (s + 3) // 4 * 4)     # 16-byte aligned views
         total = self.offsets[-1]
+        nseg = len(self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # gradient bucket + one "has a gradient" flag per parameter at its tail: one collective carries both
+        self.bucket = torch.zeros(total + (nseg + 3) // 4 * 4, dtype=torch.float32, device=dev)
+        self.grad = self.bucket[:total]
+        self.live = self.bucket[total:total + nseg]
+        self.seg_off = torch.tensor(self.offsets[:-1], dtype=torch.int64, device=dev)
+        self.seg_step = torch.zeros(nseg, dtype=torch.int32, device=dev)          # per-parameter step counts (torch.optim.Adam 'step')
+        self._seg_bc = torch.zeros((2, nseg), dtype=torch.float32, device=dev)
+        self._live_host = torch.zeros(nseg, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(nseg)
+        self.allreduce_events = None       # a list here collects (start, end) CUDA events around each all-reduce (bench.py)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_views = []
@@ -52,6 +69,9 @@ class FlatAdam:
                 view.copy_(p.data)
                 p.data = view
                 self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+        if self.world_size() > 1:          # replicas start from rank 0's parameters, as DistributedDataParallel does
+            import torch.distributed as dist
+            dist.broadcast(self.flat, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
 
     @property
     def param_groups(self):
@@ -61,10 +81,13 @@ class FlatAdam:
         """torch.optim.Adam's layout ({'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}), so the
         'optimizer_state_dict' entry of a checkpoint (train_dehazing.py:196-203) is interchangeable with the reference's."""
         state = {}
+        steps = self.seg_step.tolist() if self.step_count > 0 else []
         if self.step_count > 0:
             for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                if steps[i] == 0:          # never stepped: torch.optim.Adam holds no state for it
+                    continue
                 n = p.numel()
-                state[i] = {"step": torch.tensor(float(self.step_count)),
+                state[i] = {"step": torch.tensor(float(steps[i])),
                             "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
                             "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
@@ -79,6 +102,7 @@ class FlatAdam:
         g = groups[0]
         self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
         steps = set()
+        seg_steps = [0] * len(self.params)
         with torch.no_grad():
             self.exp_avg.zero_()
             self.exp_avg_sq.zero_()
@@ -86,15 +110,15 @@ class FlatAdam:
                 st = sd["state"].get(i, sd["state"].get(str(i)))
                 if st is None:
                     continue
+                seg_steps[i] = int(float(st["step"]))
                 if tuple(st["exp_avg"].shape) != tuple(p.shape):
                     raise ValueError(f"FlatAdam.load_state_dict: state {i} has shape {tuple(st['exp_avg'].shape)}, parameter {tuple(p.shape)}")
                 n = p.numel()
                 self.exp_avg[o:o + n].view(p.shape).copy_(st["exp_avg"])
                 self.exp_avg_sq[o:o + n].view(p.shape).copy_(st["exp_avg_sq"])
                 steps.add(int(float(st["step"])))
-        if len(steps) > 1:
-            raise ValueError("FlatAdam.load_state_dict: per-parameter step counts differ (one fused step per iteration is assumed)")
-        self.step_count = steps.pop() if steps else 0
+            self.seg_step.copy_(torch.tensor(seg_steps, dtype=torch.int32))
+        self.step_count = max(steps) if steps else 0
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -114,10 +138,23 @@ class FlatAdam:
                 torch._foreach_zero_(none)
             if have:
                 torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+            flags = [0.0 if p.grad is None else 1.0 for p in self.params]
+            if flags != getattr(self, "_last_flags", None):       # (the pinned staging buffer is rewritten only when the set changes)
+                torch.cuda.current_stream().synchronize() if self.flat.is_cuda and getattr(self, "_last_flags", None) is not None else None
+                self._live_host.copy_(torch.tensor(flags))
+                self._last_flags = flags
+            self.live.copy_(self._live_host, non_blocking=True)
         world = self.world_size()
         if world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.grad, group=self.group)
+            ev = None
+            if self.allreduce_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            dist.all_reduce(self.bucket, group=self.group)
+            if ev is not None:
+                ev[1].record()
+                self.allreduce_events.append(ev)
         return world
 
     def step(self):
@@ -126,7 +163,8 @@ class FlatAdam:
         self.step_count += 1
         world = self.reduce_gradients()
         b1, b2 = self.betas
-        _lib.call("adb_adam_step", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+        _lib.call("adb_adam_step_segments", _lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                   self.flat.numel(), float(self.lr), float(b1), float(b2), float(self.eps), float(self.weight_decay),
-                  self.step_count, 1.0 / world, _lib.current_stream())
+                  1.0 / world, _lib.ptr(self.seg_off), len(self.params), _lib.ptr(self.live), _lib.ptr(self.seg_step),
+                  _lib.ptr(self._seg_bc[0]), _lib.ptr(self._seg_bc[1]), _lib.current_stream())
         _bump_versions(self.params)

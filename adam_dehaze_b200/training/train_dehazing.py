@@ -35,9 +35,11 @@ def synthetic_loader(n_batches, batch, h, w, device, seed=42):
 
 
 def batch_psnr(pred, target):
-    """Mean over the batch of 10 log10(1 / mse_i), on the device (skimage peak_signal_noise_ratio, data_range=1)."""
-    mse = torch.mean((pred - target) ** 2, dim=(1, 2, 3)).clamp_min(1e-12)
-    return (10.0 * torch.log10(1.0 / mse)).mean()
+    """Mean over the batch of 10 log10(1 / mse_i) (skimage peak_signal_noise_ratio, data_range=1; train_dehazing.py:146-159),
+    on the device through adb_image_metrics — the same kernel evaluation/metrics.py reports from."""
+    from ..evaluation.metrics import image_metrics
+    psnr, _ = image_metrics(pred.detach(), target)
+    return psnr.mean()
 
 
 class LossMeter:
@@ -123,6 +125,12 @@ def train_dehazing_model(model, intensity_level, config, train_loader=None, val_
         for batch in train_loader:
             sel = batch["intensity"] == k
             if not bool(sel.any()):
+                # train_dehazing.py:71-75 skips a batch that holds no sample of this level.  With replicas every rank must
+                # still join the step's gradient all-reduce (FlatAdam: zero gradients + "no gradient here" flags), or the
+                # ranks that did find samples would wait for this one forever.
+                if getattr(optimizer, "world_size", lambda: 1)() > 1:
+                    optimizer.zero_grad()
+                    optimizer.step()
                 continue
             hazy, clear = batch["hazy"][sel].to(device), batch["clear"][sel].to(device)
             loss, _ = train_step(model, criterion, optimizer, hazy, clear)

@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager comparator leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the embedded BASELINE configs[4] training record")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
@@ -127,6 +129,55 @@ def cpu_sample(hden, h=512, w=1024, threads=None, repeats=1, warm=0):
     return 3.0 * scale / sec, sec, f"1 image per branch + HDEN({hden}) on the 3, {h}x{w} fp32 (rate scaled by pixel ratio {scale:.4f}), {threads} threads, oracle port"
 
 
+def gpu_eager_baseline(torch, branches, clf, hden, h, w, dev, nimg=2, reps=3):
+    """Stock PyTorch eager (cuDNN / cuBLAS) on the same B200, same synthetic recipe and weights: the on-box comparator
+    SURVEY.md 8(d) and BASELINE.md 4 ask for.  Runs the oracle's functional restatement of the reference forwards (plain
+    F.conv2d / F.batch_norm calls, i.e. exactly what the reference's nn.Modules dispatch to) in fp32 with TF32 off and in
+    bf16 autocast + channels_last.  Baseline leg only: nothing here is on the measured path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import adam_oracle as oracle
+    x, _, _ = oracle.synth_hazy(nimg, h, w, device=dev)
+    fwd = {"low": oracle.light_forward, "medium": oracle.medium_forward, "high": oracle.complex_forward}
+    out = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for mode in ("fp32", "bf16_autocast_channels_last"):
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.benchmark = True
+            cl = mode != "fp32"
+            xin = x.contiguous(memory_format=torch.channels_last) if cl else x
+
+            def prep(sd):
+                return {k: (v.detach().contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v.detach())
+                        for k, v in sd.items()}
+            sds = {k: prep(m.state_dict()) for k, m in branches.items()}
+            csd = prep(clf.state_dict())
+            res = {}
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=cl):
+                jobs = [(k, (lambda k=k: fwd[k](sds[k], xin))) for k in ("low", "medium", "high")]
+                jobs.append((hden, lambda: oracle.classifier_forward(csd, xin, hden)))
+                for name, fn in jobs:
+                    fn(); fn()                                    # warm-up (cuDNN algorithm search included)
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(reps):
+                        fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    res[name] = a.elapsed_time(b) / reps / nimg
+            per_img = (res["low"] + res["medium"] + res["high"]) / 3.0 + res[hden]
+            out[mode] = {"ms_per_image": {k: round(v, 3) for k, v in res.items()}, "mix_images_per_s": 1000.0 / per_img}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    out["what"] = (f"torch {torch.__version__} eager, cuDNN {torch.backends.cudnn.version()}, {nimg} images at {h}x{w} per call, "
+                   f"mean of {reps} after 2 warm-ups, CUDA events; mix = 1/3 Light + 1/3 Medium + 1/3 Complex + HDEN({hden}) on every image; "
+                   "fp32 = TF32 off; bf16 = torch.autocast(bfloat16) + channels_last inputs and weights; cudnn.benchmark on")
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,7 +189,11 @@ def run_reference(args):
     desc = ""
     # warm-up + timed steps, each step one bounded sample
     total = args.warmup + args.steps
+    full = None
     for it in range(total):
+        if it == 0:      # one un-extrapolated sample at the metric's own resolution, untimed for `value`
+            fv, fsec, fdesc = cpu_sample(args.hden, h=args.height, w=args.width, threads=threads)
+            full = {"value": fv, "seconds": fsec, "sample": fdesc}
         v, sec, desc = cpu_sample(args.hden, threads=threads)
         if it >= args.warmup:
             vals.append((v, sec))
@@ -149,7 +204,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"adaptive mix 1/3 Light, 1/3 Medium, 1/3 Complex + HDEN {args.hden}, 1024x2048 equivalent", "hden": args.hden},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                         "extrapolated_from": "512x1024", "full_resolution_check": full},
+        "extrapolated_from": "512x1024 (rate scaled by the pixel ratio; conv FLOPs are linear in pixels)",
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -295,9 +352,36 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, desc = cpu_sample(args.hden, threads=os.cpu_count() or 1, repeats=3, warm=1)   # ~10-15 s of host work
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + ", mean of 3 after 1 warm-up",
+        v, sec, desc = cpu_sample(args.hden, h=Hh, w=Ww, threads=os.cpu_count() or 1, repeats=1, warm=0)   # ~10-30 s of host work
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + ", one sample, no extrapolation",
                "seconds": sec}
+
+    # ---- on-box comparator: stock PyTorch eager (cuDNN) on this GPU (rank 0, N=1 only)
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        try:
+            eager = gpu_eager_baseline(torch, branches, clf, args.hden, Hh, Ww, dev)
+        except Exception as e:  # noqa: BLE001  (a baseline leg must not take the measured line down with it)
+            eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- BASELINE configs[4] in the same run: the joint training step at this N (every rank takes part)
+    train = None
+    if not args.no_train:
+        del out, logits
+        for m in branches.values():
+            eng = m.__dict__.get("_adb_engine") or getattr(m, "engine", None)
+            if eng is not None and hasattr(eng, "release_buffers"):
+                eng.release_buffers()
+        del hazy, router, branches, clf
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        _lib.call = _orig_call
+        ops._lib.call = _orig_call
+        targs = argparse.Namespace(**vars(args))
+        targs.steps, targs.warmup, targs.batch, targs.height, targs.width = max(10, args.steps), max(3, args.warmup), 16, 512, 512
+        train = run_train(targs, embedded=True)
+        torch.set_grad_enabled(False)
 
     if rank == 0:
         mix = (TFLOP_PER_IMAGE["low"] + TFLOP_PER_IMAGE["medium"] + TFLOP_PER_IMAGE["high"]) / 3 + TFLOP_PER_IMAGE[args.hden]
@@ -314,6 +398,8 @@ def main():
             "clocks": clocks, "gpu_launches": launches_per_step, "per_branch_ms_per_image": per_branch,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "model_tflops_per_gpu": value / world * mix,
+            "gpu_eager_baseline": eager,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -325,7 +411,7 @@ def main():
 TRAIN_METRIC = "training samples/sec, joint step (HDEN + SoftRouter over Light/Medium/Complex, JointLoss, Adam) @512x512"
 
 
-def run_train(args):
+def run_train(args, embedded=False):
     """One step = train_joint.py:129-150 on 16 synthetic samples per GPU at 512x512: HDEN logits, SoftRouter forward of the
     three branches in train() mode (batch-statistics BatchNorm), DehazingLoss, backward (dgrad + wgrad kernels), one NCCL
     all-reduce of the flat gradient bucket, one fused Adam launch.  Prints ONE JSON line (rank 0)."""
@@ -342,11 +428,12 @@ def run_train(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not embedded:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         quiet_nccl_stdout()
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().adb_device_check(), "adb_device_check")
+    torch.set_grad_enabled(True)
     B = 16 if args.batch == 256 else args.batch
     Hh, Ww = (512, 512) if (args.height, args.width) == (H, W) else (args.height, args.width)
     # the joint step trains HDEN through the router (train_joint.py:80-88,117-121)
@@ -490,9 +577,12 @@ def run_train(args):
             return r
         set_call(timed)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        opt.allreduce_events = []
         s0.record(); step(); s1.record()
         torch.cuda.synchronize()
         set_call(inner)
+        ar_ms = [a_.elapsed_time(b_) for a_, b_ in opt.allreduce_events]
+        opt.allreduce_events = None
         by, fl = {}, {}
         slow = []
         for nm, ea, eb, f in calls:
@@ -536,14 +626,23 @@ def run_train(args):
                        "l2": f"activations {B}x{Hh}x{Ww} per layer (> 126 MB L2 for every full-resolution map)"},
             "clocks": clocks, "gpu_launches": counts["n"] // max(1, args.steps), "loss": float(loss.item()),
             "roofline": roof, "train_detail": detail, "cpu_baseline": None,
+            "allreduce": {"collective": "NCCL all_reduce(sum) of the flat fp32 gradient bucket, one per step" if world > 1 else "none (1 GPU)",
+                          "bytes": int(opt.grad.numel()) * 4, "ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else None,
+                          "bus_GBs": (2.0 * (world - 1) / world * opt.grad.numel() * 4 / (sum(ar_ms) / len(ar_ms) * 1e-3) / 1e9) if ar_ms else None,
+                          "how": "CUDA events on the step's stream around dist.all_reduce in the instrumented step"},
             "e2e": {"value": world * B / (e2e_ms / 1000.0), "unit": "samples/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 2 * B * 3 * Hh * Ww * 4, "d2h_bytes_per_step": 4,
                     "api": "SoftRouter.forward + DehazingLoss + loss.backward() + FlatAdam.step() from pinned host batches; every step's loss read on the host through training.train_dehazing.LossMeter (pinned 4-byte D2H per step, read one step later)"},
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
+        if not embedded:
+            print(json.dumps(line), flush=True)
+    else:
+        line = None
+    del router, opt, crit, branches, clf, hazy, clear
+    if world > 1 and not embedded:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 TRAIN_LAMBDAS = (0.1, 0.1)   # (content, perceptual) terms of DehazingLoss in the training bench
@@ -628,26 +727,40 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
     if not peak:
         peak, src = 1400.0, "fallback sustained figure, B200_PROFILING.md (of fallback)"
     launches = sum(v["conv_launches"] for v in per_branch.values())
+    # one average launch of the equal-thirds mix: every image runs HDEN, a third of the images run each branch, so a model's
+    # launches, FLOPs and time all enter with weight 1 (branches) or 3 (HDEN)
+    wts = {k: (3.0 if k == hden else 1.0) for k in per_branch}
+    w_launch = sum(wts[k] * v["conv_launches"] for k, v in per_branch.items())
+    w_flops = sum(wts[k] * v["tflop_per_image"] * nimg for k, v in per_branch.items()) * 1e12
+    w_ms = sum(wts[k] * v["conv_ms"] * nimg for k, v in per_branch.items())
+    per_model = {k: {"conv_launches": v["conv_launches"], "achieved_tflops": v["conv_tflops"],
+                     "frac": (v["conv_tflops"] / peak) if v["conv_tflops"] else None,
+                     "flops_per_launch": v["tflop_per_image"] * nimg * 1e12 / max(1, v["conv_launches"]),
+                     "ms_per_launch": v["conv_ms"] * nimg / max(1, v["conv_launches"]), "mix_weight": wts[k]}
+                 for k, v in per_branch.items()}
     # dram bytes per conv launch of this same pass, from the committed ncu capture (tools/conv_traffic.py); same weighting
     # and same 8-image pass as flops_per_launch_avg, so bytes/launch and FLOPs/launch describe the same average launch
-    traffic, traffic_src = None, "profiles/r1_conv_traffic.json missing"
-    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
-    if os.path.exists(tpath):
+    traffic, traffic_src = None, "profiles/r*_conv_traffic.json missing"
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2_conv_traffic.json", "r1_conv_traffic.json")) if os.path.exists(q)), "")
+    if tpath:
         with open(tpath) as fh:
             tj = json.load(fh)
         if tj.get("images") == nimg and tj.get("hden") == hden and (tj.get("height"), tj.get("width")) == (hazy.shape[2], hazy.shape[3]):
             traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
         else:
-            traffic_src = "profiles/r1_conv_traffic.json was captured on a different pass shape"
-    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            traffic_src = os.path.basename(tpath) + " was captured on a different pass shape"
+    roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_roll_kernel (adb_conv2d)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
             "peak_source": src,
             "traffic_ref": "ncu --set full captures of representative conv shapes: profiles/r1_conv_ncu_full.md, "
                            "profiles/r1_dense_pre_ncu.md (DRAM traffic ~= algorithmic bytes: no re-reads)",
             "how": f"sum of true conv FLOPs / sum of CUDA-event durations over the {launches} conv launches of one pass of "
                    f"Light+Medium+Complex+HDEN on {nimg} images at {hazy.shape[2]}x{hazy.shape[3]} (equal-thirds mix weighting)",
-            "flops_per_launch_avg": tot_fl * 1e12 * nimg / max(1, launches) / 2,
-            "ms_per_launch_avg": tot_ms * nimg / max(1, launches) / 2}
+            "flops_per_launch_avg": w_flops / max(1.0, w_launch),
+            "ms_per_launch_avg": w_ms / max(1.0, w_launch),
+            "launch_weighting": "mix-weighted over the same pass: each model's launches, FLOPs and milliseconds enter with weight 1 "
+                                "(Light/Medium/Complex) or 3 (HDEN); achieved = flops_per_launch_avg / ms_per_launch_avg",
+            "per_model": per_model}
     return per_branch, roof
 
 

@@ -192,6 +192,11 @@ ADB_API int adb_linear(const float* x, int32_t n, int32_t fin, const float* w, c
 ADB_API int adb_route(const float* logits, const int64_t* intensity_in, int32_t b, int32_t classes,
               int64_t* intensity, uint8_t* masks, int32_t* bucket_index, int32_t* bucket_count, void* stream);
 
+/* HardRouter's output buffer (routing.py:31 `torch.zeros_like(x)`): rows whose class id is outside {0,1,2} are written by
+ * no branch and must read as zeros; every other row is overwritten in full by its branch.  Clears only the former
+ * (out: NCHW fp32 [b][row_elems], intensity int64[b] as written by adb_route) instead of memset-ing the whole batch. */
+ADB_API int adb_zero_unrouted(float* out, const int64_t* intensity, int32_t b, int64_t row_elems, void* stream);
+
 /* Soft/gated blend (routing.py:111-127, 215-221): w = softmax(logits/T) (or given weights when temperature <= 0),
  * out = sum_k w[:,k] * y_k, NCHW fp32. */
 ADB_API int adb_blend3(const float* y0, const float* y1, const float* y2, const float* logits_or_weights, float temperature,
@@ -342,6 +347,16 @@ ADB_API int adb_upsample_bilinear_bwd(const void* dy, int32_t pitch_dy, int32_t 
  * added to the gradient); grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
 ADB_API int adb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                           float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* The same step with torch.optim.Adam's per-parameter skipping: the flat tensor is cut into `n_seg` segments
+ * (seg_offsets int64[n_seg], ascending, multiples of 4, seg_offsets[0] == 0); a segment with seg_live[s] <= 0 (no rank
+ * produced a gradient for that parameter: p.grad is None everywhere) is left untouched — no moment decay, no weight
+ * decay, no step count (torch/optim/adam.py skips such parameters; train_joint.py:149-150 under HardRouter).  seg_step
+ * (int32[n_seg], device) is the per-parameter step count, advanced here; seg_bc1 / seg_bc2s are fp32[n_seg] scratch. */
+ADB_API int adb_adam_step_segments(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                   const int64_t* seg_offsets, int32_t n_seg, const float* seg_live, int32_t* seg_step,
+                                   float* seg_bc1, float* seg_bc2s, void* stream);
 
 /* Image-quality metrics on the device (evaluation/metrics.py:13-36): per image PSNR
  * (data_range 1) and SSIM with skimage's defaults on the channel-mean grayscale (7x7 uniform window, sample

@@ -311,6 +311,10 @@ ROLL_CASES = [
     (32, 0, 32, 1, 1, 128, False, None),              # a single image row
     (64, 0, 64, 1, 2, 512, True, {"stages": 2}),
     (32, 0, 32, 24, 64, 128, True, None),             # several segments per CTA: slot phases carry across segments
+    (32, 0, 32, 2, 40, 128, False, {"acc": 1}),       # one input row per operand box (default: 4 for a ring of 16)
+    (32, 0, 32, 2, 43, 256, True, {"acc": 2}),        # two rows per box, odd row count: a short last group
+    (64, 0, 64, 2, 33, 128, True, {"acc": 1}),
+    (128, 0, 32, 1, 67, 128, False, {"mt": 1}),       # 8-row segments with 4-row boxes: groups cut by segment ends
 ]
 
 

@@ -116,6 +116,15 @@ def test_hard_router_given_intensity_bit_exact_routes():
     for k, name in enumerate(("low", "medium", "high")):
         idx = buckets[k]
         assert torch.equal(out[idx], branches[name](x[idx].contiguous()))
+    # class ids outside {0,1,2} are routed nowhere: the reference leaves those rows at zeros_like(x) (routing.py:31,55-61);
+    # the output buffer is not memset as a whole, only such rows are cleared (adb_zero_unrouted)
+    odd = torch.tensor([2, 5, 1, -1, 0, 2, 3], device="cuda")
+    out2, info2 = router(x, intensity=odd)
+    ref2, ref_int2, _ = oracle.hard_route(sds, x, intensity=odd)
+    assert torch.equal(info2["intensity"], ref_int2)
+    for i in (1, 3, 6):
+        assert out2[i].abs().max().item() == 0.0 and ref2[i].abs().max().item() == 0.0
+    _check_image(out2, ref2)
 
 
 def test_hard_router_natural_and_crafted_logits():

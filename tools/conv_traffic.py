@@ -1,14 +1,14 @@
 """DRAM bytes per conv launch of bench.py's roofline pass, from an ncu CSV.
 
     ncu --nvtx --nvtx-include "adb_roofline_low/" --nvtx-include "adb_roofline_medium/" --nvtx-include "adb_roofline_high/" \
-        --nvtx-include "adb_roofline_densenet121/" -k regex:conv_igemm \
+        --nvtx-include "adb_roofline_densenet121/" -k regex:conv_ \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file gpurun_out/ncu_traffic.csv python bench.py --steps 1 --warmup 3 --batch 12 --no-e2e --no-cpu-baseline
     python tools/conv_traffic.py gpurun_out/ncu_traffic.csv > profiles/r1_conv_traffic.json
 
 bench.py wraps each model's instrumented pass (8 images at 1024x2048) in an NVTX range `adb_roofline_<model>`; the average
-uses bench.py's own weighting (Light + Medium + Complex + 3 x HDEN, halved, over the un-weighted launch count) so that
-`roofline.traffic` and `roofline.flops_per_launch_avg` describe the same average launch.
+uses bench.py's own mix weighting (every model's bytes AND launches enter with weight 1 for Light/Medium/Complex and 3 for
+HDEN, which runs on every image) so that `roofline.traffic` and `roofline.flops_per_launch_avg` describe the same average launch.
 """
 import csv
 import json
@@ -34,7 +34,7 @@ def main():
         d[r["Metric Name"]] = v
     models = {}
     for d in per.values():
-        if "conv_igemm" not in d["name"]:
+        if "conv_igemm" not in d["name"] and "conv_roll" not in d["name"]:
             continue
         rng = d["range"]
         m = next((k for k in ("low", "medium", "high", "densenet121", "resnet18") if f"adb_roofline_{k}" in rng), None)
@@ -48,10 +48,11 @@ def main():
     hden = "densenet121" if "densenet121" in models else "resnet18"
     launches = sum(a["launches"] for a in models.values())
     tot = sum((a["read"] + a["write"]) * (3 if k == hden else 1) for k, a in models.items())
-    out = {"dram_bytes_per_launch_avg": tot / max(1, launches) / 2, "launches": launches, "images": 8, "height": 1024, "width": 2048,
+    w_launches = sum(a["launches"] * (3 if k == hden else 1) for k, a in models.items())
+    out = {"dram_bytes_per_launch_avg": tot / max(1, w_launches), "launches": launches, "images": 8, "height": 1024, "width": 2048,
            "hden": hden, "per_model": {k: {"launches": a["launches"], "dram_read_bytes": a["read"], "dram_write_bytes": a["write"],
                                             "ncu_ms": a["ns"] / 1e6} for k, a in models.items()},
-           "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv_igemm launches of bench.py's roofline pass ({path}), "
+           "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the adb_conv2d (conv_igemm / conv_roll) launches of bench.py's roofline pass ({path}), "
                      "weighting as flops_per_launch_avg"}
     json.dump(out, sys.stdout, indent=1)
     sys.stdout.write("\n")

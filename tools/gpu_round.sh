@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --n
     --log-file gpurun_out/launches_${TAG}.csv python bench.py $ISMALL > gpurun_out/ncu_launches_${TAG}.log 2>&1
 # dram bytes of the conv launches of bench.py's roofline pass (NVTX ranges adb_roofline_<model>) -> roofline.traffic
 timeout 600 ncu --nvtx --nvtx-include "adb_roofline_low/" --nvtx-include "adb_roofline_medium/" --nvtx-include "adb_roofline_high/" \
-    --nvtx-include "adb_roofline_densenet121/" -k regex:conv_igemm --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+    --nvtx-include "adb_roofline_densenet121/" -k regex:conv_ --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file gpurun_out/ncu_traffic_${TAG}.csv python bench.py $ISMALL > gpurun_out/ncu_traffic_${TAG}.log 2>&1
 python tools/conv_traffic.py gpurun_out/ncu_traffic_${TAG}.csv > gpurun_out/conv_traffic_${TAG}.json 2> gpurun_out/conv_traffic_${TAG}.err
 python tools/prof_wgrad.py > gpurun_out/prof_wgrad_${TAG}.txt 2>&1
