@@ -57,6 +57,20 @@ class WgradDesc(C.Structure):
     ]
 
 
+class F32ConvDesc(C.Structure):
+    _fields_ = [
+        ("flag_index", C.c_void_p), ("flag_count", C.c_void_p), ("cursor", C.c_void_p), ("cap", C.c_int32),
+        ("x", C.c_void_p), ("x_slot", C.c_void_p), ("in_nchw", C.c_int32),
+        ("h_in", C.c_int32), ("w_in", C.c_int32), ("cin", C.c_int32), ("in_pitch", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("w", C.c_void_p), ("cout", C.c_int32),
+        ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
+        ("post_relu", C.c_int32),
+        ("residual", C.c_void_p), ("res_pitch", C.c_int32),
+        ("y", C.c_void_p), ("out_pitch", C.c_int32), ("out_c_off", C.c_int32),
+    ]
+
+
 WG_OIHW, WG_STEM = 0, 1
 
 _P, _I, _L, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -110,6 +124,18 @@ SIGNATURES = {
     "adb_head_mlp": [_P, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P],
     "adb_linear": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "adb_route": [_P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "adb_guard_flags": [_P, _I, _I, _F, _P, _P, _P, _P],
+    "adb_guard_set_slots": [_P, _P, _P, _P],
+    "adb_f32_conv2d": [C.POINTER(F32ConvDesc), _P],
+    "adb_f32_pool": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "adb_f32_global_avgpool": [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P],
+    "adb_guard_scatter": [_P, _P, _P, _I, _P, _I, _P, _P],
+    "adb_guard_advance": [_P, _P, _I, _P],
+    "adb_guard_graph_begin": [_P, _P, _I, _P, C.POINTER(C.c_void_p)],
+    "adb_guard_graph_end": [_P],
+    "adb_guard_graph_launch": [_P, _P],
+    "adb_guard_graph_destroy": [_P],
+    "adb_image_u8_to_f32": [_P, _I, _I, _I, _L, _I, _P, _P, _I, _I, _P],
     "adb_zero_unrouted": [_P, _P, _I, _L, _P],
     "adb_blend3": [_P, _P, _P, _P, _F, _I, _L, _P, _P, _P],
     "adb_l1_mse_fwd": [_P, _P, _L, _P, _P],

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadb200.so")
 STAMP = os.path.join(HERE, ".libadb200.stamp")
-SOURCES = ["adb_host.cu", "conv_igemm.cu", "conv_roll.cu", "conv_wgrad.cu", "pointwise.cu", "train.cu", "metrics.cu", "route.cu"]
+SOURCES = ["adb_host.cu", "conv_igemm.cu", "conv_roll.cu", "conv_wgrad.cu", "pointwise.cu", "train.cu", "metrics.cu", "route.cu", "guard_fp32.cu", "input_pipe.cu"]
 HEADERS = ["adb_ptx.cuh", "adb_host.h", "conv_common.cuh", os.path.join("..", "..", "include", "adb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -73,6 +73,21 @@ class FogIntensityClassifier(nn.Module):
         """x [B,3,H,W] fp32 CUDA -> (logits [B,num_classes] fp32, features [B,feature_dim] fp32)."""
         return self._hden_engine().forward(x)
 
+    def route_guard(self, **kw):
+        """The fp32 re-evaluation path for near-tie rows (adam_dehaze_b200/route_guard.py); created on first use.
+        Keyword arguments (eps, cap, use_graph) rebuild it."""
+        g = self.__dict__.get("_adb_route_guard")
+        if g is None or kw:
+            from ..route_guard import RouteGuard
+            g = RouteGuard(self, **kw)
+            self.__dict__["_adb_route_guard"] = g
+        return g
+
+    def refine_logits(self, x, logits):
+        """Patch, in place and on the device, the logits of the rows whose top-2 gap is within the bf16 error of the trunk with
+        their fp32 re-evaluation, so that argmax(logits) equals the fp32 reference's (models/routing.py:41-43)."""
+        return self.route_guard().refine(x, logits)
+
     def extract_features(self, x):
         with torch.no_grad():
             return self._hden_engine().forward(x)[1]

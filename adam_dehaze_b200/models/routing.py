@@ -20,6 +20,8 @@ class HardRouter(nn.Module):
         self.models = nn.ModuleDict(models)
         self.classifier = classifier
         self.device = device
+        # re-evaluate near-tie rows of the bf16 HDEN in fp32 before the argmax (route decisions bit-exact vs the fp32 reference)
+        self.route_guard = True
 
     def forward(self, x, intensity=None):
         """Returns (outputs, {'intensity', 'low_mask', 'medium_mask', 'high_mask'}) like routing.py:23-68.
@@ -35,6 +37,8 @@ class HardRouter(nn.Module):
         if intensity is None and self.classifier is not None:
             with torch.no_grad():
                 logits, _ = self.classifier(x)
+                if self.route_guard and not self.classifier.training and hasattr(self.classifier, "refine_logits"):
+                    logits = self.classifier.refine_logits(x, logits.contiguous())
             inten, masks, bidx, bcnt = ops.route(logits=logits)
         elif intensity is not None:
             if intensity.dim() != 1 or intensity.shape[0] != x.shape[0] or intensity.is_floating_point():

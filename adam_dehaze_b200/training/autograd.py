@@ -59,6 +59,17 @@ class Node:
             ops.conv2d(spec, src, dst=self.grad, residual=self.grad)
 
 
+# Test hook (tests/test_gpu_train.py, same-mask gradient parity): when a dict is installed here, every conv of a train()-mode
+# forward leaves its raw bf16 output under id(weight parameter), so the fp32 oracle can be differentiated AT the activations
+# this implementation actually produced (identical ReLU / clamp masks).
+_RECORD = None
+
+
+def _rec(w, z):
+    if _RECORD is not None:
+        _RECORD[id(w)] = z
+
+
 def _touch_bn_buffers(bn):
     """adb_bn_train_stats updates running_mean / running_var / num_batches_tracked through raw pointers; bump their torch
     version counters so the eval-path packings keyed on `_version` (engine._Versioned) re-fold the new statistics even when
@@ -258,6 +269,7 @@ class Tape:
         a = srcs[0]
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        _rec(w, z)
         c = fspec.cout_pad
         bnp = bn if c == fspec.cout else _PaddedBN(bn, c)     # e.g. 24 channels inside a 32-channel map: padded affine
         y, stats = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t)
@@ -312,6 +324,7 @@ class Tape:
         a = srcs[0]
         bsrc = srcs[1] if len(srcs) > 1 else None
         z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        _rec(w, z)
         c = fspec.cout_pad
         y, stats = self._bn_forward(z, c, bn, act)
         out = Node(y, c)
@@ -613,6 +626,7 @@ class Tape:
         w, b = conv.weight, conv.bias
         fspec = self.wc.get(("f", id(conv)), (w, b), lambda wt: ConvSpec.from_conv(wt, bias=b, pad=conv.padding[0]), weight=w, bias=b)
         z = ops.conv2d(fspec, src.t, c0=src.c)
+        _rec(w, z)
         n, h, wd, pitch = z.shape
         out = torch.empty_like(x)
         gptr = None if guidance is None else guidance.t

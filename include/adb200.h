@@ -364,6 +364,58 @@ ADB_API int adb_adam_step_segments(float* param, const float* grad, float* exp_a
 ADB_API int adb_image_metrics(const float* pred, const float* target, int32_t n, int32_t h, int32_t w, double* scratch,
                               float* psnr, float* ssim, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Route guard (csrc/guard_fp32.cu): fp32 re-evaluation of HDEN for the batch rows whose bf16 top-2 logit gap is below
+ * eps, so that HardRouter's argmax (routing.py:41-43) equals the fp32 reference's even for near-ties.  No host round
+ * trip: the rows are listed on the device (flag_index / flag_count), every kernel of a pass works on list positions
+ * [*cursor, *cursor + cap) and exits when they are not live, and adb_guard_graph_* wraps one pass in a CUDA-graph WHILE
+ * node that repeats it while rows remain.  Maps are NHWC fp32; arithmetic is fp32 FMA on the CUDA cores in the
+ * reference's op order (conv -> BatchNorm affine -> ReLU / residual / pool), classifier.py:80-97. */
+ADB_API int adb_guard_flags(const float* logits, int32_t b, int32_t classes, float eps, int32_t* flag_index /*[b]*/,
+                            int32_t* flag_count, int32_t* cursor /*reset to 0*/, void* stream);
+/* slots[0] = the NCHW fp32 image batch, slots[1] = the fp32 logits [b][classes] to patch: read through the slots by the
+ * stem conv and the scatter, so a captured graph serves every batch of the same shape */
+ADB_API int adb_guard_set_slots(const void** slots, const void* images, void* logits, void* stream);
+typedef struct adb_f32_conv_desc {
+  const int32_t* flag_index; const int32_t* flag_count; const int32_t* cursor; int32_t cap;   /* the live rows of this pass */
+  const float* x;               /* NHWC fp32 [cap][h_in][w_in][in_pitch] (in_nchw == 0) */
+  const float* const* x_slot;   /* in_nchw != 0: *x_slot = NCHW fp32 [B][cin][h_in][w_in]; row = flag_index[*cursor + i] */
+  int32_t in_nchw;
+  int32_t h_in, w_in, cin, in_pitch;
+  int32_t kh, kw, stride, pad;
+  const float* w; int32_t cout; /* fp32 [kh*kw][cin][cout] */
+  const float* pre_scale; const float* pre_shift;    /* nullable: input seen as relu(x*pre_scale[c] + pre_shift[c]), zero padding after it */
+  const float* post_scale; const float* post_shift;  /* nullable: y = acc*post_scale[co] + post_shift[co] */
+  int32_t post_relu;
+  const float* residual; int32_t res_pitch;          /* nullable NHWC fp32, added before the ReLU */
+  float* y; int32_t out_pitch; int32_t out_c_off;    /* NHWC fp32 [cap][h_out][w_out][out_pitch], first channel written */
+} adb_f32_conv_desc;
+ADB_API int adb_f32_conv2d(const adb_f32_conv_desc* desc, void* stream);
+/* mode 0: 3x3 stride-2 pad-1 max pool; mode 1: 2x2 stride-2 average pool */
+ADB_API int adb_f32_pool(const int32_t* flag_index, const int32_t* flag_count, const int32_t* cursor, int32_t cap, const float* x,
+                         int32_t h, int32_t w, int32_t c, int32_t in_pitch, int32_t mode, float* y, int32_t out_pitch, void* stream);
+/* feats[i][c] = mean_hw relu(x*scale + shift) (scale/shift nullable = plain mean) */
+ADB_API int adb_f32_global_avgpool(const int32_t* flag_index, const int32_t* flag_count, const int32_t* cursor, int32_t cap,
+                                   const float* x, int32_t hw, int32_t c, int32_t pitch, const float* scale, const float* shift,
+                                   float* feats, void* stream);
+/* (*logits_slot)[flag_index[*cursor + i]][:] = logits_c[i][:] for the live rows */
+ADB_API int adb_guard_scatter(const int32_t* flag_index, const int32_t* flag_count, const int32_t* cursor, int32_t cap,
+                              const float* logits_c, int32_t classes, float* const* logits_slot, void* stream);
+ADB_API int adb_guard_advance(const int32_t* flag_count, int32_t* cursor, int32_t cap, void* stream);   /* *cursor += cap */
+/* begin: starts capturing `stream` into the body of a WHILE node; the caller then issues one pass on that stream;
+ * end: appends "cursor += cap; repeat while cursor < count", instantiates; launch: cursor = 0, run while rows remain. */
+ADB_API int adb_guard_graph_begin(const int32_t* flag_count, int32_t* cursor, int32_t cap, void* stream, void** ctx_out);
+ADB_API int adb_guard_graph_end(void* ctx);
+ADB_API int adb_guard_graph_launch(void* ctx, void* stream);
+ADB_API int adb_guard_graph_destroy(void* ctx);
+
+/* Input transform of the reference loader (data/dataset.py:73-99) on the device: decoded uint8 HWC images (BGR as cv2.imread
+ * returns them when bgr != 0) -> NCHW fp32 in [0,1]: channel swap (cv2.cvtColor BGR2RGB), cv2.resize(INTER_LINEAR) for 8-bit
+ * images reproduced bit for bit when (hs, ws) != (hd, wd), transforms.ToTensor() (/255), and the training split's horizontal
+ * (bit 0) / vertical (bit 1) flips per image (flips nullable).  src: n images, src_image_stride bytes apart. */
+ADB_API int adb_image_u8_to_f32(const uint8_t* src, int32_t n, int32_t hs, int32_t ws, int64_t src_image_stride, int32_t bgr,
+                                const uint8_t* flips, float* dst, int32_t hd, int32_t wd, void* stream);
+
 /* Developer aid: copy the clock64() timeline CTA 0 recorded during the last adb_conv2d launched with tune_flags bit 2
  * ([6 roles][256 events]: A producer, B producer, MMA ready, MMA issued, epilogue start, epilogue end). Synchronises. */
 ADB_API int adb_debug_timeline(int64_t* host_out, int32_t count);

@@ -177,3 +177,31 @@ def test_detection_handoff_oracle_matches_reference():
     got = torch.stack(oracle.detection_normalize(dehazed))
     assert torch.equal(got, g["normalized"])
 
+
+
+def test_input_oracle_matches_cv2_golden_vectors():
+    """oracle/input_oracle.py (restatement of cv2.cvtColor + cv2.resize(INTER_LINEAR, uint8) + ToTensor, dataset.py:76-99) against
+    tests/golden/input_pipeline.pt, which oracle/make_golden_input.py produced with cv2 + torchvision themselves: bit-exact."""
+    import numpy as np
+    import input_oracle
+    g = golden("input_pipeline.pt")
+    assert len(g["cases"]) >= 8
+    for case in g["cases"]:
+        bgr = case["bgr"].numpy()
+        size = (case["size"], case["size"])
+        for key, flip in (("tensor", 0), ("hflip", 1), ("vflip", 2)):
+            got = input_oracle.load_transform(bgr, size, flip)
+            assert got.dtype == np.float32 and np.array_equal(got, case[key].numpy()), (bgr.shape, size, key)
+
+
+def test_input_oracle_matches_live_cv2_when_present():
+    """Wider sweep against the installed cv2 (skipped where cv2 is absent, e.g. a slim box): up/down-scales, the exact-2x
+    INTER_AREA shortcut, odd sizes, single rows/columns."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    import input_oracle
+    rng = np.random.default_rng(7)
+    for (sh, sw, dh, dw) in [(480, 640, 256, 256), (100, 130, 256, 256), (512, 512, 256, 256), (255, 257, 256, 256), (64, 64, 256, 256),
+                             (333, 777, 512, 512), (1, 50, 32, 32), (50, 1, 32, 32), (31, 33, 64, 16), (1024, 2048, 512, 512)]:
+        img = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(input_oracle.resize_linear_u8(img, dh, dw), cv2.resize(img, (dw, dh))), (sh, sw, dh, dw)
