@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Entry points of the drop-in: python main.py --mode {evaluate, demo, train_dehazing} [--config ...] [--exp_name ...]
-[--data_dir ...] [--device ...] [--seed ...]   (same flags as the reference's main.py:29-56).
+"""Entry points of the drop-in: python main.py --mode {evaluate, demo, train_dehazing, train_joint} [--config ...]
+[--exp_name ...] [--data_dir ...] [--device ...] [--seed ...]   (same flags as the reference's main.py:29-56).
 
-The hot path (HDEN -> router -> branches) runs through adam_dehaze_b200; the reference's dataset (cv2 files from a private
-corpus), detection sweep and matplotlib figures are out of scope — when the dataset directory does not
-exist the modes run on the synthetic hazy recipe of SURVEY.md §8d so that they are exercisable offline.
+The hot path (HDEN -> router -> branches) runs through adam_dehaze_b200.  When --data_dir (or config['dataset'][...]) names a
+directory laid out like the reference's dataset (<root>/<split>/<low|medium|high>/{hazy,clear,dehazed}/*.png|jpg) the modes
+read it through the device input pipeline (adam_dehaze_b200/data/pipeline.py); when it does not exist (the corpus is private)
+they run on the synthetic hazy recipe of SURVEY.md §8d so that they are exercisable offline.  The detection sweep and the
+matplotlib figures are out of scope.
 """
 import argparse
 import json
@@ -104,8 +106,26 @@ def ssim(a, b):
     return image_metrics(a, b)[1].mean().item()
 
 
-def evaluate(config, args, device, root):
+def dataset_loader(config, split, device, keys=("hazy", "clear")):
+    """The device input pipeline over config['dataset'][<split>_path]/<split>/... when that directory exists, else None."""
+    ds = config["dataset"]
+    root = ds["train_path"] if split == "train" else ds["val_path"] if split == "val" else ds["test_path"]
+    if not os.path.isdir(os.path.join(root, split)):
+        return None
+    from adam_dehaze_b200.data.pipeline import get_dataloader
+    return get_dataloader(config, split, device=device, keys=keys)
+
+
+def evaluate(config, args, device, root, loader=None):
     branches, clf, router = build(config, device)
+    loader = loader if loader is not None else dataset_loader(config, "test", device)
+    if loader is not None:
+        # evaluation/evaluate.py:33-175 over the real test split (--data_dir / config['dataset']['test_path'])
+        from adam_dehaze_b200.evaluation.evaluate import evaluate_baseline_models, evaluate_joint_model
+        results = {"baseline": evaluate_baseline_models(branches, loader, config, device),
+                   "joint": evaluate_joint_model(router, clf, loader, config, device)}
+        print(json.dumps(results))
+        return results
     hazy, clear, labels = synth_hazy(args.synthetic, args.size[0], args.size[1], device, config["seed"])
     results = {}
     with torch.no_grad():
@@ -169,9 +189,22 @@ def main():
         bs = max(3, args.synthetic)
         train = synthetic_loader(2, bs, args.size[0], args.size[1], device, seed=config["seed"])
         val = synthetic_loader(1, bs, args.size[0], args.size[1], device, seed=config["seed"] + 1)
+        real_train, real_val = dataset_loader(config, "train", device), dataset_loader(config, "val", device)
+        if real_train is not None:
+            train, val = real_train, real_val
         for level, mk in makers.items():
             print(f"Training {level} intensity dehazing model...")
             train_dehazing_model(mk(config), level, config, train_loader=train, val_loader=val, epochs=args.epochs, resume=args.resume)
+    elif args.mode == "train_joint":
+        # training/train_joint.py:29-318 — real loaders when the dataset directory exists, synthetic batches otherwise
+        from adam_dehaze_b200.training.train_dehazing import synthetic_loader
+        from adam_dehaze_b200.training.train_joint import train_joint_model
+        train, val = dataset_loader(config, "train", device), dataset_loader(config, "val", device)
+        if train is None:
+            bs = max(3, args.synthetic)
+            train = synthetic_loader(2, bs, args.size[0], args.size[1], device, seed=config["seed"])
+            val = synthetic_loader(1, bs, args.size[0], args.size[1], device, seed=config["seed"] + 1)
+        train_joint_model(config, train_loader=train, val_loader=val, epochs=args.epochs)
     else:
         raise NotImplementedError(f"--mode {args.mode} is outside the B200 hot path (SURVEY.md §2: out of scope)")
 

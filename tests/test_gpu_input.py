@@ -52,15 +52,16 @@ def test_input_kernel_full_resolution_properties():
     g = torch.Generator(device="cuda").manual_seed(3)
     src = torch.randint(0, 256, (2, 1024, 2048, 3), generator=g, device="cuda", dtype=torch.uint8)
     out = u8_to_tensor(src)
-    want = src.flip(3).permute(0, 3, 1, 2).float() / 255.0
-    assert torch.equal(out, want)
+    # (reference values on the CPU: torch's CUDA division by a scalar multiplies by the reciprocal, ToTensor on the host divides)
+    want = src.cpu().flip(3).permute(0, 3, 1, 2).float() / 255.0
+    assert torch.equal(out.cpu(), want)
     both = torch.full((2,), 3, dtype=torch.uint8, device="cuda")
     assert torch.equal(u8_to_tensor(src, flips=both).flip(2, 3), out)
     big = torch.randint(0, 256, (1, 2048, 4096, 3), generator=g, device="cuda", dtype=torch.uint8)
     half = u8_to_tensor(big, size=(1024, 2048), bgr=False)
     b = big.int()
-    area = ((b[:, 0::2, 0::2] + b[:, 0::2, 1::2] + b[:, 1::2, 0::2] + b[:, 1::2, 1::2] + 2) >> 2).permute(0, 3, 1, 2).float() / 255.0
-    assert torch.equal(half, area)
+    area = ((b[:, 0::2, 0::2] + b[:, 0::2, 1::2] + b[:, 1::2, 0::2] + b[:, 1::2, 1::2] + 2) >> 2).permute(0, 3, 1, 2).cpu().float() / 255.0
+    assert torch.equal(half.cpu(), area)
 
 
 def test_device_loader_reads_a_dataset_directory(tmp_path):
