@@ -110,7 +110,7 @@ struct ConvK {
 
 struct SmemLayout {
   // byte offsets from the 1024-aligned base
-  uint32_t a_off, b_off, slab_off, scale_off, pre_off, bar_off, total;
+  uint32_t a_off, b_off, slab_off, scale_off, pre_off, bar_off, tap_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes, int b_slots, int b_slot_bytes,
@@ -125,6 +125,7 @@ __host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes,
   L.pre_off = off; off += (uint32_t)pre_channels * 8;    // pre-activation scale then shift, fp32 (kPre kernels)
   off = (off + 15u) & ~15u;
   L.bar_off = off; off += 8u * (2 * kMaxASlots + 2 * kMaxBSlots + 4) + 16 + 8u * kMaxASlots;  // fullA, emptyA, fullB, emptyB, tmem full/empty, tmem ptr, readyA
+  L.tap_off = off; off += 4u * kMaxGroups * kMaxTaps;    // per-tap A descriptor offsets (16-byte units) for the MMA issuer
   L.total = off;
   return L;
 }
@@ -133,19 +134,54 @@ __host__ __device__ inline SmemLayout smem_layout(int a_slots, int a_slot_bytes,
 // epilogue sub-step stamp: tag in the top byte, clock below (flat sequence, warp 4 lane 0 of CTA 0)
 #define ADB_DBGE(tag) do { if (P.dbg && P.dbg_detail && blockIdx.x == 0 && ew == 0 && half == 0 && lane == 0 && e_i < 6 * 256) P.dbg[e_i++] = ((long long)(tag) << 56) | (clock64() & 0x00FFFFFFFFFFFFFFLL); } while (0)
 
-// One tap's MMAs as a straight-line UTCHMMA run: kKs K-steps of 16 (descriptor start address += 32 B each) for kMt sub-tiles.
+// D[tmem] (+)= A[smem] * B[smem]; descriptors given as (low word, high word) so that advancing a start address is one 32-bit add.
+template <bool kPair>
+__device__ __forceinline__ void umma_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if (kPair) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+struct IssueK {          // per-launch constants of the MMA issuer
+  uint32_t a_hi, b_hi;   // descriptor high words (SBO, version, swizzle) of the A views / weight boxes
+  uint32_t sub_step;     // A start-address step between the MT sub-tiles
+  uint32_t b_tap_step;   // B start-address step between the tap boxes of one weight slot
+  uint32_t idesc;
+};
+
+// The MMAs of one weight slot: `nt` taps (A view = slot + tap offset from the shared-memory table), kKs K steps of 16
+// (start address += 32 B each) for kMt sub-tiles sharing each B box.  A few integer instructions per MMA: every MMA of a
+// narrow tile takes only ~N/2 cycles, so the issue path must not cost more (measured: 250-350 cycles of descriptor
+// arithmetic per tap in the first version kept N <= 96 layers at 0.6 of the tensor peak).
 template <bool kPair, int kMt, int kKs>
-__device__ __forceinline__ void issue_mmas(uint32_t d0, uint32_t d1, uint64_t a0, uint64_t a1, uint64_t b0, uint32_t idesc,
-                                           uint32_t first) {
+__device__ __forceinline__ void issue_taps(const IssueK& K, uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b_lo, const uint32_t* tap_off,
+                                           int nt, uint32_t accumulate) {
+#pragma unroll 1
+  for (int jj = 0; jj < nt; ++jj) {
+    const uint32_t a = a_lo + tap_off[jj];
+    const uint32_t b = b_lo + (uint32_t)jj * K.b_tap_step;
 #pragma unroll
-  for (int kk = 0; kk < kKs; ++kk) {
-    const uint32_t accum = (first | (uint32_t)kk) ? 1u : 0u;
-    if (kPair) {
-      umma_bf16_pair(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
-      if (kMt == 2) umma_bf16_pair(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
-    } else {
-      umma_bf16(d0, a0 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
-      if (kMt == 2) umma_bf16(d1, a1 + (uint64_t)(kk * 2), b0 + (uint64_t)(kk * 2), idesc, accum);
+    for (int kk = 0; kk < kKs; ++kk) {
+      const uint32_t acc = (kk == 0) ? (accumulate | (uint32_t)jj) : 1u;      // only the tile's very first MMA overwrites
+      umma_lh<kPair>(d0, a + (uint32_t)(kk * 2), K.a_hi, b + (uint32_t)(kk * 2), K.b_hi, K.idesc, acc);
+      if (kMt == 2) umma_lh<kPair>(d1, a + K.sub_step + (uint32_t)(kk * 2), K.a_hi, b + (uint32_t)(kk * 2), K.b_hi, K.idesc, acc);
     }
   }
 }
@@ -307,6 +343,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       s_shift[i] = P.shift[i];
     }
   }
+  uint32_t* s_tap = reinterpret_cast<uint32_t*>(base_ptr + L.tap_off);   // A descriptor offset of every tap (16-byte units)
+  if (warp == 1) {
+    for (int i = lane; i < P.ngroups * kMaxTaps; i += 32) {
+      const int g = i / kMaxTaps, tt = i - g * kMaxTaps;
+      s_tap[i] = tt < P.ntaps ? ((uint32_t)P.taps[g][tt].shift_px * (uint32_t)P.row_bytes) >> 4 : 0u;
+    }
+  }
   float* s_pre = reinterpret_cast<float*>(base_ptr + L.pre_off);   // [ctot] scale then [ctot] shift
   if (kPre && warp >= kPreWarp0) {
     for (int i = threadIdx.x - kPreWarp0 * 32; i < P.ctot; i += 128) {
@@ -391,46 +434,47 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint64_t desc_hi = make_kmajor_desc(0, P.row_bytes);     // (weights) everything but the start address
     // A views: same, except that the 8-row groups of an 8-pixel-wide 2-D tile are one halo row apart
     const uint64_t desc_hi_a = (desc_hi & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((uint32_t)P.a_sbo_bytes >> 4) & 0x3FFF) << 32);
+    IssueK K;
+    K.a_hi = (uint32_t)(desc_hi_a >> 32); K.b_hi = (uint32_t)(desc_hi >> 32);
+    K.sub_step = ((uint32_t)P.sub_px * (uint32_t)P.row_bytes) >> 4;
+    K.b_tap_step = (uint32_t)P.b_tap_stride >> 4;
+    K.idesc = P.idesc;
+    const uint32_t lo_flags = (uint32_t)desc_hi;                  // LBO field
+    const uint32_t a_lo0 = ((a_base & 0x3FFFFu) >> 4) | lo_flags, a_step = (uint32_t)P.a_slot_bytes >> 4;
+    const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | lo_flags, b_step = (uint32_t)P.b_slot_bytes >> 4;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0;
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = decode_tile(P, t, 0);
       const int nal = P.n_aloads[tc.g];
+      const uint32_t* taps_g = s_tap + tc.g * kMaxTaps;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u, P.err_flag, 2);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)(acc * P.MT * P.bn_cols);
+      const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
       uint32_t accumulate = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int ksteps = c == P.chunks0 - 1 ? P.ks_last0 : (c == nchunks - 1 ? P.ks_last1 : ksteps_full);
         for (int a = 0; a < nal; ++a) {
-          const ALoad al = P.aloads[tc.g][a];
+          const int tap_begin = P.aloads[tc.g][a].tap_begin, tap_count = P.aloads[tc.g][a].tap_count;
           mbar_wait(kPre ? readyA(sa) : fullA(sa), pa, P.err_flag, 3);
-          const uint32_t a_slot = a_base + (uint32_t)sa * P.a_slot_bytes;
-          for (int j0 = 0; j0 < al.tap_count; j0 += P.taps_per_slot) {
-            const int nt = min(P.taps_per_slot, (int)al.tap_count - j0);
-            const bool last_of_a = j0 + nt >= al.tap_count;
+          for (int j0 = 0; j0 < tap_count; j0 += P.taps_per_slot) {
+            const int nt = min(P.taps_per_slot, tap_count - j0);
+            const bool last_of_a = j0 + nt >= tap_count;
             mbar_wait(fullB(sb), pb, P.err_flag, 6);
             tc_fence_after();
             ADB_DBG(2, dbg_i);
             if (elect_one()) {   // elect.sync lets the compiler keep the UTCHMMA stream in straight-line uniform code
-              const uint32_t b_slot = b_base + (uint32_t)sb * P.b_slot_bytes;
-              for (int jj = 0; jj < nt; ++jj) {
-                const uint32_t shift = P.taps[tc.g][al.tap_begin + j0 + jj].shift_px;
-                const uint64_t b0 = desc_hi | (uint64_t)(((b_slot + (uint32_t)jj * P.b_tap_stride) & 0x3FFFFu) >> 4);
-                const uint32_t a_addr0 = a_slot + shift * (uint32_t)P.row_bytes;
-                const uint64_t a0 = desc_hi_a | (uint64_t)((a_addr0 & 0x3FFFFu) >> 4);
-                const uint64_t a1 = a0 + (uint64_t)(((uint32_t)P.sub_px * (uint32_t)P.row_bytes) >> 4);
-                const uint32_t first = accumulate | (uint32_t)jj;
-                const uint32_t d1 = d_base + (uint32_t)P.bn_cols;
-                if (P.MT == 2) {
-                  if (ksteps == 4) issue_mmas<kPair, 2, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 3) issue_mmas<kPair, 2, 3>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 2) issue_mmas<kPair, 2, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else issue_mmas<kPair, 2, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
-                } else {
-                  if (ksteps == 4) issue_mmas<kPair, 1, 4>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 3) issue_mmas<kPair, 1, 3>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else if (ksteps == 2) issue_mmas<kPair, 1, 2>(d_base, d1, a0, a1, b0, P.idesc, first);
-                  else issue_mmas<kPair, 1, 1>(d_base, d1, a0, a1, b0, P.idesc, first);
-                }
+              const uint32_t* tp = taps_g + tap_begin + j0;
+              if (P.MT == 2) {
+                if (ksteps == 4) issue_taps<kPair, 2, 4>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else if (ksteps == 3) issue_taps<kPair, 2, 3>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else if (ksteps == 2) issue_taps<kPair, 2, 2>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else issue_taps<kPair, 2, 1>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+              } else {
+                if (ksteps == 4) issue_taps<kPair, 1, 4>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else if (ksteps == 3) issue_taps<kPair, 1, 3>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else if (ksteps == 2) issue_taps<kPair, 1, 2>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
+                else issue_taps<kPair, 1, 1>(K, d_base, d1, a_lo, b_lo, tp, nt, accumulate);
               }
               const bool tile_done = c == nchunks - 1 && a == nal - 1 && last_of_a;
               if (kPair) {   // multicast commits: the slot / accumulator barriers of BOTH CTAs
@@ -446,9 +490,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             __syncwarp();
             ADB_DBG(3, dbg_i); ++dbg_i;
             accumulate = 1;
-            if (++sb == P.b_slots) { sb = 0; pb ^= 1u; }
+            b_lo += b_step;
+            if (++sb == P.b_slots) { sb = 0; pb ^= 1u; b_lo = b_lo0; }
           }
-          if (++sa == P.a_slots) { sa = 0; pa ^= 1u; }
+          a_lo += a_step;
+          if (++sa == P.a_slots) { sa = 0; pa ^= 1u; a_lo = a_lo0; }
         }
       }
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }

@@ -17,17 +17,36 @@ import torch
 from .. import _lib
 
 
+_SETTER_FORM = [None]      # which call form of torch._C._autograd._unsafe_set_version_counter this torch accepts
+
+
 def _bump_versions(params):
     """The step writes parameter memory from a libadb200 kernel; tell torch (and the weight-packing caches keyed on
-    `_version`) that the tensors changed."""
+    `_version`) that the tensors changed.  torch >= 2.5 takes (sequence of tensors, sequence of versions), older builds
+    (tensor, version); the form is probed once — a failed pybind call formats its arguments into the exception text, which for
+    a CUDA tensor is a device synchronisation plus a tensor print."""
+    params = list(params)
+    if not params:
+        return
     setter = getattr(torch._C._autograd, "_unsafe_set_version_counter", None)
-    if setter is not None:
+    if setter is not None and _SETTER_FORM[0] != "none":
+        if _SETTER_FORM[0] in (None, "seq"):
+            try:
+                setter(tuple(params), tuple(p._version + 1 for p in params))
+                _SETTER_FORM[0] = "seq"
+                return
+            except (TypeError, RuntimeError):
+                if _SETTER_FORM[0] == "seq":
+                    raise
         try:
+            probe = torch.zeros(1)
+            setter(probe, probe._version + 1)          # probe on a CPU scalar: cheap to format if it fails
             for p in params:
                 setter(p, p._version + 1)
+            _SETTER_FORM[0] = "one"
             return
         except (TypeError, RuntimeError):
-            pass
+            _SETTER_FORM[0] = "none"
     with torch.no_grad():
         for p in params:
             p.add_(0)          # in-place no-op: bumps the version for floating-point and integer tensors alike

@@ -15,6 +15,15 @@ from helpers import CONFIG, ROOT
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _grad_on():
+    torch.set_grad_enabled(True)       # (tests/test_oracle_golden.py switches autograd off at import time)
+    yield
+    from adam_dehaze_b200 import _lib
+    torch.cuda.synchronize()
+    _lib.call("adb_kernel_error_flag")
+
+
 def _config(tmp_path, routing="soft"):
     cfg = copy.deepcopy(CONFIG)
     cfg["routing"] = {"type": routing, "temperature": 0.5}
