@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager comparator leg")
+    ap.add_argument("--no-skew", action="store_true", help="skip the skewed-mix / re-balance record (N > 1 only)")
     ap.add_argument("--no-train", action="store_true", help="skip the embedded BASELINE configs[4] training record")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
@@ -356,6 +357,11 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": desc + ", one sample, no extrapolation",
                "seconds": sec}
 
+    # ---- shard imbalance (N > 1): a 70/20/10 class mix rotated by rank, with and without the class re-balance
+    skew = None
+    if world > 1 and not args.no_skew:
+        skew = run_skew(torch, dist, world, rank, dev, clf, router, hazy, B, args)
+
     # ---- on-box comparator: stock PyTorch eager (cuDNN) on this GPU (rank 0, N=1 only)
     eager = None
     if rank == 0 and world == 1 and not args.no_eager:
@@ -399,12 +405,68 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "model_tflops_per_gpu": value / world * mix,
             "gpu_eager_baseline": eager,
+            "shard_imbalance": skew,
             "train": train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_skew(torch, dist, world, rank, dev, clf, router, hazy, B, args):
+    """"load imbalance (a shard heavy in Complex images costs far more than a Light shard) is the only scaling
+    risk".  Every rank gets a 70 / 20 / 10 class mix whose heavy class is (rank % 3); measured (a) as sharded by image count
+    alone, (b) with adam_dehaze_b200.sharding.Exchange: all-gather of the class ids, one NCCL all-to-all of whole images so
+    that every rank holds an equal share of every class, dehaze, all-to-all back.  HDEN runs on the local shard first in
+    both (the class ids come from it in production; here they are the injected labels).  Max over ranks, whole job."""
+    from adam_dehaze_b200.sharding import Exchange
+    heavy = rank % 3
+    n70, n20 = int(round(0.7 * B)), int(round(0.2 * B))
+    lab = torch.empty(B, dtype=torch.int64)
+    lab[:n70], lab[n70:n70 + n20], lab[n70 + n20:] = heavy, (heavy + 1) % 3, (heavy + 2) % 3
+    lab = lab[torch.randperm(B, generator=torch.Generator().manual_seed(100 + rank))].to(dev)
+
+    def plain():
+        clf(hazy)
+        return router(hazy, intensity=lab)[0]
+
+    state = {}
+
+    def rebalanced():
+        clf(hazy)
+        gathered = torch.empty(world * B, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, lab)                       # the only extra collective besides the image trade
+        by_rank = gathered.view(world, B).cpu().tolist()                 # (host read of world*B class ids)
+        ex = Exchange(by_rank, rank)
+        x, l2 = ex.forward(hazy)
+        y = router(x, intensity=l2)[0]
+        state["moved"], state["held"] = ex.moved, x.shape[0]
+        return ex.backward(y)
+
+    def timed(fn, steps):
+        fn()
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+    steps = max(2, min(3, args.steps))
+    ms_plain = timed(plain, steps)
+    ms_reb = timed(rebalanced, steps)
+    moved = torch.tensor([float(state["moved"])], device=dev)
+    dist.all_reduce(moved)
+    return {"mix": "each rank: 70 % of class (rank % 3), 20 % of the next, 10 % of the third, shuffled",
+            "images_per_s_by_count_only": world * B / (ms_plain / 1000.0), "ms_per_step_by_count_only": ms_plain,
+            "images_per_s_rebalanced": world * B / (ms_reb / 1000.0), "ms_per_step_rebalanced": ms_reb,
+            "images_moved_per_step": int(moved.item()), "bytes_moved_per_step": int(moved.item()) * 2 * hazy[0].numel() * 4,
+            "exchange": "all_gather of class ids + NCCL all_to_all_single of whole fp32 images (there and back), inside the timed region",
+            "steps": steps}
 
 
 # --------------------------------------------------------------------------- training step (BASELINE configs[4])

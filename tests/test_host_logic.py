@@ -330,6 +330,62 @@ def test_sharding_world2_gloo(tmp_path):
     assert all("ok" in o for o in outs)
 
 
+def test_rebalance_plan_equalises_every_class():
+    """sharding.rebalance_plan: every rank ends with its equal share (+-1) of every class, images move only off ranks that
+    hold more than their share, nothing is lost or duplicated, and unrouted class ids stay put."""
+    import random
+    rng = random.Random(0)
+    for world in (2, 3, 8):
+        for trial in range(5):
+            labels = [[rng.choice([0, 0, 0, 1, 2, 2, 7]) if (r + trial) % 2 else rng.choice([0, 1, 1, 1, 2]) for _ in range(rng.randrange(0, 40))]
+                      for r in range(world)]
+            send = sharding.unrouted_stay(labels, sharding.rebalance_plan(labels))
+            for r in range(world):
+                sent = sorted(i for d in range(world) for i in send[r][d])
+                assert sent == list(range(len(labels[r])))                       # every image goes to exactly one place
+            for k in range(3):
+                held = [sum(1 for s in range(world) for i in send[s][d] if labels[s][i] == k) for d in range(world)]
+                assert max(held) - min(held) <= 1, (k, held)
+                for r in range(world):
+                    had = sum(1 for v in labels[r] if v == k)
+                    kept = sum(1 for i in send[r][r] if labels[r][i] == k)
+                    assert kept == min(had, held[r])                             # no image leaves a rank that is not over its share
+            assert all(labels[r][i] != 7 or i in send[r][r] for r in range(world) for i in range(len(labels[r])))
+
+
+_GLOO_A2A_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["ADB_ROOT"])
+from adam_dehaze_b200 import sharding
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["ADB_PORT"], rank=rank, world_size=2)
+labels = [[2, 2, 2, 0, 2, 1, 2], [0, 0, 1, 0, 0, 0, 5]]
+ex = sharding.Exchange(labels, rank)
+x = torch.arange(7, dtype=torch.float32).view(7, 1, 1, 1) + 100 * rank
+got, lab = ex.forward(x)
+assert [int((lab == k).sum()) for k in range(3)] == ([3, 1, 3] if rank == 0 else [3, 1, 2]), lab
+src = [int(v) // 100 for v in got.flatten().tolist()]
+assert all(labels[s][int(v) % 100] == int(l) for s, v, l in zip(src, got.flatten().tolist(), lab.tolist()))   # labels travel with their images
+back = ex.backward(got * 2)
+assert torch.equal(back, x * 2)                      # results return to their owner in the original order
+dist.barrier(); dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_rebalance_exchange_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_A2A_WORKER)
+    port = str(31000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), ADB_ROOT=ROOT, ADB_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
 _GLOO_GRAD_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["ADB_ROOT"])
