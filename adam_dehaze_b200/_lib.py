@@ -106,6 +106,7 @@ SIGNATURES = {
     "adb_image_metrics": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "adb_avgpool2x2_bwd": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "adb_gather_cast": [_P, _P, _L, _P, _P],
+    "adb_gather_cast_multi": [_P, _I, _L, _P],
     "adb_upsample_bilinear_bwd": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "adb_adam_step_segments": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _I, _P, _P, _P, _P, _P],

@@ -1184,6 +1184,28 @@ __global__ void gather_cast_kernel(const float* __restrict__ src, const int* __r
   }
 }
 
+// The same for MANY packings in one launch (a training step re-packs ~600 tensors; one launch each made the re-pack
+// launch-bound: 4.6 ms for 0.3 GB).  jobs[j] = {src, idx, out, n, first_block}; a block finds its job by binary search.
+struct GatherJob { const float* src; const int* idx; __nv_bfloat16* out; long long n; long long first_block; };
+constexpr int kGatherPerBlock = 256 * 8;
+__global__ void gather_cast_multi_kernel(const GatherJob* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid;
+  }
+  const GatherJob J = jobs[lo];
+  const long long base = ((long long)blockIdx.x - J.first_block) * kGatherPerBlock;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const long long i = base + u * 256 + threadIdx.x;
+    if (i < J.n) {
+      const int k = __ldg(J.idx + i);
+      J.out[i] = __float2bfloat16(k >= 0 ? __ldg(J.src + k) : 0.f);
+    }
+  }
+}
+
 // backward of nn.UpsamplingBilinear2d(scale) (align_corners=True; medium_intensity.py:146,151, high_intensity.py:171,173)
 // as a gather: a source pixel collects from every destination pixel whose two-tap footprint touches it, with the weights
 // recomputed exactly as the forward computes them.  dy may be a channel slice of a wider map (pitch_dy, c_off).
@@ -1627,6 +1649,13 @@ int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int32_t h, i
 int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream) {
   ADB_REQUIRE(src && idx && out && n > 0, "adb_gather_cast: bad arguments");
   gather_cast_kernel<<<grid_for(n, 256, sm_count(), 8), 256, 0, (cudaStream_t)stream>>>(src, idx, n, ADB_BFM(out));
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int adb_gather_cast_multi(const void* jobs_dev, int32_t njobs, int64_t total_blocks, void* stream) {
+  ADB_REQUIRE(jobs_dev && njobs > 0 && total_blocks > 0 && total_blocks < (1LL << 31), "adb_gather_cast_multi: bad arguments");
+  gather_cast_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const GatherJob*>(jobs_dev), njobs);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;
 }

@@ -68,6 +68,9 @@ class ImageQualityMetrics:
             res = {"psnr": psnr.mean().item(), "ssim": ssim.mean().item()}
             if items[0][2] is not None:
                 res["lpips"] = torch.cat([i[2] for i in items]).mean().item()
+                if not getattr(self.lpips_fn, "pretrained", True):
+                    # LPIPS needs its trained AlexNet + lin weights; without them the number only orders images consistently
+                    res["lpips_weights"] = "random-init (not comparable with published LPIPS)"
             res["samples"] = int(psnr.numel())
             out[cat] = res
         return out
@@ -78,4 +81,5 @@ class ImageQualityMetrics:
             print(f"\n{cat.upper()} ({m['samples']} samples):")
             for k in ("psnr", "ssim", "lpips"):
                 if k in m:
-                    print(f"  {k.upper()}: {m[k]:.4f}")
+                    note = f"  [{m['lpips_weights']}]" if k == "lpips" and "lpips_weights" in m else ""
+                    print(f"  {k.upper()}: {m[k]:.4f}{note}")

@@ -118,36 +118,63 @@ def derive_index_maps(build, weight):
 
 
 class _WeightCache:
-    """bf16 packings of a parameter for the forward and the data-gradient launches.  When the parameter changes (optimizer
-    step) a packing built with `weight=` is refreshed by ONE adb_gather_cast launch through an index map derived once
-    (the same builder applied to an arange under ops.pack_as(float32)); other entries are rebuilt."""
+    """bf16 packings of a parameter for the forward and the data-gradient launches.  When parameters change (optimizer step)
+    every packing built with `weight=` is refreshed through an index map derived once (the same builder applied to an arange
+    under ops.pack_as(float32)) — ALL stale packings of the cache in ONE adb_gather_cast_multi launch, the first time any
+    of them is asked for after the step; other entries are rebuilt."""
 
     def __init__(self):
         self._c = {}
+        self._jobs = None          # (key tuple, device job table, total blocks) of the last multi-gather
+
+    @staticmethod
+    def _sig(params):
+        return tuple((p.data_ptr(), p._version) for p in params if p is not None)
+
+    def _refresh_stale(self):
+        """Re-pack every map-backed entry whose parameters changed, in one launch."""
+        stale = [(k, e) for k, e in self._c.items() if e["maps"] is not None and e["sig"] != self._sig(e["params"])
+                 and e["wptr"] == e["weight"].data_ptr()]
+        if not stale:
+            return
+        keys = tuple(k for k, _ in stale)
+        if self._jobs is None or self._jobs[0] != keys:
+            rows, block = [], 0
+            for _, e in stale:
+                for packed, idx in e["maps"]:
+                    n = idx.numel()
+                    rows.append([e["weight"].data_ptr(), idx.data_ptr(), packed.data_ptr(), n, block])
+                    block += (n + 2047) // 2048
+            dev = stale[0][1]["weight"].device
+            self._jobs = (keys, torch.tensor(rows, dtype=torch.int64).to(dev), block, len(rows))
+        _, table, blocks, njobs = self._jobs
+        _lib.call("adb_gather_cast_multi", _lib.ptr(table), njobs, blocks, _lib.current_stream())
+        for _, e in stale:
+            if e["bias"] is not None:
+                for sp in _flat_specs(e["val"]):
+                    sp.shift[:e["bias"].numel()].copy_(e["bias"].detach())
+            e["sig"] = self._sig(e["params"])
 
     def get(self, key, params, build, weight=None, bias=None):
         """build(): returns the packing (a ConvSpec, or nested lists/tuples of them).  With `weight` given, build takes
         the weight tensor as its only argument."""
-        sig = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        sig = self._sig(params)
         hit = self._c.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
+        if hit is not None and hit["sig"] == sig:
+            return hit["val"]
+        if hit is not None and hit["maps"] is not None and weight is not None and hit["wptr"] == weight.data_ptr():
+            self._refresh_stale()
+            hit = self._c[key]
+            if hit["sig"] == sig:
+                return hit["val"]
         if weight is None:
-            hit = (sig, build(), None)
-        elif hit is None or hit[2] is None or hit[3] != weight.data_ptr():
-            val, maps = derive_index_maps(build, weight)
-            hit = (sig, val, maps, weight.data_ptr())
+            hit = {"sig": sig, "val": build(), "maps": None, "wptr": None, "params": params, "weight": None, "bias": None}
         else:
-            wf = weight.detach()
-            st = _lib.current_stream()
-            for packed, idx in hit[2]:
-                _lib.call("adb_gather_cast", _lib.ptr(wf), _lib.ptr(idx), idx.numel(), _lib.ptr(packed), st)
-            if bias is not None:
-                for sp in _flat_specs(hit[1]):
-                    sp.shift[:bias.numel()].copy_(bias.detach())
-            hit = (sig, hit[1], hit[2], hit[3])
+            val, maps = derive_index_maps(build, weight)
+            hit = {"sig": sig, "val": val, "maps": maps, "wptr": weight.data_ptr(), "params": params, "weight": weight, "bias": bias}
+            self._jobs = None
         self._c[key] = hit
-        return hit[1]
+        return hit["val"]
 
 
 def _pad_rows16(w):

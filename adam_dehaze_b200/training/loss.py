@@ -6,9 +6,13 @@ Every term runs on libadb200 kernels, forward AND backward, wrapped in torch.aut
   * L1 / cross-entropy: fused warp-shuffle reductions (adb_l1_mse_fwd / adb_l1_bwd / adb_ce_fwd_bwd);
   * ContentLoss (VGG16 features at indices 9/16/23) and PerceptualLoss (LPIPS-alex): frozen conv trunks on the tcgen05
     conv kernel, data gradients back to `pred` (training/perceptual.py).
-Pretrained VGG16 / AlexNet / LPIPS-lin weights cannot be downloaded here; when the torch hub cache does not hold them
-the trunks keep torchvision's random init (seeded by the caller) and a one-line notice is printed — the arithmetic is
-the same, load real weights with load_state_dict (the sub-module names follow torchvision / lpips).
+Pretrained weights.  VGG16 / AlexNet come from the torch hub cache; the LPIPS 'lin' layers from the installed `lpips`
+package (lpips/weights/v0.1/alex.pth) or the file named by $ADB_LPIPS_WEIGHTS.  Nothing can be downloaded on the GPU box.
+When a set is missing the module falls back to a FIXED-SEED random init (the same on every rank and in every process,
+independent of the caller's RNG state), prints a one-line notice, and records it in `.pretrained = False`;
+`allow_random_weights=False` turns the fallback into an error, and evaluation/metrics.py labels an 'lpips' number computed
+from such weights as not comparable.  The arithmetic is the same either way (sub-module names follow torchvision / lpips,
+so real checkpoints load with load_state_dict).
 """
 import torch
 import torch.nn as nn
@@ -65,10 +69,39 @@ def _hub_file(name):
     return path if os.path.exists(path) else None
 
 
+def _lpips_lin_file():
+    """The LPIPS-alex linear-layer weights: $ADB_LPIPS_WEIGHTS, or the file the `lpips` package ships."""
+    env = os.environ.get("ADB_LPIPS_WEIGHTS")
+    if env and os.path.exists(env):
+        return env
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("lpips")
+        if spec and spec.origin:
+            path = os.path.join(os.path.dirname(spec.origin), "weights", "v0.1", "alex.pth")
+            return path if os.path.exists(path) else None
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+def _seeded_reinit(module, seed):
+    """Re-draw a module's random init from a private fixed-seed generator: identical on every rank, whatever the caller's RNG
+    state is (replicas seeded differently would otherwise optimise different losses)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in module.parameters():
+            if p.dim() > 1:
+                fan_in = p[0].numel()
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * (6.0 / fan_in) ** 0.5)     # He-uniform: keeps the activation scale through the ReLU trunk
+            else:
+                p.zero_()
+
+
 class ContentLoss(nn.Module):
     """VGG16 feature MSE at `features` indices 9 / 16 / 23, mean of the three (reference loss.py:7-84)."""
 
-    def __init__(self, pretrained_model="vgg16", content_layers=None):
+    def __init__(self, pretrained_model="vgg16", content_layers=None, allow_random_weights=True):
         super().__init__()
         import torchvision.models as tvm
         if pretrained_model not in ("vgg16",):
@@ -79,10 +112,14 @@ class ContentLoss(nn.Module):
             raise NotImplementedError("ContentLoss on the B200 path taps the reference's default layers (indices 9/16/23)")
         vgg = tvm.vgg16(weights=None)
         ck = _hub_file("vgg16-397923af.pth")
+        self.pretrained = bool(ck)
         if ck:
             vgg.load_state_dict(torch.load(ck, map_location="cpu"))
         else:
-            print("ContentLoss: pretrained VGG16 weights are not in the torch hub cache — using random-init features", file=sys.stderr)
+            if not allow_random_weights:
+                raise FileNotFoundError("ContentLoss: vgg16-397923af.pth is not in the torch hub cache (loss.py:20 needs the pretrained VGG16)")
+            _seeded_reinit(vgg.features, 16)
+            print("ContentLoss: pretrained VGG16 weights are not in the torch hub cache — using fixed-seed random-init features", file=sys.stderr)
         self.model = vgg.features.eval()
         for p in self.model.parameters():
             p.requires_grad = False
@@ -99,15 +136,21 @@ class _LPIPSAlex(nn.Module):
     """Parameter container with lpips.LPIPS(net='alex')'s state_dict names (net.slice{1..5}.{0,3,6,8,10}.*,
     lin{0..4}.model.1.weight, scaling_layer.{shift,scale})."""
 
-    def __init__(self):
+    def __init__(self, allow_random_weights=True):
         super().__init__()
         import torchvision.models as tvm
         alex = tvm.alexnet(weights=None)
         ck = _hub_file("alexnet-owt-7be5be79.pth")
+        lin_ck = _lpips_lin_file()
+        self.pretrained = bool(ck) and bool(lin_ck)
+        if not self.pretrained and not allow_random_weights:
+            raise FileNotFoundError("PerceptualLoss: LPIPS needs alexnet-owt-7be5be79.pth in the torch hub cache and the lpips package's "
+                                    "weights/v0.1/alex.pth (or $ADB_LPIPS_WEIGHTS); neither can be downloaded here")
         if ck:
             alex.load_state_dict(torch.load(ck, map_location="cpu"))
         else:
-            print("PerceptualLoss: pretrained AlexNet / LPIPS weights are not available offline — using random-init weights", file=sys.stderr)
+            _seeded_reinit(alex.features, 17)
+            print("PerceptualLoss: pretrained AlexNet / LPIPS weights are not available offline — using fixed-seed random-init weights", file=sys.stderr)
         f = alex.features
         self.net = nn.Module()
         for i, idx in enumerate((0, 3, 6, 8, 10)):
@@ -115,11 +158,16 @@ class _LPIPSAlex(nn.Module):
         self.scaling_layer = nn.Module()
         self.scaling_layer.register_buffer("shift", torch.tensor(_perc.LPIPS_SHIFT).view(1, 3, 1, 1))
         self.scaling_layer.register_buffer("scale", torch.tensor(_perc.LPIPS_SCALE).view(1, 3, 1, 1))
+        lin_sd = torch.load(lin_ck, map_location="cpu") if lin_ck else None
+        g = torch.Generator().manual_seed(18)
         for i, c in enumerate((64, 192, 384, 256, 256)):
             lin = nn.Module()
             conv = nn.Conv2d(c, 1, 1, bias=False)
             with torch.no_grad():
-                conv.weight.copy_(torch.rand_like(conv.weight) / c)     # LPIPS' lin layers are non-negative
+                if lin_sd is not None:
+                    conv.weight.copy_(lin_sd[f"lin{i}.model.1.weight"])
+                else:
+                    conv.weight.copy_(torch.rand(conv.weight.shape, generator=g) / c)     # LPIPS' lin layers are non-negative
             lin.model = nn.Sequential(OrderedDict([("0", nn.Dropout()), ("1", conv)]))
             setattr(self, f"lin{i}", lin)
         for p in self.parameters():
@@ -136,11 +184,12 @@ class _LPIPSAlex(nn.Module):
 class PerceptualLoss(nn.Module):
     """LPIPS(net='alex') on inputs mapped to [-1, 1]; returns [B,1,1,1] like lpips (reference loss.py:86-108)."""
 
-    def __init__(self, net="alex"):
+    def __init__(self, net="alex", allow_random_weights=True):
         super().__init__()
         if net != "alex":
             raise NotImplementedError("PerceptualLoss on the B200 path implements LPIPS(net='alex')")
-        self.loss_fn = _LPIPSAlex()
+        self.loss_fn = _LPIPSAlex(allow_random_weights)
+        self.pretrained = self.loss_fn.pretrained
         self.__dict__["_net"] = None
 
     def forward(self, x, target):

@@ -338,6 +338,10 @@ ADB_API int adb_avgpool2x2_bwd(const void* dy, int32_t pitch_dy, int32_t n, int3
 /* Weight re-packing after an optimizer step: out[i] = bf16(src[idx[i]]), 0 where idx[i] < 0 (idx = the packing's
  * permutation of the fp32 parameter, derived once on the host side). */
 ADB_API int adb_gather_cast(const float* src, const int32_t* idx, int64_t n, void* out, void* stream);
+/* Many re-packs in one launch.  jobs_dev: device array of njobs records {const float* src; const int32_t* idx; void* out;
+ * int64_t n; int64_t first_block} (40 bytes each); job j owns blocks [first_block_j, first_block_j + ceil(n_j / 2048)) of the
+ * total_blocks-block grid. */
+ADB_API int adb_gather_cast_multi(const void* jobs_dev, int32_t njobs, int64_t total_blocks, void* stream);
 
 /* backward of adb_upsample_bilinear (align_corners=True): dx[n,h,w,c] from dy[n, h*scale, w*scale, c_off : c_off+c] */
 ADB_API int adb_upsample_bilinear_bwd(const void* dy, int32_t pitch_dy, int32_t c_off, int32_t n, int32_t h, int32_t w,

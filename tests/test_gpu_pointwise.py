@@ -205,3 +205,51 @@ def test_image_metrics_on_device():
     assert abs(avg["all"]["psnr"] - psnr[1:].mean().item()) < 1e-4
     p_same, s_same = image_metrics(tgt, tgt)
     assert torch.isinf(p_same).all() and (s_same - 1).abs().max().item() < 1e-5
+
+
+def test_image_metrics_closed_form_cases():
+    """PSNR / SSIM pins that need no skimage (evaluation/metrics.py:13-36; skimage is absent offline, so the oracle's restatement
+    is otherwise unpinned): identical images -> SSIM exactly 1 and PSNR = +inf (or the 1e-12 floor's 120 dB); a constant offset d
+    -> PSNR = -20 log10(d) analytically and SSIM = (2 mu1 mu2 + C1) / (mu1^2 + mu2^2 + C1) on a constant image (zero variance);
+    SSIM is symmetric in its arguments and decreases as noise grows.  Values from the definitions in Wang et al. 2004 with
+    skimage's defaults (K1 = 0.01, K2 = 0.03, 7x7 uniform window, data_range = 1)."""
+    from adam_dehaze_b200.evaluation.metrics import image_metrics
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.rand((2, 3, 48, 64), generator=g, device="cuda")
+    psnr, ssim = image_metrics(x, x.clone())
+    assert (ssim - 1.0).abs().max().item() <= 1e-6 and (psnr >= 100).all()
+    d = 0.1
+    psnr, _ = image_metrics((x * 0.8), (x * 0.8 + d))
+    assert (psnr - 20.0).abs().max().item() <= 1e-3                     # -20 log10(0.1) = 20 dB
+    a, b = torch.full((1, 3, 32, 32), 0.4, device="cuda"), torch.full((1, 3, 32, 32), 0.6, device="cuda")
+    _, ssim = image_metrics(a, b)
+    c1 = 0.01 ** 2
+    want = (2 * 0.4 * 0.6 + c1) / (0.4 ** 2 + 0.6 ** 2 + c1)
+    assert abs(ssim.item() - want) <= 1e-5, (ssim.item(), want)
+    n1, n2 = x + 0.05 * torch.randn_like(x), x + 0.2 * torch.randn_like(x)
+    s_ab = image_metrics(x, n1.clamp(0, 1))[1]
+    s_ba = image_metrics(n1.clamp(0, 1), x)[1]
+    assert (s_ab - s_ba).abs().max().item() <= 1e-6
+    assert (image_metrics(x, n2.clamp(0, 1))[1] < s_ab).all()
+
+
+def test_lpips_structure_without_the_package():
+    """LPIPS pins that hold for ANY weights (lpips is absent offline, loss.py:86-108 -> parity unpinned): d(x, x) = 0 exactly,
+    d is symmetric, non-negative (lin layers are non-negative, features are unit-normalised), scale-consistent with the
+    published definition (a sum over five taps of spatial means), and the fallback init is the same in every process."""
+    from adam_dehaze_b200.training.loss import PerceptualLoss
+    torch.manual_seed(1)
+    a = PerceptualLoss().cuda()
+    torch.manual_seed(2)
+    b = PerceptualLoss().cuda()
+    assert all(torch.equal(p, q) for p, q in zip(a.state_dict().values(), b.state_dict().values()))   # rank-independent fallback
+    assert a.pretrained is False
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x, y = torch.rand((2, 3, 96, 96), generator=g, device="cuda"), torch.rand((2, 3, 96, 96), generator=g, device="cuda")
+    with torch.no_grad():
+        assert a(x, x.clone()).abs().max().item() == 0.0
+        dxy, dyx = a(x, y), a(y, x)
+    assert dxy.shape == (2, 1, 1, 1) and (dxy > 0).all()
+    assert (dxy - dyx).abs().max().item() <= 1e-3 * dxy.abs().max().item()
+    with pytest.raises(FileNotFoundError):
+        PerceptualLoss(allow_random_weights=False)

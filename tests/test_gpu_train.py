@@ -796,3 +796,54 @@ def test_train_driver_resume_continues_the_same_run(tmp_path):
     sa, sb = a["optimizer_state_dict"]["state"], b["optimizer_state_dict"]["state"]
     assert float(sa[0]["step"]) == float(sb[0]["step"]) > 0
     assert torch.allclose(sa[0]["exp_avg"], sb[0]["exp_avg"], rtol=1e-3, atol=1e-7)
+
+
+def test_weight_cache_refreshes_every_packing_in_one_launch():
+    """After an optimizer step the bf16 packings of ALL parameters (forward, row-folded, data-gradient layouts) are refreshed
+    by one adb_gather_cast_multi launch; each must equal a fresh packing of the updated weight."""
+    from helpers import make_branch, rand_image
+    from adam_dehaze_b200 import _lib
+    from adam_dehaze_b200.training import autograd as ag
+    from adam_dehaze_b200.training.loss import DehazingLoss
+    from adam_dehaze_b200.training.optim import FlatAdam
+    m = make_branch("medium").cuda().train()
+    opt = FlatAdam(m.parameters(), lr=1e-2)
+    crit = DehazingLoss(1.0, 0.0, 0.0)
+    x, tgt = rand_image(2, 64, 128, 3).cuda(), rand_image(2, 64, 128, 4).cuda()
+    calls = []
+    inner = _lib.call
+
+    def spy(name, *a):
+        calls.append(name)
+        return inner(name, *a)
+    for it in range(3):
+        opt.zero_grad()
+        if it == 2:
+            _lib.call = ag._lib.call = spy
+        try:
+            loss, _ = crit(m(x), tgt)
+        finally:
+            _lib.call = ag._lib.call = inner
+        loss.backward()
+        opt.step()
+    assert calls.count("adb_gather_cast_multi") == 1 and calls.count("adb_gather_cast") == 0
+    # one more forward refreshes against the latest weights; compare with fresh packings
+    opt.zero_grad()
+    crit(m(x), tgt)[0].backward()
+    cache = m.__dict__["_adb_engine"].train_cache if "_adb_engine" in m.__dict__ else m.engine.train_cache
+    checked = 0
+    for key, e in cache._c.items():
+        if e["maps"] is None or key[0] != "f":
+            continue
+        w = e["weight"].detach()
+        if w.dim() != 4 or w.shape[2] != 3 or w.shape[1] % 16:
+            continue
+        spec = e["val"]
+        fresh = ag.ConvSpec.from_conv(w, stride=1, pad=1) if spec.kind == 0 else None
+        if fresh is None or fresh.w_packed.shape != spec.w_packed.shape:
+            continue
+        assert torch.equal(spec.w_packed, fresh.w_packed)
+        if spec.w_fold is not None:
+            assert torch.equal(spec.w_fold, fresh.w_fold)
+        checked += 1
+    assert checked >= 8

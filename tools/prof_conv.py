@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--only", default=None)
     ap.add_argument("--ab-flags", type=int, default=None, help="time each shape with default tuning and with these tune flags (e.g. 128 = no ragged 64-channel boxes)")
+    ap.add_argument("--flags", type=int, default=None, help="time each shape with exactly these tune flags (16 = CTA pair, 32 = 1-CTA, 512 = no rolling-row kernel)")
     args = ap.parse_args()
     peak = 1414.7
     try:
@@ -134,6 +135,8 @@ def main():
     tunes = [None]
     if args.ab_flags is not None:
         tunes = [None, {"flags": args.ab_flags}]
+    if args.flags is not None:
+        tunes = [{"flags": args.flags}]
     if args.sweep:
         tunes = [{"flags": 32}, {"flags": 16}, {"flags": 16, "mt": 1}, {"flags": 16, "mt": 2}, {"flags": 32, "mt": 1}, {"flags": 32, "mt": 2}]
     for shape in SHAPES:
