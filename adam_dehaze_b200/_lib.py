@@ -11,7 +11,7 @@ _LIB_PATH = os.path.join(_HERE, "libadb200.so")
 
 # --- enums (mirror include/adb200.h)
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_SIGMOID2 = 0, 1, 2, 3, 4
-CONV_S1, CONV_S2, CONVT_4X4S2 = 0, 1, 2
+CONV_S1, CONV_S2, CONVT_4X4S2, CONV_K4_S2D = 0, 1, 2, 3
 EPI_FEATURE, EPI_DOT, EPI_IMAGE = 0, 1, 2
 IMG_BLEND, IMG_RESIDUAL, IMG_GUIDED = 0, 1, 2
 

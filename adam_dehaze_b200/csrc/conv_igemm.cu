@@ -728,6 +728,13 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
         raw[0][r * d->kw + s] = {v - 2 * fl2(v), u - 2 * fl2(u), fl2(v), fl2(u), r * d->kw + s};
       }
     P.grid_h = out_h; P.grid_w = out_w;
+  } else if (d->kind == ADB_CONV_K4_S2D) {
+    ADB_REQUIRE(d->kh == 4 && d->kw == 4, "adb_conv2d: the space-to-depth stem form is a 4x4 tap grid");
+    out_h = d->h_in; out_w = d->w_in;
+    P.ngroups = 1; P.ntaps = 16;
+    for (int r = 0; r < 4; ++r)
+      for (int s = 0; s < 4; ++s) raw[0][r * 4 + s] = {0, 0, s - 2, r - 2, r * 4 + s};
+    P.grid_h = out_h; P.grid_w = out_w;
   } else if (d->kind == ADB_CONVT_4X4S2) {
     out_h = d->h_in * 2; out_w = d->w_in * 2;
     P.ngroups = 4; P.ntaps = 4;

@@ -58,6 +58,11 @@ struct RollK {
   int res_pitch;
   int Cs, n_slabs, stage_bytes;    // epilogue slab channels, slabs per row, staging bytes per epilogue warp
   int out_c_off;
+  // DOT / IMAGE heads (cout_pad 16 or 32): same meaning as in conv_igemm.cu
+  int epi;
+  const float* dot_w; float dot_b; float* dot_out;
+  int img_mode;
+  const float* img_x; float* img_out; const int* img_index; const float* img_guidance; const float* img_alpha;
   int* err_flag;
   long long* dbg;                  // tune_flags bit 2: wait-cycle statistics of CTA `dbg_cta` (see tools/roll_stats.py)
   int dbg_cta;
@@ -297,7 +302,84 @@ __device__ __forceinline__ void roll_epilogue(const RollK& P, const CUtensorMap*
   }
 }
 
-template <int kAct>
+// Epilogue of the 3-channel image heads and the 1-channel guidance / transmission heads on the rolling-row schedule: one
+// accumulator row of 16 (or 32) columns per pixel, no staging and no TMA store — the result is fp32 NCHW (IMAGE, written
+// through the routed-bucket index) or an fp32 [n,h,w] map (DOT), one coalesced 128-byte store per warp and plane.
+template <int kEpi>
+__device__ __forceinline__ void roll_epilogue_head(const RollK& P, uint32_t tmem_base, uint32_t bar_full0, uint32_t bar_empty0,
+                                                   const float* s_scale, const float* s_shift, int ew, int set, int lane, int unit,
+                                                   int nunits, int total) {
+  const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+  const uint32_t rmask = (uint32_t)P.R - 1u;
+  for (int s = set; s < P.R; s += kEpiSets) {
+    for (int c = 0; c < P.CP; c += 16) tmem_st16_zero(lane_base + (uint32_t)(s * P.CP + c));
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty0 + 8u * s);
+  }
+  float dotw[32];
+  if (kEpi == ADB_EPI_DOT) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dotw[i] = i < P.CP ? __ldg(P.dot_w + i) : 0.f;
+  }
+  const size_t plane = (size_t)P.H * P.W;
+  const float alpha = (kEpi == ADB_EPI_IMAGE && P.img_mode == ADB_IMG_BLEND) ? __ldg(P.img_alpha) : 0.f;
+  uint32_t g_base = 0, rem = 0;
+  for (int t = unit; t < total; t += nunits) {
+    const Seg sg = decode_seg(P, t);
+    const int first = (set + kEpiSets - (int)rem) % kEpiSets;
+    const int w = sg.w0 + ew * 32 + lane;
+    const bool inb = w < P.W;
+    size_t img_row = 0;
+    if (kEpi == ADB_EPI_IMAGE) {
+      const int pos = P.n_start + sg.img;
+      img_row = P.img_index ? (size_t)__ldg(P.img_index + pos) : (size_t)pos;
+    }
+    for (int i = first; i < sg.rows; i += kEpiSets) {
+      const int h = sg.h0 + i;
+      const uint32_t g = g_base + (uint32_t)i;
+      const uint32_t slot = g & rmask, par = (g >> P.logR) & 1u;
+      // the hazy pixel / guidance this lane combines with its accumulator row: fetched before the accumulator is ready
+      float xin[3] = {0.f, 0.f, 0.f}, gd = 1.f;
+      const size_t img_o = img_row * 3 * plane + (size_t)h * P.W + w;
+      if (kEpi == ADB_EPI_IMAGE && inb) {
+        if (P.img_mode == ADB_IMG_GUIDED) gd = __ldg(P.img_guidance + ((size_t)sg.img * P.H + h) * P.W + w);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xin[c] = __ldg(P.img_x + img_o + c * plane);
+      }
+      mbar_wait(bar_full0 + 8u * slot, par, P.err_flag, 4);
+      tc_fence_after();
+      float v[32];
+      tmem_ld16(lane_base + slot * (uint32_t)P.CP, v);
+      if (kEpi == ADB_EPI_DOT && P.CP > 16) tmem_ld16(lane_base + slot * (uint32_t)P.CP + 16u, v + 16);
+      tmem_ld_wait();
+      for (int c = 0; c < P.CP; c += 16) tmem_st16_zero(lane_base + slot * (uint32_t)P.CP + (uint32_t)c);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(bar_empty0 + 8u * slot);
+      if (kEpi == ADB_EPI_DOT) {
+        float acc = P.dot_b;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < P.CP) acc = fmaf(apply_act(fmaf(v[c], s_scale[c], s_shift[c]), P.act), dotw[c], acc);
+        if (inb) P.dot_out[((size_t)sg.img * P.H + h) * P.W + w] = 1.f / (1.f + __expf(-acc));
+      } else if (inb) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float y = apply_act(fmaf(v[c], s_scale[c], s_shift[c]), P.act);
+          const float o = (P.img_mode == ADB_IMG_BLEND) ? (1.f - alpha) * xin[c] + alpha * y : fminf(fmaxf(xin[c] + y * gd, 0.f), 1.f);
+          P.img_out[img_o + c * plane] = o;
+        }
+      }
+    }
+    g_base += (uint32_t)sg.rows;
+    rem = (rem + (uint32_t)sg.rows) % kEpiSets;
+  }
+}
+
+template <int kAct, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -471,7 +553,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int ewi = warp - kEpiWarp0;
     const int ew = ewi & 3, set = ewi >> 2;
     const uint32_t sbuf = base + L.stage_off + (uint32_t)ewi * (uint32_t)P.stage_bytes;
-    if (P.residual) roll_epilogue<kAct, true>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, set, lane, unit, nunits, total);
+    if (kEpi != ADB_EPI_FEATURE) roll_epilogue_head<kEpi>(P, tmem_base, full0, empty0, s_scale, s_shift, ew, set, lane, unit, nunits, total);
+    else if (P.residual) roll_epilogue<kAct, true>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, set, lane, unit, nunits, total);
     else roll_epilogue<kAct, false>(P, &tmOut, tmem_base, full0, empty0, sbuf, s_scale, s_shift, ew, set, lane, unit, nunits, total);
   }
 
@@ -489,8 +572,16 @@ int debug_buffer(long long** out, void* stream);   // conv_igemm.cu
 // Whether adb_conv2d should take the rolling-row kernel for this descriptor (w_fold given by the caller).
 bool roll_eligible(const adb_conv_desc* d) {
   if (!d->w_fold || (d->tune_flags & 512)) return false;
-  if (d->kind != ADB_CONV_S1 || d->kh != 3 || d->kw != 3 || d->pad != 1 || d->epi != ADB_EPI_FEATURE || d->pre_scale) return false;
-  if (d->cout_pad % 32 != 0 || 3 * d->cout_pad > 256) return false;
+  if (d->kind != ADB_CONV_S1 || d->kh != 3 || d->kw != 3 || d->pad != 1 || d->pre_scale) return false;
+  if (d->epi == ADB_EPI_FEATURE) {
+    if (d->cout_pad % 32 != 0 || 3 * d->cout_pad > 256) return false;
+  } else if (d->epi == ADB_EPI_IMAGE) {
+    if (d->cout_pad != 16 || d->cout != 3) return false;
+  } else if (d->epi == ADB_EPI_DOT) {
+    if (d->cout_pad != 16 && d->cout_pad != 32) return false;
+  } else {
+    return false;
+  }
   if (d->w_in < kStripW) return false;
   if (d->c0 % 16 || d->c1 % 16) return false;
   // the resident filter + three operand slots + staging must fit shared memory
@@ -509,9 +600,17 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   ADB_REQUIRE(d->src0 && d->c0 > 0 && d->c0_pitch >= d->c0 && d->c0_pitch % 8 == 0, "adb_conv2d(roll): bad src0");
   ADB_REQUIRE((d->src1 == nullptr) == (d->c1 == 0), "adb_conv2d(roll): src1/c1 mismatch");
   ADB_REQUIRE(d->n > 0 && d->h_in > 0 && d->w_in >= kStripW, "adb_conv2d(roll): bad n/h/w");
-  ADB_REQUIRE(d->dst && d->dst_pitch % 8 == 0 && d->dst_c_off >= 0 && d->dst_c_off % 8 == 0 && d->dst_c_off + d->cout_pad <= d->dst_pitch,
-              "adb_conv2d(roll): dst pitch %d cannot hold channels [%d, %d)", d->dst_pitch, d->dst_c_off, d->dst_c_off + d->cout_pad);
-  if (d->residual) ADB_REQUIRE(d->res_pitch >= d->cout_pad && d->res_pitch % 8 == 0, "adb_conv2d(roll): residual pitch %d too small", d->res_pitch);
+  if (d->epi == ADB_EPI_FEATURE) {
+    ADB_REQUIRE(d->dst && d->dst_pitch % 8 == 0 && d->dst_c_off >= 0 && d->dst_c_off % 8 == 0 && d->dst_c_off + d->cout_pad <= d->dst_pitch,
+                "adb_conv2d(roll): dst pitch %d cannot hold channels [%d, %d)", d->dst_pitch, d->dst_c_off, d->dst_c_off + d->cout_pad);
+    if (d->residual) ADB_REQUIRE(d->res_pitch >= d->cout_pad && d->res_pitch % 8 == 0, "adb_conv2d(roll): residual pitch %d too small", d->res_pitch);
+  } else if (d->epi == ADB_EPI_DOT) {
+    ADB_REQUIRE(d->dot_w && d->dot_out, "adb_conv2d(roll): DOT epilogue needs dot_w/dot_out");
+  } else {
+    ADB_REQUIRE(d->img_x && d->img_out && d->cout == 3, "adb_conv2d(roll): IMAGE epilogue needs img_x/img_out, cout == 3");
+    ADB_REQUIRE(d->img_mode != ADB_IMG_GUIDED || d->img_guidance, "adb_conv2d(roll): GUIDED needs img_guidance");
+    ADB_REQUIRE(d->img_mode != ADB_IMG_BLEND || d->img_alpha, "adb_conv2d(roll): BLEND needs img_alpha");
+  }
   adbh::DeviceInfo di;
   int st = adbh::device_info(&di);
   if (st != ADB_OK) return st;
@@ -528,7 +627,7 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   P.c0 = d->c0;
   const int nchunks = P.chunks0 + P.chunks1;
   const int ctot = d->c0 + d->c1;
-  P.CP = d->cout_pad; P.R = 512 / P.CP;
+  P.CP = d->cout_pad; P.R = std::min(512 / P.CP, kMaxRing);
   P.logR = 0;
   while ((1 << P.logR) < P.R) ++P.logR;
   ADB_REQUIRE(P.R >= 8 && P.R <= kMaxRing && (P.R & (P.R - 1)) == 0, "adb_conv2d(roll): ring of %d rows unsupported (power of two)", P.R);
@@ -566,8 +665,12 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
   if (d->tune_stages > 0) a_slots = std::min(a_slots, std::max(2, d->tune_stages));
   P.a_slots = a_slots;
   P.act = d->act; P.scale = d->scale; P.shift = d->shift;
-  P.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); P.res_pitch = d->res_pitch;
+  P.residual = d->epi == ADB_EPI_FEATURE ? reinterpret_cast<const __nv_bfloat16*>(d->residual) : nullptr; P.res_pitch = d->res_pitch;
   P.out_c_off = d->dst_c_off;
+  P.epi = d->epi;
+  P.dot_w = d->dot_w; P.dot_b = d->dot_b; P.dot_out = d->dot_out;
+  P.img_mode = d->img_mode; P.img_x = d->img_x; P.img_out = d->img_out; P.img_index = d->img_index;
+  P.img_guidance = d->img_guidance; P.img_alpha = d->img_alpha;
   P.err_flag = adbh::kernel_err_flag();
   if (d->tune_flags & 4) {
     st = debug_buffer(&P.dbg, stream);
@@ -591,15 +694,22 @@ int conv_roll_launch(const adb_conv_desc* d, void* stream) {
     st = adbh::make_tmap_bf16(&tmB, d->w_fold, 2, dims, strides, box, P.row_bytes);
     if (st != ADB_OK) return st;
   }
-  st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->dst_pitch, d->n, P.H, P.W, false, P.Cs, 32, 1, P.Cs * 2);
-  if (st != ADB_OK) return st;
+  if (d->epi == ADB_EPI_FEATURE) {
+    st = make_act_tmap(&tmOut, d->dst, d->dst_pitch, d->dst_pitch, d->n, P.H, P.W, false, P.Cs, 32, 1, P.Cs * 2);
+    if (st != ADB_OK) return st;
+  } else {
+    tmOut = tmA0;
+  }
 
   const RollSmem L = roll_smem(P.a_slots, P.a_slot_bytes, P.b_bytes_total, P.stage_bytes, P.CP);
   int smem = std::max((int)L.total + 1024, 120 * 1024);     // one CTA per SM: the CTA owns the SM's TMEM
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, RollK);
-  const int which = d->act == ADB_ACT_RELU ? 0 : (d->act == ADB_ACT_NONE ? 1 : 2);
-  KernelFn fn = which == 0 ? conv_roll_kernel<ADB_ACT_RELU> : (which == 1 ? conv_roll_kernel<ADB_ACT_NONE> : conv_roll_kernel<-1>);
-  static bool configured[3] = {false, false, false};
+  int which = d->act == ADB_ACT_RELU ? 0 : (d->act == ADB_ACT_NONE ? 1 : 2);
+  KernelFn fn = which == 0 ? conv_roll_kernel<ADB_ACT_RELU, ADB_EPI_FEATURE>
+                           : (which == 1 ? conv_roll_kernel<ADB_ACT_NONE, ADB_EPI_FEATURE> : conv_roll_kernel<-1, ADB_EPI_FEATURE>);
+  if (d->epi == ADB_EPI_DOT) { fn = conv_roll_kernel<-1, ADB_EPI_DOT>; which = 3; }
+  if (d->epi == ADB_EPI_IMAGE) { fn = conv_roll_kernel<-1, ADB_EPI_IMAGE>; which = 4; }
+  static bool configured[5] = {false, false, false, false, false};
   if (!configured[which]) {
     ADB_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
     configured[which] = true;

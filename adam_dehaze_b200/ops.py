@@ -9,11 +9,11 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_S1, CONV_S2, CONVT_4X4S2, EPI_DOT, EPI_FEATURE,
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, CONV_K4_S2D, CONV_S1, CONV_S2, CONVT_4X4S2, EPI_DOT, EPI_FEATURE,
                    EPI_IMAGE, IMG_BLEND, IMG_GUIDED, IMG_RESIDUAL, WG_OIHW, WG_STEM, ConvDesc, WgradDesc)
 
 __all__ = [
-    "pad16", "fold_bn", "pack_conv_weight", "pack_conv_weight_fold", "fold_eligible", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
+    "pad16", "fold_bn", "pack_conv_weight", "pack_stem_s2d_weight", "pack_conv_weight_fold", "fold_eligible", "pack_convT_weight", "pack_stem_weight", "ConvSpec", "conv2d",
     "stem_pack", "nchw_to_nhwc", "nhwc_to_nchw", "attention", "maxpool3x3s2", "global_avgpool", "affine_relu", "avgpool2x2", "maxpool_kxk", "upsample_bilinear", "head_mlp",
     "linear", "route", "blend3", "l1_mse", "cross_entropy", "wgrad",
 ]
@@ -83,7 +83,8 @@ def pack_conv_weight(w, cout_pad=None):
 def fold_eligible(co, kh, kw, stride, pad, cout_pad=None):
     """3x3 stride-1 'same' convs whose three filter rows fit one MMA's N (3*cout_pad <= 256): the rolling-row kernel."""
     cp = cout_pad or pad16(co)
-    return kh == 3 and kw == 3 and stride == 1 and pad == 1 and cp % 32 == 0 and 3 * cp <= 256
+    # (cout_pad 16: the 3-channel image heads and the 16-channel guidance / transmission heads, IMAGE / DOT epilogues only)
+    return kh == 3 and kw == 3 and stride == 1 and pad == 1 and cp in (16, 32, 64)
 
 
 def pack_conv_weight_fold(w, cout_pad=None):
@@ -126,6 +127,28 @@ def pack_stem_weight(w, kp, cout_pad=None):
     return out.reshape(cout_pad, kh * kp).to(pack_dtype()).contiguous()
 
 
+def pack_stem_s2d_weight(w, cout_pad=None):
+    """7x7 stride-2 pad-3 stem weight [co, 3, 7, 7] -> the 4x4-tap form over the space-to-depth image (ADB_CONV_K4_S2D):
+    [cout_pad, 16 taps * 16], column (R*4 + S)*16 + (py*2 + px)*3 + c = W[co][c][2R+py-1][2S+px-1], zero outside the 7x7."""
+    co, ci, kh, kw = w.shape
+    assert ci == 3 and kh == 7 and kw == 7
+    cout_pad = cout_pad or pad16(co)
+    out = torch.zeros(cout_pad, 4, 4, 16, dtype=torch.float32, device=w.device)
+    wf = w.detach().float()
+    for R in range(4):
+        for py in range(2):
+            u = 2 * R + py - 1
+            if not 0 <= u < 7:
+                continue
+            for S in range(4):
+                for px in range(2):
+                    v = 2 * S + px - 1
+                    if 0 <= v < 7:
+                        q = (py * 2 + px) * 3
+                        out[:co, R, S, q:q + 3] = wf[:, :, u, v]
+    return out.reshape(cout_pad, 256).to(pack_dtype()).contiguous()
+
+
 class ConvSpec:
     """Packed parameters + geometry of one fused conv launch."""
 
@@ -149,6 +172,13 @@ class ConvSpec:
         ci, co, kh, kw = weight.shape
         scale, shift = fold_bn(co, bias, bn, device=weight.device)
         return ConvSpec(CONVT_4X4S2, 4, 4, 1, co, pack_convT_weight(weight), scale, shift, act)
+
+    @staticmethod
+    def from_stem_s2d(weight, bn=None, act=ACT_NONE):
+        """torchvision's 7x7 stride-2 stem over the space-to-depth operand of stem_pack(x, 2, 0, 16, stride=2, kh=2)."""
+        co = weight.shape[0]
+        scale, shift = fold_bn(co, None, bn, device=weight.device)
+        return ConvSpec(CONV_K4_S2D, 4, 4, 2, co, pack_stem_s2d_weight(weight), scale, shift, act)
 
     @staticmethod
     def from_stem(weight, kp, bias=None, bn=None, act=ACT_NONE):

@@ -840,6 +840,8 @@ def conv_flops(spec, src0, src1, n, kw):
         k = spec.kh * spec.kh * 3
     if spec.kh == 1 and cin == 160:                               # full-im2col stem: real K = 147
         k = 147
+    if spec.kind == _lib.CONV_K4_S2D:                             # 7x7 stride-2 stem over the space-to-depth image: real K = 147
+        k = 147
     return 2.0 * n * h * w * k * spec.cout
 
 

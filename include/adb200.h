@@ -47,7 +47,11 @@ enum { ADB_ACT_NONE = 0, ADB_ACT_RELU = 1, ADB_ACT_TANH = 2, ADB_ACT_SIGMOID = 3
 enum {
   ADB_CONV_S1 = 0,     /* kh x kw, stride 1, zero padding `pad` (nn.Conv2d in ConvBlock, base_model.py:11-13) */
   ADB_CONV_S2 = 1,     /* kh x kw, stride 2, zero padding `pad`; H and W even (encoder downsamples, medium:25,35; high:26,36) */
-  ADB_CONVT_4X4S2 = 2  /* nn.ConvTranspose2d(k=4, s=2, p=1) as four 2x2 sub-pixel phases (medium:53,63; high:57,68) */
+  ADB_CONVT_4X4S2 = 2, /* nn.ConvTranspose2d(k=4, s=2, p=1) as four 2x2 sub-pixel phases (medium:53,63; high:57,68) */
+  ADB_CONV_K4_S2D = 3  /* 4x4 taps at offsets -2..+1, stride 1, same-size output: a 7x7 stride-2 pad-3 stem (torchvision resnet /
+                          densenet conv1 / conv0 called from classifier.py:24-36) over the SPACE-TO-DEPTH image
+                          [n, H/2, W/2, 16] (channel (py*2+px)*3 + c, 12 real): out(y,x) = sum W[u][v] X[2y+u-3][2x+v-3] with
+                          u = 2R + py - 1.  32 bytes of operand per output pixel instead of the 320 of a full im2col. */
 };
 
 /* epilogue kinds */
@@ -112,6 +116,7 @@ typedef struct adb_conv_desc {
  *   ADB_CONVT_4X4S2:            phase g = a*2 + b (a = oh&1, b = ow&1); tap (i,j), i,j in {0,1};
  *                               r = a ? 2*i : 1 + 2*i   (input row  q + (a ? 1-i : -i));  s likewise from b, j
  *                               w_packed[g][co][(i*2 + j)*cin + ci] = Wt[ci][co][r][s]
+ *   ADB_CONV_K4_S2D:            w_packed[co][(R*4 + S)*16 + (py*2 + px)*3 + c] = W[co][c][2R+py-1][2S+px-1] (0 outside the 7x7)
  *   c0 and c1 are multiples of 16; the kernel walks K in 64-channel chunks (ragged last chunk per source).
  */
 

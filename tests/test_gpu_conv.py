@@ -359,3 +359,73 @@ def test_conv_roll_channel_slice_in_place_and_bucket_count():
     fn = ops.nchw_to_nhwc(f)
     ops.conv2d(ops.ConvSpec.from_conv(w2, act=ops.ACT_RELU), fn.clone(), dst=fn, residual=fn)
     _close(ops.nhwc_to_nchw(fn), F.relu(F.conv2d(f, w2, padding=1) + f))
+
+
+@pytest.mark.parametrize("mode", ["blend", "residual", "guided"])
+@pytest.mark.parametrize("cin,h,w", [(32, 24, 160), (48, 9, 128)])
+def test_conv_roll_image_head(mode, cin, h, w):
+    """The 3-channel output heads on the rolling-row schedule (N = 3 x 16): same arithmetic and tolerance as test_image_epilogue,
+    and the same result as the tap-by-tap kernel."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(50)
+    xb = torch.rand(5, 3, h, w, generator=g).cuda()
+    index = torch.tensor([4, 1, 3], dtype=torch.int32, device="cuda")
+    feat = _rand_fm(3, cin, h, w, 51)
+    wt = _rand_w((3, cin, 3, 3), 52, cin * 9)
+    bias = torch.randn(3, device="cuda") * 0.1
+    guid = torch.rand(3, h, w, device="cuda")
+    alpha = torch.tensor(0.1, device="cuda")
+    act = ops.ACT_SIGMOID if mode == "blend" else ops.ACT_TANH
+    spec = ops.ConvSpec.from_conv(wt, bias=bias, act=act)
+    assert spec.w_fold is not None
+
+    def run(tune):
+        out = torch.zeros_like(xb)
+        img = {"blend": dict(mode=ops.IMG_BLEND, x=xb, out=out, index=index, alpha=alpha),
+               "residual": dict(mode=ops.IMG_RESIDUAL, x=xb, out=out, index=index),
+               "guided": dict(mode=ops.IMG_GUIDED, x=xb, out=out, index=index, guidance=guid)}[mode]
+        ops.conv2d(spec, ops.nchw_to_nhwc(feat), epi=ops.EPI_IMAGE, image=img, tune=tune)
+        return out
+    out = run(None)
+    v = F.conv2d(feat, wt, bias, padding=1)
+    xs = xb[index.long()]
+    ref = {"blend": 0.9 * xs + 0.1 * torch.sigmoid(v), "residual": torch.clamp(xs + torch.tanh(v), 0, 1),
+           "guided": torch.clamp(xs + torch.tanh(v) * guid.unsqueeze(1), 0, 1)}[mode]
+    _close(out[index.long()], ref, rel=2e-3, abs_=2e-4)
+    assert out[[0, 2]].abs().max().item() == 0.0
+    _close(out, run({"flags": 512}), rel=1e-3, abs_=1e-4)
+
+
+@pytest.mark.parametrize("c", [16, 32])
+def test_conv_roll_dot_head(c):
+    ops = _ops()
+    x = _rand_fm(2, c, 20, 256, 53)
+    wt = _rand_w((c, c, 3, 3), 54, c * 9)
+    bn = _bn(c, 55)
+    dw = torch.randn(c, device="cuda")
+    out = torch.empty((2, 20, 256), dtype=torch.float32, device="cuda")
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU)
+    ops.conv2d(spec, ops.nchw_to_nhwc(x), epi=ops.EPI_DOT, dot=(dw, 0.25, out))
+    feat = F.relu(_bn_ref(F.conv2d(x, wt, padding=1), bn))
+    ref = torch.sigmoid((feat * dw.view(1, -1, 1, 1)).sum(1) + 0.25)
+    _close(out, ref, rel=2e-3, abs_=1e-4)
+    old = torch.empty_like(out)
+    ops.conv2d(spec, ops.nchw_to_nhwc(x), epi=ops.EPI_DOT, dot=(dw, 0.25, old), tune={"flags": 512})
+    _close(out, old, rel=1e-3, abs_=1e-4)
+
+
+@pytest.mark.parametrize("cout,h,w,n", [(64, 64, 256, 2), (64, 32, 96, 1)])
+def test_stem_7x7_stride2_space_to_depth(cout, h, w, n):
+    """HDEN stem (torchvision conv1 / conv0 + BatchNorm + ReLU): space-to-depth operand (adb_stem_pack kh = kw = 2, stride 2) +
+    the 4x4-tap conv kind ADB_CONV_K4_S2D against F.conv2d(7x7, stride 2, pad 3) on the bf16-rounded image."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(60)
+    x = torch.rand(n, 3, h, w, generator=g).cuda()
+    wt = _rand_w((cout, 3, 7, 7), 61, 147)
+    bn = _bn(cout, 62)
+    spec = ops.ConvSpec.from_stem_s2d(wt, bn=bn, act=ops.ACT_RELU)
+    cols = ops.stem_pack(x, 2, 0, 16, stride=2, kh=2)
+    assert cols.shape == (n, h // 2, w // 2, 16)
+    y = ops.conv2d(spec, cols)
+    ref = F.relu(_bn_ref(F.conv2d(x.to(torch.bfloat16).float(), wt, stride=2, padding=3), bn))
+    _close(ops.nhwc_to_nchw(y, cout), ref)

@@ -108,7 +108,9 @@ def test_pack_conv_fold_rows_accumulate_into_adjacent_output_rows():
         wf = ops.pack_conv_weight_fold(wt)            # [3][3*cp][ci]
     cp = ops.pad16(co)
     assert wf.shape == (3, 3 * cp, ci) and cp == 32
-    assert ops.fold_eligible(co, 3, 3, 1, 1) and not ops.fold_eligible(96, 3, 3, 1, 1) and not ops.fold_eligible(16, 3, 3, 1, 1)
+    # 3*cout_pad <= 256 -> cout_pad 16 (image / guidance heads), 32, 64; 96 channels do not fit one MMA's N
+    assert ops.fold_eligible(co, 3, 3, 1, 1) and ops.fold_eligible(16, 3, 3, 1, 1) and ops.fold_eligible(3, 3, 3, 1, 1)
+    assert not ops.fold_eligible(96, 3, 3, 1, 1) and not ops.fold_eligible(32, 3, 3, 2, 1) and not ops.fold_eligible(32, 1, 1, 1, 0)
     xp = F.pad(x, (1, 1, 0, 0))[0].permute(1, 2, 0)    # [h][w+2][ci]
     out = torch.zeros(h, w, cp)
     for j in range(h):
@@ -120,6 +122,28 @@ def test_pack_conv_fold_rows_accumulate_into_adjacent_output_rows():
     ref = F.conv2d(x, wt, padding=1)[0].permute(1, 2, 0)
     assert torch.allclose(out[..., :co], ref, atol=1e-4)
     assert out[..., co:].abs().max() == 0
+
+
+def test_pack_stem_space_to_depth_form_equals_the_7x7_stride2_conv():
+    """ops.pack_stem_s2d_weight: torchvision's 7x7 / stride 2 / pad 3 stem (classifier.py:24-36) == a 4x4-tap conv at offsets
+    -2..+1 over the space-to-depth image (ADB_CONV_K4_S2D, include/adb200.h)."""
+    import torch.nn.functional as F
+    from adam_dehaze_b200 import ops
+    torch.manual_seed(1)
+    w = torch.randn(24, 3, 7, 7)
+    x = torch.randn(2, 3, 20, 28)
+    with ops.pack_as(torch.float32):
+        wp = ops.pack_stem_s2d_weight(w)                                    # [32, 256]
+    assert wp.shape == (32, 256)
+    xs = torch.zeros(2, 16, 10, 14)
+    for py in range(2):
+        for px in range(2):
+            q = (py * 2 + px) * 3
+            xs[:, q:q + 3] = x[:, :, py::2, px::2]
+    w4 = wp.view(32, 4, 4, 16).permute(0, 3, 1, 2)                           # [co, ch, R, S]
+    got = F.conv2d(F.pad(xs, (2, 1, 2, 1)), w4)                              # taps at offsets -2..+1
+    ref = F.conv2d(x, w, stride=2, padding=3)
+    assert torch.allclose(got[:, :24], ref, atol=1e-4) and got[:, 24:].abs().max() == 0
 
 
 @pytest.mark.parametrize("k,pad", [(4, 1), (3, 1), (1, 0)])
