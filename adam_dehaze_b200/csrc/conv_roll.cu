@@ -579,6 +579,7 @@ bool roll_eligible(const adb_conv_desc* d) {
     if (d->cout_pad != 16 || d->cout != 3) return false;
   } else if (d->epi == ADB_EPI_DOT) {
     if (d->cout_pad != 16 && d->cout_pad != 32) return false;
+    if (d->c0 + d->c1 < 32) return false;      // 16 input channels = 32-byte operand rows: measured slower than the tap-by-tap kernel
   } else {
     return false;
   }

@@ -547,6 +547,12 @@ class ResNetEngine:
         self.S = S
         return S
 
+    @staticmethod
+    def chunk_size(b, h, w):
+        """Images per trunk pass: bounds the activation footprint at 24 GB."""
+        per_img = (h // 2) * (w // 2) * (32 + 2 * 128) + (h // 4) * (w // 4) * 3 * 128
+        return max(1, min(b, (24 << 30) // max(1, per_img)))
+
     def forward(self, x, chunk=None):
         require_cuda(x, "FogIntensityClassifier")
         if self.clf.training:
@@ -556,9 +562,7 @@ class ResNetEngine:
         if h % 32 or w % 32:
             raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
         S = self.specs()
-        # bound the activation footprint
-        per_img = (h // 2) * (w // 2) * (32 + 2 * 128) + (h // 4) * (w // 4) * 3 * 128
-        chunk = chunk or max(1, min(b, (24 << 30) // max(1, per_img)))
+        chunk = chunk or self.chunk_size(b, h, w)
         feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
         for s in range(0, b, chunk):
             n = min(chunk, b - s)
@@ -606,6 +610,12 @@ class DenseNetEngine:
     _forward_train = ResNetEngine._forward_train
 
     @staticmethod
+    def chunk_size(b, h, w):
+        """Images per trunk pass: bounds the activation footprint at 24 GB."""
+        per_img = (h // 2) * (w // 2) * (32 + 128) + (h // 4) * (w // 4) * 2 * (256 + 256 + 128)
+        return max(1, min(b, (24 << 30) // max(1, per_img)))
+
+    @staticmethod
     def _affine(bn):
         s, b = ops.fold_bn(bn.num_features, None, bn_args(bn), cout_pad=bn.num_features, device=bn.weight.device)
         return s, b
@@ -642,8 +652,7 @@ class DenseNetEngine:
         if h % 32 or w % 32:
             raise ValueError(f"FogIntensityClassifier (B200 path): H and W must be multiples of 32, got {h}x{w}")
         S = self.specs()
-        per_img = (h // 2) * (w // 2) * (32 + 128) + (h // 4) * (w // 4) * 2 * (256 + 256 + 128)
-        chunk = chunk or max(1, min(b, (24 << 30) // max(1, per_img)))
+        chunk = chunk or self.chunk_size(b, h, w)
         feats = torch.empty((b, self.clf.feature_dim), dtype=torch.float32, device=x.device)
         dev = x.device
         for s in range(0, b, chunk):

@@ -728,8 +728,13 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
         rec.append((a, b, conv_flops(spec, src0, src1, n, kw)))
         return r
 
-    nimg = min(8, hazy.shape[0])
-    x = hazy[:nimg].contiguous()
+    # every model is measured at the launch shape the timed step gives it: a branch walks its bucket 16 images at a time
+    # (engine micro-batch), HDEN runs the chunk its engine cuts a 256-image batch into (capped at 32 here to bound the pass)
+    B_all = hazy.shape[0]
+    n_of = {}
+    for name, m in branches.items():
+        n_of[name] = min(B_all, m._branch_engine().micro_batch(hazy.shape[2], hazy.shape[3], max(1, B_all // 3)))
+    n_of[hden] = min(B_all, 32, clf._hden_engine().chunk_size(B_all, hazy.shape[2], hazy.shape[3]))
     per_branch = {}
     import adam_dehaze_b200.engine as eng
     eng.ops.conv2d = timed_conv
@@ -748,6 +753,8 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
 
     try:
         for name, m in list(branches.items()) + [(hden, clf)]:
+            nimg = n_of[name]
+            x = hazy[:nimg].contiguous()
             m(x)  # warm
             torch.cuda.synchronize()
             rec.clear()
@@ -760,7 +767,7 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
             flops = sum(f for _, _, f in rec)
             per_branch[name] = {"ms": s.elapsed_time(e) / nimg, "conv_ms": conv_ms / nimg, "conv_launches": len(rec),
                                 "conv_tflops": flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
-                                "tflop_per_image": flops / nimg / 1e12}
+                                "tflop_per_image": flops / nimg / 1e12, "images": nimg}
             eng.ops.conv2d = orig
             ops_mod.conv2d = orig
             _lib.call = timed_call
@@ -793,12 +800,12 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
     # launches, FLOPs and time all enter with weight 1 (branches) or 3 (HDEN)
     wts = {k: (3.0 if k == hden else 1.0) for k in per_branch}
     w_launch = sum(wts[k] * v["conv_launches"] for k, v in per_branch.items())
-    w_flops = sum(wts[k] * v["tflop_per_image"] * nimg for k, v in per_branch.items()) * 1e12
-    w_ms = sum(wts[k] * v["conv_ms"] * nimg for k, v in per_branch.items())
-    per_model = {k: {"conv_launches": v["conv_launches"], "achieved_tflops": v["conv_tflops"],
+    w_flops = sum(wts[k] * v["tflop_per_image"] * v["images"] for k, v in per_branch.items()) * 1e12
+    w_ms = sum(wts[k] * v["conv_ms"] * v["images"] for k, v in per_branch.items())
+    per_model = {k: {"conv_launches": v["conv_launches"], "images_per_launch": v["images"], "achieved_tflops": v["conv_tflops"],
                      "frac": (v["conv_tflops"] / peak) if v["conv_tflops"] else None,
-                     "flops_per_launch": v["tflop_per_image"] * nimg * 1e12 / max(1, v["conv_launches"]),
-                     "ms_per_launch": v["conv_ms"] * nimg / max(1, v["conv_launches"]), "mix_weight": wts[k]}
+                     "flops_per_launch": v["tflop_per_image"] * v["images"] * 1e12 / max(1, v["conv_launches"]),
+                     "ms_per_launch": v["conv_ms"] * v["images"] / max(1, v["conv_launches"]), "mix_weight": wts[k]}
                  for k, v in per_branch.items()}
     # dram bytes per conv launch of this same pass, from the committed ncu capture (tools/conv_traffic.py); same weighting
     # and same 8-image pass as flops_per_launch_avg, so bytes/launch and FLOPs/launch describe the same average launch
@@ -807,17 +814,22 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
     if tpath:
         with open(tpath) as fh:
             tj = json.load(fh)
-        if tj.get("images") == nimg and tj.get("hden") == hden and (tj.get("height"), tj.get("width")) == (hazy.shape[2], hazy.shape[3]):
-            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+        pm = tj.get("per_model", {})
+        if tj.get("hden") == hden and (tj.get("height"), tj.get("width")) == (hazy.shape[2], hazy.shape[3]) and all(
+                k in pm and pm[k]["launches"] == per_branch[k]["conv_launches"] for k in per_branch):
+            # DRAM bytes of a conv launch scale with its image count (weights are < 1 % of the traffic): the capture's
+            # bytes per image times this pass's images per launch, mix-weighted like flops_per_launch_avg
+            tot = sum(wts[k] * (pm[k]["dram_read_bytes"] + pm[k]["dram_write_bytes"]) / pm[k].get("images", tj.get("images", 8)) * per_branch[k]["images"]
+                      for k in per_branch)
+            traffic, traffic_src = tot / max(1.0, w_launch), tj["source"]
         else:
-            traffic_src = os.path.basename(tpath) + " was captured on a different pass shape"
+            traffic_src = os.path.basename(tpath) + " was captured on a different pass (model, resolution or launch count)"
     roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_roll_kernel (adb_conv2d)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
             "peak_source": src,
-            "traffic_ref": "ncu --set full captures of representative conv shapes: profiles/r1_conv_ncu_full.md, "
-                           "profiles/r1_dense_pre_ncu.md (DRAM traffic ~= algorithmic bytes: no re-reads)",
+            "traffic_ref": "ncu --set full captures of representative conv shapes: profiles/r2/README.md (DRAM traffic ~= algorithmic bytes)",
             "how": f"sum of true conv FLOPs / sum of CUDA-event durations over the {launches} conv launches of one pass of "
-                   f"Light+Medium+Complex+HDEN on {nimg} images at {hazy.shape[2]}x{hazy.shape[3]} (equal-thirds mix weighting)",
+                   f"Light+Medium+Complex+HDEN at {hazy.shape[2]}x{hazy.shape[3]}, each at its own launch size ({n_of}) (equal-thirds mix weighting)",
             "flops_per_launch_avg": w_flops / max(1.0, w_launch),
             "ms_per_launch_avg": w_ms / max(1.0, w_launch),
             "launch_weighting": "mix-weighted over the same pass: each model's launches, FLOPs and milliseconds enter with weight 1 "

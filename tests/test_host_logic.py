@@ -488,14 +488,15 @@ def test_weight_repack_index_maps():
 
 
 def test_roofline_traffic_json_follows_from_the_committed_ncu_capture():
-    """bench.py's roofline.traffic is read from profiles/r1_conv_traffic.json; that file must be exactly what
+    """bench.py's roofline.traffic is read from profiles/r2_conv_traffic.json; that file must be exactly what
     tools/conv_traffic.py computes from the committed ncu csv of the roofline pass (no hand-edited number)."""
     import json
     import subprocess
-    csv_path = os.path.join(ROOT, "profiles", "r1m", "ncu_conv_traffic.csv")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "conv_traffic.py"), csv_path], capture_output=True, text=True, check=True)
+    csv_path = os.path.join(ROOT, "profiles", "r2", "ncu_conv_traffic.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "conv_traffic.py"), csv_path], capture_output=True, text=True, check=True,
+                         cwd=ROOT)
     got = json.loads(out.stdout)
-    want = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic.json")))
+    want = json.load(open(os.path.join(ROOT, "profiles", "r2_conv_traffic.json")))
     assert got["launches"] == want["launches"] == 179
     assert abs(got["dram_bytes_per_launch_avg"] - want["dram_bytes_per_launch_avg"]) <= 1e-6 * want["dram_bytes_per_launch_avg"]
     assert set(got["per_model"]) == {"low", "medium", "high", "densenet121"}

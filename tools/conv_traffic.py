@@ -4,7 +4,7 @@
         --nvtx-include "adb_roofline_densenet121/" -k regex:conv_ \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file gpurun_out/ncu_traffic.csv python bench.py --steps 1 --warmup 3 --batch 12 --no-e2e --no-cpu-baseline
-    python tools/conv_traffic.py gpurun_out/ncu_traffic.csv > profiles/r1_conv_traffic.json
+    python tools/conv_traffic.py gpurun_out/ncu_traffic.csv [bench line of the same command.json] > profiles/r2_conv_traffic.json
 
 bench.py wraps each model's instrumented pass (8 images at 1024x2048) in an NVTX range `adb_roofline_<model>`; the average
 uses bench.py's own mix weighting (every model's bytes AND launches enter with weight 1 for Light/Medium/Complex and 3 for
@@ -17,6 +17,12 @@ import sys
 
 def main():
     path = sys.argv[1]
+    # images per model of the captured pass: from the bench line of the same command (roofline.per_model[*].images_per_launch)
+    images = {}
+    if len(sys.argv) > 2:
+        with open(sys.argv[2]) as fh:
+            line = json.load(fh)
+        images = {k: v.get("images_per_launch") for k, v in line["roofline"]["per_model"].items()}
     with open(path, newline="") as fh:
         lines = [ln for ln in fh if ln.startswith('"')]
     rd = csv.DictReader(lines)
@@ -50,8 +56,8 @@ def main():
     tot = sum((a["read"] + a["write"]) * (3 if k == hden else 1) for k, a in models.items())
     w_launches = sum(a["launches"] * (3 if k == hden else 1) for k, a in models.items())
     out = {"dram_bytes_per_launch_avg": tot / max(1, w_launches), "launches": launches, "images": 8, "height": 1024, "width": 2048,
-           "hden": hden, "per_model": {k: {"launches": a["launches"], "dram_read_bytes": a["read"], "dram_write_bytes": a["write"],
-                                            "ncu_ms": a["ns"] / 1e6} for k, a in models.items()},
+           "hden": hden, "per_model": {k: {"launches": a["launches"], "images": images.get(k) or 8, "dram_read_bytes": a["read"],
+                                            "dram_write_bytes": a["write"], "ncu_ms": a["ns"] / 1e6} for k, a in models.items()},
            "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the adb_conv2d (conv_igemm / conv_roll) launches of bench.py's roofline pass ({path}), "
                      "weighting as flops_per_launch_avg"}
     json.dump(out, sys.stdout, indent=1)

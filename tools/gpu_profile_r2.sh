@@ -13,7 +13,7 @@ python bench.py $ISMALL > /dev/null 2>&1 &&
 timeout 900 ncu --nvtx --nvtx-include "adb_roofline_low/" --nvtx-include "adb_roofline_medium/" --nvtx-include "adb_roofline_high/" \
     --nvtx-include "adb_roofline_densenet121/" -k regex:conv_ --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
     --clock-control none --csv --log-file gpurun_out/ncu_traffic_${TAG}.csv python bench.py $ISMALL > gpurun_out/ncu_traffic_${TAG}.log 2>&1
-python tools/conv_traffic.py gpurun_out/ncu_traffic_${TAG}.csv > gpurun_out/conv_traffic_${TAG}.json 2> gpurun_out/conv_traffic_${TAG}.err
+python tools/conv_traffic.py gpurun_out/ncu_traffic_${TAG}.csv gpurun_out/plain_small_${TAG}.json > gpurun_out/conv_traffic_${TAG}.json 2> gpurun_out/conv_traffic_${TAG}.err
 for shape in light_32_3x3 med_64_3x3 dense_3x3_128_32; do
   python tools/prof_conv.py --only $shape --reps 2 > gpurun_out/plain_${shape}.log 2>&1 &&
   timeout 300 ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:conv_roll -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_roll_${shape} \
