@@ -675,6 +675,35 @@ def run_train(args, embedded=False):
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                 "how": f"launch FLOPs (padded-channel 2*MAC of every conv fwd/dgrad/wgrad launch) / CUDA-event time over the {n_mma} tensor-pipe launches of one step",
                 "flops_per_launch_avg": mma_fl / max(1, n_mma), "ms_per_launch_avg": mma_ms / max(1, n_mma)}
+    # ---- the same step as ONE CUDA graph replay (training/graphed.py): removes the host's launch queueing from the step
+    graphed = None
+    if (world == 1 or os.environ.get("ADB_TRAIN_GRAPH") == "1") and not os.environ.get("ADB_NO_TRAIN_GRAPH"):
+        try:
+            from adam_dehaze_b200.training.graphed import GraphedStep
+            gs = GraphedStep(step, warmup=2)
+            for _ in range(2):
+                gs()
+            barrier()
+            ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.record()
+            for _ in range(args.steps):
+                gloss = gs()
+            gb.record()
+            barrier()
+            tg = torch.tensor([ga.elapsed_time(gb)], device=dev)
+            if world > 1:
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            g_ms = tg.item() / args.steps
+            graphed = {"ms_per_step": g_ms, "samples_per_s": world * B / (g_ms / 1000.0), "loss": float(gloss.item()),
+                       "what": "the identical step (forward, JointLoss, backward, gradient all-reduce, Adam) captured once in a torch.cuda.CUDAGraph "
+                               "and replayed: one host call per step instead of ~1.7 k launches from Python"}
+            del gs
+        except Exception as e:  # noqa: BLE001  (an optional leg must not take the measured line down)
+            graphed = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
     if rank == 0:
         line = {
             "metric": TRAIN_METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -687,7 +716,7 @@ def run_train(args, embedded=False):
                        "samples_per_gpu_per_step": B, "height": Hh, "width": Ww, "trainable_params": nparams,
                        "l2": f"activations {B}x{Hh}x{Ww} per layer (> 126 MB L2 for every full-resolution map)"},
             "clocks": clocks, "gpu_launches": counts["n"] // max(1, args.steps), "loss": float(loss.item()),
-            "roofline": roof, "train_detail": detail, "cpu_baseline": None,
+            "roofline": roof, "train_detail": detail, "cpu_baseline": None, "graphed_step": graphed,
             "allreduce": {"collective": "NCCL all_reduce(sum) of the flat fp32 gradient bucket, one per step" if world > 1 else "none (1 GPU)",
                           "bytes": int(opt.grad.numel()) * 4, "ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else None,
                           "bus_GBs": (2.0 * (world - 1) / world * opt.grad.numel() * 4 / (sum(ar_ms) / len(ar_ms) * 1e-3) / 1e9) if ar_ms else None,

@@ -847,3 +847,39 @@ def test_weight_cache_refreshes_every_packing_in_one_launch():
             assert torch.equal(spec.w_fold, fresh.w_fold)
         checked += 1
     assert checked >= 8
+
+
+def test_graphed_step_matches_eager_steps():
+    """training/graphed.GraphedStep: the captured step (forward, loss, backward, FlatAdam) replayed N times leaves the same
+    parameters, Adam moments / step counts and BatchNorm statistics as N eager steps (capture records, it does not execute)."""
+    from helpers import make_branch, rand_image
+    from adam_dehaze_b200.training.graphed import GraphedStep
+    from adam_dehaze_b200.training.loss import DehazingLoss
+    from adam_dehaze_b200.training.optim import FlatAdam
+    x, tgt = rand_image(2, 64, 128, 7).cuda(), rand_image(2, 64, 128, 8).cuda()
+    crit = DehazingLoss(1.0, 0.0, 0.0)
+
+    def make():
+        m = make_branch("low").cuda().train()
+        opt = FlatAdam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+
+        def step():
+            opt.zero_grad()
+            loss, _ = crit(m(x), tgt)
+            loss.backward()
+            opt.step()
+            return loss
+        return m, opt, step
+    m_e, opt_e, step_e = make()
+    for _ in range(4):
+        loss_e = step_e()
+    m_g, opt_g, step_g = make()
+    gs = GraphedStep(step_g, warmup=2)          # 2 eager steps + 1 capture (recorded, not executed)
+    for _ in range(2):
+        loss_g = gs()
+    torch.cuda.synchronize()
+    assert abs(loss_g.item() - loss_e.item()) <= 1e-5 * abs(loss_e.item())
+    for (k, a), (_, b) in zip(m_e.state_dict().items(), m_g.state_dict().items()):
+        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-7), k
+    assert torch.equal(opt_e.seg_step, opt_g.seg_step) and int(opt_g.seg_step[0]) == 4
+    assert torch.allclose(opt_e.exp_avg, opt_g.exp_avg, rtol=1e-5, atol=1e-9)
