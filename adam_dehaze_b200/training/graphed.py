@@ -19,15 +19,21 @@ class GraphedStep:
     def __init__(self, step_fn, static_inputs=(), warmup=3):
         """step_fn(): one step over `static_inputs` (tensors it closes over); returns a tensor or tuple of tensors (e.g. the loss)."""
         self.step_fn, self.static_inputs = step_fn, tuple(static_inputs)
+        # Warm up and capture on ONE side stream: autograd pins every AccumulateGrad node to the stream it was created on, and a
+        # node of another stream (e.g. from eager steps on the default stream whose loss tensor is still referenced somewhere —
+        # drop such references first) would make the capture wait on that stream, which invalidates it.
+        import gc
+        gc.collect()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                step_fn()
+                out = step_fn()
+            del out
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.outputs = step_fn()
 
     def copy_inputs(self, *tensors):

@@ -677,6 +677,12 @@ def run_train(args, embedded=False):
                 "flops_per_launch_avg": mma_fl / max(1, n_mma), "ms_per_launch_avg": mma_ms / max(1, n_mma)}
     # ---- the same step as ONE CUDA graph replay (training/graphed.py): removes the host's launch queueing from the step
     graphed = None
+    loss_value = float(loss.item())
+    # (autograd keeps the AccumulateGrad nodes of the eager steps alive through any surviving loss tensor; they belong to the
+    # default stream and would invalidate a capture on another stream)
+    del loss
+    meter = None
+    gc.collect()
     if (world == 1 or os.environ.get("ADB_TRAIN_GRAPH") == "1") and not os.environ.get("ADB_NO_TRAIN_GRAPH"):
         try:
             from adam_dehaze_b200.training.graphed import GraphedStep
@@ -715,7 +721,7 @@ def run_train(args, embedded=False):
                                    f"{nparams * 4 / 2**20:.0f} MiB gradient all-reduce per step",
                        "samples_per_gpu_per_step": B, "height": Hh, "width": Ww, "trainable_params": nparams,
                        "l2": f"activations {B}x{Hh}x{Ww} per layer (> 126 MB L2 for every full-resolution map)"},
-            "clocks": clocks, "gpu_launches": counts["n"] // max(1, args.steps), "loss": float(loss.item()),
+            "clocks": clocks, "gpu_launches": counts["n"] // max(1, args.steps), "loss": loss_value,
             "roofline": roof, "train_detail": detail, "cpu_baseline": None, "graphed_step": graphed,
             "allreduce": {"collective": "NCCL all_reduce(sum) of the flat fp32 gradient bucket, one per step" if world > 1 else "none (1 GPU)",
                           "bytes": int(opt.grad.numel()) * 4, "ms": (sum(ar_ms) / len(ar_ms)) if ar_ms else None,
