@@ -69,8 +69,8 @@ def test_batch_composition_independence():
 
 @pytest.mark.parametrize("arch", ["resnet18", "densenet121"])
 def test_classifier_logits(arch):
-    """HDEN in bf16 vs the fp32 oracle: logits within 2e-2 abs (stated), argmax identical whenever the fp32 top-2
-    margin exceeds twice that."""
+    """HDEN in bf16 vs the fp32 oracle: logits within 2e-2 abs (stated); argmax identical on all samples after the route
+    guard's fp32 re-evaluation of the rows whose bf16 top-2 gap is below 4e-2."""
     clf = randomize_bn(make_classifier(arch)).cuda()
     x, _, _ = oracle.synth_hazy(4, 128, 160 if arch == "resnet18" else 128, seed=3, device="cuda")
     ref_logits, ref_feats = oracle.classifier_forward(clf.state_dict(), x, arch)
@@ -79,9 +79,12 @@ def test_classifier_logits(arch):
     assert (logits - ref_logits).abs().max().item() <= 2e-2, (logits - ref_logits).abs().max().item()
     rel = (feats - ref_feats).abs().max().item() / ref_feats.abs().max().item()
     assert rel <= 3e-2, rel
+    # argmax vs the fp32 reference on ALL samples: near-ties are re-evaluated in fp32 by the route guard (route_guard.py);
+    # two fp32 implementations agree to ~2e-4 on these logits, hence the 5e-4 floor
+    guarded = clf.refine_logits(x, logits.clone())
     top2 = ref_logits.topk(2, dim=1).values
-    safe = (top2[:, 0] - top2[:, 1]) > 4e-2
-    assert torch.equal(logits.argmax(1)[safe], ref_logits.argmax(1)[safe])
+    resolvable = (top2[:, 0] - top2[:, 1]) > 5e-4
+    assert torch.equal(guarded.argmax(1)[resolvable], ref_logits.argmax(1)[resolvable])
 
 
 def test_classifier_golden_fixture():
