@@ -167,9 +167,11 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        if not build_if_missing:
-            raise AdbError(f"{_LIB_PATH} is missing; run `python -m adam_dehaze_b200.build`")
+    if not os.path.exists(_LIB_PATH) and not build_if_missing:
+        raise AdbError(f"{_LIB_PATH} is missing; run `python -m adam_dehaze_b200.build`")
+    if build_if_missing:
+        # build() is a no-op when the library's stamp matches the digest of csrc/ + include/ + flags; after an edit of the
+        # sources it rebuilds instead of silently loading the stale library
         from . import build as _build
         _build.build()
     lib = C.CDLL(_LIB_PATH)

@@ -127,7 +127,7 @@ int adb_kernel_error_flag(void) {
   if (e != cudaSuccess) return adbh::fail(ADB_ERR_CUDA, "error flag read: %s", cudaGetErrorString(e));
   if (v != 0) {
     cudaMemset(f, 0, sizeof(int));
-    return adbh::fail(ADB_ERR_KERNEL, "kernel protocol time-out flag = %d", v);
+    return adbh::fail(ADB_ERR_KERNEL, "device-side error flag = %d (1-30: a pipeline wait of a conv kernel timed out; 31: class label outside [0, classes) in adb_ce_fwd_bwd)", v);
   }
   return ADB_OK;
 }

@@ -694,21 +694,39 @@ __global__ void pix_bwd_kernel(const float* __restrict__ p, const float* __restr
   }
 }
 
+// nn.CrossEntropyLoss semantics (loss.py:177): mean over the rows whose label is not ignore_index (-100); a label outside
+// [0, classes) that is not ignore_index raises the library's device error flag (torch raises on the host) and the row is skipped.
 __global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int b, int classes,
-                          float grad_scale, float* __restrict__ loss, float* __restrict__ grad) {
+                          float grad_scale, float* __restrict__ loss, float* __restrict__ grad, int* __restrict__ err_flag) {
+  __shared__ int s_cnt[32];
+  int cnt = 0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    const long long y = labels[i];
+    if (y >= 0 && y < classes) ++cnt;
+    else if (y != -100 && err_flag) atomicExch(err_flag, 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  int valid = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) valid += s_cnt[i];
+  const float inv = valid > 0 ? 1.f / (float)valid : 0.f;
   float acc = 0.f;
   for (int i = threadIdx.x; i < b; i += blockDim.x) {
     const float* l = logits + (size_t)i * classes;
+    const long long yl = labels[i];
+    const bool ok = yl >= 0 && yl < classes;
+    const int y = ok ? (int)yl : 0;
     float m = -INFINITY;
     for (int k = 0; k < classes; ++k) m = fmaxf(m, l[k]);
     float s = 0.f;
     for (int k = 0; k < classes; ++k) s += expf(l[k] - m);
     const float lse = m + logf(s);
-    const int y = (int)labels[i];
-    acc += lse - l[y];
+    if (ok) acc += lse - l[y];
     if (grad)
       for (int k = 0; k < classes; ++k)
-        grad[(size_t)i * classes + k] = (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) * grad_scale / (float)b;
+        grad[(size_t)i * classes + k] = ok ? (expf(l[k] - lse) - (k == y ? 1.f : 0.f)) * grad_scale * inv : 0.f;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -719,7 +737,7 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += sa[i];
-    *loss = tot / (float)b;
+    *loss = tot * inv;
   }
 }
 
@@ -1003,7 +1021,8 @@ int adb_mse_bwd(const float* pred, const float* target, int64_t numel, float gra
 int adb_ce_fwd_bwd(const float* logits, const int64_t* labels, int32_t b, int32_t classes, float grad_scale, float* loss,
                    float* grad_logits, void* stream) {
   ADB_REQUIRE(logits && labels && loss && b > 0 && classes > 0, "adb_ce_fwd_bwd: bad arguments");
-  ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(labels), b, classes, grad_scale, loss, grad_logits);
+  ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(labels), b, classes, grad_scale, loss, grad_logits,
+                                                 adbh::kernel_err_flag());
   ADB_LAUNCH_OK();
   return ADB_OK;
 }

@@ -22,16 +22,33 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 _DETECTORS = ("faster_rcnn_resnet50_fpn", "faster_rcnn_mobilenet_v3_large_fpn", "mask_rcnn_resnet50_fpn")
 
 
+def _affine3(x, scale3, shift3):
+    n, _, h, w = x.shape
+    out = torch.empty_like(x)
+    scale = (C.c_float * 3)(*scale3)
+    shift = (C.c_float * 3)(*shift3)
+    _lib.call("adb_image_affine", _lib.ptr(x), n, h, w, scale, shift, _lib.ptr(out), _lib.current_stream())
+    return out
+
+
+class _NormalizeFn(torch.autograd.Function):
+    """(x - mean[c]) / std[c]; the reference's sub / div are differentiable (detection.py:109-121), so is this: dx = g / std[c]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return _affine3(x.contiguous(), [1.0 / s for s in IMAGENET_STD], [-m / s for m, s in zip(IMAGENET_MEAN, IMAGENET_STD)])
+
+    @staticmethod
+    def backward(ctx, g):
+        return _affine3(g.contiguous().float(), [1.0 / s for s in IMAGENET_STD], [0.0, 0.0, 0.0])
+
+
 def normalize_for_detection(images):
     """(x - mean[c]) / std[c] over an NCHW fp32 CUDA batch in one launch (detection.py:109-121)."""
     _engine.require_cuda(images, "normalize_for_detection")
-    x = images.contiguous()
-    n, _, h, w = x.shape
-    out = torch.empty_like(x)
-    scale = (C.c_float * 3)(*[1.0 / s for s in IMAGENET_STD])
-    shift = (C.c_float * 3)(*[-m / s for m, s in zip(IMAGENET_MEAN, IMAGENET_STD)])
-    _lib.call("adb_image_affine", _lib.ptr(x), n, h, w, scale, shift, _lib.ptr(out), _lib.current_stream())
-    return out
+    if torch.is_grad_enabled() and images.requires_grad:
+        return _NormalizeFn.apply(images)
+    return _affine3(images.contiguous(), [1.0 / s for s in IMAGENET_STD], [-m / s for m, s in zip(IMAGENET_MEAN, IMAGENET_STD)])
 
 
 class DetectionModel(nn.Module):

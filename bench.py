@@ -857,6 +857,15 @@ def instrumented_pass(torch, ops, _lib, branches, clf, hazy, hden):
             tot = sum(wts[k] * (pm[k]["dram_read_bytes"] + pm[k]["dram_write_bytes"]) / pm[k].get("images", tj.get("images", 8)) * per_branch[k]["images"]
                       for k in per_branch)
             traffic, traffic_src = tot / max(1.0, w_launch), tj["source"]
+            # the same launches against the HBM roofline: Light and the DenseNet trunk sit below the ridge (arithmetic intensity
+            # 104 and 122 FLOP/B against 219), so for them this — not the tensor fraction — is the bound that matters
+            hbm = peaks.get("hbm_gbs") or 6450.9
+            for k in per_branch:
+                gb_img = (pm[k]["dram_read_bytes"] + pm[k]["dram_write_bytes"]) / pm[k].get("images", tj.get("images", 8)) / 1e9
+                per_model[k]["dram_gb_per_image"] = gb_img
+                per_model[k]["achieved_gbs"] = gb_img / (per_branch[k]["conv_ms"] * 1e-3) if per_branch[k]["conv_ms"] else None
+                per_model[k]["hbm_frac"] = per_model[k]["achieved_gbs"] / hbm if per_model[k]["achieved_gbs"] else None
+                per_model[k]["bound"] = "hbm" if (per_branch[k]["tflop_per_image"] * 1e12 / (gb_img * 1e9)) < (peak * 1e12) / (hbm * 1e9) else "tensor"
         else:
             traffic_src = os.path.basename(tpath) + " was captured on a different pass (model, resolution or launch count)"
     roof = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_roll_kernel (adb_conv2d)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -254,3 +254,33 @@ def test_lpips_structure_without_the_package():
     assert (dxy - dyx).abs().max().item() <= 1e-3 * dxy.abs().max().item()
     with pytest.raises(FileNotFoundError):
         PerceptualLoss(allow_random_weights=False)
+
+
+def test_cross_entropy_ignore_index_and_bad_labels():
+    """nn.CrossEntropyLoss semantics (loss.py:177): rows labelled -100 are ignored (mean over the others, zero gradient); a
+    label outside [0, classes) raises through the device error flag instead of reading out of bounds."""
+    from adam_dehaze_b200 import _lib, ops
+    logits = torch.randn(6, 3, device="cuda")
+    labels = torch.tensor([0, -100, 2, 1, -100, 2], device="cuda")
+    loss, grad = ops.cross_entropy(logits, labels)
+    keep = labels != -100
+    ref_logits = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(ref_logits, labels, ignore_index=-100)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 and (grad - ref_logits.grad).abs().max().item() <= 1e-6
+    assert grad[~keep].abs().max().item() == 0.0
+    ops.cross_entropy(logits, torch.tensor([0, 1, 7, 1, 0, 2], device="cuda"))
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.AdbError):
+        _lib.call("adb_kernel_error_flag")
+    _lib.call("adb_kernel_error_flag")            # reading the flag clears it
+
+
+def test_detection_normalisation_is_differentiable():
+    from adam_dehaze_b200.models.detection import IMAGENET_STD, normalize_for_detection
+    x = torch.rand(2, 3, 16, 24, device="cuda", requires_grad=True)
+    y = normalize_for_detection(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    want = g / torch.tensor(IMAGENET_STD, device="cuda").view(1, 3, 1, 1)
+    assert (x.grad - want).abs().max().item() <= 1e-6
