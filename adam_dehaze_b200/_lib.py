@@ -41,6 +41,7 @@ class ConvDesc(C.Structure):
         ("tune_flags", C.c_int32),
         ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p),
         ("w_fold", C.c_void_p),
+        ("stat_out", C.c_void_p), ("stat_mode", C.c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ SIGNATURES = {
     "adb_conv2d": [C.POINTER(ConvDesc), _P],
     "adb_debug_timeline": [_P, _I],
     "adb_wgrad": [C.POINTER(WgradDesc), _P],
+    "adb_bn_finalize_stats": [_P, _L, _I, _L, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "adb_bn_train_stats": [_P, _L, _I, _I, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "adb_affine_act": [_P, _I, _L, _I, _P, _P, _P, _I, _I, _P, _I, _P],
     "adb_bn_bwd": [_P, _I, _P, _I, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P],
@@ -113,6 +115,7 @@ SIGNATURES = {
     "adb_stem_pack": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "adb_nchw_to_nhwc_bf16": [_P, _I, _I, _I, _I, _I, _P, _P],
     "adb_nhwc_bf16_to_nchw": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "adb_attn_pool_from_stats": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     "adb_attn_pool": [_P, _I, _I, _I, _I, _P, _I, _P, _P],
     "adb_attn_gate_stats": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, _P, _P],
     "adb_attn_apply": [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P],
@@ -147,9 +150,12 @@ SIGNATURES = {
 _SPECIAL = {
     "adb_last_error": ([], C.c_char_p),
     "adb_conv2d_flops": ([C.POINTER(ConvDesc)], C.c_double),
+    "adb_conv2d_stat_slots": ([C.POINTER(ConvDesc)], C.c_int64),
     "adb_pool_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
+    "adb_attn_pool_stat_scratch_floats": ([_I, _I, _I], C.c_int64),
     "adb_wgrad_workspace_bytes": ([C.POINTER(WgradDesc)], C.c_int64),
     "adb_bn_scratch_floats": ([_L, _I], C.c_int64),
+    "adb_bn_stat_scratch_floats": ([_L, _I], C.c_int64),
     "adb_attn_bwd_scratch_floats": ([_I, _I, _I, _I], C.c_int64),
     "adb_wgrad_flops": ([C.POINTER(WgradDesc)], C.c_double),
 }

@@ -103,6 +103,8 @@ struct ConvK {
   int a_sbo_bytes;                    // byte distance between the 8-row groups of an A view (8*row_bytes, or one halo row for 8-wide 2-D tiles)
   const float* pre_scale;             // optional pre-activation relu(x*pre_scale[c] + pre_shift[c]) applied to the A operand
   const float* pre_shift;
+  float* stat_out;                    // optional per-(32-row group, channel) partials of the stored output (adb_conv_desc.stat_out)
+  int stat_mode;                      // 1: (sum, sum of squares)   2: (sum, max)
   int* err_flag;
   long long* dbg;   // optional timeline buffer (tune_flags bit 2): [6 roles][256 events] of clock64() from CTA 0
   int dbg_detail;   // tune_flags bit 6: the buffer instead holds a flat sequence of epilogue sub-step stamps (warp 4, lane 0)
@@ -221,13 +223,45 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvK& P, int t, int rank
   return c;
 }
 
+// Channel partials of one staged slab (32 tile rows x CS16*16 channels, bf16, swizzled — exactly what the TMA store is about to
+// write): lane l sums channels 2l, 2l+1 down the 32 rows (one conflict-free 4-byte shared load per row: the 32 lanes read one
+// whole staging row), skipping rows outside the image.  Fixed order -> deterministic.  Consumers: BatchNorm2d(train) statistics
+// without a pass over z (stat_mode 1 -> adb_bn_finalize_stats); AttentionBlock's global average / max pool without a pass over
+// its input (stat_mode 2 -> adb_attn_pool_from_stats).
+template <int CS16>
+__device__ __forceinline__ void slab_stats(const ConvK& P, uint32_t sbuf, int lane, uint32_t valid_rows, size_t slot, int ch) {
+  constexpr uint32_t span = CS16 * 32;
+  constexpr int pairs = CS16 * 8;
+  if (lane < pairs) {
+    const bool mx = P.stat_mode == 2;
+    float s0 = 0.f, s1 = 0.f;
+    float a0 = mx ? -INFINITY : 0.f, a1 = a0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      uint32_t w;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbuf + swizzle_addr((uint32_t)r * span + (uint32_t)lane * 4u, span)) : "memory");
+      if ((valid_rows >> r) & 1u) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
+        const float v0 = __low2float(b2), v1 = __high2float(b2);
+        s0 += v0; s1 += v1;
+        if (mx) { a0 = fmaxf(a0, v0); a1 = fmaxf(a1, v1); }
+        else { a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); }
+      }
+    }
+    float* o = P.stat_out + slot * 2 * (size_t)P.cout_pad + ch + 2 * lane;
+    *reinterpret_cast<float2*>(o) = make_float2(s0, s1);
+    *reinterpret_cast<float2*>(o + P.cout_pad) = make_float2(a0, a1);
+  }
+  __syncwarp();
+}
+
 // FEATURE epilogue of one tile for one epilogue warp.  The tile's work items are its (sub-tile, slab) pairs in order; the two
 // warps that share a TMEM lane quarter (`half` 0 / 1) take alternate items.  Each warp owns one staging buffer and one
 // TMA-store bulk group stream; no cross-warp barrier anywhere.
 template <int kAct, int CS16>
 __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* tmOut, const TileCoord& tc, uint32_t tfull,
                                              uint32_t tfull_phase, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
-                                             const float* s_shift, int ew, int half, int lane, int& e_i) {
+                                             const float* s_shift, int ew, int half, int lane, int& e_i, size_t slot_base) {
   constexpr int Cs = CS16 * 16;
   const int items = P.MT * P.n_slabs;
   const int ch0 = tc.nt * P.BN;                        // first output channel of this N tile
@@ -262,6 +296,12 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
     if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
       tma_store_5d(tmOut, sbuf, P.out_c_off[tc.g] + ch0 + cl, tc.w0 + q_tw, P.out_p[tc.g], tc.h0 + mt * P.TH + q_th, tc.img);
       tma_store_commit();
+    }
+    if (P.stat_out) {
+      const int row = q_row0 + lane;
+      const bool ok = (tc.h0 + mt * P.TH + (row >> P.tw_shift) < P.grid_h) && (tc.w0 + (row & (P.TW - 1)) < P.grid_w);
+      const uint32_t valid_rows = __ballot_sync(0xffffffffu, ok);
+      slab_stats<CS16>(P, sbuf, lane, valid_rows, (slot_base + (size_t)mt) * 4 + (size_t)ew, ch0 + cl);
     }
     ADB_DBGE(6);
   }
@@ -578,9 +618,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t tmem_tile = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * P.MT * P.bn_cols);
       if (kEpi == ADB_EPI_FEATURE) {
         // (kPre kernels run 512 threads = 128 registers each: their epilogue uses the 32-channel slab at most)
-        if (!kPre && P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
-        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
-        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i);
+        // partial-statistics slot of this CTA's first sub-tile: one slot per (pixel tile, CTA of a pair, sub-tile, lane quarter);
+        // the N tiles of one pixel tile share it (they own disjoint channel ranges)
+        const size_t slot_base = (((size_t)t / (size_t)P.n_tiles_n) * (size_t)P.ncta + (size_t)rank) * (size_t)P.MT;
+        if (!kPre && P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
         if (ewi == 0) { ADB_DBG(4, dbg_i); }
       } else {
         // DOT / IMAGE: one work item per sub-tile; `half` takes sub-tile `half`
@@ -919,11 +962,17 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
     }
     P.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
     P.res_pitch = d->res_pitch;
+    if (d->stat_out) {
+      ADB_REQUIRE(d->stat_mode >= 0 && d->stat_mode <= 2, "adb_conv2d: stat_mode must be 1 (sum, sum of squares) or 2 (sum, max)");
+      ADB_REQUIRE(d->kind != ADB_CONVT_4X4S2 && !pre, "adb_conv2d: stat_out is built for plain / stride-2 FEATURE convs");
+      P.stat_out = d->stat_out; P.stat_mode = d->stat_mode == 2 ? 2 : 1;
+    }
     for (int g = 0; g < P.ngroups; ++g) {
       if (d->kind == ADB_CONVT_4X4S2) { P.out_c_off[g] = (g & 1) * d->dst_pitch + d->dst_c_off; P.out_p[g] = g >> 1; }
       else { P.out_c_off[g] = d->dst_c_off; P.out_p[g] = 0; }
     }
   } else if (d->epi == ADB_EPI_DOT) {
+    ADB_REQUIRE(!d->stat_out, "adb_conv2d: stat_out needs the FEATURE epilogue");
     ADB_REQUIRE(d->dot_w && d->dot_out && d->kind != ADB_CONVT_4X4S2, "adb_conv2d: DOT epilogue needs dot_w/dot_out");
     P.dot_w = d->dot_w; P.dot_b = d->dot_b; P.dot_out = d->dot_out;
   } else if (d->epi == ADB_EPI_IMAGE) {
@@ -1066,6 +1115,17 @@ extern "C" int adb_conv2d(const adb_conv_desc* d, void* stream) {
   }
   ADB_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, tmA0, tmA1, tmB, tmOut, P));
   return ADB_OK;
+}
+
+extern "C" int64_t adb_conv2d_stat_slots(const adb_conv_desc* d) {
+  ConvK P;
+  int out_h = 0, out_w = 0, ktot = 0, box_w = 0, box_h = 0;
+  adb_conv_desc q = *d;
+  q.stat_out = nullptr;
+  if (adbc::roll_eligible(&q)) return 0;   // the rolling-row kernel is the faster path for this launch: statistics stay a separate pass
+  if (d->epi != ADB_EPI_FEATURE || d->kind == ADB_CONVT_4X4S2 || d->pre_scale) return 0;
+  if (build(&q, P, out_h, out_w, ktot, box_w, box_h) != ADB_OK) return -1;
+  return (int64_t)P.tiles_w * P.tiles_h * P.ngroups * P.ncta * P.MT * 4 * d->n;
 }
 
 extern "C" double adb_conv2d_flops(const adb_conv_desc* d) {

@@ -571,7 +571,7 @@ int debug_buffer(long long** out, void* stream);   // conv_igemm.cu
 
 // Whether adb_conv2d should take the rolling-row kernel for this descriptor (w_fold given by the caller).
 bool roll_eligible(const adb_conv_desc* d) {
-  if (!d->w_fold || (d->tune_flags & 512)) return false;
+  if (!d->w_fold || (d->tune_flags & 512) || d->stat_out) return false;
   if (d->kind != ADB_CONV_S1 || d->kh != 3 || d->kw != 3 || d->pad != 1 || d->pre_scale) return false;
   if (d->epi == ADB_EPI_FEATURE) {
     if (d->cout_pad % 32 != 0 || 3 * d->cout_pad > 256) return false;

@@ -287,6 +287,49 @@ __global__ void attn_pool_kernel(const __nv_bfloat16* __restrict__ x, int n, lon
   }
 }
 
+// The same [n][2][c] (sum, max) from the producing conv's epilogue partials (adb_conv_desc.stat_out, stat_mode 2: per image
+// `slots` x [2][cpitch], one slot per 32 output pixels) instead of a pass over x: CTA (cx, y, img) folds slot chunk y of the image
+// for channels 32cx..32cx+31 in a fixed order and writes out[img][y][2][c].  Run twice (slots -> gridDim.y chunks -> 1).
+// block = 32 channels x 8 slot lanes.
+__global__ void pool_fold_kernel(const float* __restrict__ stat, int slots, int cpitch, int c, int n, const int* n_dev, int n_start,
+                                 float* __restrict__ out) {
+  const int img = blockIdx.z;
+  if (img >= live_images(n, n_dev, n_start)) return;
+  __shared__ float s_part[2][8][32];
+  const int ch = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+  const int per = (slots + gridDim.y - 1) / gridDim.y;
+  const int k0 = blockIdx.y * per, k1 = min(slots, k0 + per);
+  const float* base = stat + (size_t)img * slots * 2 * cpitch;
+  float a = 0.f, m = -INFINITY;
+  if (ch < c) {
+    int k = k0 + ly;
+    for (; k + 24 < k1; k += 32) {         // four slots in flight per thread
+      float va[4], vm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        va[u] = __ldg(base + (size_t)(k + 8 * u) * 2 * cpitch + ch);
+        vm[u] = __ldg(base + (size_t)(k + 8 * u) * 2 * cpitch + cpitch + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += va[u]; m = fmaxf(m, vm[u]); }
+    }
+    for (; k < k1; k += 8) {
+      a += __ldg(base + (size_t)k * 2 * cpitch + ch);
+      m = fmaxf(m, __ldg(base + (size_t)k * 2 * cpitch + cpitch + ch));
+    }
+  }
+  s_part[0][ly][threadIdx.x] = a;
+  s_part[1][ly][threadIdx.x] = m;
+  __syncthreads();
+  if (ly == 0 && ch < c) {
+    float t = 0.f, mm = -INFINITY;
+    for (int l = 0; l < 8; ++l) { t += s_part[0][l][threadIdx.x]; mm = fmaxf(mm, s_part[1][l][threadIdx.x]); }
+    float* o = out + ((size_t)img * gridDim.y + blockIdx.y) * 2 * c;
+    o[ch] = t;
+    o[c + ch] = mm;
+  }
+}
+
 // gate[n][c] = sigmoid(W2 relu(W1 avg) + W2 relu(W1 max));  one block per image
 __global__ void attn_gate_kernel(const float* __restrict__ pool, int n, float inv_hw, int c, int cr, const int* n_dev,
                                  int n_start, const float* __restrict__ w1, const float* __restrict__ w2,
@@ -841,6 +884,28 @@ int64_t adb_pool_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c) {
 int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                   float* pool_buf, void* stream) {
   return launch_pool(x, n, h, w, c, n_dev, n_start, pool_buf, (cudaStream_t)stream);
+}
+
+// first-level chunk count of pool_fold_kernel
+static int pool_fold_chunks(int slots) { return std::max(1, std::min(64, slots / 64)); }
+
+int64_t adb_attn_pool_stat_scratch_floats(int32_t n, int32_t slots_per_image, int32_t c) {
+  return (int64_t)n * pool_fold_chunks(slots_per_image) * 2 * c;
+}
+
+int adb_attn_pool_from_stats(const float* stat, int32_t n, int32_t slots_per_image, int32_t cpitch, int32_t c, const int32_t* n_dev,
+                             int32_t n_start, float* scratch, float* pool_buf, void* stream) {
+  ADB_REQUIRE(stat && scratch && pool_buf && n > 0 && slots_per_image > 0 && c > 0 && c <= cpitch, "adb_attn_pool_from_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = pool_fold_chunks(slots_per_image);
+  const dim3 block(32, 8);
+  pool_fold_kernel<<<dim3((c + 31) / 32, S, n), block, 0, st>>>(stat, slots_per_image, cpitch, c, n, n_dev, n_start, S > 1 ? scratch : pool_buf);
+  ADB_LAUNCH_OK();
+  if (S > 1) {
+    pool_fold_kernel<<<dim3((c + 31) / 32, 1, n), block, 0, st>>>(scratch, S, c, c, n, n_dev, n_start, pool_buf);
+    ADB_LAUNCH_OK();
+  }
+  return ADB_OK;
 }
 
 int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,

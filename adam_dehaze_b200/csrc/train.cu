@@ -218,6 +218,42 @@ __device__ __forceinline__ void fold_partials8(const float* __restrict__ partial
   __syncthreads();
 }
 
+// First fold of the conv epilogue's channel partials (adb_conv_desc.stat_out: [slots][2][cpitch], one slot per 32 output pixels):
+// CTA (x, y) sums slot chunk y for channels 32x..32x+31 in fp64, slot order fixed, and writes [y][2][c] float partials for
+// bn_finalize_kernel.  block = 32 channels x 8 slot lanes: a warp reads 128 contiguous bytes of one slot.
+__global__ void stat_fold_kernel(const float* __restrict__ stat, long long slots, int cpitch, int c, float* __restrict__ out) {
+  __shared__ double s_part[2][8][32];
+  const int ch = blockIdx.x * 32 + threadIdx.x, ly = threadIdx.y;
+  const long long per = (slots + gridDim.y - 1) / gridDim.y;
+  const long long k0 = (long long)blockIdx.y * per, k1 = min(slots, k0 + per);
+  double a = 0.0, b = 0.0;
+  if (ch < c) {
+    long long k = k0 + ly;
+    for (; k + 24 < k1; k += 32) {         // four slots in flight per thread
+      float va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        va[u] = __ldg(stat + (size_t)(k + 8 * u) * 2 * cpitch + ch);
+        vb[u] = __ldg(stat + (size_t)(k + 8 * u) * 2 * cpitch + cpitch + ch);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+    }
+    for (; k < k1; k += 8) {
+      a += (double)__ldg(stat + (size_t)k * 2 * cpitch + ch);
+      b += (double)__ldg(stat + (size_t)k * 2 * cpitch + cpitch + ch);
+    }
+  }
+  s_part[0][ly][threadIdx.x] = a;
+  s_part[1][ly][threadIdx.x] = b;
+  __syncthreads();
+  if (ly < 2 && ch < c) {
+    double t = 0.0;
+    for (int l = 0; l < 8; ++l) t += s_part[ly][l][threadIdx.x];
+    out[((size_t)blockIdx.y * 2 + ly) * c + ch] = (float)t;
+  }
+}
+
 // BatchNorm2d(train) statistics -> the epilogue affine, plus the running-statistics update (momentum, unbiased variance).
 // grid = c/8 CTAs of 256 threads.
 __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nblocks, int c, double count,
@@ -1318,6 +1354,9 @@ __global__ void adam_seg_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// slot chunks of stat_fold_kernel: enough CTAs to keep the fold short, at least 64 slots per chunk
+inline int stat_fold_chunks(int64_t slots) { return (int)std::max<int64_t>(1, std::min<int64_t>(256, slots / 64)); }
+
 }  // namespace
 
 #define ADB_BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
@@ -1342,6 +1381,27 @@ int adb_bn_train_stats(const void* z, int64_t pixels, int32_t c, int32_t pitch, 
                                                                                    nullptr, nullptr, nullptr, 0, scratch);
   ADB_CUDA_OK(cudaGetLastError());
   bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, nb, c, (double)pixels, gamma, beta, eps, momentum, running_mean, running_var,
+                                                      reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
+  ADB_CUDA_OK(cudaGetLastError());
+  return ADB_OK;
+}
+
+int64_t adb_bn_stat_scratch_floats(int64_t slots, int32_t c) {
+  return (int64_t)stat_fold_chunks(slots) * 2 * c;
+}
+
+int adb_bn_finalize_stats(const float* stat, int64_t slots, int32_t cpitch, int64_t pixels, int32_t c, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, float* scratch, float* mean, float* rstd, float* scale, float* shift,
+                          void* stream) {
+  ADB_REQUIRE(stat && gamma && beta && scratch && mean && rstd && scale && shift, "adb_bn_finalize_stats: null pointer");
+  ADB_REQUIRE(slots > 0 && pixels > 0 && c > 0 && c <= cpitch && c <= 2048, "adb_bn_finalize_stats: bad shape (slots=%lld pixels=%lld c=%d cpitch=%d)",
+              (long long)slots, (long long)pixels, c, cpitch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = stat_fold_chunks(slots);
+  stat_fold_kernel<<<dim3((c + 31) / 32, chunks), dim3(32, 8), 0, st>>>(stat, slots, cpitch, c, scratch);
+  ADB_CUDA_OK(cudaGetLastError());
+  bn_finalize_kernel<<<(c + 7) / 8, 256, 0, st>>>(scratch, chunks, c, (double)pixels, gamma, beta, eps, momentum, running_mean, running_var,
                                                       reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift);
   ADB_CUDA_OK(cudaGetLastError());
   return ADB_OK;

@@ -271,11 +271,19 @@ class BranchEngine:
             kw["tune"] = self.tune
         return kw
 
-    def _res(self, specs, f, tmp, kw):
-        """ResidualBlock (base_model.py:36-41): conv-bn-relu -> conv-bn -> += f -> relu, in place on f."""
+    def _res(self, specs, f, tmp, kw, pool=False):
+        """ResidualBlock (base_model.py:36-41): conv-bn-relu -> conv-bn -> += f -> relu, in place on f.
+        pool=True (the block feeds an AttentionBlock): the second conv's epilogue also leaves the per-channel (sum, max) partials of
+        the block output, returned (None when that launch does not produce them) — the attention's pool pass folds them instead of
+        re-reading f."""
         ops.conv2d(specs[0], f, dst=tmp, **kw)
-        ops.conv2d(specs[1], tmp, dst=f, residual=f, **kw)
-        return f
+        if not pool:
+            ops.conv2d(specs[1], tmp, dst=f, residual=f, **kw)
+            return None
+        dev = f.device
+        _, part = ops.conv2d(specs[1], tmp, dst=f, residual=f, stats="pool",
+                             stat_alloc=lambda shape: self._buf("pool_part", shape, dev, torch.float32), **kw)
+        return part
 
     def _run_light(self, S, x, out, index, n_dev, n_start, n, cap):
         dev = x.device
@@ -402,8 +410,8 @@ class BranchEngine:
         kw = self._kw(n_dev, n_start, n)
         scratch = self._bufs.setdefault(("attn_scratch", cap, str(dev)), {})
 
-        def attend(ap, f):
-            return ops.attention(f, ap, n=n, n_dev=n_dev, n_start=n_start, out=f, scratch=scratch)
+        def attend(ap, f, part=None):
+            return ops.attention(f, ap, n=n, n_dev=n_dev, n_start=n_start, out=f, scratch=scratch, pool_partials=part)
 
         guidance = None
         if attn:
@@ -427,36 +435,36 @@ class BranchEngine:
             f = self._buf(f"f{li + 1}", (cap, hh, ww, cc), dev)
             t = self._buf(f"t{li + 1}", (cap, hh, ww, cc), dev)
             ops.conv2d(e["down"], feats[-1], dst=f, **kw)
-            for specs in e["res"]:
-                self._res(specs, f, t, kw)
+            for ri, specs in enumerate(e["res"]):
+                part = self._res(specs, f, t, kw, pool=attn and ri == len(e["res"]) - 1)
             if attn:
-                attend(e["attn"], f)
+                attend(e["attn"], f, part)
             feats.append(f)
 
         # bottleneck works on a copy-free alias: feats[-1] is only needed as the bottleneck input
         bt = feats[-1]
         t2 = self._buf("t2", tuple(bt.shape), dev)
         for specs, ap in S["bott"]:
-            self._res(specs, bt, t2, kw)
+            part = self._res(specs, bt, t2, kw, pool=ap is not None)
             if ap is not None:
-                attend(ap, bt)
+                attend(ap, bt, part)
 
         # decoder 0: up(bottleneck) -> res (-> attn); then cat with feats[1]
         d0 = S["dec"][0]
         x1 = self._buf("x1", tuple(feats[1].shape), dev)
         t1 = self._buf("t1", tuple(feats[1].shape), dev)
         ops.conv2d(d0["up"], bt, dst=x1, **kw)
-        self._res(d0["res"], x1, t1, kw)
+        part = self._res(d0["res"], x1, t1, kw, pool=attn)
         if attn:
-            attend(d0["attn"], x1)
+            attend(d0["attn"], x1, part)
         # decoder 1 reads cat([x1, feats[1]]) without materialising it
         d1 = S["dec"][1]
         x2 = self._buf("x2", tuple(f0.shape), dev)
         tf = self._buf("tf", tuple(f0.shape), dev)
         ops.conv2d(d1["up"], x1, feats[1], dst=x2, **kw)
-        self._res(d1["res"], x2, tf, kw)
+        part = self._res(d1["res"], x2, tf, kw, pool=attn)
         if attn:
-            attend(d1["attn"], x2)
+            attend(d1["attn"], x2, part)
         # head reads cat([x2, f0])
         ops.conv2d(S["out0"], x2, f0, dst=tf, **kw)
         r1 = self._buf("r1", (cap, h, w, S["out1"].cout_pad), dev)

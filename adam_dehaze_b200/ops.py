@@ -206,8 +206,11 @@ def _pitch(t):
 
 
 def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, residual=None, n=None, n_dev=None,
-           n_start=0, epi=EPI_FEATURE, dot=None, image=None, tune=None, pre=None):
+           n_start=0, epi=EPI_FEATURE, dot=None, image=None, tune=None, pre=None, stats=False, stat_alloc=None):
     """Launch one fused conv.  src*/dst/residual: NHWC bf16.  Returns dst (FEATURE), dot_out (DOT) or None (IMAGE).
+    stats=True / "pool" (FEATURE): returns (dst, partials) — partials = fp32 [n, slots_per_image, 2, cout_pad] per-32-pixel (sum,
+    sum of squares) / (sum, max) of the stored output written by the epilogue (adb_conv_desc.stat_out), or None when this
+    launch does not produce them.  stat_alloc(shape) -> fp32 tensor supplies the partials buffer (engine buffer cache).
 
     dot   = (dot_w fp32[16], dot_b float, dot_out fp32[n,h,w])
     image = dict(mode=IMG_*, x=NCHW fp32, out=NCHW fp32, index=int32|None, guidance=fp32|None, alpha=fp32 scalar|None)
@@ -259,6 +262,16 @@ def conv2d(spec, src0, src1=None, *, c0=None, c1=None, dst=None, dst_c_off=0, re
     if tune:
         d.tune_mt, d.tune_stages, d.tune_acc_stages = tune.get("mt", 0), tune.get("stages", 0), tune.get("acc", 0)
         d.tune_flags = tune.get("flags", 0)
+    if stats:
+        assert epi == EPI_FEATURE
+        slots = int(_lib.load().adb_conv2d_stat_slots(C.byref(d)))
+        part = None
+        if slots > 0:
+            shape = (n, slots // n, 2, spec.cout_pad)
+            part = stat_alloc(shape) if stat_alloc else torch.empty(shape, dtype=torch.float32, device=src0.device)
+            d.stat_out, d.stat_mode = part.data_ptr(), (2 if stats == "pool" else 1)
+        _lib.call("adb_conv2d", C.byref(d), _lib.current_stream())
+        return ret, part
     _lib.call("adb_conv2d", C.byref(d), _lib.current_stream())
     return ret
 
@@ -353,8 +366,10 @@ def pool_scratch_floats(n, h, w, c):
     return int(_lib.load().adb_pool_scratch_floats(n, h, w, c))
 
 
-def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
-    """AttentionBlock forward on an NHWC bf16 map: pool -> gate + channel stats -> spatial gate apply."""
+def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None, pool_partials=None):
+    """AttentionBlock forward on an NHWC bf16 map: pool -> gate + channel stats -> spatial gate apply.
+    pool_partials: the (sum, max) partials the conv that produced x wrote (conv2d(stats="pool")): the pool pass over x is
+    replaced by a fold of them."""
     nb, h, w, c = x.shape
     assert c == ap.c and x.is_contiguous()
     n = nb if n is None else n
@@ -371,7 +386,17 @@ def attention(x, ap, *, n=None, n_dev=None, n_start=0, out=None, scratch=None):
         out = torch.empty_like(x)
     st = _lib.current_stream()
     nd = _lib.ptr(n_dev)
-    _lib.call("adb_attn_pool", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(pool), st)
+    if pool_partials is not None:
+        assert pool_partials.shape[0] >= n and pool_partials.shape[3] >= c and pool_partials.is_contiguous()
+        spi = pool_partials.shape[1]
+        key = ("pool_fold", nb, spi, c)
+        fold = scratch.get(key)
+        if fold is None:
+            fold = scratch[key] = torch.empty(int(_lib.load().adb_attn_pool_stat_scratch_floats(nb, spi, c)), dtype=torch.float32, device=dev)
+        _lib.call("adb_attn_pool_from_stats", _lib.ptr(pool_partials), n, spi, pool_partials.shape[3], c, nd, n_start, _lib.ptr(fold),
+                  _lib.ptr(pool), st)
+    else:
+        _lib.call("adb_attn_pool", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(pool), st)
     _lib.call("adb_attn_gate_stats", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(pool), _lib.ptr(ap.w1),
               _lib.ptr(ap.w2), ap.c_red, _lib.ptr(gate), _lib.ptr(stats), st)
     _lib.call("adb_attn_apply", _lib.ptr(x), n, h, w, c, nd, n_start, _lib.ptr(gate), _lib.ptr(stats),

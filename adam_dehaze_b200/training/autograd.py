@@ -12,6 +12,8 @@ parameter's own layout, handed to autograd by `BranchTrainFn` so optimizers/DDP 
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from .. import _lib, ops
@@ -231,6 +233,10 @@ class _PaddedBN:
             self.bn.running_var.copy_(self.running_var[:co])
 
 
+# BatchNorm statistics from the conv epilogue's partials where the launch produces them (False: always a pass over z)
+EPILOGUE_STATS = os.environ.get("ADB_NO_EPILOGUE_STATS", "") == ""
+
+
 class Tape:
     def __init__(self, model_cache):
         self.back = []
@@ -238,18 +244,26 @@ class Tape:
         self.wc = model_cache
 
     # ------------------------------------------------------------------ helpers
-    def _bn_forward(self, z, c, bn, act, residual=None):
+    def _bn_forward(self, z, c, bn, act, residual=None, partials=None):
+        """partials: the producing conv's epilogue statistics (ops.conv2d(stats=True)); None -> one pass over z."""
         n, h, w, pitch = z.shape
         dev = z.device
         px = n * h * w
-        scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
         stats = _f32(4 * c, dev)
         mean, rstd, scale, shift = stats[:c], stats[c:2 * c], stats[2 * c:3 * c], stats[3 * c:]
         st = _lib.current_stream()
         mom = 0.1 if bn.momentum is None else float(bn.momentum)
-        _lib.call("adb_bn_train_stats", _lib.ptr(z), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
-                  _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
-                  _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        if partials is not None:
+            slots = partials.shape[0] * partials.shape[1]
+            scratch = _f32(int(_lib.load().adb_bn_stat_scratch_floats(slots, c)), dev)
+            _lib.call("adb_bn_finalize_stats", _lib.ptr(partials), slots, partials.shape[3], px, c, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
+                      float(bn.eps), mom, _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked),
+                      _lib.ptr(scratch), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
+        else:
+            scratch = _f32(int(_lib.load().adb_bn_scratch_floats(px, c)), dev)
+            _lib.call("adb_bn_train_stats", _lib.ptr(z), px, c, pitch, _lib.ptr(bn.weight), _lib.ptr(bn.bias), float(bn.eps), mom,
+                      _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(bn.num_batches_tracked), _lib.ptr(scratch),
+                      _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift), st)
         _touch_bn_buffers(bn)
         y = torch.empty_like(z)
         _lib.call("adb_affine_act", _lib.ptr(z), pitch, px, c, _lib.ptr(scale), _lib.ptr(shift),
@@ -295,11 +309,12 @@ class Tape:
                                 weight=w, bias=b)
         a = srcs[0]
         bsrc = srcs[1] if len(srcs) > 1 else None
-        z = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c)
+        r = ops.conv2d(fspec, a.t, None if bsrc is None else bsrc.t, c0=a.c, c1=None if bsrc is None else bsrc.c, stats=EPILOGUE_STATS)
+        z, part = r if EPILOGUE_STATS else (r, None)
         _rec(w, z)
         c = fspec.cout_pad
         bnp = bn if c == fspec.cout else _PaddedBN(bn, c)     # e.g. 24 channels inside a 32-channel map: padded affine
-        y, stats = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t)
+        y, stats = self._bn_forward(z, c, bnp, act, None if residual is None else residual.t, partials=part)
         if bnp is not bn:
             bnp.write_back()
         out = Node(y, c)

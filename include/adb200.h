@@ -109,6 +109,14 @@ typedef struct adb_conv_desc {
          dimension and accumulate into adjacent output rows held in TMEM.
          w_fold[s][(2 - r)*cout_pad + co][c] = W[co][c][r][s], bf16 [3][3*cout_pad][c0+c1]. */
   const void* w_fold;
+  /* --- optional channel partials of the STORED output (FEATURE epilogue, plain / stride-2 kinds): for every group of 32 tile rows
+         the epilogue also writes, per output channel, two partials of the bf16 values it stores.  stat_mode 0/1: (sum, sum of
+         squares) — BatchNorm2d(train) statistics without a pass over the conv output (base_model.py:15-16 under model.train()),
+         folded by adb_bn_finalize_stats.  stat_mode 2: (sum, max) — AttentionBlock's AdaptiveAvgPool2d(1) / AdaptiveMaxPool2d(1)
+         of the block input (base_model.py:64-66) without a pass over it, folded by adb_attn_pool_from_stats.  Layout fp32
+         [slots][2][cout_pad], slots = adb_conv2d_stat_slots(), image-major (slots / n consecutive slots per image); rows outside
+         the image count nothing; every slot of a live image is written; a launch with stat_out takes conv_igemm_kernel. */
+  float* stat_out; int32_t stat_mode;
 } adb_conv_desc;
 
 /* Weight packing order expected in w_packed (done on the host side by adam_dehaze_b200/engine.py):
@@ -132,6 +140,9 @@ ADB_API int adb_device_check(void);                 /* 0 when the current device
 ADB_API int adb_conv2d(const adb_conv_desc* desc, void* stream);
 /* FLOPs (2*MAC) the descriptor's launch performs for n images — the figure bench.py's roofline uses. */
 ADB_API double adb_conv2d_flops(const adb_conv_desc* desc);
+/* number of partial-statistics slots a launch with stat_out writes; 0 = this launch does not produce them (it takes the
+ * rolling-row kernel, or is not a plain / stride-2 FEATURE conv): leave stat_out null and use adb_bn_train_stats; < 0 = bad desc */
+ADB_API int64_t adb_conv2d_stat_slots(const adb_conv_desc* desc);
 
 /* Image -> stem operand (bf16, kp channels, zero padded):
  *   out[i,ho,wo,(r*kw+s)*3+c] = x[idx(i), c, ho*sh + r - ph, wo*stride + s - pad]   (0 outside the image)
@@ -156,6 +167,11 @@ ADB_API int adb_nhwc_bf16_to_nchw(const void* x, int32_t n, int32_t c, int32_t h
 ADB_API int64_t adb_pool_scratch_floats(int32_t n, int32_t h, int32_t w, int32_t c);
 ADB_API int adb_attn_pool(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                   float* pool_buf, void* stream);
+/* adb_attn_pool's result from the producing conv's stat_mode-2 partials (`slots_per_image` x [2][cpitch] per image) instead of a pass
+ * over x; writes the first n*2*c floats of pool_buf (what adb_attn_gate_stats reads).  scratch: adb_attn_pool_stat_scratch_floats. */
+ADB_API int64_t adb_attn_pool_stat_scratch_floats(int32_t n, int32_t slots_per_image, int32_t c);
+ADB_API int adb_attn_pool_from_stats(const float* stat, int32_t n, int32_t slots_per_image, int32_t cpitch, int32_t c,
+                                     const int32_t* n_dev, int32_t n_start, float* scratch, float* pool_buf, void* stream);
 ADB_API int adb_attn_gate_stats(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, const int32_t* n_dev, int32_t n_start,
                         const float* pool_buf, const float* w1 /*[c/r][c]*/, const float* w2 /*[c][c/r]*/, int32_t c_red,
                         float* gate /*[n][c]*/, float* stats /*[n,h,w,2]*/, void* stream);
@@ -253,6 +269,13 @@ ADB_API double adb_wgrad_flops(const adb_wgrad_desc* desc);
  *   mean[c], rstd[c] are kept for backward, scale = gamma*rstd and shift = beta - mean*scale feed adb_affine_act.
  * scratch: adb_bn_scratch_floats(pixels, c) floats.  running_* / num_batches_tracked are nullable. */
 ADB_API int64_t adb_bn_scratch_floats(int64_t pixels, int32_t c);
+/* The same result as adb_bn_train_stats from the conv epilogue's partials (adb_conv_desc.stat_out, `slots` x [2][cpitch]) instead of
+ * a pass over z.  scratch: adb_bn_stat_scratch_floats(slots, c) floats. */
+ADB_API int64_t adb_bn_stat_scratch_floats(int64_t slots, int32_t c);
+ADB_API int adb_bn_finalize_stats(const float* stat, int64_t slots, int32_t cpitch, int64_t pixels, int32_t c, const float* gamma,
+                                  const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                  int64_t* num_batches_tracked, float* scratch, float* mean, float* rstd, float* scale,
+                                  float* shift, void* stream);
 ADB_API int adb_bn_train_stats(const void* z, int64_t pixels, int32_t c, int32_t pitch, const float* gamma, const float* beta,
                                float eps, float momentum, float* running_mean, float* running_var,
                                int64_t* num_batches_tracked, float* scratch, float* mean, float* rstd, float* scale,

@@ -429,3 +429,127 @@ def test_stem_7x7_stride2_space_to_depth(cout, h, w, n):
     y = ops.conv2d(spec, cols)
     ref = F.relu(_bn_ref(F.conv2d(x.to(torch.bfloat16).float(), wt, stride=2, padding=3), bn))
     _close(ops.nhwc_to_nchw(y, cout), ref)
+
+
+# ----------------------------------------------------------------------------- epilogue channel statistics (adb_conv_desc.stat_out)
+STAT_CASES = [
+    # (c0, c1, cout, k, stride, n, h, w, tune)
+    (128, 0, 128, 3, 1, 2, 32, 64, None),
+    (128, 0, 128, 3, 1, 2, 32, 64, {"flags": 16}),       # CTA pair: both CTAs own slots
+    (128, 0, 128, 3, 1, 1, 24, 40, None),                # ragged tiles: rows outside the image count nothing
+    (96, 96, 96, 3, 1, 2, 16, 48, None),                 # two sources, 32-channel slabs
+    (64, 0, 128, 4, 2, 2, 64, 64, None),                 # stride-2 encoder conv
+    (256, 0, 256, 3, 1, 1, 16, 16, None),
+    (192, 0, 48, 1, 1, 2, 16, 32, None),                 # 1x1, 16-channel slabs, cout 48 of 48
+    (64, 0, 64, 3, 1, 2, 64, 96, {"mt": 2}),             # several sub-tiles per CTA tile (w < 128: not the rolling-row kernel)
+    (512, 0, 512, 3, 1, 2, 8, 16, None),                 # two N tiles share the pixel tile's slots
+]
+
+
+@pytest.mark.parametrize("c0,c1,cout,k,stride,n,h,w,tune", STAT_CASES)
+def test_conv_epilogue_statistics(c0, c1, cout, k, stride, n, h, w, tune):
+    """(sum, sum of squares) per channel folded from the epilogue partials == the same sums over the stored bf16 output
+    (fp64 on the host), to fp32 rounding of the per-slot partials: 1e-5 relative."""
+    ops = _ops()
+    a = _rand_fm(n, c0, h, w, 70)
+    b = _rand_fm(n, c1, h, w, 71) if c1 else None
+    wt = _rand_w((cout, c0 + c1, k, k), 72, (c0 + c1) * k * k)
+    bias = torch.randn(cout, device="cuda") * 0.1
+    spec = ops.ConvSpec.from_conv(wt, bias=bias, stride=stride, pad=1 if k > 1 else 0)
+    y, part = ops.conv2d(spec, ops.nchw_to_nhwc(a), None if b is None else ops.nchw_to_nhwc(b), tune=tune, stats=True)
+    assert part is not None and part.shape[0] == n and part.shape[2:] == (2, spec.cout_pad)
+    y_plain = ops.conv2d(spec, ops.nchw_to_nhwc(a), None if b is None else ops.nchw_to_nhwc(b), tune=tune)
+    assert torch.equal(y, y_plain)                       # the statistics do not disturb the output
+    yd = y.double().reshape(-1, spec.cout_pad)
+    s = part.double().sum((0, 1))
+    ref0, ref1 = yd.sum(0), (yd * yd).sum(0)
+    assert (s[0] - ref0).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item() + 1e-6
+    assert (s[1] - ref1).abs().max().item() <= 1e-5 * ref1.max().item() + 1e-6
+
+
+def test_conv_epilogue_statistics_not_offered_by_rolling_row_launch():
+    ops = _ops()
+    x = _rand_fm(1, 64, 16, 256, 73)
+    wt = _rand_w((64, 64, 3, 3), 74, 576)
+    spec = ops.ConvSpec.from_conv(wt)
+    assert spec.w_fold is not None
+    y, part = ops.conv2d(spec, ops.nchw_to_nhwc(x), stats=True)
+    assert part is None
+    _close(ops.nhwc_to_nchw(y), F.conv2d(x, wt, padding=1))
+
+
+@pytest.mark.parametrize("c,n,h,w", [(128, 4, 32, 32), (256, 2, 16, 24), (48, 2, 40, 40)])
+def test_bn_finalize_from_epilogue_statistics(c, n, h, w):
+    """adb_bn_finalize_stats(partials) == adb_bn_train_stats(z): mean / rstd / scale / shift and the running statistics
+    (both fp64 folds of fp32 partials of the same bf16 values; 2e-5 relative)."""
+    import ctypes as C
+    from adam_dehaze_b200 import _lib
+    ops = _ops()
+    x = _rand_fm(n, 64, h, w, 75)
+    wt = _rand_w((c, 64, 3, 3), 76, 576) * 3.0
+    bias = torch.randn(c, device="cuda")
+    spec = ops.ConvSpec.from_conv(wt, bias=bias)
+    spec.w_fold = None
+    z, part = ops.conv2d(spec, ops.nchw_to_nhwc(x), stats=True)
+    assert part is not None
+    cp = spec.cout_pad
+    px = n * h * w
+    g = torch.rand(cp, device="cuda") + 0.5
+    bt = torch.randn(cp, device="cuda")
+    outs = []
+    for use_part in (False, True):
+        rm, rv = torch.zeros(cp, device="cuda"), torch.ones(cp, device="cuda")
+        nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+        stats = torch.empty(4 * cp, device="cuda")
+        ptrs = [_lib.ptr(stats[i * cp:(i + 1) * cp]) for i in range(4)]
+        if use_part:
+            slots = part.shape[0] * part.shape[1]
+            scratch = torch.empty(int(_lib.load().adb_bn_stat_scratch_floats(slots, cp)), device="cuda")
+            _lib.call("adb_bn_finalize_stats", _lib.ptr(part), slots, cp, px, cp, _lib.ptr(g), _lib.ptr(bt), 1e-5, 0.1,
+                      _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(nbt), _lib.ptr(scratch), *ptrs, _lib.current_stream())
+        else:
+            scratch = torch.empty(int(_lib.load().adb_bn_scratch_floats(px, cp)), device="cuda")
+            _lib.call("adb_bn_train_stats", _lib.ptr(z), px, cp, cp, _lib.ptr(g), _lib.ptr(bt), 1e-5, 0.1,
+                      _lib.ptr(rm), _lib.ptr(rv), _lib.ptr(nbt), _lib.ptr(scratch), *ptrs, _lib.current_stream())
+        outs.append((stats.clone(), rm, rv, int(nbt.item())))
+    (s0, rm0, rv0, k0), (s1, rm1, rv1, k1) = outs
+    assert k0 == k1 == 1
+    for u, v in ((s0, s1), (rm0, rm1), (rv0, rv1)):
+        assert (u - v).abs().max().item() <= 2e-5 * u.abs().max().item() + 1e-6
+    # and against torch's batch statistics of the stored z
+    zf = z.float().reshape(-1, cp)
+    assert (s1[:cp] - zf.mean(0)).abs().max().item() <= 1e-4 * zf.abs().max().item()
+    assert (s1[cp:2 * cp] - 1.0 / torch.sqrt(zf.var(0, unbiased=False) + 1e-5)).abs().max().item() <= 1e-3 * s1[cp:2 * cp].abs().max().item()
+
+
+@pytest.mark.parametrize("c,n,live,h,w", [(96, 3, 3, 64, 128), (192, 4, 2, 32, 64), (384, 2, 2, 16, 32)])
+def test_attention_pool_from_epilogue_partials(c, n, live, h, w):
+    """AttentionBlock's (avg, max) pool folded from the producing conv's (sum, max) partials == adb_attn_pool over the stored
+    map: max bit-exact, sums to fp32 reassociation (1e-5 relative); and the attention output built on it stays within the
+    conv tolerance of the one built on the pool pass.  `live` < n: the device-side image count of a routed bucket."""
+    from adam_dehaze_b200 import _lib
+    ops = _ops()
+    x = _rand_fm(n, c, h, w, 80)
+    res = _rand_fm(n, c, h, w, 81)
+    wt = _rand_w((c, c, 3, 3), 82, 9 * c)
+    spec = ops.ConvSpec.from_conv(wt, bn=_bn(c, 83), act=ops.ACT_RELU)
+    n_dev = torch.tensor([live], dtype=torch.int32, device="cuda")
+    f = ops.nchw_to_nhwc(res).clone()
+    f, part = ops.conv2d(spec, ops.nchw_to_nhwc(x), dst=f, residual=f, stats="pool", n_dev=n_dev)
+    assert part is not None and part.shape[0] == n
+    pool_ref = torch.empty(ops.pool_scratch_floats(n, h, w, c), device="cuda")
+    _lib.call("adb_attn_pool", _lib.ptr(f), n, h, w, c, _lib.ptr(n_dev), 0, _lib.ptr(pool_ref), _lib.current_stream())
+    pool = torch.full((n * 2 * c,), float("nan"), device="cuda")
+    scratch = torch.empty(int(_lib.load().adb_attn_pool_stat_scratch_floats(n, part.shape[1], c)), device="cuda")
+    _lib.call("adb_attn_pool_from_stats", _lib.ptr(part), n, part.shape[1], part.shape[3], c, _lib.ptr(n_dev), 0, _lib.ptr(scratch),
+              _lib.ptr(pool), _lib.current_stream())
+    a = pool.view(n, 2, c)[:live]
+    b = pool_ref[:n * 2 * c].view(n, 2, c)[:live]
+    assert torch.equal(a[:, 1], b[:, 1])
+    assert (a[:, 0] - b[:, 0]).abs().max().item() <= 1e-5 * f[:live].float().abs().sum((1, 2)).max().item()
+    g = torch.Generator(device="cpu").manual_seed(84)
+    ap = ops.AttnParams((torch.randn(c // 16, c, 1, 1, generator=g) * 0.1).cuda(), (torch.randn(c, c // 16, 1, 1, generator=g) * 0.1).cuda(),
+                        (torch.randn(1, 2, 7, 7, generator=g) * 0.1).cuda())
+    y0 = ops.attention(f, ap, n=n, n_dev=n_dev)
+    y1 = ops.attention(f, ap, n=n, n_dev=n_dev, pool_partials=part)
+    _close(y1[:live].float(), y0[:live].float(), rel=1e-3, abs_=1e-4)
