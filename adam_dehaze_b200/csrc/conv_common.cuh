@@ -40,35 +40,49 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
   return apply_act(v, act_rt);
 }
 
-// TMEM -> registers -> affine / residual / activation -> bf16 -> the warp's swizzled staging buffer (TMA-store source).
-template <int kAct, int CS16>
-__device__ __forceinline__ void compute_slab(uint32_t taddr, uint4 (&q)[CS16 * 2], bool has_res, const float* sc_ptr,
-                                             const float* sh_ptr, uint32_t sbuf, int lane, int act_rt) {
+// FEATURE epilogue arithmetic of one slab (32 tile rows x CS16*16 channels; lane = row), in three steps so that the caller can
+// order them around the staging buffer's availability:
+//   slab_tmem_load   issue the TMEM loads of all the slab's columns (one tcgen05.wait::ld later)
+//   slab_bounce      kRes: the residual arrives lane-transposed (coalesced global reads); pass it through the (free) staging
+//                    buffer so every lane ends up with its own row
+//   slab_math        affine (+ residual) + activation -> packed bf16 pairs.  Two channels per instruction: FFMA2 (+ FADD2),
+//                    and ReLU rides inside the bf16 conversion (cvt.rn.relu) — bit-identical to the scalar fma / add / max / cvt
+//   slab_stage       the packed row -> this lane's swizzled row of the staging buffer (TMA-store source)
+template <int NG>
+__device__ __forceinline__ void slab_tmem_load(uint32_t taddr, float (&v)[NG * 16]) {
+#pragma unroll
+  for (int c = 0; c < NG; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v + c * 16);
+}
+
+template <int CS16>
+__device__ __forceinline__ void slab_bounce(uint4 (&q)[CS16 * 2], uint32_t sbuf, int lane) {
   constexpr uint32_t span = CS16 * 32;
   constexpr int CPR = CS16 * 2;                      // 16-byte chunks per slab row
-  float v[CS16 * 16];
 #pragma unroll
-  for (int c = 0; c < CS16; ++c) tmem_ld16(taddr + (uint32_t)(c * 16), v + c * 16);
-  if (has_res) {
-    // q holds the residual lane-transposed (load i, lane l = row i*(32/CPR) + l/CPR, chunk l%CPR: coalesced global
-    // reads).  Bounce it through the (free) staging buffer so every lane ends up with its own row.
-#pragma unroll
-    for (int i = 0; i < CPR; ++i) {
-      const uint32_t r = (uint32_t)(i * (32 / CPR) + lane / CPR), c = (uint32_t)(lane % CPR);
-      const uint32_t a = sbuf + swizzle_addr(r * span + c * 16u, span);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < CPR; ++i) {
-      const uint32_t a = sbuf + swizzle_addr((uint32_t)lane * span + (uint32_t)i * 16u, span);
-      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w) : "r"(a) : "memory");
-    }
-    __syncwarp();
+  for (int i = 0; i < CPR; ++i) {                    // load i, lane l holds row i*(32/CPR) + l/CPR, chunk l%CPR
+    const uint32_t r = (uint32_t)(i * (32 / CPR) + lane / CPR), c = (uint32_t)(lane % CPR);
+    const uint32_t a = sbuf + swizzle_addr(r * span + c * 16u, span);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
   }
-  tmem_ld_wait();
+  __syncwarp();
 #pragma unroll
-  for (int c16 = 0; c16 < CS16; ++c16) {
+  for (int i = 0; i < CPR; ++i) {
+    const uint32_t a = sbuf + swizzle_addr((uint32_t)lane * span + (uint32_t)i * 16u, span);
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w) : "r"(a) : "memory");
+  }
+  __syncwarp();
+}
+
+// slab_math handles the 16-channel groups G0 .. G0+NG-1 of a CS16-group slab; v holds just those groups' accumulators.
+// kStageNow: each group is written to the staging row as soon as it is packed (keeps 8 instead of CS16*8 packed registers
+// live — the residual path also holds this and the next slab's residual rows); pk is then scratch.
+template <int kAct, int CS16, int G0, int NG, bool kRes, bool kStageNow>
+__device__ __forceinline__ void slab_math(const float (&v)[NG * 16], const uint4 (&q)[CS16 * 2], const float* sc_ptr,
+                                          const float* sh_ptr, int act_rt, uint32_t (&pk)[CS16 * 8], uint32_t sbuf, int lane) {
+  constexpr uint32_t span = CS16 * 32;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const int c16 = G0 + g;
     const float4* sc4 = reinterpret_cast<const float4*>(sc_ptr + c16 * 16);
     const float4* sh4 = reinterpret_cast<const float4*>(sh_ptr + c16 * 16);
     float sc[16], sh[16];
@@ -78,21 +92,35 @@ __device__ __forceinline__ void compute_slab(uint32_t taddr, uint4 (&q)[CS16 * 2
       sc[4 * i] = a.x; sc[4 * i + 1] = a.y; sc[4 * i + 2] = a.z; sc[4 * i + 3] = a.w;
       sh[4 * i] = b.x; sh[4 * i + 1] = b.y; sh[4 * i + 2] = b.z; sh[4 * i + 3] = b.w;
     }
-    const uint4 q0 = q[2 * c16], q1 = q[2 * c16 + 1];
-    const uint32_t qs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    uint32_t pk[8];
+    const uint32_t qs[8] = {q[2 * c16].x, q[2 * c16].y, q[2 * c16].z, q[2 * c16].w,
+                            q[2 * c16 + 1].x, q[2 * c16 + 1].y, q[2 * c16 + 1].z, q[2 * c16 + 1].w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[i]);
-      const float y0 = act_t<kAct>(fmaf(v[c16 * 16 + 2 * i], sc[2 * i], sh[2 * i]) + __low2float(b2), act_rt);
-      const float y1 = act_t<kAct>(fmaf(v[c16 * 16 + 2 * i + 1], sc[2 * i + 1], sh[2 * i + 1]) + __high2float(b2), act_rt);
-      pk[i] = pack_bf16x2(y0, y1);
+      float y0, y1;
+      ffma2(y0, y1, v[g * 16 + 2 * i], v[g * 16 + 2 * i + 1], sc[2 * i], sc[2 * i + 1], sh[2 * i], sh[2 * i + 1]);
+      if (kRes) fadd2(y0, y1, y0, y1, __uint_as_float(qs[i] << 16), __uint_as_float(qs[i] & 0xffff0000u));   // bf16 pair -> fp32
+      if (kAct == ADB_ACT_RELU) pk[c16 * 8 + i] = pack_bf16x2_relu(y0, y1);
+      else if (kAct == ADB_ACT_NONE) pk[c16 * 8 + i] = pack_bf16x2(y0, y1);
+      else pk[c16 * 8 + i] = pack_bf16x2(apply_act(y0, act_rt), apply_act(y1, act_rt));
     }
-    const uint32_t row_off = (uint32_t)lane * span + (uint32_t)c16 * 32u;
-    const uint32_t a0 = sbuf + swizzle_addr(row_off, span);
-    const uint32_t a1 = sbuf + swizzle_addr(row_off + 16u, span);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+    if (kStageNow) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t a = sbuf + swizzle_addr((uint32_t)lane * span + (uint32_t)(c16 * 2 + i) * 16u, span);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pk[c16 * 8 + 4 * i]), "r"(pk[c16 * 8 + 4 * i + 1]),
+                     "r"(pk[c16 * 8 + 4 * i + 2]), "r"(pk[c16 * 8 + 4 * i + 3]) : "memory");
+      }
+    }
+  }
+}
+
+template <int CS16>
+__device__ __forceinline__ void slab_stage(const uint32_t (&pk)[CS16 * 8], uint32_t sbuf, int lane) {
+  constexpr uint32_t span = CS16 * 32;
+#pragma unroll
+  for (int i = 0; i < CS16 * 2; ++i) {
+    const uint32_t a = sbuf + swizzle_addr((uint32_t)lane * span + (uint32_t)i * 16u, span);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(pk[4 * i]), "r"(pk[4 * i + 1]), "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3]) : "memory");
   }
 }
 

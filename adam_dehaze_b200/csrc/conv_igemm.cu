@@ -193,21 +193,50 @@ struct TileCoord { int nt, g, w0, h0, img; };
 // Epilogue building blocks.  An epilogue warp handles "slabs": 32 tile rows x CS16*16 channels.  The residual row of the
 // NEXT slab is requested while the current one is computed, and all TMEM columns of a slab are requested before the
 // single tcgen05.wait::ld, so a slab exposes neither a global-load latency nor one TMEM round trip per 16 channels.
+// Per-tile addressing of this lane's residual fetches: load i of a slab covers tile row ew*32 + i*(32/CPR) + lane/CPR, 16-byte
+// chunk lane%CPR (consecutive lanes read consecutive chunks of a row: coalesced).  With tiles at least 32 pixels wide (every
+// map wider than 16 pixels) a warp's 32 rows lie in one image row, so load i sits i*(32/CPR) pixels after load 0: a base
+// pointer and the count of in-image loads describe the lane; narrower tiles take the general form.
+struct ResLane {
+  const __nv_bfloat16* base;   // load 0 of item (sub-tile 0, slab 0)
+  int nvalid;                  // loads 0 .. nvalid-1 are inside the image width (wide tiles)
+  int dh0;                     // image-row offset of this warp's rows inside a sub-tile (wide tiles)
+};
 template <int CS16>
-__device__ __forceinline__ void load_residual(const ConvK& P, const TileCoord& tc, int j, int items, int ew, int lane,
-                                              uint4 (&q)[CS16 * 2]) {
-  constexpr int CPR = CS16 * 2;                      // 16-byte chunks per slab row
+__device__ __forceinline__ ResLane res_lane(const ConvK& P, const TileCoord& tc, int ew, int lane) {
+  constexpr int CPR = CS16 * 2, RS = 32 / CPR;
+  ResLane r;
+  const int row0 = ew * 32 + lane / CPR;
+  r.dh0 = row0 >> P.tw_shift;
+  const int w = tc.w0 + (row0 & (P.TW - 1));
+  r.base = P.residual + (((size_t)tc.img * P.grid_h + tc.h0 + r.dh0) * (size_t)P.grid_w + w) * P.res_pitch + tc.nt * P.BN + (lane % CPR) * 8;
+  r.nvalid = min(CPR, max(0, (P.grid_w - w + RS - 1) / RS));
+  return r;
+}
+// (mt, sl) = the item's sub-tile and slab
+template <int CS16>
+__device__ __forceinline__ void load_residual(const ConvK& P, const TileCoord& tc, const ResLane& rl, int mt, int sl, bool live,
+                                              int ew, int lane, uint4 (&q)[CS16 * 2]) {
+  constexpr int CPR = CS16 * 2, RS = 32 / CPR;
   constexpr int Cs = CS16 * 16;
-  if (!P.residual || j >= items) return;             // (q is not read when there is no residual)
-  const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
-  const int ch = tc.nt * P.BN + sl * Cs + (lane % CPR) * 8;
+  if (!live) return;
+  const int h_left = P.grid_h - tc.h0 - mt * P.TH;       // image rows left from the sub-tile's first row on
+  if (P.TW >= 32) {
+    const __nv_bfloat16* p = rl.base + (size_t)(mt * P.TH) * (size_t)P.grid_w * P.res_pitch + sl * Cs;
+    const int nv = rl.dh0 < h_left ? rl.nvalid : 0;
+    const size_t step = (size_t)RS * P.res_pitch;
 #pragma unroll
-  for (int i = 0; i < CPR; ++i) {
-    const int row = ew * 32 + i * (32 / CPR) + lane / CPR;          // tile row this lane fetches in load i
-    const int h = tc.h0 + mt * P.TH + (row >> P.tw_shift), w = tc.w0 + (row & (P.TW - 1));
-    q[i] = (h < P.grid_h && w < P.grid_w)
-               ? __ldg(reinterpret_cast<const uint4*>(P.residual + (((size_t)tc.img * P.grid_h + h) * P.grid_w + w) * P.res_pitch + ch))
-               : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < CPR; ++i) q[i] = i < nv ? __ldg(reinterpret_cast<const uint4*>(p + i * step)) : make_uint4(0, 0, 0, 0);
+  } else {
+    const int ch = tc.nt * P.BN + sl * Cs + (lane % CPR) * 8;
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {
+      const int row = ew * 32 + i * RS + lane / CPR;
+      const int h = tc.h0 + mt * P.TH + (row >> P.tw_shift), w = tc.w0 + (row & (P.TW - 1));
+      q[i] = (h < P.grid_h && w < P.grid_w)
+                 ? __ldg(reinterpret_cast<const uint4*>(P.residual + (((size_t)tc.img * P.grid_h + h) * P.grid_w + w) * P.res_pitch + ch))
+                 : make_uint4(0, 0, 0, 0);
+    }
   }
 }
 
@@ -236,16 +265,26 @@ __device__ __forceinline__ void slab_stats(const ConvK& P, uint32_t sbuf, int la
     const bool mx = P.stat_mode == 2;
     float s0 = 0.f, s1 = 0.f;
     float a0 = mx ? -INFINITY : 0.f, a1 = a0;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      uint32_t w;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(sbuf + swizzle_addr((uint32_t)r * span + (uint32_t)lane * 4u, span)) : "memory");
-      if ((valid_rows >> r) & 1u) {
-        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w);
-        const float v0 = __low2float(b2), v1 = __high2float(b2);
-        s0 += v0; s1 += v1;
-        if (mx) { a0 = fmaxf(a0, v0); a1 = fmaxf(a1, v1); }
-        else { a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); }
+    // the loads below are plain (non-volatile) asm so that eight of them are in flight at a time; their base address is
+    // produced by a volatile asm that cannot move above the staging stores / fence before it, and the global stores of the
+    // sums cannot sink below the next memory-clobbering asm, so the loads stay between this warp's writes of the buffer
+    uint32_t base;
+    asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"(sbuf) : "memory");
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      uint32_t w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        asm("ld.shared.b32 %0, [%1];" : "=r"(w[u]) : "r"(base + swizzle_addr((uint32_t)(r0 + u) * span + (uint32_t)lane * 4u, span)));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if ((valid_rows >> (r0 + u)) & 1u) {
+          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[u]);
+          const float v0 = __low2float(b2), v1 = __high2float(b2);
+          s0 += v0; s1 += v1;
+          if (mx) { a0 = fmaxf(a0, v0); a1 = fmaxf(a1, v1); }
+          else { a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); }
+        }
       }
     }
     float* o = P.stat_out + slot * 2 * (size_t)P.cout_pad + ch + 2 * lane;
@@ -255,46 +294,85 @@ __device__ __forceinline__ void slab_stats(const ConvK& P, uint32_t sbuf, int la
   __syncwarp();
 }
 
+// This warp has read its share of an accumulator stage: order the TMEM reads before the arrival and hand the stage back
+// (8 arrivals per CTA complete the phase; a pair's arrivals all go to the leader CTA's barrier).
+template <bool kPair>
+__device__ __forceinline__ void release_acc(uint32_t tempty, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty); else mbar_arrive_relaxed(tempty); }
+}
+
 // FEATURE epilogue of one tile for one epilogue warp.  The tile's work items are its (sub-tile, slab) pairs in order; the two
 // warps that share a TMEM lane quarter (`half` 0 / 1) take alternate items.  Each warp owns one staging buffer and one
-// TMA-store bulk group stream; no cross-warp barrier anywhere.
-template <int kAct, int CS16>
+// TMA-store bulk group stream; no cross-warp barrier anywhere.  The accumulator read and (without a residual) the whole slab
+// arithmetic run BEFORE the wait for the previous TMA store to have read the staging buffer, so that wait hides behind them.
+// The accumulator stage goes back to the MMA issuer (`tempty`) as soon as this warp's LAST slab is in registers — the rest of that
+// slab's work (arithmetic, staging, store) no longer touches TMEM and overlaps the next tile's first MMAs.
+template <int kAct, int CS16, bool kRes, bool kPair>
 __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* tmOut, const TileCoord& tc, uint32_t tfull,
-                                             uint32_t tfull_phase, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
+                                             uint32_t tfull_phase, uint32_t tempty, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
                                              const float* s_shift, int ew, int half, int lane, int& e_i, size_t slot_base) {
   constexpr int Cs = CS16 * 16;
   const int items = P.MT * P.n_slabs;
   const int ch0 = tc.nt * P.BN;                        // first output channel of this N tile
   const int q_row0 = ew * 32;                          // first tile row of this warp
   const int q_th = q_row0 >> P.tw_shift, q_tw = q_row0 & (P.TW - 1);
-  const bool has_res = P.residual != nullptr;
-  uint4 qn[CS16 * 2];
+  // TMA-store coordinates of this warp's rows: fixed for the tile (pinned so that they are not re-derived from the tile index
+  // on the one lane that issues every store)
+  int st_c = P.out_c_off[tc.g] + ch0, st_w = tc.w0 + q_tw, st_p = P.out_p[tc.g], st_h = tc.h0 + q_th, st_n = tc.img;
+  asm volatile("" : "+r"(st_c), "+r"(st_w), "+r"(st_p), "+r"(st_h), "+r"(st_n));
+  uint4 q[CS16 * 2], qn[CS16 * 2];
 #pragma unroll
-  for (int i = 0; i < CS16 * 2; ++i) qn[i] = make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i] = make_uint4(0, 0, 0, 0);
   ADB_DBGE(1);
-  load_residual<CS16>(P, tc, half, items, ew, lane, qn);   // independent of the accumulator: overlaps this tile's main loop
+  ResLane rl;
+  // items advance by 2 per warp: (mt, sl) of the current item and (mtn, sln) of the one whose residual is in flight, stepped
+  // without a division
+  int mt = 0, sl = half;
+  while (sl >= P.n_slabs) { sl -= P.n_slabs; ++mt; }
+  int mtn = mt, sln = sl;
+  if (kRes) {
+    rl = res_lane<CS16>(P, tc, ew, lane);
+    load_residual<CS16>(P, tc, rl, mtn, sln, half < items, ew, lane, qn);   // independent of the accumulator: overlaps this tile's main loop
+  }
   mbar_wait(tfull, tfull_phase, P.err_flag, 4);
   tc_fence_after();
   ADB_DBGE(2);
 #pragma unroll 1
   for (int j = half; j < items; j += 2) {
-    uint4 q[CS16 * 2];
-#pragma unroll
-    for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i];
-    load_residual<CS16>(P, tc, j + 2, items, ew, lane, qn);   // next item's residual rides under this item's arithmetic
-    const int mt = j / P.n_slabs, sl = j - mt * P.n_slabs;
     const int cl = sl * Cs;                            // channel offset of the slab inside the N tile
-    // this warp's previous TMA store must have finished reading the staging buffer
-    if (lane == 0) tma_store_wait_read<0>();
-    __syncwarp();
-    ADB_DBGE(3);
-    compute_slab<kAct, CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), q, has_res, s_scale + ch0 + cl, s_shift + ch0 + cl, sbuf, lane, P.act);
+    const bool last = j + 2 >= items;
+    float v[Cs];
+    slab_tmem_load<CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), v);
+    uint32_t pk[CS16 * 8];
+    if (kRes) {
+#pragma unroll
+      for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i];
+      sln += 2;
+      while (sln >= P.n_slabs) { sln -= P.n_slabs; ++mtn; }
+      load_residual<CS16>(P, tc, rl, mtn, sln, !last, ew, lane, qn);  // next item's residual rides under this item's arithmetic
+      // the bounce needs the staging buffer: this warp's previous TMA store must have finished reading it
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      ADB_DBGE(3);
+      slab_bounce<CS16>(q, sbuf, lane);
+    }
+    tmem_ld_wait();
+    if (last) release_acc<kPair>(tempty, lane);
+    slab_math<kAct, CS16, 0, CS16, kRes, kRes>(v, q, s_scale + ch0 + cl, s_shift + ch0 + cl, P.act, pk, sbuf, lane);
+    if (!kRes) {
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      ADB_DBGE(3);
+      slab_stage<CS16>(pk, sbuf, lane);
+    }
     ADB_DBGE(4);
     fence_proxy_async_smem();
     __syncwarp();
     ADB_DBGE(5);
     if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
-      tma_store_5d(tmOut, sbuf, P.out_c_off[tc.g] + ch0 + cl, tc.w0 + q_tw, P.out_p[tc.g], tc.h0 + mt * P.TH + q_th, tc.img);
+      tma_store_5d(tmOut, sbuf, st_c + cl, st_w, st_p, st_h + mt * P.TH, st_n);
       tma_store_commit();
     }
     if (P.stat_out) {
@@ -304,7 +382,18 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
       slab_stats<CS16>(P, sbuf, lane, valid_rows, (slot_base + (size_t)mt) * 4 + (size_t)ew, ch0 + cl);
     }
     ADB_DBGE(6);
+    sl += 2;
+    while (sl >= P.n_slabs) { sl -= P.n_slabs; ++mt; }
   }
+  if (half >= items) release_acc<kPair>(tempty, lane);   // a warp without an item in this tile still owes its arrival
+}
+
+template <int kAct, int CS16, bool kPair>
+__device__ __forceinline__ void feature_tile_any(const ConvK& P, const CUtensorMap* tmOut, const TileCoord& tc, uint32_t tfull,
+                                                 uint32_t tfull_phase, uint32_t tempty, uint32_t tmem_tile, uint32_t sbuf, const float* s_scale,
+                                                 const float* s_shift, int ew, int half, int lane, int& e_i, size_t slot_base) {
+  if (P.residual) feature_tile<kAct, CS16, true, kPair>(P, tmOut, tc, tfull, tfull_phase, tempty, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+  else feature_tile<kAct, CS16, false, kPair>(P, tmOut, tc, tfull, tfull_phase, tempty, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
 }
 
 template <int kAct, bool kPair, int kEpi, bool kPre = false>
@@ -621,9 +710,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // partial-statistics slot of this CTA's first sub-tile: one slot per (pixel tile, CTA of a pair, sub-tile, lane quarter);
         // the N tiles of one pixel tile share it (they own disjoint channel ranges)
         const size_t slot_base = (((size_t)t / (size_t)P.n_tiles_n) * (size_t)P.ncta + (size_t)rank) * (size_t)P.MT;
-        if (!kPre && P.Cs == 64) feature_tile<kAct, 4>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
-        else if (P.Cs == 32) feature_tile<kAct, 2>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
-        else feature_tile<kAct, 1>(P, &tmOut, tc, tfull_bar(acc), acc_phase, tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+        if (!kPre && P.Cs == 64) feature_tile_any<kAct, 4, kPair>(P, &tmOut, tc, tfull_bar(acc), acc_phase, kPair ? tempty_lead(acc) : tempty_bar(acc), tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+        else if (P.Cs == 32) feature_tile_any<kAct, 2, kPair>(P, &tmOut, tc, tfull_bar(acc), acc_phase, kPair ? tempty_lead(acc) : tempty_bar(acc), tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
+        else feature_tile_any<kAct, 1, kPair>(P, &tmOut, tc, tfull_bar(acc), acc_phase, kPair ? tempty_lead(acc) : tempty_bar(acc), tmem_tile, sbuf, s_scale, s_shift, ew, half, lane, e_i, slot_base);
         if (ewi == 0) { ADB_DBG(4, dbg_i); }
       } else {
         // DOT / IMAGE: one work item per sub-tile; `half` takes sub-tile `half`
@@ -686,10 +775,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // accumulator stage fully read by this warp -> hand it back to the MMA issuer (8 arrivals per CTA complete the phase)
       if (ewi == 0) { ADB_DBG(5, dbg_i); ++dbg_i; }
       ADB_DBGE(9);
-      tc_fence_before();
-      ADB_DBGE(10);
-      __syncwarp();
-      if (lane == 0) { if (kPair) mbar_arrive_cluster(tempty_lead(acc)); else mbar_arrive_relaxed(tempty_bar(acc)); }
+      if (kEpi != ADB_EPI_FEATURE) release_acc<kPair>(kPair ? tempty_lead(acc) : tempty_bar(acc), lane);   // (FEATURE: inside feature_tile)
       ADB_DBGE(11);
       if (++acc == P.acc_stages) { acc = 0; acc_phase ^= 1u; }
     }
@@ -798,6 +884,12 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
     ADB_REQUIRE(d->cout_pad % 32 == 0, "adb_conv2d: cout_pad %d > 256 must split evenly", d->cout_pad);
     P.n_tiles_n = 2; P.BN = d->cout_pad / 2;
   }
+  // 256 output channels run as two 128-channel N tiles: two sub-tiles per CTA then fit TMEM double-buffered (2 x 2 x 128
+  // columns), which beats one 256-column tile per stage by 11 % (0.844 -> 0.754 ms on med_256_3x3, profiles/r2/prof_nsplit.txt);
+  // the same split loses at 192 (operand A is fetched twice for too little gain) and at 128.  tune_flags bit 10 forces a split,
+  // bit 11 forbids it.
+  const bool split_n = (d->tune_flags & 1024) || (P.BN == 256 && !(d->tune_flags & 2048));
+  if (split_n && P.BN % 32 == 0 && P.BN >= 64) { P.n_tiles_n *= 2; P.BN /= 2; }
   ADB_REQUIRE(P.BN % 16 == 0 && P.BN >= 16 && P.BN <= 256, "adb_conv2d: N tile %d invalid", P.BN);
   P.cout_pad = d->cout_pad;
   P.bn_cols = (2 * round_up(P.BN, 32) <= 512) ? round_up(P.BN, 32) : P.BN;

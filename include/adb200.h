@@ -97,7 +97,8 @@ typedef struct adb_conv_desc {
   /* --- tuning (0 = choose automatically) */
   int32_t tune_mt, tune_stages, tune_acc_stages;
   int32_t tune_flags;   /* bit 0: one TMA box per tap (no halo re-use); bit 1: descriptor base-offset experiment;
-                           bit 9 (512): never take the rolling-row kernel (w_fold ignored) */
+                           bit 9 (512): never take the rolling-row kernel (w_fold ignored);
+                           bit 10 (1024): halve the N tile (twice the N tiles); bit 11 (2048): never split 256 channels in two */
   /* --- optional pre-activation fused into the input operand (1x1 stride-1 FEATURE convs): the conv sees
          relu(x[..., c]*pre_scale[c] + pre_shift[c]) over the c0+c1 input channels.  DenseNet's norm1/relu1 ahead of conv1
          and the transition norm/relu (torchvision densenet121 called as the north_star's HDEN) — every dense layer applies

@@ -526,7 +526,7 @@ def test_bn_finalize_from_epilogue_statistics(c, n, h, w):
 def test_attention_pool_from_epilogue_partials(c, n, live, h, w):
     """AttentionBlock's (avg, max) pool folded from the producing conv's (sum, max) partials == adb_attn_pool over the stored
     map: max bit-exact, sums to fp32 reassociation (1e-5 relative); and the attention output built on it stays within the
-    conv tolerance of the one built on the pool pass.  `live` < n: the device-side image count of a routed bucket."""
+    one bf16 ulp of the one built on the pool pass.  `live` < n: the device-side image count of a routed bucket."""
     from adam_dehaze_b200 import _lib
     ops = _ops()
     x = _rand_fm(n, c, h, w, 80)
@@ -552,4 +552,4 @@ def test_attention_pool_from_epilogue_partials(c, n, live, h, w):
                         (torch.randn(1, 2, 7, 7, generator=g) * 0.1).cuda())
     y0 = ops.attention(f, ap, n=n, n_dev=n_dev)
     y1 = ops.attention(f, ap, n=n, n_dev=n_dev, pool_partials=part)
-    _close(y1[:live].float(), y0[:live].float(), rel=1e-3, abs_=1e-4)
+    _close(y1[:live].float(), y0[:live].float(), rel=1e-2, abs_=1e-4)     # one bf16 ulp of the output

@@ -20,6 +20,12 @@ SHAPES = [
     ("med_64_3x3", "s1", (64,), 64, 3, 2, 1024, 2048),
     ("med_128_3x3", "s1", (128,), 128, 3, 4, 512, 1024),
     ("med_256_3x3", "s1", (256,), 256, 3, 8, 256, 512),
+    ("med_cat_128_64", "s1", (64, 64), 64, 3, 2, 1024, 2048),
+    ("med_down_64_128", "s2", (64,), 128, 4, 2, 1024, 2048),
+    ("med_down_128_256", "s2", (128,), 256, 4, 4, 512, 1024),
+    ("med_up_256_128", "t", (256,), 128, 4, 8, 256, 512),
+    ("med_up_cat_256_64", "t", (128, 128), 64, 4, 4, 512, 1024),
+    ("med_256_3x3_resdst", "resdst", (256,), 256, 3, 8, 256, 512),
     ("cpx_96_3x3", "s1", (96,), 96, 3, 2, 1024, 2048),
     ("cpx_192_3x3", "s1", (192,), 192, 3, 4, 512, 1024),
     ("cpx_384_3x3", "s1", (384,), 384, 3, 8, 256, 512),
@@ -47,6 +53,21 @@ SHAPES = [
     ("dense_pre_480_128", "pre", (480, 512), 128, 1, 8, 128, 256),
     ("dense_pre_992_128", "pre", (992, 1024), 128, 1, 8, 64, 128),
 ]
+
+
+STATS = None   # None | True (sum, sum of squares) | "pool" (sum, max): epilogue channel partials on the launches that offer them
+_STAT_BUF = {}
+
+
+def _stat_kwargs():
+    if STATS is None:
+        return {}
+
+    def alloc(shape):
+        if shape not in _STAT_BUF:
+            _STAT_BUF[shape] = torch.empty(shape, dtype=torch.float32, device="cuda")
+        return _STAT_BUF[shape]
+    return dict(stats=STATS, stat_alloc=alloc)
 
 
 def run(shape, tune, reps):
@@ -106,6 +127,8 @@ def run(shape, tune, reps):
     if kwargs.get("epi") is None:
         dst = ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
         kwargs.setdefault("dst", dst)
+        if kind != "t":
+            kwargs.update(_stat_kwargs())
     else:
         ops.conv2d(spec, srcs[0], src1, tune=tune, **kwargs)
     torch.cuda.synchronize()
@@ -126,7 +149,10 @@ def main():
     ap.add_argument("--only", default=None)
     ap.add_argument("--ab-flags", type=int, default=None, help="time each shape with default tuning and with these tune flags (e.g. 128 = no ragged 64-channel boxes)")
     ap.add_argument("--flags", type=int, default=None, help="time each shape with exactly these tune flags (16 = CTA pair, 32 = 1-CTA, 512 = no rolling-row kernel)")
+    ap.add_argument("--stats", default=None, choices=["bn", "pool"], help="also write the epilogue channel partials (adb_conv_desc.stat_out)")
     args = ap.parse_args()
+    global STATS
+    STATS = {None: None, "bn": True, "pool": "pool"}[args.stats]
     peak = 1414.7
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
