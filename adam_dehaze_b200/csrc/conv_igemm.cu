@@ -884,12 +884,6 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
     ADB_REQUIRE(d->cout_pad % 32 == 0, "adb_conv2d: cout_pad %d > 256 must split evenly", d->cout_pad);
     P.n_tiles_n = 2; P.BN = d->cout_pad / 2;
   }
-  // 256 output channels run as two 128-channel N tiles: two sub-tiles per CTA then fit TMEM double-buffered (2 x 2 x 128
-  // columns), which beats one 256-column tile per stage by 11 % (0.844 -> 0.754 ms on med_256_3x3, profiles/r2/prof_nsplit.txt);
-  // the same split loses at 192 (operand A is fetched twice for too little gain) and at 128.  tune_flags bit 10 forces a split,
-  // bit 11 forbids it.
-  const bool split_n = (d->tune_flags & 1024) || (P.BN == 256 && !(d->tune_flags & 2048));
-  if (split_n && P.BN % 32 == 0 && P.BN >= 64) { P.n_tiles_n *= 2; P.BN /= 2; }
   ADB_REQUIRE(P.BN % 16 == 0 && P.BN >= 16 && P.BN <= 256, "adb_conv2d: N tile %d invalid", P.BN);
   P.cout_pad = d->cout_pad;
   P.bn_cols = (2 * round_up(P.BN, 32) <= 512) ? round_up(P.BN, 32) : P.BN;
@@ -906,7 +900,7 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   bool tile2d = (d->tune_flags & 256) && d->kind == ADB_CONV_S1 && d->kw > 1 && P.grid_w >= 8;
   if (tile2d) TW = 8;
   P.TW = TW; P.TH = 128 / TW;
-  const long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
+  long long sub_tiles = (long long)d->n * ((P.grid_h + P.TH - 1) / P.TH) * ((P.grid_w + TW - 1) / TW) * P.n_tiles_n * P.ngroups;
   // CTA-pair mode (cta_group::2): halves the weight-operand traffic per CTA (operand reads and TMA fill), which is what
   // bounds the 1-CTA kernel.  Worth it once the weights are a real share of the shared-memory traffic
   // (N tile >= 48, or >= 32 with a deep K; more than one tap) and there are enough tiles to fill 74 pairs for a few waves.
@@ -916,6 +910,15 @@ int build(const adb_conv_desc* d, ConvK& P, int& out_h, int& out_w, int& ktot, i
   if (d->tune_flags & 32) ncta = 1;
   if (pre) ncta = 1;
   P.ncta = ncta;
+  // 256 output channels of a CTA pair run as two 128-channel N tiles: two sub-tiles per CTA then fit TMEM double-buffered
+  // (2 x 2 x 128 columns), which beats one 256-column tile per stage by 11 % (0.844 -> 0.754 ms on med_256_3x3,
+  // profiles/r2/prof_nsplit.txt).  The same split loses at 192 and 128 (operand A is fetched twice for too little gain) and
+  // without the pair (1.06 -> 1.21 ms).  tune_flags bit 10 forces a split, bit 11 forbids it.
+  const bool split_n = (d->tune_flags & 1024) || (P.BN == 256 && ncta == 2 && !(d->tune_flags & 2048));
+  if (split_n && P.BN % 32 == 0 && P.BN >= 64) {
+    P.n_tiles_n *= 2; P.BN /= 2; sub_tiles *= 2;
+    P.bn_cols = (2 * round_up(P.BN, 32) <= 512) ? round_up(P.BN, 32) : P.BN;
+  }
   // sub-tiles per CTA: two share every weight box when their accumulators fit TMEM; measured (profiles/r1_pair_sweep.txt):
   // pairs prefer MT = 2 even single-buffered (N = 192), except at N = 256 where double buffering wins.
   int mt = d->tune_mt > 0 ? d->tune_mt : (ncta == 2 ? (P.bn_cols <= 192 ? 2 : 1) : (P.bn_cols <= 128 ? 2 : 1));

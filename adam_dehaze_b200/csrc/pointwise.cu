@@ -445,26 +445,49 @@ __global__ void attn_spatial_kernel(const float* __restrict__ stats, int n, int 
   sp[((size_t)img * h + py) * w + px] = 1.f / (1.f + __expf(-acc));
 }
 
-// pass 3b: y = x * gate[c] * sp[pixel] — pure streaming, one 16-byte group per thread
-__global__ void attn_scale_kernel(const __nv_bfloat16* __restrict__ x, int n, long long hw, int c, const int* n_dev,
-                                  int n_start, const float* __restrict__ gate, const float* __restrict__ sp,
-                                  __nv_bfloat16* __restrict__ y) {
-  const int n_eff = live_images(n, n_dev, n_start);
-  const int G = c / 8;
-  const long long total = (long long)n_eff * hw * G;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % G);
-    const long long p = t / G;
-    const int img = (int)(p / hw);
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)p * c + g * 8)), f);
-    const float s = __ldg(sp + p);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c + g * 8));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)img * c + g * 8 + 4));
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+// pass 3b: y = x * gate[c] * sp[pixel] — pure streaming.  grid = (blocks, images); a thread walks 16-byte channel groups of
+// its image four at a time (four independent loads in flight), all index arithmetic in 32 bits with the division by the
+// group count as one multiply-high (gmul = floor(2^32 / G) + 1, exact for hw * G < 2^32, checked on the host).
+__global__ void __launch_bounds__(256)
+attn_scale_kernel(const __nv_bfloat16* __restrict__ x, int n, uint32_t hw, int c, uint32_t gmul, const int* n_dev,
+                  int n_start, const float* __restrict__ gate, const float* __restrict__ sp, __nv_bfloat16* __restrict__ y) {
+  const int img = blockIdx.y;
+  if (img >= live_images(n, n_dev, n_start)) return;
+  const uint32_t G = (uint32_t)c >> 3;
+  const uint32_t total = hw * G;
+  const uint4* xi = reinterpret_cast<const uint4*>(x + (size_t)img * hw * c);
+  uint4* yi = reinterpret_cast<uint4*>(y + (size_t)img * hw * c);
+  const float* spi = sp + (size_t)img * hw;
+  const float* gi = gate + (size_t)img * c;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += 4 * stride) {
+    uint4 v[4];
+    float s[4];
+    uint32_t g[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) f[q] = f[q] * gg[q] * s;
-    *reinterpret_cast<uint4*>(y + (size_t)p * c + g * 8) = pack8(f);
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t t = t0 + u * stride;
+      if (t < total) {
+        const uint32_t p = G == 1 ? t : __umulhi(t, gmul);
+        g[u] = t - p * G;
+        v[u] = __ldg(xi + t);
+        s[u] = __ldg(spi + p);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t t = t0 + u * stride;
+      if (t < total) {
+        float f[8];
+        unpack8(v[u], f);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gi + g[u] * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gi + g[u] * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = f[q] * gg[q] * s[u];
+        yi[t] = pack8(f);
+      }
+    }
   }
 }
 
@@ -943,9 +966,14 @@ int adb_attn_apply(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, co
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((w + kSpTW - 1) / kSpTW, (h + kSpTH - 1) / kSpTH, n), block(kSpTW, kSpTH);
   attn_spatial_kernel<<<grid, block, 0, st>>>(stats, n, h, w, n_dev, n_start, w_spatial, spatial);
-  const long long total = (long long)n * h * w * (c / 8);
-  attn_scale_kernel<<<grid_for(total, 256, sms, 16), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, (long long)h * w, c,
-                                                                  n_dev, n_start, gate, spatial, reinterpret_cast<__nv_bfloat16*>(y));
+  const long long per_img = (long long)h * w * (c / 8);
+  const uint32_t G = (uint32_t)c / 8;
+  ADB_REQUIRE(per_img * G < (1LL << 32), "adb_attn_apply: %lld channel groups per image exceed the 32-bit index range", per_img);
+  const uint32_t gmul = G <= 1 ? 0u : (uint32_t)((1ULL << 32) / G) + 1u;
+  // ~16 waves over the whole batch, each thread taking four groups per trip
+  const int bx = (int)std::max<long long>(1, std::min<long long>((per_img + 1023) / 1024, ((long long)sms * 16 * 8 + n - 1) / n));
+  attn_scale_kernel<<<dim3(bx, n), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, (uint32_t)((long long)h * w), c, gmul,
+                                                 n_dev, n_start, gate, spatial, reinterpret_cast<__nv_bfloat16*>(y));
   ADB_LAUNCH_OK();
   return ADB_OK;
 }
