@@ -9,6 +9,8 @@ eval(): BatchNorm uses running statistics folded into the conv epilogues (the la
 hand the forward to training/autograd.py (batch-statistics BatchNorm on a tape, kernel-built backward).  There is no
 fallback to torch ops in either mode; CPU tensors raise.
 """
+import os
+
 import torch
 
 from . import ops
@@ -96,6 +98,10 @@ def _res_specs(rb):
 
 def _attn_params(ab):
     return AttnParams(ab.fc[0].weight, ab.fc[2].weight, ab.conv_spatial.weight)
+
+
+# AttentionBlock pools folded from the producing conv's epilogue partials (False: a separate pass over the map)
+POOL_FOLD = os.environ.get("ADB_NO_POOL_FOLD", "") == ""
 
 
 class BranchEngine:
@@ -277,7 +283,7 @@ class BranchEngine:
         the block output, returned (None when that launch does not produce them) — the attention's pool pass folds them instead of
         re-reading f."""
         ops.conv2d(specs[0], f, dst=tmp, **kw)
-        if not pool:
+        if not pool or not POOL_FOLD:
             ops.conv2d(specs[1], tmp, dst=f, residual=f, **kw)
             return None
         dev = f.device
