@@ -272,13 +272,10 @@ __device__ __forceinline__ void roll_epilogue(const RollK& P, const CUtensorMap*
           const uint32_t qs[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
           uint32_t pk[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float y0 = fmaf(v[k * 8 + 2 * e], sc[2 * e], sh[2 * e]);
-            float y1 = fmaf(v[k * 8 + 2 * e + 1], sc[2 * e + 1], sh[2 * e + 1]);
-            if (kRes) {
-              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qs[e]);
-              y0 += __low2float(b2); y1 += __high2float(b2);
-            }
+          for (int e = 0; e < 4; ++e) {                       // two channels per instruction (FFMA2 / FADD2): same bits as fmaf / +
+            float y0, y1;
+            ffma2(y0, y1, v[k * 8 + 2 * e], v[k * 8 + 2 * e + 1], sc[2 * e], sc[2 * e + 1], sh[2 * e], sh[2 * e + 1]);
+            if (kRes) fadd2(y0, y1, y0, y1, __uint_as_float(qs[e] << 16), __uint_as_float(qs[e] & 0xffff0000u));
             pk[e] = (kAct == ADB_ACT_RELU) ? pack_bf16x2_relu(y0, y1) : pack_bf16x2(act_t<kAct>(y0, P.act), act_t<kAct>(y1, P.act));
           }
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sw_row[k]), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");

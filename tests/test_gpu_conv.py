@@ -78,6 +78,10 @@ CONV_CASES = [
     (64, 48, 3, 1, 32, 32, None),
     (64, 64, 3, 4, 128, 256, None),          # many tiles per CTA: pipeline/accumulator phase wrap
     (64, 64, 3, 2, 64, 128, {"mt": 2}),
+    (256, 256, 3, 2, 64, 128, {"flags": 16}),            # CTA pair: 256 channels as two 128-channel N tiles (the default rule)
+    (256, 256, 3, 2, 64, 128, {"flags": 16 + 2048}),     # ... and with the split forbidden: one 256-column tile
+    (192, 192, 3, 2, 32, 128, {"flags": 16 + 1024}),     # forced split: two 96-channel N tiles
+    (384, 384, 3, 1, 32, 64, {"flags": 16 + 1024}),      # forced split of both 192-channel tiles: four N tiles
     (96, 96, 3, 2, 64, 128, {"mt": 2}),
     (64, 64, 3, 2, 64, 128, {"stages": 2, "acc": 1}),
     (64, 64, 3, 2, 64, 256, None),           # halo re-use path: tile = one image row (TW = 128), 128-byte swizzle
