@@ -43,8 +43,8 @@ __device__ __forceinline__ float act_t(float v, int act_rt) {
 // FEATURE epilogue arithmetic of one slab (32 tile rows x CS16*16 channels; lane = row), in three steps so that the caller can
 // order them around the staging buffer's availability:
 //   slab_tmem_load   issue the TMEM loads of all the slab's columns (one tcgen05.wait::ld later)
-//   slab_bounce      kRes: the residual arrives lane-transposed (coalesced global reads); pass it through the (free) staging
-//                    buffer so every lane ends up with its own row
+//   slab_bounce      kRes: the residual arrives lane-transposed (coalesced global reads, `src`); pass it through the (free)
+//                    staging buffer so every lane ends up with its own row (`q`)
 //   slab_math        affine (+ residual) + activation -> packed bf16 pairs.  Two channels per instruction: FFMA2 (+ FADD2),
 //                    and ReLU rides inside the bf16 conversion (cvt.rn.relu) — bit-identical to the scalar fma / add / max / cvt
 //   slab_stage       the packed row -> this lane's swizzled row of the staging buffer (TMA-store source)
@@ -55,14 +55,14 @@ __device__ __forceinline__ void slab_tmem_load(uint32_t taddr, float (&v)[NG * 1
 }
 
 template <int CS16>
-__device__ __forceinline__ void slab_bounce(uint4 (&q)[CS16 * 2], uint32_t sbuf, int lane) {
+__device__ __forceinline__ void slab_bounce(const uint4 (&src)[CS16 * 2], uint4 (&q)[CS16 * 2], uint32_t sbuf, int lane) {
   constexpr uint32_t span = CS16 * 32;
   constexpr int CPR = CS16 * 2;                      // 16-byte chunks per slab row
 #pragma unroll
   for (int i = 0; i < CPR; ++i) {                    // load i, lane l holds row i*(32/CPR) + l/CPR, chunk l%CPR
     const uint32_t r = (uint32_t)(i * (32 / CPR) + lane / CPR), c = (uint32_t)(lane % CPR);
     const uint32_t a = sbuf + swizzle_addr(r * span + c * 16u, span);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(src[i].x), "r"(src[i].y), "r"(src[i].z), "r"(src[i].w) : "memory");
   }
   __syncwarp();
 #pragma unroll

@@ -201,6 +201,8 @@ struct ResLane {
   const __nv_bfloat16* base;   // load 0 of item (sub-tile 0, slab 0)
   int nvalid;                  // loads 0 .. nvalid-1 are inside the image width (wide tiles)
   int dh0;                     // image-row offset of this warp's rows inside a sub-tile (wide tiles)
+  uint32_t step;               // elements between consecutive loads of an item (wide tiles)
+  uint32_t mt_step;            // elements between the sub-tiles of a tile
 };
 template <int CS16>
 __device__ __forceinline__ ResLane res_lane(const ConvK& P, const TileCoord& tc, int ew, int lane) {
@@ -211,10 +213,18 @@ __device__ __forceinline__ ResLane res_lane(const ConvK& P, const TileCoord& tc,
   const int w = tc.w0 + (row0 & (P.TW - 1));
   r.base = P.residual + (((size_t)tc.img * P.grid_h + tc.h0 + r.dh0) * (size_t)P.grid_w + w) * P.res_pitch + tc.nt * P.BN + (lane % CPR) * 8;
   r.nvalid = min(CPR, max(0, (P.grid_w - w + RS - 1) / RS));
+  r.step = (uint32_t)(RS * P.res_pitch);
+  r.mt_step = (uint32_t)(P.TH * P.grid_w * P.res_pitch);     // < 2^31: at most 16 image rows of one map
+  // kept in registers (or a cheap local-memory slot): left alone, the compiler re-derives all of it from the tile index in
+  // front of every slab's loads — a 500-cycle chain of 64-bit multiplies and constant-bank reads on the epilogue's critical path
+  asm volatile("" : "+l"(r.base), "+r"(r.nvalid), "+r"(r.dh0), "+r"(r.step), "+r"(r.mt_step));
   return r;
 }
-// (mt, sl) = the item's sub-tile and slab
-template <int CS16>
+// (mt, sl) = the item's sub-tile and slab.  kPrefetch: only pull the rows into L2 (prefetch.global.L2; no registers held) — the
+// later register load then pays an L2 round trip instead of a DRAM one.
+// Loads [I0, I1) of the item only (the caller spreads an item's loads over its slab: eight warps firing all of theirs at once
+// stall at issue for about a memory round trip).
+template <int CS16, bool kPrefetch = false, int I0 = 0, int I1 = CS16 * 2>
 __device__ __forceinline__ void load_residual(const ConvK& P, const TileCoord& tc, const ResLane& rl, int mt, int sl, bool live,
                                               int ew, int lane, uint4 (&q)[CS16 * 2]) {
   constexpr int CPR = CS16 * 2, RS = 32 / CPR;
@@ -222,15 +232,20 @@ __device__ __forceinline__ void load_residual(const ConvK& P, const TileCoord& t
   if (!live) return;
   const int h_left = P.grid_h - tc.h0 - mt * P.TH;       // image rows left from the sub-tile's first row on
   if (P.TW >= 32) {
-    const __nv_bfloat16* p = rl.base + (size_t)(mt * P.TH) * (size_t)P.grid_w * P.res_pitch + sl * Cs;
+    const __nv_bfloat16* p = rl.base + ((uint32_t)mt * rl.mt_step + (uint32_t)(sl * Cs));
     const int nv = rl.dh0 < h_left ? rl.nvalid : 0;
-    const size_t step = (size_t)RS * P.res_pitch;
+    if (kPrefetch) {
 #pragma unroll
-    for (int i = 0; i < CPR; ++i) q[i] = i < nv ? __ldg(reinterpret_cast<const uint4*>(p + i * step)) : make_uint4(0, 0, 0, 0);
-  } else {
+      for (int i = I0; i < I1; ++i)
+        if (i < nv) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (uint32_t)i * rl.step));
+      return;
+    }
+#pragma unroll
+    for (int i = I0; i < I1; ++i) q[i] = i < nv ? __ldg(reinterpret_cast<const uint4*>(p + (uint32_t)i * rl.step)) : make_uint4(0, 0, 0, 0);
+  } else if (!kPrefetch) {
     const int ch = tc.nt * P.BN + sl * Cs + (lane % CPR) * 8;
 #pragma unroll
-    for (int i = 0; i < CPR; ++i) {
+    for (int i = I0; i < I1; ++i) {
       const int row = ew * 32 + i * RS + lane / CPR;
       const int h = tc.h0 + mt * P.TH + (row >> P.tw_shift), w = tc.w0 + (row & (P.TW - 1));
       q[i] = (h < P.grid_h && w < P.grid_w)
@@ -333,8 +348,17 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
   while (sl >= P.n_slabs) { sl -= P.n_slabs; ++mt; }
   int mtn = mt, sln = sl;
   if (kRes) {
+    // Independent of the accumulator, so all of it overlaps this tile's main loop: the first item's rows go to registers, the
+    // later items' rows are pulled into L2 (their register loads are issued one item ahead, which covers an L2 round trip but
+    // not a DRAM one).
     rl = res_lane<CS16>(P, tc, ew, lane);
-    load_residual<CS16>(P, tc, rl, mtn, sln, half < items, ew, lane, qn);   // independent of the accumulator: overlaps this tile's main loop
+    load_residual<CS16>(P, tc, rl, mtn, sln, half < items, ew, lane, qn);
+    int mtp = mt, slp = sl;
+    for (int jp = half + 2; jp < items; jp += 2) {
+      slp += 2;
+      while (slp >= P.n_slabs) { slp -= P.n_slabs; ++mtp; }
+      load_residual<CS16, true>(P, tc, rl, mtp, slp, true, ew, lane, qn);
+    }
   }
   mbar_wait(tfull, tfull_phase, P.err_flag, 4);
   tc_fence_after();
@@ -347,20 +371,24 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
     slab_tmem_load<CS16>(tmem_tile + (uint32_t)(mt * P.bn_cols + cl), v);
     uint32_t pk[CS16 * 8];
     if (kRes) {
-#pragma unroll
-      for (int i = 0; i < CS16 * 2; ++i) q[i] = qn[i];
-      sln += 2;
-      while (sln >= P.n_slabs) { sln -= P.n_slabs; ++mtn; }
-      load_residual<CS16>(P, tc, rl, mtn, sln, !last, ew, lane, qn);  // next item's residual rides under this item's arithmetic
       // the bounce needs the staging buffer: this warp's previous TMA store must have finished reading it
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
       ADB_DBGE(3);
-      slab_bounce<CS16>(q, sbuf, lane);
+      slab_bounce<CS16>(qn, q, sbuf, lane);
+      ADB_DBGE(13);
+      // The next item's rows are requested only now, after this item's have left their registers: a request issued earlier
+      // would share the scoreboard wait of the bounce above and expose its whole latency (measured: 2-4 k cycles per slab).
+      sln += 2;
+      while (sln >= P.n_slabs) { sln -= P.n_slabs; ++mtn; }
+      load_residual<CS16, false, 0, CS16>(P, tc, rl, mtn, sln, !last, ew, lane, qn);            // first half of the loads
+      ADB_DBGE(14);
     }
     tmem_ld_wait();
+    if (kRes) { ADB_DBGE(15); }
     if (last) release_acc<kPair>(tempty, lane);
     slab_math<kAct, CS16, 0, CS16, kRes, kRes>(v, q, s_scale + ch0 + cl, s_shift + ch0 + cl, P.act, pk, sbuf, lane);
+    if (kRes) load_residual<CS16, false, CS16, CS16 * 2>(P, tc, rl, mtn, sln, !last, ew, lane, qn);   // second half, after the arithmetic
     if (!kRes) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();

@@ -223,6 +223,20 @@ __device__ __forceinline__ void roll_epilogue(const RollK& P, const CUtensorMap*
         for (int k = 0; k < 4; ++k)
           q[k] = (sg.w0 + px + k * 8 < P.W) ? __ldg(reinterpret_cast<const uint4*>(res_row + (size_t)(px + k * 8) * P.res_pitch))
                                             : make_uint4(0, 0, 0, 0);
+        // Pull into L2 what this warp reads later without a register to park it in: the other slabs of this row (their loads
+        // are issued right before use) and the whole next row this warp owns, kEpiSets rows down — those loads then pay an L2
+        // round trip instead of a DRAM one.
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (sg.w0 + px + k * 8 < P.W) {
+            const __nv_bfloat16* a = res_row + (size_t)(px + k * 8) * P.res_pitch;
+            for (int sl = 1; sl < P.n_slabs; ++sl) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + sl * 32));
+            if (i + kEpiSets < sg.rows) {
+              const __nv_bfloat16* b = a + (size_t)kEpiSets * P.W * P.res_pitch;
+              for (int sl = 0; sl < P.n_slabs; ++sl) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + sl * 32));
+            }
+          }
+        }
       }
       { ROLL_T0(); mbar_wait(bar_full0 + 8u * slot, par, P.err_flag, 4); ROLL_ACC(0); }
       if (dbg_on) dbg_acc[4] += 1;
