@@ -401,6 +401,7 @@ __device__ __forceinline__ void feature_tile(const ConvK& P, const CUtensorMap* 
     ADB_DBGE(5);
     if (lane == 0) {   // the same thread owns this warp's bulk-group bookkeeping (commit / wait_group)
       tma_store_5d(tmOut, sbuf, st_c + cl, st_w, st_p, st_h + mt * P.TH, st_n);
+      ADB_DBGE(16);
       tma_store_commit();
     }
     if (P.stat_out) {

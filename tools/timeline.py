@@ -12,7 +12,8 @@ def detail(names):
     """Epilogue sub-step stamps (tune flag 64): tag:delta sequence of warp 4 / lane 0 of CTA 0.
     tags: 1 before tfull wait, 2 after, 3 slab staging free, 4 slab computed (TMEM+residual -> smem), 5 fenced,
     6 TMA store issued, 7 DOT tmem ready, 8 DOT stored, 9 tile done; residual path: 13 residual bounced through the staging
-    buffer, 14 first half of the next item's residual loads issued, 15 accumulator in registers (tcgen05.wait::ld)."""
+    buffer, 14 first half of the next item's residual loads issued, 15 accumulator in registers (tcgen05.wait::ld); 16 TMA store
+    instruction issued (6 then follows its commit_group)."""
     for shape in prof_conv.SHAPES:
         if shape[0] not in names:
             continue
