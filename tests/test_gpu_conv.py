@@ -139,6 +139,35 @@ def test_conv_bias_residual(tune):
     _close(ops.nhwc_to_nchw(y), ref)
 
 
+RES_CASES = [
+    # (c, n, h, w, tune): the residual epilogue's addressing forms and slab widths
+    (192, 2, 16, 128, {"flags": 16}),                    # CTA pair, two sub-tiles, three 64-channel slabs per warp pair (Complex)
+    (192, 1, 9, 200, {"flags": 16}),                     # ... ragged in both directions (rows outside the image load nothing)
+    (96, 2, 16, 128, None),                              # 32-channel slabs
+    (48, 1, 12, 64, None),                               # 16-channel slabs
+    (128, 2, 24, 24, None),                              # 16-pixel-wide tiles: a warp's rows span several image rows
+    (384, 1, 16, 16, {"flags": 16}),                     # ... with two N tiles
+    (256, 2, 32, 128, {"flags": 16}),                    # 256 channels as two 128-channel N tiles, accumulators double-buffered
+]
+
+
+@pytest.mark.parametrize("c,n,h,w,tune", RES_CASES)
+@pytest.mark.parametrize("in_place", [False, True], ids=["res", "res_is_dst"])
+def test_conv_residual_forms(c, n, h, w, tune, in_place):
+    """relu(bn(conv(x)) + r) with r a separate map and with r == dst (ResidualBlock.conv2 in the engine), 1e-2 relative."""
+    ops = _ops()
+    x = _rand_fm(n, c, h, w, 90)
+    res = _rand_fm(n, c, h, w, 91)
+    wt = _rand_w((c, c, 3, 3), 92, 9 * c)
+    bn = _bn(c, 93)
+    spec = ops.ConvSpec.from_conv(wt, bn=bn, act=ops.ACT_RELU)
+    spec.w_fold = None                                   # the tap-by-tap kernel is the one under test
+    r = ops.nchw_to_nhwc(res)
+    y = ops.conv2d(spec, ops.nchw_to_nhwc(x), residual=r, dst=r if in_place else None, tune=tune)
+    ref = F.relu(_bn_ref(F.conv2d(x, wt, padding=1), bn) + res)
+    _close(ops.nhwc_to_nchw(y), ref)
+
+
 @pytest.mark.parametrize("act", ["tanh", "sigmoid", "none"])
 def test_conv_activations(act):
     ops = _ops()
