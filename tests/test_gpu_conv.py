@@ -83,6 +83,13 @@ CONV_CASES = [
     (192, 192, 3, 2, 32, 128, {"flags": 16 + 1024}),     # forced split: two 96-channel N tiles
     (384, 384, 3, 1, 32, 64, {"flags": 16 + 1024}),      # forced split of both 192-channel tiles: four N tiles
     (96, 96, 3, 2, 64, 128, {"mt": 2}),
+    # single accumulator stage with two sub-tiles per CTA (N = 160 .. 192: the epilogue is exposed, accumulator released early)
+    (192, 192, 3, 2, 32, 256, {"flags": 16}),            # N = 192 CTA pair, many tiles per CTA
+    (192, 192, 3, 1, 24, 200, {"flags": 32}),            # 1-CTA, ragged
+    (384, 384, 3, 1, 16, 128, {"flags": 16}),            # two N tiles of 192, six channel chunks
+    (128, 128, 3, 2, 64, 128, {"flags": 16, "mt": 2, "acc": 1}),   # forced single stage on a shape that would double-buffer
+    (96, 96, 3, 4, 64, 128, {"mt": 2, "acc": 1}),        # 32-channel slabs, ragged last K chunk
+    (160, 160, 3, 2, 32, 128, {"flags": 16}),            # N = 160: five 32-channel slabs per sub-tile
     (64, 64, 3, 2, 64, 128, {"stages": 2, "acc": 1}),
     (64, 64, 3, 2, 64, 256, None),           # halo re-use path: tile = one image row (TW = 128), 128-byte swizzle
     (96, 96, 3, 1, 32, 128, None),           # halo path with 64-byte swizzle rows (Ck = 32)
